@@ -1,0 +1,1314 @@
+// oracle/oracle.cc — TEST INFRASTRUCTURE ONLY. Never linked into or called from libskeres.so.
+//
+// CPU (FP64, dependency-free C++17) restatement of the algorithm the reference executes for
+// ceres.solve (SimpleBundleAdjuster.scala:152, CurveFitting.scala:127):
+//   * in-tree part: cost functors + the Jet autodiff bridge (oracle/jet.h, and
+//     AutodiffCostFunction.scala:74-134 restated in autodiff_evaluate below);
+//   * out-of-tree part: Ceres Solver (linked by the reference as -lceres, build.sh:43; NOT vendored
+//     and NOT version-pinned: configuration.sh:8,11; inferred 1.12–1.13).  Its
+//     source is absent from /root/reference, so the trust-region minimizer, LM strategy, Schur
+//     eliminator, implicit Schur complement, SchurJacobi preconditioner, conjugate gradients and
+//     dense QR / Cholesky below restate the *published algorithm* of those components
+//     (upstream file names are given beside each function).
+//
+// PARITY PIN STATUS
+//   pinned   : evaluate boundary (AutodiffCostFuntionSpec.scala golden vectors), angleAxisRotatePoint
+//              (RotationSpec.scala:616-655), CurveFitting known answers.
+//   UNPINNED : solver-level results (final cost, iteration count, termination).  No test in the
+//              reference calls ceres.solve and libceres cannot be built here, so for those this
+//              file says "parity unpinned".  The CurveFitting trajectory is checked against the
+//              upstream Ceres tutorial log as recalled in BASELINE.md §3 (tests/test_oracle_solver.py).
+//
+// Threading: deterministic OpenMP (fixed work partition, per-block sequential sums), so results do
+// not depend on the thread count.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "../include/skeres.h"
+#include "jet.h"
+
+namespace oracle {
+
+constexpr int kMaxBlocks = SK_MAX_PARAMETER_BLOCKS;
+constexpr int kMaxResiduals = 3;
+constexpr int kMaxConsts = SK_MAX_CONSTS;
+
+// ------------------------------------------------------------------------------------------------
+// Functor registry + AutoDiffCostFunction.evaluate (AutodiffCostFunction.scala:74-134)
+// ------------------------------------------------------------------------------------------------
+struct FunctorInfo { int id, nres, nblk, sizes[kMaxBlocks], nconsts; };
+static const FunctorInfo kFunctors[] = {
+    {SK_FUNCTOR_SNAVELY_REPROJECTION_ERROR, 2, 2, {9, 3}, 2},
+    {SK_FUNCTOR_EXPONENTIAL_RESIDUAL, 1, 2, {1, 1}, 2},
+    {SK_FUNCTOR_TEST_BILINEAR_SCALAR, 1, 2, {2, 2}, 1},
+    {SK_FUNCTOR_TEST_BILINEAR_VECTOR3, 3, 2, {2, 2}, 1},
+    {SK_FUNCTOR_TEST_SUM10, 1, 10, {1, 1, 1, 1, 1, 1, 1, 1, 1, 1}, 0},
+};
+static const FunctorInfo* find_functor(int id) {
+  for (const auto& f : kFunctors) if (f.id == id) return &f;
+  return nullptr;
+}
+
+template <int NRES, int NBLK, int NTOT, class F>
+static bool autodiff_evaluate(F f, const int* sizes, const double* consts,
+                              double const* const* parameters, double* residuals, double** jacobians) {
+  if (jacobians == nullptr) {                                   // :80
+    double y[NRES];
+    if (!f(consts, parameters, y)) return false;                // :86-89 (empty array == failure)
+    for (int r = 0; r < NRES; ++r) residuals[r] = y[r];         // :91
+    return true;
+  }
+  using J = Jet<NTOT>;
+  J jx[NTOT];
+  const J* jp[NBLK];
+  int k = 0;
+  for (int i = 0; i < NBLK; ++i) {                              // :97-106
+    jp[i] = &jx[k];
+    for (int j = 0; j < sizes[i]; ++j) { jx[k] = J(parameters[i][j], k); ++k; }
+  }
+  J jy[NRES];
+  if (!f(consts, (J const* const*)jp, jy)) return false;        // :108-111
+  for (int r = 0; r < NRES; ++r) residuals[r] = jy[r].a;        // :113
+  int off = 0;
+  for (int i = 0; i < NBLK; ++i) {                              // :115-130
+    const int ni = sizes[i];
+    if (jacobians[i] != nullptr) {                              // :118 hasRow
+      int col = 0;
+      for (int r = 0; r < NRES; ++r)
+        for (int p = 0; p < ni; ++p) jacobians[i][col++] = jy[r].v[off + p];   // row-major
+    }
+    off += ni;
+  }
+  return true;
+}
+
+static bool evaluate_functor(const FunctorInfo& fi, const double* consts, double const* const* params,
+                             double* residuals, double** jacobians) {
+  switch (fi.id) {
+    case SK_FUNCTOR_SNAVELY_REPROJECTION_ERROR:
+      return autodiff_evaluate<2, 2, 12>([](const double* c, auto const* const* p, auto* r) {
+        return snavelyReprojectionError(c, p, r); }, fi.sizes, consts, params, residuals, jacobians);
+    case SK_FUNCTOR_EXPONENTIAL_RESIDUAL:
+      return autodiff_evaluate<1, 2, 2>([](const double* c, auto const* const* p, auto* r) {
+        return exponentialResidual(c, p, r); }, fi.sizes, consts, params, residuals, jacobians);
+    case SK_FUNCTOR_TEST_BILINEAR_SCALAR:
+      return autodiff_evaluate<1, 2, 4>([](const double* c, auto const* const* p, auto* r) {
+        return testBilinearScalar(c, p, r); }, fi.sizes, consts, params, residuals, jacobians);
+    case SK_FUNCTOR_TEST_BILINEAR_VECTOR3:
+      return autodiff_evaluate<3, 2, 4>([](const double* c, auto const* const* p, auto* r) {
+        return testBilinearVector3(c, p, r); }, fi.sizes, consts, params, residuals, jacobians);
+    case SK_FUNCTOR_TEST_SUM10:
+      return autodiff_evaluate<1, 10, 10>([](const double* c, auto const* const* p, auto* r) {
+        return testSum10(c, p, r); }, fi.sizes, consts, params, residuals, jacobians);
+  }
+  return false;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Loss functions (ceres/loss_function.cc) and Corrector (internal/ceres/corrector.cc) — A.2
+// ------------------------------------------------------------------------------------------------
+static void loss_evaluate(int type, double a, double s, double rho[3]) {
+  const double kMin = std::numeric_limits<double>::min();
+  switch (type) {
+    case SK_LOSS_HUBER: {
+      const double b = a * a;
+      if (s > b) {
+        const double r = std::sqrt(s);
+        rho[0] = 2.0 * a * r - b;
+        rho[1] = std::max(kMin, a / r);
+        rho[2] = -rho[1] / (2.0 * s);
+      } else { rho[0] = s; rho[1] = 1.0; rho[2] = 0.0; }
+      return;
+    }
+    case SK_LOSS_CAUCHY: {
+      const double b = a * a, c = 1.0 / b;
+      const double sum = 1.0 + s * c, inv = 1.0 / sum;
+      rho[0] = b * std::log(sum);
+      rho[1] = std::max(kMin, inv);
+      rho[2] = -c * (inv * inv);
+      return;
+    }
+    default: rho[0] = s; rho[1] = 1.0; rho[2] = 0.0; return;
+  }
+}
+
+struct Corrector {
+  double sqrt_rho1, residual_scaling, alpha_sq_norm;
+  Corrector(double sq_norm, const double rho[3]) {
+    sqrt_rho1 = std::sqrt(rho[1]);
+    if (sq_norm == 0.0 || rho[2] <= 0.0) { residual_scaling = sqrt_rho1; alpha_sq_norm = 0.0; return; }
+    const double D = 1.0 + 2.0 * sq_norm * rho[2] / rho[1];
+    const double alpha = 1.0 - ((D > 0.0) ? std::sqrt(D) : 0.0);
+    residual_scaling = sqrt_rho1 / (1 - alpha);
+    alpha_sq_norm = alpha / sq_norm;
+  }
+  void correct_residuals(int n, double* r) const { for (int i = 0; i < n; ++i) r[i] *= residual_scaling; }
+  void correct_jacobian(int nrow, int ncol, const double* r, double* J) const {
+    if (alpha_sq_norm == 0.0) { for (int i = 0; i < nrow * ncol; ++i) J[i] *= sqrt_rho1; return; }
+    for (int c = 0; c < ncol; ++c) {
+      double rtj = 0.0;
+      for (int q = 0; q < nrow; ++q) rtj += J[q * ncol + c] * r[q];
+      for (int q = 0; q < nrow; ++q) J[q * ncol + c] = sqrt_rho1 * (J[q * ncol + c] - alpha_sq_norm * r[q] * rtj);
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Problem / Program
+// ------------------------------------------------------------------------------------------------
+struct RB {
+  const FunctorInfo* fi;
+  int loss; double loss_a;
+  double consts[kMaxConsts];
+  int64_t off[kMaxBlocks];
+};
+
+struct Problem {
+  double* params; int64_t n;
+  std::vector<RB> rbs;
+};
+
+struct PB { int64_t offset; int size; int64_t col; };
+
+struct Program {
+  std::vector<PB> pbs;               // program order (e-blocks first for Schur solvers)
+  std::vector<int32_t> row_rb;       // row order -> index into Problem::rbs
+  std::vector<int32_t> rb_pb;        // [row order][kMaxBlocks] -> pb index
+  std::vector<int64_t> rb_row;       // first scalar row of each rb (row order)
+  std::vector<int64_t> rb_jpos;      // first Jacobian value of each rb (row order)
+  int64_t num_rows = 0, num_cols = 0, num_jvals = 0;
+  int32_t num_e_blocks = 0; int64_t num_cols_e = 0;
+  std::vector<int64_t> chunk_start;  // e-block -> first rb (row order); size num_e_blocks + 1
+  // pb -> list of (rb row-order index, cell) in row order (deterministic parallel column sums)
+  std::vector<int64_t> pb_ptr; std::vector<int32_t> pb_rb; std::vector<int8_t> pb_cell;
+  int64_t num_rbs() const { return (int64_t)row_rb.size(); }
+};
+
+static bool is_schur(int t) { return t == SK_DENSE_SCHUR || t == SK_SPARSE_SCHUR || t == SK_ITERATIVE_SCHUR; }
+
+static bool build_program(const Problem& prob, bool schur, Program* out, std::string* err) {
+  Program& P = *out;
+  const int64_t nrb = (int64_t)prob.rbs.size();
+  std::unordered_map<int64_t, int32_t> index;
+  index.reserve((size_t)nrb);
+  std::vector<PB> first;                   // first-appearance order (Ceres Program order)
+  std::vector<int32_t> rbpb((size_t)nrb * kMaxBlocks, -1);
+  for (int64_t i = 0; i < nrb; ++i) {
+    const RB& rb = prob.rbs[i];
+    for (int k = 0; k < rb.fi->nblk; ++k) {
+      auto it = index.find(rb.off[k]);
+      int32_t id;
+      if (it == index.end()) {
+        id = (int32_t)first.size(); index.emplace(rb.off[k], id);
+        first.push_back({rb.off[k], rb.fi->sizes[k], 0});
+      } else {
+        id = it->second;
+        if (first[id].size != rb.fi->sizes[k]) { *err = "parameter block used with two different sizes"; return false; }
+      }
+      rbpb[i * kMaxBlocks + k] = id;
+    }
+  }
+  const int32_t npb = (int32_t)first.size();
+  std::vector<int32_t> perm(npb);          // first-appearance id -> program position
+  std::vector<int32_t> eblock_of_rb;
+  if (schur) {
+    // with no user ordering Ceres picks a maximal independent set (points on BAL).
+    // The oracle fixes "e-blocks = the blocks that only ever appear as the LAST block of a residual
+    // block" (the point in SnavelyReprojectionError(2, 9, 3)).
+    std::vector<char> last_only(npb, 1), seen_last(npb, 0);
+    for (int64_t i = 0; i < nrb; ++i) {
+      const int nb = prob.rbs[i].fi->nblk;
+      if (nb < 2) { for (int k = 0; k < nb; ++k) last_only[rbpb[i * kMaxBlocks + k]] = 0; continue; }
+      for (int k = 0; k + 1 < nb; ++k) last_only[rbpb[i * kMaxBlocks + k]] = 0;
+      seen_last[rbpb[i * kMaxBlocks + nb - 1]] = 1;
+    }
+    std::vector<int32_t> e, f;
+    for (int32_t b = 0; b < npb; ++b) ((last_only[b] && seen_last[b]) ? e : f).push_back(b);
+    auto by_off = [&](int32_t a, int32_t b) { return first[a].offset < first[b].offset; };
+    std::sort(e.begin(), e.end(), by_off);
+    std::sort(f.begin(), f.end(), by_off);
+    P.num_e_blocks = (int32_t)e.size();
+    int32_t pos = 0;
+    for (int32_t b : e) perm[b] = pos++;
+    for (int32_t b : f) perm[b] = pos++;
+    if (P.num_e_blocks == 0) { *err = "Schur solver requested but no e-blocks found"; return false; }
+  } else {
+    for (int32_t b = 0; b < npb; ++b) perm[b] = b;
+    P.num_e_blocks = 0;
+  }
+  P.pbs.resize(npb);
+  for (int32_t b = 0; b < npb; ++b) P.pbs[perm[b]] = first[b];
+  int64_t col = 0; P.num_cols_e = 0;
+  for (int32_t b = 0; b < npb; ++b) {
+    P.pbs[b].col = col; col += P.pbs[b].size;
+    if (b + 1 == P.num_e_blocks) P.num_cols_e = col;
+  }
+  P.num_cols = col;
+  // Row order: stable sort by e-block (rows without an e-block last) — Ceres' reordering of the
+  // residual blocks for the Schur eliminator.
+  P.row_rb.resize(nrb);
+  for (int64_t i = 0; i < nrb; ++i) P.row_rb[i] = (int32_t)i;
+  std::vector<int32_t> ekey;
+  if (schur) {
+    ekey.assign(nrb, std::numeric_limits<int32_t>::max());
+    for (int64_t i = 0; i < nrb; ++i) {
+      const int nb = prob.rbs[i].fi->nblk;
+      const int32_t last = perm[rbpb[i * kMaxBlocks + nb - 1]];
+      if (last < P.num_e_blocks) ekey[i] = last;
+    }
+    std::stable_sort(P.row_rb.begin(), P.row_rb.end(), [&](int32_t a, int32_t b) { return ekey[a] < ekey[b]; });
+  }
+  P.rb_pb.assign((size_t)nrb * kMaxBlocks, -1);
+  P.rb_row.resize(nrb); P.rb_jpos.resize(nrb);
+  int64_t row = 0, jp = 0;
+  for (int64_t r = 0; r < nrb; ++r) {
+    const int32_t i = P.row_rb[r];
+    const RB& rb = prob.rbs[i];
+    P.rb_row[r] = row; P.rb_jpos[r] = jp;
+    row += rb.fi->nres;
+    for (int k = 0; k < rb.fi->nblk; ++k) {
+      P.rb_pb[r * kMaxBlocks + k] = perm[rbpb[(int64_t)i * kMaxBlocks + k]];
+      jp += (int64_t)rb.fi->nres * rb.fi->sizes[k];
+    }
+  }
+  P.num_rows = row; P.num_jvals = jp;
+  if (schur) {
+    P.chunk_start.assign(P.num_e_blocks + 1, 0);
+    int64_t r = 0;
+    for (int32_t e = 0; e < P.num_e_blocks; ++e) {
+      P.chunk_start[e] = r;
+      while (r < nrb && ekey[P.row_rb[r]] == e) ++r;
+    }
+    P.chunk_start[P.num_e_blocks] = r;   // rows r..nrb-1 have no e-block
+  }
+  // pb -> (rb, cell) lists
+  P.pb_ptr.assign(npb + 1, 0);
+  for (int64_t r = 0; r < nrb; ++r) {
+    const int nb = prob.rbs[P.row_rb[r]].fi->nblk;
+    for (int k = 0; k < nb; ++k) P.pb_ptr[P.rb_pb[r * kMaxBlocks + k] + 1]++;
+  }
+  for (int32_t b = 0; b < npb; ++b) P.pb_ptr[b + 1] += P.pb_ptr[b];
+  P.pb_rb.resize(P.pb_ptr[npb]); P.pb_cell.resize(P.pb_ptr[npb]);
+  std::vector<int64_t> fill(P.pb_ptr.begin(), P.pb_ptr.end() - 1);
+  for (int64_t r = 0; r < nrb; ++r) {
+    const int nb = prob.rbs[P.row_rb[r]].fi->nblk;
+    for (int k = 0; k < nb; ++k) {
+      const int32_t b = P.rb_pb[r * kMaxBlocks + k];
+      P.pb_rb[fill[b]] = (int32_t)r; P.pb_cell[fill[b]] = (int8_t)k; fill[b]++;
+    }
+  }
+  return true;
+}
+
+// Offset of cell k's values inside the rb's Jacobian storage.
+static inline int64_t cell_pos(const RB& rb, int k) {
+  int64_t p = 0;
+  for (int j = 0; j < k; ++j) p += (int64_t)rb.fi->nres * rb.fi->sizes[j];
+  return p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Evaluator (internal/ceres/program_evaluator.h, residual_block.cc) — A.2
+// x is the state vector in program order.  jvals == nullptr -> no Jacobian / gradient.
+// ------------------------------------------------------------------------------------------------
+static bool evaluate(const Problem& prob, const Program& P, const double* x, double* cost,
+                     double* residuals, double* gradient, double* jvals) {
+  const int64_t nrb = P.num_rbs();
+  std::vector<double> block_cost((size_t)nrb);
+  int failed = 0;
+#pragma omp parallel for schedule(static) reduction(|:failed)
+  for (int64_t r = 0; r < nrb; ++r) {
+    const RB& rb = prob.rbs[P.row_rb[r]];
+    const FunctorInfo& fi = *rb.fi;
+    const double* params[kMaxBlocks];
+    double* jac[kMaxBlocks];
+    int64_t jp = jvals ? P.rb_jpos[r] : 0;
+    for (int k = 0; k < fi.nblk; ++k) {
+      params[k] = x + P.pbs[P.rb_pb[r * kMaxBlocks + k]].col;
+      if (jvals) { jac[k] = jvals + jp; jp += (int64_t)fi.nres * fi.sizes[k]; }
+    }
+    double res[kMaxResiduals];
+    if (!evaluate_functor(fi, rb.consts, params, res, jvals ? jac : nullptr)) { failed |= 1; block_cost[r] = 0; continue; }
+    double sq = 0.0;
+    for (int q = 0; q < fi.nres; ++q) sq += res[q] * res[q];
+    double rho[3];
+    loss_evaluate(rb.loss, rb.loss_a, sq, rho);
+    block_cost[r] = 0.5 * rho[0];
+    if (jvals || residuals) {
+      Corrector corr(sq, rho);
+      if (jvals) for (int k = 0; k < fi.nblk; ++k) corr.correct_jacobian(fi.nres, fi.sizes[k], res, jac[k]);
+      corr.correct_residuals(fi.nres, res);
+      if (residuals) for (int q = 0; q < fi.nres; ++q) residuals[P.rb_row[r] + q] = res[q];
+    }
+  }
+  if (failed) return false;
+  double c = 0.0;
+  for (int64_t r = 0; r < nrb; ++r) c += block_cost[r];
+  *cost = c;
+  if (gradient && jvals && residuals) {
+    const int32_t npb = (int32_t)P.pbs.size();
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int32_t b = 0; b < npb; ++b) {
+      const int sz = P.pbs[b].size;
+      double* g = gradient + P.pbs[b].col;
+      for (int c2 = 0; c2 < sz; ++c2) g[c2] = 0.0;
+      for (int64_t t = P.pb_ptr[b]; t < P.pb_ptr[b + 1]; ++t) {
+        const int64_t r = P.pb_rb[t];
+        const RB& rb = prob.rbs[P.row_rb[r]];
+        const double* J = jvals + P.rb_jpos[r] + cell_pos(rb, P.pb_cell[t]);
+        const double* res = residuals + P.rb_row[r];
+        for (int q = 0; q < rb.fi->nres; ++q)
+          for (int c2 = 0; c2 < sz; ++c2) g[c2] += J[q * sz + c2] * res[q];
+      }
+    }
+  }
+  return true;
+}
+
+static void squared_column_norm(const Problem& prob, const Program& P, const double* jvals, double* out) {
+  const int32_t npb = (int32_t)P.pbs.size();
+#pragma omp parallel for schedule(dynamic, 256)
+  for (int32_t b = 0; b < npb; ++b) {
+    const int sz = P.pbs[b].size;
+    double* o = out + P.pbs[b].col;
+    for (int c = 0; c < sz; ++c) o[c] = 0.0;
+    for (int64_t t = P.pb_ptr[b]; t < P.pb_ptr[b + 1]; ++t) {
+      const int64_t r = P.pb_rb[t];
+      const RB& rb = prob.rbs[P.row_rb[r]];
+      const double* J = jvals + P.rb_jpos[r] + cell_pos(rb, P.pb_cell[t]);
+      for (int q = 0; q < rb.fi->nres; ++q)
+        for (int c = 0; c < sz; ++c) o[c] += J[q * sz + c] * J[q * sz + c];
+    }
+  }
+}
+
+static void scale_columns(const Problem& prob, const Program& P, const double* scale, double* jvals) {
+  const int64_t nrb = P.num_rbs();
+#pragma omp parallel for schedule(static)
+  for (int64_t r = 0; r < nrb; ++r) {
+    const RB& rb = prob.rbs[P.row_rb[r]];
+    double* J = jvals + P.rb_jpos[r];
+    for (int k = 0; k < rb.fi->nblk; ++k) {
+      const int sz = rb.fi->sizes[k];
+      const double* s = scale + P.pbs[P.rb_pb[r * kMaxBlocks + k]].col;
+      for (int q = 0; q < rb.fi->nres; ++q)
+        for (int c = 0; c < sz; ++c) J[q * sz + c] *= s[c];
+      J += (int64_t)rb.fi->nres * sz;
+    }
+  }
+}
+
+// y += J x  (BlockSparseMatrix::RightMultiply)
+static void right_multiply(const Problem& prob, const Program& P, const double* jvals, const double* x, double* y) {
+  const int64_t nrb = P.num_rbs();
+#pragma omp parallel for schedule(static)
+  for (int64_t r = 0; r < nrb; ++r) {
+    const RB& rb = prob.rbs[P.row_rb[r]];
+    const double* J = jvals + P.rb_jpos[r];
+    double* yr = y + P.rb_row[r];
+    for (int k = 0; k < rb.fi->nblk; ++k) {
+      const int sz = rb.fi->sizes[k];
+      const double* xb = x + P.pbs[P.rb_pb[r * kMaxBlocks + k]].col;
+      for (int q = 0; q < rb.fi->nres; ++q)
+        for (int c = 0; c < sz; ++c) yr[q] += J[q * sz + c] * xb[c];
+      J += (int64_t)rb.fi->nres * sz;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Small dense kernels
+// ------------------------------------------------------------------------------------------------
+// In-place upper Cholesky A = U^T U of the upper triangle of row-major n x n (ld = n). Eigen LLT<Upper>.
+static bool cholesky_upper(double* A, int64_t n) {
+  for (int64_t j = 0; j < n; ++j) {
+    double d = A[j * n + j];
+    for (int64_t k = 0; k < j; ++k) d -= A[k * n + j] * A[k * n + j];
+    if (!(d > 0.0)) return false;
+    d = std::sqrt(d);
+    A[j * n + j] = d;
+    const double inv = 1.0 / d;
+#pragma omp parallel for schedule(static) if (n - j > 512)
+    for (int64_t i = j + 1; i < n; ++i) {
+      double s = A[j * n + i];
+      for (int64_t k = 0; k < j; ++k) s -= A[k * n + j] * A[k * n + i];
+      A[j * n + i] = s * inv;
+    }
+  }
+  return true;
+}
+static void cholesky_upper_solve(const double* U, int64_t n, double* b) {
+  for (int64_t i = 0; i < n; ++i) {          // U^T y = b
+    double s = b[i];
+    for (int64_t k = 0; k < i; ++k) s -= U[k * n + i] * b[k];
+    b[i] = s / U[i * n + i];
+  }
+  for (int64_t i = n - 1; i >= 0; --i) {     // U x = y
+    double s = b[i];
+    for (int64_t k = i + 1; k < n; ++k) s -= U[i * n + k] * b[k];
+    b[i] = s / U[i * n + i];
+  }
+}
+// InvertPSDMatrix (internal/ceres/invert_psd_matrix.h): m.selfadjointView<Upper>().llt().solve(I)
+static bool invert_psd(const double* m, int n, double* inv) {
+  double U[81];
+  for (int i = 0; i < n * n; ++i) U[i] = m[i];
+  if (!cholesky_upper(U, n)) return false;
+  for (int c = 0; c < n; ++c) {
+    double e[9];
+    for (int i = 0; i < n; ++i) e[i] = (i == c) ? 1.0 : 0.0;
+    cholesky_upper_solve(U, n, e);
+    for (int i = 0; i < n; ++i) inv[i * n + c] = e[i];
+  }
+  return true;
+}
+
+enum LinTerm { LIN_SUCCESS = 0, LIN_NO_CONVERGENCE = 1, LIN_FAILURE = 2, LIN_FATAL = 3 };
+struct LinSummary { int termination = LIN_SUCCESS; int num_iterations = 0; };
+
+struct SolveCtx {
+  const Problem& prob; const Program& P; const sk_solver_options& opt;
+};
+
+// ------------------------------------------------------------------------------------------------
+// DENSE_QR (internal/ceres/dense_qr_solver.cc): x = householderQr([J; D]).solve([b; 0]) — A.8
+// Unpivoted Householder with Eigen's reflector convention (beta = -sign(c0)*||col||).
+// ------------------------------------------------------------------------------------------------
+static LinSummary dense_qr_solve(const SolveCtx& c, const double* jvals, const double* b, const double* D, double* x) {
+  const Program& P = c.P;
+  const int64_t m0 = P.num_rows, n = P.num_cols, m = m0 + n;
+  std::vector<double> A((size_t)m * n, 0.0), rhs((size_t)m, 0.0);   // column-major
+  for (int64_t r = 0; r < P.num_rbs(); ++r) {
+    const RB& rb = c.prob.rbs[P.row_rb[r]];
+    const double* J = jvals + P.rb_jpos[r];
+    for (int k = 0; k < rb.fi->nblk; ++k) {
+      const int sz = rb.fi->sizes[k];
+      const int64_t col = P.pbs[P.rb_pb[r * kMaxBlocks + k]].col;
+      for (int q = 0; q < rb.fi->nres; ++q)
+        for (int cc = 0; cc < sz; ++cc) A[(col + cc) * m + P.rb_row[r] + q] += J[q * sz + cc];
+      J += (int64_t)rb.fi->nres * sz;
+    }
+  }
+  for (int64_t j = 0; j < n; ++j) A[j * m + m0 + j] = D[j];
+  for (int64_t i = 0; i < m0; ++i) rhs[i] = b[i];
+  for (int64_t k = 0; k < n; ++k) {
+    double* ck = &A[k * m];
+    const double c0 = ck[k];
+    double tail = 0.0;
+    for (int64_t i = k + 1; i < m; ++i) tail += ck[i] * ck[i];
+    double tau, beta;
+    if (tail <= std::numeric_limits<double>::min()) { tau = 0.0; beta = c0; for (int64_t i = k + 1; i < m; ++i) ck[i] = 0.0; }
+    else {
+      beta = std::sqrt(c0 * c0 + tail);
+      if (c0 >= 0.0) beta = -beta;
+      const double d = c0 - beta;
+      for (int64_t i = k + 1; i < m; ++i) ck[i] /= d;
+      tau = (beta - c0) / beta;
+    }
+    ck[k] = beta;
+    for (int64_t j = k + 1; j <= n; ++j) {     // remaining columns, then the rhs (j == n)
+      double* cj = (j < n) ? &A[j * m] : rhs.data();
+      double s = 0.0;
+      for (int64_t i = k + 1; i < m; ++i) s += ck[i] * cj[i];
+      s += cj[k];
+      cj[k] -= tau * s;
+      for (int64_t i = k + 1; i < m; ++i) cj[i] -= tau * s * ck[i];
+    }
+  }
+  for (int64_t i = n - 1; i >= 0; --i) {
+    double s = rhs[i];
+    for (int64_t j = i + 1; j < n; ++j) s -= A[j * m + i] * x[j];
+    x[i] = s / A[i * m + i];
+  }
+  LinSummary sum; sum.num_iterations = 1; return sum;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SchurEliminator (internal/ceres/schur_eliminator_impl.h) — A.5.  lhs is either the dense reduced
+// camera matrix (upper block triangle filled) or only its diagonal blocks (SchurJacobi).
+// ------------------------------------------------------------------------------------------------
+struct ReducedMatrix {
+  bool diagonal_only;
+  int64_t nf = 0;                       // scalar size
+  std::vector<double> dense;            // nf x nf row-major (diagonal_only == false)
+  std::vector<int64_t> blk_pos;         // per f-block: position of its diagonal block (diagonal_only)
+  std::vector<double> blocks;
+};
+
+struct Schur {
+  const SolveCtx& c;
+  explicit Schur(const SolveCtx& ctx) : c(ctx) {}
+  int fsize(int32_t pb) const { return c.P.pbs[pb].size; }
+  int64_t fcol(int32_t pb) const { return c.P.pbs[pb].col - c.P.num_cols_e; }
+
+  void init_lhs(ReducedMatrix* S, bool diagonal_only) const {
+    const Program& P = c.P;
+    S->diagonal_only = diagonal_only; S->nf = P.num_cols - P.num_cols_e;
+    if (!diagonal_only) S->dense.assign((size_t)S->nf * S->nf, 0.0);
+    else {
+      S->blk_pos.assign(P.pbs.size(), 0);
+      int64_t pos = 0;
+      for (size_t b = P.num_e_blocks; b < P.pbs.size(); ++b) { S->blk_pos[b] = pos; pos += (int64_t)P.pbs[b].size * P.pbs[b].size; }
+      S->blocks.assign((size_t)pos, 0.0);
+    }
+  }
+  // cell (b1 <= b2): pointer + row stride; nullptr when not stored.
+  double* cell(ReducedMatrix* S, int32_t b1, int32_t b2, int64_t* stride) const {
+    if (S->diagonal_only) { if (b1 != b2) return nullptr; *stride = fsize(b1); return &S->blocks[S->blk_pos[b1]]; }
+    *stride = S->nf; return &S->dense[fcol(b1) * S->nf + fcol(b2)];
+  }
+
+  bool eliminate(const double* jvals, const double* b, const double* D, ReducedMatrix* S, double* rhs) const {
+    const Program& P = c.P; const Problem& prob = c.prob;
+    if (!S->diagonal_only) std::fill(S->dense.begin(), S->dense.end(), 0.0); else std::fill(S->blocks.begin(), S->blocks.end(), 0.0);
+    std::fill(rhs, rhs + S->nf, 0.0);
+    // Add the diagonal to the Schur complement.
+    if (D) for (size_t fb = P.num_e_blocks; fb < P.pbs.size(); ++fb) {
+      int64_t st; double* m = cell(S, (int32_t)fb, (int32_t)fb, &st);
+      for (int i = 0; i < fsize((int32_t)fb); ++i) { const double d = D[P.pbs[fb].col + i]; m[i * st + i] += d * d; }
+    }
+    struct Slot { int32_t fb; int pos; };
+    std::vector<Slot> layout; std::vector<double> buffer;
+    for (int32_t e = 0; e < P.num_e_blocks; ++e) {
+      const int es = P.pbs[e].size;
+      double ete[81] = {0}, g[9] = {0};
+      if (D) for (int i = 0; i < es; ++i) { const double d = D[P.pbs[e].col + i]; ete[i * es + i] = d * d; }
+      layout.clear(); buffer.clear();
+      for (int64_t r = P.chunk_start[e]; r < P.chunk_start[e + 1]; ++r) {
+        const RB& rb = prob.rbs[P.row_rb[r]];
+        const int nres = rb.fi->nres, nb = rb.fi->nblk;
+        const double* J = jvals + P.rb_jpos[r];
+        const double* E = J + cell_pos(rb, nb - 1);
+        for (int q = 0; q < nres; ++q) for (int i = 0; i < es; ++i) for (int j = 0; j < es; ++j) ete[i * es + j] += E[q * es + i] * E[q * es + j];
+        if (b) for (int q = 0; q < nres; ++q) for (int i = 0; i < es; ++i) g[i] += E[q * es + i] * b[P.rb_row[r] + q];
+        const double* F = J;
+        for (int k = 0; k + 1 < nb; ++k) {
+          const int32_t fb = P.rb_pb[r * kMaxBlocks + k]; const int fs = fsize(fb);
+          int pos = -1;
+          for (auto& s : layout) if (s.fb == fb) { pos = s.pos; break; }
+          if (pos < 0) { pos = (int)buffer.size(); layout.push_back({fb, pos}); buffer.resize(buffer.size() + (size_t)es * fs, 0.0); }
+          double* buf = &buffer[pos];
+          for (int q = 0; q < nres; ++q) for (int i = 0; i < es; ++i) for (int j = 0; j < fs; ++j) buf[i * fs + j] += E[q * es + i] * F[q * fs + j];
+          // EBlockRowOuterProduct: S(k1,k2) += F_k1^T F_k2 for k1 <= k2 (block order)
+          const double* F2 = F;
+          for (int k2 = k; k2 + 1 < nb; ++k2) {
+            const int32_t fb2 = P.rb_pb[r * kMaxBlocks + k2]; const int fs2 = fsize(fb2);
+            const bool swap = fb2 < fb;
+            int64_t st; double* m = swap ? cell(S, fb2, fb, &st) : cell(S, fb, fb2, &st);
+            if (m) for (int q = 0; q < nres; ++q) for (int i = 0; i < fs; ++i) for (int j = 0; j < fs2; ++j) {
+              if (swap) m[j * st + i] += F[q * fs + i] * F2[q * fs2 + j]; else m[i * st + j] += F[q * fs + i] * F2[q * fs2 + j];
+            }
+            F2 += (int64_t)nres * fs2;
+          }
+          F += (int64_t)nres * fs;
+        }
+      }
+      double inv[81];
+      if (!invert_psd(ete, es, inv)) return false;
+      double invg[9];
+      for (int i = 0; i < es; ++i) { double s = 0; for (int j = 0; j < es; ++j) s += inv[i * es + j] * g[j]; invg[i] = s; }
+      // UpdateRhs: rhs += F^T (b - E inv g)
+      if (b) for (int64_t r = P.chunk_start[e]; r < P.chunk_start[e + 1]; ++r) {
+        const RB& rb = prob.rbs[P.row_rb[r]];
+        const int nres = rb.fi->nres, nb = rb.fi->nblk;
+        const double* J = jvals + P.rb_jpos[r];
+        const double* E = J + cell_pos(rb, nb - 1);
+        double sj[kMaxResiduals];
+        for (int q = 0; q < nres; ++q) { double s = b[P.rb_row[r] + q]; for (int i = 0; i < es; ++i) s -= E[q * es + i] * invg[i]; sj[q] = s; }
+        const double* F = J;
+        for (int k = 0; k + 1 < nb; ++k) {
+          const int32_t fb = P.rb_pb[r * kMaxBlocks + k]; const int fs = fsize(fb);
+          double* rr = rhs + fcol(fb);
+          for (int q = 0; q < nres; ++q) for (int j = 0; j < fs; ++j) rr[j] += F[q * fs + j] * sj[q];
+          F += (int64_t)nres * fs;
+        }
+      }
+      // ChunkOuterProduct: S(b1,b2) -= (E^T F_b1)^T inv (E^T F_b2), b1 <= b2 in block order
+      std::sort(layout.begin(), layout.end(), [](const Slot& a, const Slot& bb) { return a.fb < bb.fb; });
+      for (size_t i1 = 0; i1 < layout.size(); ++i1) {
+        const int32_t b1 = layout[i1].fb; const int f1 = fsize(b1);
+        const double* B1 = &buffer[layout[i1].pos];
+        double b1t_inv[81];   // f1 x es
+        for (int i = 0; i < f1; ++i) for (int j = 0; j < es; ++j) { double s = 0; for (int k = 0; k < es; ++k) s += B1[k * f1 + i] * inv[k * es + j]; b1t_inv[i * es + j] = s; }
+        for (size_t i2 = i1; i2 < layout.size(); ++i2) {
+          const int32_t b2 = layout[i2].fb; const int f2 = fsize(b2);
+          int64_t st; double* m = cell(S, b1, b2, &st);
+          if (!m) continue;
+          const double* B2 = &buffer[layout[i2].pos];
+          for (int i = 0; i < f1; ++i) for (int j = 0; j < f2; ++j) { double s = 0; for (int k = 0; k < es; ++k) s += b1t_inv[i * es + k] * B2[k * f2 + j]; m[i * st + j] -= s; }
+        }
+      }
+    }
+    // NoEBlockRowsUpdate
+    for (int64_t r = P.chunk_start[P.num_e_blocks]; r < P.num_rbs(); ++r) {
+      const RB& rb = prob.rbs[P.row_rb[r]];
+      const int nres = rb.fi->nres, nb = rb.fi->nblk;
+      const double* F = jvals + P.rb_jpos[r];
+      for (int k = 0; k < nb; ++k) {
+        const int32_t fb = P.rb_pb[r * kMaxBlocks + k]; const int fs = fsize(fb);
+        if (b) for (int q = 0; q < nres; ++q) for (int j = 0; j < fs; ++j) rhs[fcol(fb) + j] += F[q * fs + j] * b[P.rb_row[r] + q];
+        const double* F2 = F;
+        for (int k2 = k; k2 < nb; ++k2) {
+          const int32_t fb2 = P.rb_pb[r * kMaxBlocks + k2]; const int fs2 = fsize(fb2);
+          const bool swap = fb2 < fb;
+          int64_t st; double* m = swap ? cell(S, fb2, fb, &st) : cell(S, fb, fb2, &st);
+          if (m) for (int q = 0; q < nres; ++q) for (int i = 0; i < fs; ++i) for (int j = 0; j < fs2; ++j) {
+            if (swap) m[j * st + i] += F[q * fs + i] * F2[q * fs2 + j]; else m[i * st + j] += F[q * fs + i] * F2[q * fs2 + j];
+          }
+          F2 += (int64_t)nres * fs2;
+        }
+        F += (int64_t)nres * fs;
+      }
+    }
+    return true;
+  }
+
+  // y_e = (E^T E + D_e^2)^-1 sum E^T (b - F z)
+  bool back_substitute(const double* jvals, const double* b, const double* D, const double* z, double* y) const {
+    const Program& P = c.P; const Problem& prob = c.prob;
+    int bad = 0;
+#pragma omp parallel for schedule(dynamic, 512) reduction(|:bad)
+    for (int32_t e = 0; e < P.num_e_blocks; ++e) {
+      const int es = P.pbs[e].size;
+      double ete[81] = {0}, acc[9] = {0};
+      if (D) for (int i = 0; i < es; ++i) { const double d = D[P.pbs[e].col + i]; ete[i * es + i] = d * d; }
+      for (int64_t r = P.chunk_start[e]; r < P.chunk_start[e + 1]; ++r) {
+        const RB& rb = prob.rbs[P.row_rb[r]];
+        const int nres = rb.fi->nres, nb = rb.fi->nblk;
+        const double* J = jvals + P.rb_jpos[r];
+        const double* E = J + cell_pos(rb, nb - 1);
+        double sj[kMaxResiduals];
+        for (int q = 0; q < nres; ++q) sj[q] = b[P.rb_row[r] + q];
+        const double* F = J;
+        for (int k = 0; k + 1 < nb; ++k) {
+          const int32_t fb = P.rb_pb[r * kMaxBlocks + k]; const int fs = fsize(fb);
+          const double* zz = z + fcol(fb);
+          for (int q = 0; q < nres; ++q) for (int j = 0; j < fs; ++j) sj[q] -= F[q * fs + j] * zz[j];
+          F += (int64_t)nres * fs;
+        }
+        for (int q = 0; q < nres; ++q) for (int i = 0; i < es; ++i) acc[i] += E[q * es + i] * sj[q];
+        for (int q = 0; q < nres; ++q) for (int i = 0; i < es; ++i) for (int j = 0; j < es; ++j) ete[i * es + j] += E[q * es + i] * E[q * es + j];
+      }
+      double inv[81];
+      if (!invert_psd(ete, es, inv)) { bad |= 1; continue; }
+      double* ye = y + P.pbs[e].col;
+      for (int i = 0; i < es; ++i) { double s = 0; for (int j = 0; j < es; ++j) s += inv[i * es + j] * acc[j]; ye[i] = s; }
+    }
+    return !bad;
+  }
+};
+
+// DENSE_SCHUR / SPARSE_SCHUR (schur_complement_solver.cc).  SPARSE_SCHUR differs from DENSE_SCHUR
+// only in how the same reduced system is factorised, so the oracle uses the dense factorisation
+// (Eigen LLT<Upper> restated as cholesky_upper) for both.
+static LinSummary schur_solve(const SolveCtx& c, const double* jvals, const double* b, const double* D, double* x) {
+  const Program& P = c.P;
+  Schur se(c);
+  ReducedMatrix S; se.init_lhs(&S, false);
+  std::vector<double> rhs((size_t)S.nf);
+  LinSummary sum;
+  std::fill(x, x + P.num_cols, 0.0);
+  if (!se.eliminate(jvals, b, D, &S, rhs.data())) { sum.termination = LIN_FAILURE; return sum; }
+  sum.num_iterations = 1;
+  if (!cholesky_upper(S.dense.data(), S.nf)) { sum.termination = LIN_FAILURE; return sum; }
+  cholesky_upper_solve(S.dense.data(), S.nf, rhs.data());
+  double* z = x + P.num_cols_e;
+  for (int64_t i = 0; i < S.nf; ++i) z[i] = rhs[i];
+  if (!se.back_substitute(jvals, b, D, z, x)) sum.termination = LIN_FAILURE;
+  return sum;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ImplicitSchurComplement (implicit_schur_complement.cc) — A.6
+// ------------------------------------------------------------------------------------------------
+struct ImplicitSchur {
+  const SolveCtx& c; const double* jvals; const double* b; const double* D;
+  int64_t ne, nf, nrows;
+  std::vector<double> ete_inv;      // per e-block es x es
+  std::vector<int64_t> ete_pos;
+  std::vector<double> ftf_inv;      // JACOBI preconditioner blocks (per f-block)
+  std::vector<int64_t> ftf_pos;
+  std::vector<double> rhs, tmp_rows, tmp_e, tmp_e2;
+  bool ok = true;
+
+  ImplicitSchur(const SolveCtx& ctx, const double* J, const double* bb, const double* DD, bool jacobi)
+      : c(ctx), jvals(J), b(bb), D(DD) {
+    const Program& P = c.P;
+    ne = P.num_cols_e; nf = P.num_cols - ne; nrows = P.num_rows;
+    ete_pos.resize(P.num_e_blocks + 1);
+    int64_t pos = 0;
+    for (int32_t e = 0; e < P.num_e_blocks; ++e) { ete_pos[e] = pos; pos += (int64_t)P.pbs[e].size * P.pbs[e].size; }
+    ete_pos[P.num_e_blocks] = pos;
+    ete_inv.assign((size_t)pos, 0.0);
+    int bad = 0;
+#pragma omp parallel for schedule(dynamic, 512) reduction(|:bad)
+    for (int32_t e = 0; e < P.num_e_blocks; ++e) {        // block-diagonal E^T E, + D^2, inverted
+      const int es = P.pbs[e].size;
+      double m[81] = {0};
+      for (int64_t r = P.chunk_start[e]; r < P.chunk_start[e + 1]; ++r) {
+        const RB& rb = c.prob.rbs[P.row_rb[r]];
+        const double* E = jvals + P.rb_jpos[r] + cell_pos(rb, rb.fi->nblk - 1);
+        for (int q = 0; q < rb.fi->nres; ++q) for (int i = 0; i < es; ++i) for (int j = 0; j < es; ++j) m[i * es + j] += E[q * es + i] * E[q * es + j];
+      }
+      if (D) for (int i = 0; i < es; ++i) { const double d = D[P.pbs[e].col + i]; m[i * es + i] += d * d; }
+      if (!invert_psd(m, es, &ete_inv[ete_pos[e]])) bad |= 1;
+    }
+    if (bad) { ok = false; return; }
+    if (jacobi) {
+      ftf_pos.assign(P.pbs.size() + 1, 0);
+      pos = 0;
+      for (size_t fb = P.num_e_blocks; fb < P.pbs.size(); ++fb) { ftf_pos[fb] = pos; pos += (int64_t)P.pbs[fb].size * P.pbs[fb].size; }
+      ftf_inv.assign((size_t)pos, 0.0);
+      for (size_t fb = P.num_e_blocks; fb < P.pbs.size(); ++fb) {
+        const int fs = P.pbs[fb].size;
+        double m[81] = {0};
+        for (int64_t t = P.pb_ptr[fb]; t < P.pb_ptr[fb + 1]; ++t) {
+          const int64_t r = P.pb_rb[t];
+          const RB& rb = c.prob.rbs[P.row_rb[r]];
+          const double* F = jvals + P.rb_jpos[r] + cell_pos(rb, P.pb_cell[t]);
+          for (int q = 0; q < rb.fi->nres; ++q) for (int i = 0; i < fs; ++i) for (int j = 0; j < fs; ++j) m[i * fs + j] += F[q * fs + i] * F[q * fs + j];
+        }
+        if (D) for (int i = 0; i < fs; ++i) { const double d = D[P.pbs[fb].col + i]; m[i * fs + i] += d * d; }
+        if (!invert_psd(m, fs, &ftf_inv[ftf_pos[fb]])) { ok = false; return; }
+      }
+    }
+    rhs.assign((size_t)nf, 0.0); tmp_rows.assign((size_t)nrows, 0.0); tmp_e.assign((size_t)ne, 0.0); tmp_e2.assign((size_t)ne, 0.0);
+    update_rhs();
+  }
+  // PartitionedMatrixView products
+  void right_multiply_f(const double* xf, double* y) const {
+    const Program& P = c.P; const int64_t nrb = P.num_rbs();
+#pragma omp parallel for schedule(static)
+    for (int64_t r = 0; r < nrb; ++r) {
+      const RB& rb = c.prob.rbs[P.row_rb[r]];
+      const int nres = rb.fi->nres; const bool has_e = r < P.chunk_start[P.num_e_blocks];
+      const int nfc = rb.fi->nblk - (has_e ? 1 : 0);
+      const double* F = jvals + P.rb_jpos[r];
+      for (int k = 0; k < nfc; ++k) {
+        const int32_t fb = P.rb_pb[r * kMaxBlocks + k]; const int fs = P.pbs[fb].size;
+        const double* xx = xf + (P.pbs[fb].col - ne);
+        for (int q = 0; q < nres; ++q) for (int j = 0; j < fs; ++j) y[P.rb_row[r] + q] += F[q * fs + j] * xx[j];
+        F += (int64_t)nres * fs;
+      }
+    }
+  }
+  void left_multiply_f(const double* xr, double* yf) const {
+    const Program& P = c.P; const int32_t npb = (int32_t)P.pbs.size();
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int32_t fb = P.num_e_blocks; fb < npb; ++fb) {
+      const int fs = P.pbs[fb].size; double* yy = yf + (P.pbs[fb].col - ne);
+      for (int64_t t = P.pb_ptr[fb]; t < P.pb_ptr[fb + 1]; ++t) {
+        const int64_t r = P.pb_rb[t];
+        const RB& rb = c.prob.rbs[P.row_rb[r]];
+        const double* F = jvals + P.rb_jpos[r] + cell_pos(rb, P.pb_cell[t]);
+        for (int q = 0; q < rb.fi->nres; ++q) for (int j = 0; j < fs; ++j) yy[j] += F[q * fs + j] * xr[P.rb_row[r] + q];
+      }
+    }
+  }
+  void right_multiply_e(const double* xe, double* y) const {
+    const Program& P = c.P; const int64_t nrb = P.chunk_start[P.num_e_blocks];
+#pragma omp parallel for schedule(static)
+    for (int64_t r = 0; r < nrb; ++r) {
+      const RB& rb = c.prob.rbs[P.row_rb[r]];
+      const int32_t e = P.rb_pb[r * kMaxBlocks + rb.fi->nblk - 1]; const int es = P.pbs[e].size;
+      const double* E = jvals + P.rb_jpos[r] + cell_pos(rb, rb.fi->nblk - 1);
+      const double* xx = xe + P.pbs[e].col;
+      for (int q = 0; q < rb.fi->nres; ++q) for (int j = 0; j < es; ++j) y[P.rb_row[r] + q] += E[q * es + j] * xx[j];
+    }
+  }
+  void left_multiply_e(const double* xr, double* ye) const {
+    const Program& P = c.P;
+#pragma omp parallel for schedule(dynamic, 512)
+    for (int32_t e = 0; e < P.num_e_blocks; ++e) {
+      const int es = P.pbs[e].size; double* yy = ye + P.pbs[e].col;
+      for (int64_t r = P.chunk_start[e]; r < P.chunk_start[e + 1]; ++r) {
+        const RB& rb = c.prob.rbs[P.row_rb[r]];
+        const double* E = jvals + P.rb_jpos[r] + cell_pos(rb, rb.fi->nblk - 1);
+        for (int q = 0; q < rb.fi->nres; ++q) for (int j = 0; j < es; ++j) yy[j] += E[q * es + j] * xr[P.rb_row[r] + q];
+      }
+    }
+  }
+  void ete_inv_multiply(const double* x, double* y) const {   // y += blockdiag * x
+    const Program& P = c.P;
+#pragma omp parallel for schedule(static)
+    for (int32_t e = 0; e < P.num_e_blocks; ++e) {
+      const int es = P.pbs[e].size; const double* m = &ete_inv[ete_pos[e]];
+      const int64_t col = P.pbs[e].col;
+      for (int i = 0; i < es; ++i) { double s = 0; for (int j = 0; j < es; ++j) s += m[i * es + j] * x[col + j]; y[col + i] += s; }
+    }
+  }
+  // y = S x
+  void right_multiply(const double* x, double* y) {
+    std::fill(tmp_rows.begin(), tmp_rows.end(), 0.0);
+    right_multiply_f(x, tmp_rows.data());                       // y1 = F x
+    std::fill(tmp_e.begin(), tmp_e.end(), 0.0);
+    left_multiply_e(tmp_rows.data(), tmp_e.data());             // y2 = E' y1
+    std::fill(tmp_e2.begin(), tmp_e2.end(), 0.0);
+    ete_inv_multiply(tmp_e.data(), tmp_e2.data());              // y3 = -(E'E)^-1 y2
+    for (auto& v : tmp_e2) v *= -1.0;
+    right_multiply_e(tmp_e2.data(), tmp_rows.data());           // y1 = y1 + E y3
+    if (D) { for (int64_t i = 0; i < nf; ++i) y[i] = (D[ne + i] * D[ne + i]) * x[i]; }   // y5 = D^2 x
+    else std::fill(y, y + nf, 0.0);
+    left_multiply_f(tmp_rows.data(), y);                        // y = y5 + F' y1
+  }
+  void update_rhs() {
+    std::fill(tmp_e.begin(), tmp_e.end(), 0.0);
+    left_multiply_e(b, tmp_e.data());                           // y1 = E'b
+    std::vector<double> y2((size_t)ne, 0.0);
+    ete_inv_multiply(tmp_e.data(), y2.data());                  // y2 = (E'E)^-1 y1
+    std::fill(tmp_rows.begin(), tmp_rows.end(), 0.0);
+    right_multiply_e(y2.data(), tmp_rows.data());               // y3 = E y2
+    for (int64_t i = 0; i < nrows; ++i) tmp_rows[i] = b[i] - tmp_rows[i];
+    std::fill(rhs.begin(), rhs.end(), 0.0);
+    left_multiply_f(tmp_rows.data(), rhs.data());               // rhs = F' y3
+  }
+  void back_substitute(const double* x, double* y) {
+    std::fill(tmp_rows.begin(), tmp_rows.end(), 0.0);
+    right_multiply_f(x, tmp_rows.data());                       // y1 = F x
+    for (int64_t i = 0; i < nrows; ++i) tmp_rows[i] = b[i] - tmp_rows[i];
+    std::fill(tmp_e.begin(), tmp_e.end(), 0.0);
+    left_multiply_e(tmp_rows.data(), tmp_e.data());             // y3 = E' y2
+    std::fill(y, y + ne, 0.0);
+    ete_inv_multiply(tmp_e.data(), y);                          // y = (E'E)^-1 y3
+    for (int64_t i = 0; i < nf; ++i) y[ne + i] = x[i];
+  }
+};
+
+static double dot(const double* a, const double* b, int64_t n) { double s = 0; for (int64_t i = 0; i < n; ++i) s += a[i] * b[i]; return s; }
+static double norm2(const double* a, int64_t n) { return std::sqrt(dot(a, a, n)); }
+static bool is_zero_or_inf(double x) { return x == 0.0 || std::isinf(x); }
+
+// ITERATIVE_SCHUR (iterative_schur_complement_solver.cc + conjugate_gradients_solver.cc) — A.7
+static LinSummary iterative_schur_solve(const SolveCtx& c, const double* jvals, const double* b, const double* D,
+                                        double q_tolerance, double r_tolerance, double* xout) {
+  const Program& P = c.P;
+  LinSummary sum;
+  const int prec = c.opt.preconditioner_type;
+  ImplicitSchur A(c, jvals, b, D, prec == SK_JACOBI);
+  if (!A.ok) { sum.termination = LIN_FAILURE; return sum; }
+  const int64_t n = A.nf;
+  std::vector<double> x((size_t)n, 0.0);
+  // Preconditioner
+  Schur se(c);
+  ReducedMatrix M;
+  if (prec == SK_SCHUR_JACOBI) {          // schur_jacobi_preconditioner.cc: Eliminate with b = 0, keep diagonal blocks, invert
+    se.init_lhs(&M, true);
+    std::vector<double> dummy_rhs((size_t)n);
+    if (!se.eliminate(jvals, nullptr, D, &M, dummy_rhs.data())) { sum.termination = LIN_FAILURE; return sum; }
+    for (size_t fb = P.num_e_blocks; fb < P.pbs.size(); ++fb) {
+      const int fs = P.pbs[fb].size; double inv[81];
+      if (!invert_psd(&M.blocks[M.blk_pos[fb]], fs, inv)) { sum.termination = LIN_FAILURE; return sum; }
+      std::memcpy(&M.blocks[M.blk_pos[fb]], inv, sizeof(double) * fs * fs);
+    }
+  }
+  auto precondition = [&](const double* r, double* z) {
+    if (prec == SK_IDENTITY) { for (int64_t i = 0; i < n; ++i) z[i] = r[i]; return; }
+    for (size_t fb = P.num_e_blocks; fb < P.pbs.size(); ++fb) {
+      const int fs = P.pbs[fb].size; const int64_t col = P.pbs[fb].col - A.ne;
+      const double* m = (prec == SK_SCHUR_JACOBI) ? &M.blocks[M.blk_pos[fb]] : &A.ftf_inv[A.ftf_pos[fb]];
+      for (int i = 0; i < fs; ++i) { double s = 0; for (int j = 0; j < fs; ++j) s += m[i * fs + j] * r[col + j]; z[col + i] = s; }
+    }
+  };
+  // ConjugateGradientsSolver::Solve
+  const double* bref = A.rhs.data();
+  sum.termination = LIN_NO_CONVERGENCE; sum.num_iterations = 0;
+  const int min_it = c.opt.min_linear_solver_iterations, max_it = c.opt.max_linear_solver_iterations;
+  const int residual_reset_period = 10;
+  const double norm_b = norm2(bref, n);
+  if (norm_b == 0.0) { sum.termination = LIN_SUCCESS; A.back_substitute(x.data(), xout); return sum; }
+  std::vector<double> r((size_t)n), p((size_t)n), z((size_t)n), tmp((size_t)n);
+  const double tol_r = r_tolerance * norm_b;
+  A.right_multiply(x.data(), tmp.data());
+  for (int64_t i = 0; i < n; ++i) r[i] = bref[i] - tmp[i];
+  double norm_r = norm2(r.data(), n);
+  if (min_it == 0 && norm_r <= tol_r) { sum.termination = LIN_SUCCESS; A.back_substitute(x.data(), xout); return sum; }
+  double rho = 1.0;
+  auto Qval = [&]() { double s = 0; for (int64_t i = 0; i < n; ++i) s += x[i] * (bref[i] + r[i]); return -1.0 * s; };
+  double Q0 = Qval();
+  for (sum.num_iterations = 1;; ++sum.num_iterations) {
+    precondition(r.data(), z.data());
+    const double last_rho = rho;
+    rho = dot(r.data(), z.data(), n);
+    if (is_zero_or_inf(rho)) { sum.termination = LIN_FAILURE; break; }
+    if (sum.num_iterations == 1) p = z;
+    else {
+      const double beta = rho / last_rho;
+      if (is_zero_or_inf(beta)) { sum.termination = LIN_FAILURE; break; }
+      for (int64_t i = 0; i < n; ++i) p[i] = z[i] + beta * p[i];
+    }
+    std::vector<double>& q = z;
+    A.right_multiply(p.data(), q.data());
+    const double pq = dot(p.data(), q.data(), n);
+    if (pq <= 0 || std::isinf(pq)) { sum.termination = LIN_NO_CONVERGENCE; break; }
+    const double alpha = rho / pq;
+    if (std::isinf(alpha)) { sum.termination = LIN_FAILURE; break; }
+    for (int64_t i = 0; i < n; ++i) x[i] = x[i] + alpha * p[i];
+    if (sum.num_iterations % residual_reset_period == 0) {
+      A.right_multiply(x.data(), tmp.data());
+      for (int64_t i = 0; i < n; ++i) r[i] = bref[i] - tmp[i];
+    } else {
+      for (int64_t i = 0; i < n; ++i) r[i] = r[i] - alpha * q[i];
+    }
+    const double Q1 = Qval();
+    const double zeta = sum.num_iterations * (Q1 - Q0) / Q1;
+    if (zeta < q_tolerance && sum.num_iterations >= min_it) { sum.termination = LIN_SUCCESS; break; }
+    Q0 = Q1;
+    norm_r = norm2(r.data(), n);
+    if (norm_r <= tol_r && sum.num_iterations >= min_it) { sum.termination = LIN_SUCCESS; break; }
+    if (sum.num_iterations >= max_it) break;
+  }
+  if (sum.termination != LIN_FAILURE && sum.termination != LIN_FATAL) A.back_substitute(x.data(), xout);
+  return sum;
+}
+
+// ------------------------------------------------------------------------------------------------
+// TrustRegionMinimizer (trust_region_minimizer.cc) + LevenbergMarquardtStrategy — A.3, A.4
+// ------------------------------------------------------------------------------------------------
+static double wall() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+struct Minimizer {
+  const Problem& prob; const Program& P; const sk_solver_options& opt;
+  sk_solver_summary_data* S; std::vector<sk_iteration_summary>* its; std::string* message;
+  // LM strategy state
+  double radius, max_radius, decrease_factor = 2.0; bool reuse_diagonal = false;
+  std::vector<double> diagonal, lm_diagonal;
+  // minimizer state
+  std::vector<double> x, residuals, gradient, jvals, scale, step, delta, cand, model_res;
+  double x_cost = 0, x_norm = 0, minimum_cost = 0, cand_cost = 0, model_cost_change = 0;
+  int num_consecutive_invalid = 0;
+  sk_iteration_summary it;
+  double t_start = 0, t_iter = 0;
+  // step evaluator (monotonic steps only: use_nonmonotonic_steps = false)
+  double se_current_cost = 0;
+
+  Minimizer(const Problem& pr, const Program& pg, const sk_solver_options& o, sk_solver_summary_data* s,
+            std::vector<sk_iteration_summary>* iters, std::string* msg)
+      : prob(pr), P(pg), opt(o), S(s), its(iters), message(msg) {}
+
+  bool evaluate_gradient_and_jacobian() {
+    if (!evaluate(prob, P, x.data(), &x_cost, residuals.data(), gradient.data(), jvals.data())) {
+      *message = "Residual and Jacobian evaluation failed."; S->termination_type = SK_FAILURE; return false;
+    }
+    S->num_jacobian_evaluations++;
+    it.cost = x_cost + S->fixed_cost;
+    if (opt.jacobi_scaling) {
+      if (it.iteration == 0) {
+        squared_column_norm(prob, P, jvals.data(), scale.data());
+        for (auto& v : scale) v = 1.0 / (1.0 + std::sqrt(v));
+      }
+      scale_columns(prob, P, scale.data(), jvals.data());
+    }
+    // gradient norms via Plus(x, -g): (x - (x + (-g)))
+    double gmax = 0, gsq = 0;
+    for (int64_t i = 0; i < P.num_cols; ++i) {
+      const double pg = x[i] + (-gradient[i]);
+      const double d = x[i] - pg;
+      gmax = std::max(gmax, std::fabs(d)); gsq += d * d;
+    }
+    it.gradient_max_norm = gmax; it.gradient_norm = std::sqrt(gsq);
+    return true;
+  }
+
+  // LevenbergMarquardtStrategy::ComputeStep
+  LinSummary compute_step() {
+    const int64_t n = P.num_cols;
+    if (!reuse_diagonal) {
+      squared_column_norm(prob, P, jvals.data(), diagonal.data());
+      for (auto& v : diagonal) v = std::min(std::max(v, opt.min_lm_diagonal), opt.max_lm_diagonal);
+    }
+    for (int64_t i = 0; i < n; ++i) lm_diagonal[i] = std::sqrt(diagonal[i] / radius);
+    for (auto& v : step) v = std::numeric_limits<double>::quiet_NaN();   // InvalidateArray
+    SolveCtx c{prob, P, opt};
+    LinSummary ls;
+    S->num_linear_solves++;
+    switch (opt.linear_solver_type) {
+      case SK_DENSE_QR: ls = dense_qr_solve(c, jvals.data(), residuals.data(), lm_diagonal.data(), step.data()); break;
+      case SK_DENSE_SCHUR: case SK_SPARSE_SCHUR: ls = schur_solve(c, jvals.data(), residuals.data(), lm_diagonal.data(), step.data()); break;
+      case SK_ITERATIVE_SCHUR: ls = iterative_schur_solve(c, jvals.data(), residuals.data(), lm_diagonal.data(), opt.eta, -1.0, step.data()); break;
+      default: ls.termination = LIN_FATAL;
+    }
+    if (ls.termination != LIN_FATAL && ls.termination != LIN_FAILURE) {
+      bool valid = true;
+      for (int64_t i = 0; i < n; ++i) if (!std::isfinite(step[i])) { valid = false; break; }
+      if (!valid) ls.termination = LIN_FAILURE;
+      else for (auto& v : step) v *= -1.0;
+    }
+    reuse_diagonal = true;
+    return ls;
+  }
+  void step_accepted(double q) {
+    radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * q - 1.0, 3));
+    radius = std::min(max_radius, radius);
+    decrease_factor = 2.0; reuse_diagonal = false;
+  }
+  void step_rejected() { radius = radius / decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true; }
+
+  void print_header_and_row() const {
+    if (!opt.minimizer_progress_to_stdout) return;
+    if (it.iteration == 0)
+      std::printf("iter      cost      cost_change  |gradient|   |step|    tr_ratio  tr_radius  ls_iter  iter_time  total_time\n");
+    std::printf("% 4d % 8e   % 3.2e   % 3.2e  % 3.2e  % 3.2e % 3.2e     % 4d   % 3.2e   % 3.2e\n", it.iteration, it.cost,
+                it.cost_change, it.gradient_max_norm, it.step_norm, it.relative_decrease, it.trust_region_radius,
+                it.linear_solver_iterations, it.iteration_time_in_seconds, it.cumulative_time_in_seconds);
+  }
+
+  bool finalize_iteration_and_check_if_can_continue() {
+    if (it.step_is_successful) {
+      ++S->num_successful_steps;
+      if (x_cost < minimum_cost) {
+        minimum_cost = x_cost;
+        for (size_t b = 0; b < P.pbs.size(); ++b)                      // parameters_ = x_
+          for (int k = 0; k < P.pbs[b].size; ++k) prob.params[P.pbs[b].offset + k] = x[P.pbs[b].col + k];
+        it.step_is_nonmonotonic = 0;
+      } else it.step_is_nonmonotonic = 1;
+    } else ++S->num_unsuccessful_steps;
+    it.trust_region_radius = radius;
+    const double now = wall();
+    it.iteration_time_in_seconds = now - t_iter;
+    it.cumulative_time_in_seconds = now - t_start + S->preprocessor_time_in_seconds;
+    its->push_back(it);
+    print_header_and_row();
+    char buf[256];
+    if (it.iteration >= opt.max_num_iterations) {
+      std::snprintf(buf, sizeof buf, "Maximum number of iterations reached. Number of iterations: %d.", it.iteration);
+      *message = buf; S->termination_type = SK_NO_CONVERGENCE; return false;
+    }
+    if (it.step_is_successful && it.gradient_max_norm <= opt.gradient_tolerance) {
+      std::snprintf(buf, sizeof buf, "Gradient tolerance reached. Gradient max norm: %e <= %e", it.gradient_max_norm, opt.gradient_tolerance);
+      *message = buf; S->termination_type = SK_CONVERGENCE; return false;
+    }
+    if (it.trust_region_radius <= opt.min_trust_region_radius) {
+      std::snprintf(buf, sizeof buf, "Minimum trust region radius reached. Trust region radius: %e <= %e", it.trust_region_radius, opt.min_trust_region_radius);
+      *message = buf; S->termination_type = SK_CONVERGENCE; return false;
+    }
+    return true;
+  }
+
+  void minimize() {
+    t_start = wall(); t_iter = t_start;
+    const int64_t n = P.num_cols;
+    S->termination_type = SK_NO_CONVERGENCE; S->num_successful_steps = 0; S->num_unsuccessful_steps = 0;
+    radius = opt.initial_trust_region_radius; max_radius = opt.max_trust_region_radius;
+    x.resize(n); residuals.assign(P.num_rows, 0.0); gradient.assign(n, 0.0); jvals.assign(P.num_jvals, 0.0);
+    scale.assign(n, 1.0); step.assign(n, 0.0); delta.assign(n, 0.0); cand.assign(n, 0.0); model_res.assign(P.num_rows, 0.0);
+    diagonal.assign(n, 0.0); lm_diagonal.assign(n, 0.0);
+    for (size_t b = 0; b < P.pbs.size(); ++b)
+      for (int k = 0; k < P.pbs[b].size; ++k) x[P.pbs[b].col + k] = prob.params[P.pbs[b].offset + k];
+    x_norm = norm2(x.data(), n);
+    x_cost = std::numeric_limits<double>::max(); minimum_cost = x_cost;
+    // IterationZero
+    std::memset(&it, 0, sizeof it);
+    it.eta = opt.eta;
+    if (!evaluate_gradient_and_jacobian()) return;
+    S->initial_cost = x_cost + S->fixed_cost;
+    it.step_is_valid = 1; it.step_is_successful = 1;
+    se_current_cost = x_cost;
+    char buf[256];
+    while (finalize_iteration_and_check_if_can_continue()) {
+      t_iter = wall();
+      const int prev_iter = its->back().iteration;
+      std::memset(&it, 0, sizeof it);
+      it.iteration = prev_iter + 1;
+      // ComputeTrustRegionStep
+      it.step_is_valid = 0;
+      LinSummary ls = compute_step();
+      if (ls.termination == LIN_FATAL) {
+        *message = "Linear solver failed due to unrecoverable non-numeric causes. Please see the error log for clues. ";
+        S->termination_type = SK_FAILURE; return;
+      }
+      it.linear_solver_iterations = ls.num_iterations;
+      S->total_linear_solver_iterations += ls.num_iterations;
+      if (ls.termination != LIN_FAILURE) {
+        std::fill(model_res.begin(), model_res.end(), 0.0);
+        right_multiply(prob, P, jvals.data(), step.data(), model_res.data());
+        double s = 0;
+        for (int64_t i = 0; i < P.num_rows; ++i) s += model_res[i] * (residuals[i] + model_res[i] / 2.0);
+        model_cost_change = -s;
+        it.step_is_valid = (model_cost_change > 0.0);
+        if (it.step_is_valid) {
+          for (int64_t i = 0; i < n; ++i) delta[i] = step[i] * scale[i];
+          num_consecutive_invalid = 0;
+        }
+      }
+      if (!it.step_is_valid) {                                  // HandleInvalidStep
+        ++num_consecutive_invalid;
+        if (num_consecutive_invalid >= opt.max_num_consecutive_invalid_steps) {
+          std::snprintf(buf, sizeof buf, "Number of consecutive invalid steps more than Solver::Options::max_num_consecutive_invalid_steps: %d", opt.max_num_consecutive_invalid_steps);
+          *message = buf; S->termination_type = SK_FAILURE; return;
+        }
+        step_rejected();                                        // StepIsInvalid
+        it.cost = x_cost + S->fixed_cost; it.cost_change = 0.0;
+        it.gradient_max_norm = its->back().gradient_max_norm; it.gradient_norm = its->back().gradient_norm;
+        it.step_norm = 0.0; it.relative_decrease = 0.0; it.eta = opt.eta;
+        continue;
+      }
+      // ComputeCandidatePointAndEvaluateCost
+      for (int64_t i = 0; i < n; ++i) cand[i] = x[i] + delta[i];
+      S->num_residual_evaluations++;
+      if (!evaluate(prob, P, cand.data(), &cand_cost, nullptr, nullptr, nullptr)) cand_cost = std::numeric_limits<double>::max();
+      // ParameterToleranceReached
+      { double s = 0; for (int64_t i = 0; i < n; ++i) { const double d = x[i] - cand[i]; s += d * d; } it.step_norm = std::sqrt(s); }
+      const double step_size_tolerance = opt.parameter_tolerance * (x_norm + opt.parameter_tolerance);
+      if (it.step_norm <= step_size_tolerance) {
+        std::snprintf(buf, sizeof buf, "Parameter tolerance reached. Relative step_norm: %e <= %e.", it.step_norm / (x_norm + opt.parameter_tolerance), opt.parameter_tolerance);
+        *message = buf; S->termination_type = SK_CONVERGENCE; return;
+      }
+      // FunctionToleranceReached
+      it.cost_change = x_cost - cand_cost;
+      const double absolute_function_tolerance = opt.function_tolerance * x_cost;
+      if (std::fabs(it.cost_change) <= absolute_function_tolerance) {
+        std::snprintf(buf, sizeof buf, "Function tolerance reached. |cost_change|/cost: %e <= %e", std::fabs(it.cost_change) / x_cost, opt.function_tolerance);
+        *message = buf; S->termination_type = SK_CONVERGENCE; return;
+      }
+      // IsStepSuccessful (TrustRegionStepEvaluator::StepQuality, monotonic)
+      it.relative_decrease = (se_current_cost - cand_cost) / model_cost_change;
+      it.eta = opt.eta;
+      if (it.relative_decrease > opt.min_relative_decrease) {    // HandleSuccessfulStep
+        x = cand; x_norm = norm2(x.data(), n);
+        if (!evaluate_gradient_and_jacobian()) return;
+        it.step_is_successful = 1;
+        step_accepted(it.relative_decrease);
+        se_current_cost = cand_cost;
+        continue;
+      }
+      it.step_is_successful = 0;                                 // HandleUnsuccessfulStep
+      step_rejected();
+      it.cost = cand_cost + S->fixed_cost;
+    }
+  }
+};
+
+}  // namespace oracle
+
+// ================================================================================================
+// extern "C" surface used by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg only.
+// ================================================================================================
+using namespace oracle;
+struct oracle_problem { Problem p; };
+
+extern "C" {
+
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  omp_set_num_threads(n > 0 ? n : 1);
+#else
+  (void)n;
+#endif
+}
+int oracle_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+int oracle_functor_info(int id, int* nres, int* nblk, int* sizes, int* nconsts) {
+  const FunctorInfo* f = find_functor(id);
+  if (!f) return 0;
+  *nres = f->nres; *nblk = f->nblk; *nconsts = f->nconsts;
+  for (int i = 0; i < f->nblk; ++i) sizes[i] = f->sizes[i];
+  return 1;
+}
+
+// CostFunction::Evaluate ABI (AutodiffCostFunction.scala:74-78). Returns 1 = true, 0 = false.
+int oracle_evaluate(int functor_id, const double* consts, double const* const* parameters,
+                    double* residuals, double** jacobians) {
+  const FunctorInfo* f = find_functor(functor_id);
+  if (!f) return 0;
+  return evaluate_functor(*f, consts, parameters, residuals, jacobians) ? 1 : 0;
+}
+
+void oracle_angle_axis_rotate_point(const double* aa, const double* pt, double* out) { angleAxisRotatePoint(aa, pt, out); }
+void oracle_angle_axis_to_rotation_matrix(const double* aa, double* R) { angleAxisToRotationMatrix(aa, R); }
+void oracle_loss_evaluate(int type, double a, double s, double* rho) { loss_evaluate(type, a, s, rho); }
+
+oracle_problem* oracle_problem_create(double* params, int64_t n) {
+  auto* o = new oracle_problem; o->p.params = params; o->p.n = n; return o;
+}
+void oracle_problem_destroy(oracle_problem* o) { delete o; }
+
+int oracle_problem_add_residual_blocks(oracle_problem* o, int functor_id, int64_t n, const double* consts,
+                                       int loss_type, double loss_a, const int64_t* block_offsets) {
+  const FunctorInfo* f = find_functor(functor_id);
+  if (!f) return 0;
+  o->p.rbs.reserve(o->p.rbs.size() + (size_t)n);
+  for (int64_t i = 0; i < n; ++i) {
+    RB rb{}; rb.fi = f; rb.loss = loss_type; rb.loss_a = loss_a;
+    for (int k = 0; k < f->nconsts; ++k) rb.consts[k] = consts[i * f->nconsts + k];
+    for (int k = 0; k < f->nblk; ++k) {
+      rb.off[k] = block_offsets[i * f->nblk + k];
+      if (rb.off[k] < 0 || rb.off[k] + f->sizes[k] > o->p.n) return 0;
+    }
+    o->p.rbs.push_back(rb);
+  }
+  return 1;
+}
+
+// Evaluate at the current parameters.  Outputs are in USER order so they do not depend on the
+// internal ordering: residuals/jacobians per residual block in insertion order (jacobian blocks
+// concatenated, each row-major), gradient laid out like the parameter array (zeros elsewhere).
+int oracle_problem_evaluate(oracle_problem* o, double* cost, double* residuals, double* gradient, double* jacobians) {
+  Program P; std::string err;
+  if (!build_program(o->p, false, &P, &err)) return 0;
+  std::vector<double> x((size_t)P.num_cols), r((size_t)P.num_rows), g((size_t)P.num_cols), J((size_t)P.num_jvals);
+  for (auto& b : P.pbs) for (int k = 0; k < b.size; ++k) x[b.col + k] = o->p.params[b.offset + k];
+  if (!evaluate(o->p, P, x.data(), cost, r.data(), g.data(), J.data())) return 0;
+  if (residuals) std::copy(r.begin(), r.end(), residuals);
+  if (jacobians) std::copy(J.begin(), J.end(), jacobians);
+  if (gradient) {
+    std::fill(gradient, gradient + o->p.n, 0.0);
+    for (auto& b : P.pbs) for (int k = 0; k < b.size; ++k) gradient[b.offset + k] = g[b.col + k];
+  }
+  return 1;
+}
+
+// ceres.solve restated.  iterations: caller buffer of `capacity` rows; *count = rows produced.
+int oracle_solve(const sk_solver_options* options, oracle_problem* o, sk_solver_summary_data* summary,
+                 sk_iteration_summary* iterations, int capacity, int* count, char* message, int message_len) {
+  std::memset(summary, 0, sizeof *summary);
+  std::string msg;
+  const double t0 = wall();
+  auto fail = [&](const char* m) {
+    summary->termination_type = SK_FAILURE; std::snprintf(message, message_len, "%s", m); *count = 0; return 0; };
+  if (options->minimizer_type != SK_TRUST_REGION || options->trust_region_strategy_type != SK_LEVENBERG_MARQUARDT)
+    return fail("oracle supports TRUST_REGION + LEVENBERG_MARQUARDT only");
+  const int lst = options->linear_solver_type;
+  if (lst != SK_DENSE_QR && !is_schur(lst)) return fail("oracle supports DENSE_QR, DENSE_SCHUR, SPARSE_SCHUR, ITERATIVE_SCHUR");
+  if (lst == SK_ITERATIVE_SCHUR && options->preconditioner_type != SK_SCHUR_JACOBI &&
+      options->preconditioner_type != SK_JACOBI && options->preconditioner_type != SK_IDENTITY)
+    return fail("oracle supports IDENTITY, JACOBI and SCHUR_JACOBI preconditioners");
+  Program P;
+  if (!build_program(o->p, is_schur(lst), &P, &msg)) return fail(msg.c_str());
+  summary->num_parameter_blocks = (int64_t)P.pbs.size(); summary->num_parameters = P.num_cols;
+  summary->num_residual_blocks = P.num_rbs(); summary->num_residuals = P.num_rows;
+  summary->linear_solver_type_used = lst; summary->preconditioner_type_used = options->preconditioner_type;
+  summary->preprocessor_time_in_seconds = wall() - t0;
+  std::vector<sk_iteration_summary> its;
+  Minimizer m(o->p, P, *options, summary, &its, &msg);
+  const double t1 = wall();
+  m.minimize();
+  summary->minimizer_time_in_seconds = wall() - t1;
+  // SetSummaryFinalCost (solver.cc)
+  summary->final_cost = summary->initial_cost;
+  for (auto& i : its) summary->final_cost = std::min(i.cost, summary->final_cost);
+  summary->num_iterations = (int32_t)its.size();
+  *count = (int)its.size();
+  for (int i = 0; i < (int)its.size() && i < capacity; ++i) iterations[i] = its[i];
+  std::snprintf(message, message_len, "%s", msg.c_str());
+  summary->total_time_in_seconds = wall() - t0;
+  return 1;
+}
+
+}  // extern "C"
