@@ -1,0 +1,504 @@
+// ba_kernels.cu — sm_100a tile kernels of the bundle-adjustment hot path.
+//
+// One CTA (256 threads) per tile of <= 256 observations holding whole points (ba_layout.h).
+// Thread i of the CTA owns observation i of the tile: it reads its 12 Jacobian planes as coalesced
+// 16-byte vectors, keeps them in registers and reuses them for every phase of the kernel, so each
+// kernel reads the stored Jacobian exactly once (algorithmic bytes == DRAM bytes).
+// Per-point sums are formed by one thread per point in observation order (the order Ceres'
+// SchurEliminator walks a chunk); per-camera sums go through the tile-local camera segments
+// (seg_reduce9) and a second-level fixed-order reduction (k_cam_reduce): no atomics anywhere.
+//
+// What each kernel restates (Ceres sources are NOT in the reference tree):
+//   k_ba_evaluate         ProgramEvaluator / ResidualBlock::Evaluate / Corrector  (A.2) on top of
+//                         AutodiffCostFunction.scala:74-134 + SimpleBundleAdjuster.scala:79-119
+//   k_ba_schur_setup      SchurEliminator::Eliminate  (A.5) restricted to rhs + diagonal blocks
+//                         (= SchurJacobiPreconditioner::UpdateImpl, A.7) + ImplicitSchurComplement::Init
+//   k_ba_matvec           ImplicitSchurComplement::RightMultiply (A.6), the four passes fused
+//   k_ba_back_substitute  ImplicitSchurComplement::BackSubstitute / SchurEliminator::BackSubstitute
+//                         + the model-cost-change product of TrustRegionMinimizer (A.3 step 3)
+#include "ba_kernels.cuh"
+
+namespace sk {
+
+namespace {
+
+constexpr int T = kTileObs;
+constexpr int VLD = T + 1;   // padded leading dimension of the per-observation staging planes
+
+struct Tile { int ob, no, pb, np, sb, ns; };
+
+__device__ __forceinline__ Tile load_tile(const BaDev& L, int t) {
+  Tile q;
+  q.ob = L.tile_obs[t]; q.no = L.tile_obs[t + 1] - q.ob;
+  q.pb = L.tile_pt[t];  q.np = L.tile_pt[t + 1] - q.pb;
+  q.sb = L.tile_seg[t]; q.ns = L.tile_seg[t + 1] - q.sb;
+  return q;
+}
+
+// out[(sb+s)*ostride + ooff + k] = sum over segment s of v[k][local obs], fixed (point) order.
+__device__ __forceinline__ void seg_reduce9(const BaDev& L, const Tile& q, const double* v, double* out,
+                                            int ostride, int ooff) {
+  for (int idx = threadIdx.x; idx < q.ns * 9; idx += blockDim.x) {
+    const int s = idx / 9, k = idx - s * 9;
+    const int b = L.seg_ptr[q.sb + s], e = L.seg_ptr[q.sb + s + 1];
+    double sum = 0.0;
+    for (int pos = b; pos < e; ++pos) sum += v[k * VLD + L.seg_perm[pos]];
+    out[(size_t)(q.sb + s) * ostride + ooff + k] = sum;
+  }
+}
+
+// Deterministic block sum (fixed shuffle tree, then warp 0 over the 8 warp totals).
+__device__ __forceinline__ double block_sum(double x, double* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) red[w] = x;
+  __syncthreads();
+  double r = 0.0;
+  if (w == 0) {
+    r = (l < (int)(blockDim.x >> 5)) ? red[l] : 0.0;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
+  }
+  return r;   // valid in thread 0
+}
+
+__device__ __forceinline__ double2 ldcs2(const double2* p) { return __ldcs(p); }
+
+// ------------------------------------------------------------------------------------------------
+template <bool JAC>
+__global__ void __launch_bounds__(T) k_ba_evaluate(BaDev L, const double* __restrict__ x, const double* __restrict__ scale,
+                                                   LossSpec loss, int write_j, double2* __restrict__ J2,
+                                                   double2* __restrict__ r2, double* __restrict__ grad,
+                                                   double* __restrict__ cnorm2, double* __restrict__ seg_g,
+                                                   double* __restrict__ seg_n, double* __restrict__ tile_cost,
+                                                   int* fail_flag, const int* guard) {
+  if (guard != nullptr && *guard == 0) return;
+  extern __shared__ double sm[];
+  const Tile q = load_tile(L, blockIdx.x);
+  const int tid = threadIdx.x;
+  double* cam_s = sm;                               // [max_seg][9]
+  double* pt_s = cam_s + L.max_seg_tile * 9;        // [max_pt][3]
+  double* csc_s = pt_s + L.max_pt_tile * 3;         // [max_seg][9]  column scales (JAC)
+  double* psc_s = csc_s + L.max_seg_tile * 9;       // [max_pt][3]
+  double* v = psc_s + L.max_pt_tile * 3;            // [9][VLD]      (JAC)
+  double* red = JAC ? (v + 9 * VLD) : csc_s;        // [8]
+  const size_t pbase = (size_t)9 * L.n_cams;
+  for (int idx = tid; idx < q.ns * 9; idx += T) {
+    const int s = idx / 9, k = idx - s * 9;
+    const int c = L.seg_cam[q.sb + s];
+    cam_s[idx] = x[(size_t)c * 9 + k];
+    if (JAC) csc_s[idx] = scale ? scale[(size_t)c * 9 + k] : 1.0;
+  }
+  for (int idx = tid; idx < q.np * 3; idx += T) {
+    pt_s[idx] = x[pbase + (size_t)q.pb * 3 + idx];
+    if (JAC) psc_s[idx] = scale ? scale[pbase + (size_t)q.pb * 3 + idx] : 1.0;
+  }
+  __syncthreads();
+  const bool active = tid < q.no;
+  const int i = q.ob + tid;
+  double cost = 0.0, res[2] = {0.0, 0.0};
+  double F[18], E[6];
+  int slot = 0, ptl = 0;
+  if (active) {
+    const double2 o = L.obs[i];
+    slot = L.obs_slot[i]; ptl = L.obs_ptl[i];
+    if (JAC) snavely_residual_jacobian(cam_s + slot * 9, pt_s + ptl * 3, o.x, o.y, res, F, E);
+    else snavely_residual(cam_s + slot * 9, pt_s + ptl * 3, o.x, o.y, res);
+    const double sq = res[0] * res[0] + res[1] * res[1];
+    double rho[3];
+    loss_evaluate(loss, sq, rho);
+    cost = 0.5 * rho[0];
+    if (!(cost == cost)) atomicOr(fail_flag, 1);    // NaN residual == failed evaluation
+    if (JAC && loss.type != SK_LOSS_TRIVIAL) {
+      const Corrector corr(sq, rho);
+      corr.correct_jacobian(2, 9, 9, res, F);
+      corr.correct_jacobian(2, 3, 3, res, E);
+      corr.correct_residuals(2, res);
+    }
+  }
+  const double csum = block_sum(cost, red);
+  if (tid == 0) tile_cost[blockIdx.x] = csum;
+  if (!JAC) return;
+  if (active) {
+    // point part: gradient (unscaled J, as the evaluator computes it) and squared column norms of
+    // the column-scaled J (what the LM strategy sees after TrustRegionMinimizer scales in place).
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double sc = psc_s[ptl * 3 + k];
+      const double e0 = E[k] * sc, e1 = E[3 + k] * sc;
+      v[k * VLD + tid] = E[k] * res[0] + E[3 + k] * res[1];
+      v[(3 + k) * VLD + tid] = e0 * e0 + e1 * e1;
+      if (write_j) J2[(size_t)(9 + k) * L.n_obs + i] = make_double2(e0, e1);
+    }
+    if (write_j) r2[i] = make_double2(res[0], res[1]);
+  }
+  __syncthreads();
+  if (tid < q.np) {
+    const int p = q.pb + tid;
+    const int b = L.pt_ptr[p] - q.ob, e = L.pt_ptr[p + 1] - q.ob;
+    double s6[6] = {0, 0, 0, 0, 0, 0};
+    for (int j = b; j < e; ++j) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s6[k] += v[k * VLD + j];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { grad[pbase + (size_t)p * 3 + k] = s6[k]; cnorm2[pbase + (size_t)p * 3 + k] = s6[3 + k]; }
+  }
+  __syncthreads();
+  double fs[18];
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const double sc = csc_s[slot * 9 + k];
+      fs[k] = F[k] * sc; fs[9 + k] = F[9 + k] * sc;
+      v[k * VLD + tid] = F[k] * res[0] + F[9 + k] * res[1];
+      if (write_j) J2[(size_t)k * L.n_obs + i] = make_double2(fs[k], fs[9 + k]);
+    }
+  }
+  __syncthreads();
+  seg_reduce9(L, q, v, seg_g, 9, 0);
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) v[k * VLD + tid] = fs[k] * fs[k] + fs[9 + k] * fs[9 + k];
+  }
+  __syncthreads();
+  seg_reduce9(L, q, v, seg_n, 9, 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void k_cam_reduce(BaDev L, int K, const double* __restrict__ seg, double* __restrict__ out, const int* guard) {
+  if (guard != nullptr && *guard == 0) return;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= L.n_cams * K) return;
+  const int c = idx / K, k = idx - c * K;
+  double sum = 0.0;
+  for (int t = L.cam_seg_ptr[c]; t < L.cam_seg_ptr[c + 1]; ++t) sum += seg[(size_t)L.cam_seg[t] * K + k];
+  out[idx] = sum;
+}
+
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int upper_row(int idx) {   // row k of the idx-th entry of a packed 9x9 upper triangle
+  int k = 0, start = 0;
+  while (idx >= start + (9 - k)) { start += 9 - k; ++k; }
+  return k;
+}
+__host__ __device__ constexpr int upper_col(int idx) {
+  int k = 0, start = 0;
+  while (idx >= start + (9 - k)) { start += 9 - k; ++k; }
+  return k + (idx - start);
+}
+
+__global__ void __launch_bounds__(T) k_ba_schur_setup(BaDev L, const double2* __restrict__ J2, const double2* __restrict__ r2,
+                                                      const double* __restrict__ D, double* __restrict__ einv,
+                                                      double* __restrict__ seg_rhs, double* __restrict__ seg_M,
+                                                      int* error_flag) {
+  extern __shared__ double sm[];
+  const Tile q = load_tile(L, blockIdx.x);
+  const int tid = threadIdx.x;
+  double* v = sm;                      // [9][VLD]
+  double* pinv = v + 9 * VLD;          // [max_pt][9]: inverse (6, upper) + inverse * g (3)
+  const bool active = tid < q.no;
+  const int i = q.ob + tid;
+  const size_t O = (size_t)L.n_obs;
+  double2 Fv[9], Ev[3], r = make_double2(0.0, 0.0);
+  int ptl = 0;
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Fv[k] = ldcs2(J2 + k * O + i);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) Ev[k] = ldcs2(J2 + (9 + k) * O + i);
+    r = r2[i];
+    ptl = L.obs_ptl[i];
+    // E^T E (upper: 00 01 02 11 12 22) and E^T r
+    v[0 * VLD + tid] = Ev[0].x * Ev[0].x + Ev[0].y * Ev[0].y;
+    v[1 * VLD + tid] = Ev[0].x * Ev[1].x + Ev[0].y * Ev[1].y;
+    v[2 * VLD + tid] = Ev[0].x * Ev[2].x + Ev[0].y * Ev[2].y;
+    v[3 * VLD + tid] = Ev[1].x * Ev[1].x + Ev[1].y * Ev[1].y;
+    v[4 * VLD + tid] = Ev[1].x * Ev[2].x + Ev[1].y * Ev[2].y;
+    v[5 * VLD + tid] = Ev[2].x * Ev[2].x + Ev[2].y * Ev[2].y;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v[(6 + k) * VLD + tid] = Ev[k].x * r.x + Ev[k].y * r.y;
+  }
+  __syncthreads();
+  if (tid < q.np) {
+    const int p = q.pb + tid;
+    const int b = L.pt_ptr[p] - q.ob, e = L.pt_ptr[p + 1] - q.ob;
+    const double* Dp = D + (size_t)9 * L.n_cams + (size_t)p * 3;
+    double m[6] = {Dp[0] * Dp[0], 0.0, 0.0, Dp[1] * Dp[1], 0.0, Dp[2] * Dp[2]};
+    double g[3] = {0.0, 0.0, 0.0};
+    for (int j = b; j < e; ++j) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) m[k] += v[k * VLD + j];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) g[k] += v[(6 + k) * VLD + j];
+    }
+    double inv[6];
+    if (!invert_spd3(m, inv)) {
+      atomicOr(error_flag, 1);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) inv[k] = 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { einv[(size_t)p * 6 + k] = inv[k]; pinv[tid * 9 + k] = inv[k]; }
+    pinv[tid * 9 + 6] = inv[0] * g[0] + inv[1] * g[1] + inv[2] * g[2];
+    pinv[tid * 9 + 7] = inv[1] * g[0] + inv[3] * g[1] + inv[4] * g[2];
+    pinv[tid * 9 + 8] = inv[2] * g[0] + inv[4] * g[1] + inv[5] * g[2];
+  }
+  __syncthreads();
+  double G[3][9], H[3][9];
+  if (active) {
+    const double* pi = pinv + ptl * 9;
+    // reduced rhs: F^T (r - E (E^T E)^-1 E^T r)
+    const double q0 = r.x - (Ev[0].x * pi[6] + Ev[1].x * pi[7] + Ev[2].x * pi[8]);
+    const double q1 = r.y - (Ev[0].y * pi[6] + Ev[1].y * pi[7] + Ev[2].y * pi[8]);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) v[k * VLD + tid] = Fv[k].x * q0 + Fv[k].y * q1;
+    // G = E^T F (3 x 9), H = (E^T E)^-1 G
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) G[a][k] = Ev[a].x * Fv[k].x + Ev[a].y * Fv[k].y;
+      H[0][k] = pi[0] * G[0][k] + pi[1] * G[1][k] + pi[2] * G[2][k];
+      H[1][k] = pi[1] * G[0][k] + pi[3] * G[1][k] + pi[4] * G[2][k];
+      H[2][k] = pi[2] * G[0][k] + pi[4] * G[1][k] + pi[5] * G[2][k];
+    }
+  }
+  __syncthreads();
+  seg_reduce9(L, q, v, seg_rhs, 9, 0);
+  // diagonal block contribution F^T F - G^T (E^T E)^-1 G, packed upper triangle, 5 rounds of 9
+#pragma unroll
+  for (int round = 0; round < 5; ++round) {
+    __syncthreads();
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        const int k = upper_row(round * 9 + j), l = upper_col(round * 9 + j);
+        v[j * VLD + tid] = (Fv[k].x * Fv[l].x + Fv[k].y * Fv[l].y) - (G[0][k] * H[0][l] + G[1][k] * H[1][l] + G[2][k] * H[2][l]);
+      }
+    }
+    __syncthreads();
+    seg_reduce9(L, q, v, seg_M, 45, round * 9);
+  }
+}
+
+__global__ void k_ba_precond_invert(BaDev L, const double* __restrict__ M45, const double* __restrict__ D,
+                                    double* __restrict__ Minv, int* error_flag) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= L.n_cams) return;
+  double A[81];
+  int idx = 0;
+  for (int k = 0; k < 9; ++k)
+    for (int l = k; l < 9; ++l) { const double m = M45[(size_t)c * 45 + idx++]; A[k * 9 + l] = m; A[l * 9 + k] = m; }
+  for (int k = 0; k < 9; ++k) { const double d = D[(size_t)c * 9 + k]; A[k * 9 + k] += d * d; }
+  if (!invert_spd<9>(A, 9)) {
+    atomicOr(error_flag, 2);
+    for (int k = 0; k < 81; ++k) A[k] = 0.0;
+  }
+  for (int k = 0; k < 81; ++k) Minv[(size_t)c * 81 + k] = A[k];
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(T) k_ba_matvec(BaDev L, const double2* __restrict__ J2, const double* __restrict__ p,
+                                                 const double* __restrict__ einv, double* __restrict__ seg_y,
+                                                 const int* guard) {
+  if (guard != nullptr && *guard == 0) return;
+  extern __shared__ double sm[];
+  const Tile q = load_tile(L, blockIdx.x);
+  const int tid = threadIdx.x;
+  double* xs = sm;                           // [max_seg][9]
+  double* v = xs + L.max_seg_tile * 9;       // [9][VLD]
+  double* w = v + 9 * VLD;                   // [3][T]  E^T t per observation
+  double* u = w + 3 * T;                     // [3][T]  (E^T E)^-1 w per point
+  const bool active = tid < q.no;
+  const int i = q.ob + tid;
+  const size_t O = (size_t)L.n_obs;
+  double2 Fv[9], Ev[3];
+  int slot = 0, ptl = 0;
+  if (active) {                              // issue the streaming loads first
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Fv[k] = ldcs2(J2 + k * O + i);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) Ev[k] = ldcs2(J2 + (9 + k) * O + i);
+    slot = L.obs_slot[i]; ptl = L.obs_ptl[i];
+  }
+  for (int idx = tid; idx < q.ns * 9; idx += T) {
+    const int s = idx / 9, k = idx - s * 9;
+    xs[idx] = p[(size_t)L.seg_cam[q.sb + s] * 9 + k];
+  }
+  __syncthreads();
+  double t0 = 0.0, t1 = 0.0;
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { const double xk = xs[slot * 9 + k]; t0 += Fv[k].x * xk; t1 += Fv[k].y * xk; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) w[k * T + tid] = Ev[k].x * t0 + Ev[k].y * t1;
+  }
+  __syncthreads();
+  if (tid < q.np) {
+    const int pnt = q.pb + tid;
+    const int b = L.pt_ptr[pnt] - q.ob, e = L.pt_ptr[pnt + 1] - q.ob;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    for (int j = b; j < e; ++j) { a0 += w[j]; a1 += w[T + j]; a2 += w[2 * T + j]; }
+    const double* m = einv + (size_t)pnt * 6;
+    u[tid] = m[0] * a0 + m[1] * a1 + m[2] * a2;
+    u[T + tid] = m[1] * a0 + m[3] * a1 + m[4] * a2;
+    u[2 * T + tid] = m[2] * a0 + m[4] * a1 + m[5] * a2;
+  }
+  __syncthreads();
+  if (active) {
+    const double u0 = u[ptl], u1 = u[T + ptl], u2 = u[2 * T + ptl];
+    const double s0 = t0 - (Ev[0].x * u0 + Ev[1].x * u1 + Ev[2].x * u2);
+    const double s1 = t1 - (Ev[0].y * u0 + Ev[1].y * u1 + Ev[2].y * u2);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) v[k * VLD + tid] = Fv[k].x * s0 + Fv[k].y * s1;
+  }
+  __syncthreads();
+  seg_reduce9(L, q, v, seg_y, 9, 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(T) k_ba_back_substitute(BaDev L, const double2* __restrict__ J2,
+                                                          const double2* __restrict__ r2, const double* __restrict__ z,
+                                                          const double* __restrict__ einv, double* __restrict__ step,
+                                                          double* __restrict__ tile_mcc) {
+  extern __shared__ double sm[];
+  const Tile q = load_tile(L, blockIdx.x);
+  const int tid = threadIdx.x;
+  double* zs = sm;                           // [max_seg][9]
+  double* w = zs + L.max_seg_tile * 9;       // [3][T]
+  double* u = w + 3 * T;                     // [3][T]
+  double* red = u + 3 * T;                   // [8]
+  const bool active = tid < q.no;
+  const int i = q.ob + tid;
+  const size_t O = (size_t)L.n_obs;
+  double2 Fv[9], Ev[3], r = make_double2(0.0, 0.0);
+  int slot = 0, ptl = 0;
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Fv[k] = ldcs2(J2 + k * O + i);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) Ev[k] = ldcs2(J2 + (9 + k) * O + i);
+    r = r2[i];
+    slot = L.obs_slot[i]; ptl = L.obs_ptl[i];
+  }
+  for (int idx = tid; idx < q.ns * 9; idx += T) {
+    const int s = idx / 9, k = idx - s * 9;
+    zs[idx] = z[(size_t)L.seg_cam[q.sb + s] * 9 + k];
+  }
+  __syncthreads();
+  double s0 = 0.0, s1 = 0.0;
+  if (active) {
+    double f0 = 0.0, f1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { const double zk = zs[slot * 9 + k]; f0 += Fv[k].x * zk; f1 += Fv[k].y * zk; }
+    s0 = r.x - f0; s1 = r.y - f1;             // b - F z
+#pragma unroll
+    for (int k = 0; k < 3; ++k) w[k * T + tid] = Ev[k].x * s0 + Ev[k].y * s1;
+  }
+  __syncthreads();
+  if (tid < q.np) {
+    const int pnt = q.pb + tid;
+    const int b = L.pt_ptr[pnt] - q.ob, e = L.pt_ptr[pnt + 1] - q.ob;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    for (int j = b; j < e; ++j) { a0 += w[j]; a1 += w[T + j]; a2 += w[2 * T + j]; }
+    const double* m = einv + (size_t)pnt * 6;
+    const double y0 = m[0] * a0 + m[1] * a1 + m[2] * a2;
+    const double y1 = m[1] * a0 + m[3] * a1 + m[4] * a2;
+    const double y2 = m[2] * a0 + m[4] * a1 + m[5] * a2;
+    double* sp = step + (size_t)9 * L.n_cams + (size_t)pnt * 3;
+    sp[0] = -y0; sp[1] = -y1; sp[2] = -y2;      // LM solves J y = r and steps by -y (A.4)
+    u[tid] = -y0; u[T + tid] = -y1; u[2 * T + tid] = -y2;
+  }
+  __syncthreads();
+  double mc = 0.0;
+  if (active) {
+    const double u0 = u[ptl], u1 = u[T + ptl], u2 = u[2 * T + ptl];
+    // model residual m = J * step = F * (-z) + E * step_p = (s - r) + E * step_p
+    const double m0 = (s0 - r.x) + (Ev[0].x * u0 + Ev[1].x * u1 + Ev[2].x * u2);
+    const double m1 = (s1 - r.y) + (Ev[0].y * u0 + Ev[1].y * u1 + Ev[2].y * u2);
+    mc = m0 * (r.x + m0 / 2.0) + m1 * (r.y + m1 / 2.0);
+  }
+  const double tot = block_sum(mc, red);
+  if (tid == 0) tile_mcc[blockIdx.x] = tot;
+}
+
+__global__ void k_ba_export_jacobian(BaDev L, const double2* __restrict__ J2, double* __restrict__ F, double* __restrict__ E) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L.n_obs) return;
+  const size_t O = (size_t)L.n_obs;
+  for (int k = 0; k < 9; ++k) { const double2 f = J2[k * O + i]; F[(size_t)i * 18 + k] = f.x; F[(size_t)i * 18 + 9 + k] = f.y; }
+  for (int k = 0; k < 3; ++k) { const double2 e = J2[(9 + k) * O + i]; E[(size_t)i * 6 + k] = e.x; E[(size_t)i * 6 + 3 + k] = e.y; }
+}
+
+template <class K>
+void set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) SK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+
+}  // namespace
+
+void launch_ba_evaluate(const BaDev& L, const double* x, const double* scale, LossSpec loss, bool with_jacobian,
+                        bool write_jacobian, double2* J2, double2* r2, double* grad, double* cnorm2, double* seg_g,
+                        double* seg_n, double* tile_cost, int* fail_flag, const int* guard, cudaStream_t s) {
+  if (L.n_tiles == 0) return;
+  if (with_jacobian) {
+    const size_t smem = sizeof(double) * ((size_t)2 * (L.max_seg_tile * 9 + L.max_pt_tile * 3) + 9 * VLD + 8);
+    set_smem(k_ba_evaluate<true>, smem);
+    k_ba_evaluate<true><<<L.n_tiles, T, smem, s>>>(L, x, scale, loss, write_jacobian ? 1 : 0, J2, r2, grad, cnorm2, seg_g,
+                                                   seg_n, tile_cost, fail_flag, guard);
+  } else {
+    const size_t smem = sizeof(double) * ((size_t)(L.max_seg_tile * 9 + L.max_pt_tile * 3) + 8);
+    set_smem(k_ba_evaluate<false>, smem);
+    k_ba_evaluate<false><<<L.n_tiles, T, smem, s>>>(L, x, scale, loss, 0, J2, r2, grad, cnorm2, seg_g, seg_n, tile_cost,
+                                                    fail_flag, guard);
+  }
+  check_launch("k_ba_evaluate");
+}
+
+void launch_cam_reduce(const BaDev& L, int K, const double* seg, double* out, const int* guard, cudaStream_t s) {
+  const int n = L.n_cams * K;
+  k_cam_reduce<<<cdiv(n, 256), 256, 0, s>>>(L, K, seg, out, guard);
+  check_launch("k_cam_reduce");
+}
+
+void launch_ba_schur_setup(const BaDev& L, const double2* J2, const double2* r2, const double* D, double* einv,
+                           double* seg_rhs, double* seg_M, int* error_flag, cudaStream_t s) {
+  if (L.n_tiles == 0) return;
+  const size_t smem = sizeof(double) * ((size_t)9 * VLD + (size_t)L.max_pt_tile * 9);
+  set_smem(k_ba_schur_setup, smem);
+  k_ba_schur_setup<<<L.n_tiles, T, smem, s>>>(L, J2, r2, D, einv, seg_rhs, seg_M, error_flag);
+  check_launch("k_ba_schur_setup");
+}
+
+void launch_ba_precond_invert(const BaDev& L, const double* M45, const double* D, double* Minv, int* error_flag,
+                              cudaStream_t s) {
+  k_ba_precond_invert<<<cdiv(L.n_cams, 64), 64, 0, s>>>(L, M45, D, Minv, error_flag);
+  check_launch("k_ba_precond_invert");
+}
+
+void launch_ba_matvec(const BaDev& L, const double2* J2, const double* p, const double* einv, double* seg_y,
+                      const int* guard, cudaStream_t s) {
+  if (L.n_tiles == 0) return;
+  const size_t smem = sizeof(double) * ((size_t)L.max_seg_tile * 9 + 9 * VLD + 6 * T);
+  set_smem(k_ba_matvec, smem);
+  k_ba_matvec<<<L.n_tiles, T, smem, s>>>(L, J2, p, einv, seg_y, guard);
+  check_launch("k_ba_matvec");
+}
+
+void launch_ba_back_substitute(const BaDev& L, const double2* J2, const double2* r2, const double* z, const double* einv,
+                               double* step, double* tile_mcc, cudaStream_t s) {
+  if (L.n_tiles == 0) return;
+  const size_t smem = sizeof(double) * ((size_t)L.max_seg_tile * 9 + 6 * T + 8);
+  set_smem(k_ba_back_substitute, smem);
+  k_ba_back_substitute<<<L.n_tiles, T, smem, s>>>(L, J2, r2, z, einv, step, tile_mcc);
+  check_launch("k_ba_back_substitute");
+}
+
+void launch_ba_export_jacobian(const BaDev& L, const double2* J2, double* F, double* E, cudaStream_t s) {
+  k_ba_export_jacobian<<<cdiv(L.n_obs, 256), 256, 0, s>>>(L, J2, F, E);
+  check_launch("k_ba_export_jacobian");
+}
+
+}  // namespace sk

@@ -1,0 +1,166 @@
+// ba_layout.cu — host-side construction of the tiled BA layout (see ba_layout.h).
+#include "ba_layout.h"
+
+#include <algorithm>
+#include <numeric>
+
+#include "common.cuh"
+
+namespace sk {
+
+void partition_points(int64_t n_points, const int64_t* point_ptr, int world_size, int64_t* out_begin) {
+  const int64_t total = point_ptr[n_points];
+  out_begin[0] = 0;
+  for (int r = 1; r < world_size; ++r) {
+    // first point whose observation prefix reaches r/world of the total
+    const int64_t target = (total * r) / world_size;
+    const int64_t* it = std::lower_bound(point_ptr, point_ptr + n_points + 1, target);
+    int64_t p = it - point_ptr;
+    if (p > n_points) p = n_points;
+    if (p < out_begin[r - 1]) p = out_begin[r - 1];
+    out_begin[r] = p;
+  }
+  out_begin[world_size] = n_points;
+}
+
+// Maps arbitrary block offsets to dense ids ordered by offset.
+static void dense_ids(int64_t n, const int64_t* off, int block_size, std::vector<int64_t>* uniq,
+                      std::vector<int32_t>* ids) {
+  int64_t lo = off[0], hi = off[0];
+  for (int64_t i = 1; i < n; ++i) { lo = std::min(lo, off[i]); hi = std::max(hi, off[i]); }
+  const int64_t range = hi - lo + 1;
+  ids->resize(n);
+  if (range <= std::max<int64_t>(64 * n, 1 << 20)) {           // direct table
+    std::vector<int32_t> table((size_t)range, -1);
+    for (int64_t i = 0; i < n; ++i) table[off[i] - lo] = 0;
+    int32_t next = 0;
+    int64_t last = -(int64_t)block_size;
+    uniq->clear();
+    for (int64_t k = 0; k < range; ++k) if (table[k] == 0) {
+      SK_REQUIRE(k - last >= block_size, SK_ERR_INVALID_ARGUMENT, "overlapping parameter blocks at offsets %lld and %lld",
+                 (long long)(last + lo), (long long)(k + lo));
+      table[k] = next++; uniq->push_back(k + lo); last = k;
+    }
+    for (int64_t i = 0; i < n; ++i) (*ids)[i] = table[off[i] - lo];
+  } else {                                                       // sort + binary search
+    std::vector<int64_t> u(off, off + n);
+    std::sort(u.begin(), u.end());
+    u.erase(std::unique(u.begin(), u.end()), u.end());
+    for (size_t k = 1; k < u.size(); ++k)
+      SK_REQUIRE(u[k] - u[k - 1] >= block_size, SK_ERR_INVALID_ARGUMENT, "overlapping parameter blocks");
+    for (int64_t i = 0; i < n; ++i) (*ids)[i] = (int32_t)(std::lower_bound(u.begin(), u.end(), off[i]) - u.begin());
+    uniq->swap(u);
+  }
+}
+
+void build_ba_layout(int64_t n, const int64_t* cam_off, const int64_t* pt_off, const double* obs_xy,
+                     int rank, int world_size, BaLayoutHost* out) {
+  BaLayoutHost& L = *out;
+  SK_REQUIRE(n > 0, SK_ERR_INVALID_ARGUMENT, "bundle adjustment problem without observations");
+  SK_REQUIRE(n < (int64_t)2000000000, SK_ERR_UNSUPPORTED, "more than 2e9 observations");
+  std::vector<int32_t> cam_id, pt_id;
+  std::vector<int64_t> pt_offsets_all;
+  dense_ids(n, cam_off, 9, &L.cam_offset, &cam_id);
+  dense_ids(n, pt_off, 3, &pt_offsets_all, &pt_id);
+  L.n_cams = (int32_t)L.cam_offset.size();
+  const int64_t n_pts_all = (int64_t)pt_offsets_all.size();
+  {  // camera and point blocks must not overlap each other
+    std::vector<std::pair<int64_t, int>> all;
+    all.reserve(L.cam_offset.size() + pt_offsets_all.size());
+    for (auto o : L.cam_offset) all.push_back({o, 9});
+    for (auto o : pt_offsets_all) all.push_back({o, 3});
+    std::sort(all.begin(), all.end());
+    for (size_t k = 1; k < all.size(); ++k)
+      SK_REQUIRE(all[k].first >= all[k - 1].first + all[k - 1].second, SK_ERR_INVALID_ARGUMENT,
+                 "camera and point parameter blocks overlap at offset %lld", (long long)all[k].first);
+  }
+  // ---- sort by (point, camera) -------------------------------------------------------------
+  bool sorted = true;
+  for (int64_t i = 1; i < n && sorted; ++i)
+    sorted = (pt_id[i] > pt_id[i - 1]) || (pt_id[i] == pt_id[i - 1] && cam_id[i] >= cam_id[i - 1]);
+  L.input_was_sorted = sorted;
+  std::vector<int32_t> order((size_t)n);
+  std::iota(order.begin(), order.end(), 0);
+  if (!sorted) {
+    std::vector<uint64_t> key((size_t)n);
+    for (int64_t i = 0; i < n; ++i) key[i] = ((uint64_t)(uint32_t)pt_id[i] << 32) | (uint32_t)cam_id[i];
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
+  }
+  // global point CSR over the sorted list, then this rank's point range
+  std::vector<int64_t> gptr((size_t)n_pts_all + 1, 0);
+  for (int64_t i = 0; i < n; ++i) gptr[pt_id[i] + 1]++;
+  for (int64_t p = 0; p < n_pts_all; ++p) gptr[p + 1] += gptr[p];
+  std::vector<int64_t> begin((size_t)world_size + 1);
+  partition_points(n_pts_all, gptr.data(), world_size, begin.data());
+  const int64_t p0 = begin[rank], p1 = begin[rank + 1];
+  const int64_t o0 = gptr[p0], o1 = gptr[p1];
+  L.n_pts = (int32_t)(p1 - p0);
+  L.n_obs = (int32_t)(o1 - o0);
+  L.pt_offset.assign(pt_offsets_all.begin() + p0, pt_offsets_all.begin() + p1);
+  L.perm.resize(L.n_obs); L.obs.resize((size_t)2 * L.n_obs); L.obs_cam.resize(L.n_obs); L.obs_pt.resize(L.n_obs);
+  for (int64_t j = 0; j < L.n_obs; ++j) {
+    const int32_t i = order[o0 + j];
+    L.perm[j] = i;
+    L.obs[2 * j] = obs_xy[2 * (int64_t)i]; L.obs[2 * j + 1] = obs_xy[2 * (int64_t)i + 1];
+    L.obs_cam[j] = cam_id[i];
+    L.obs_pt[j] = (int32_t)(pt_id[i] - p0);
+  }
+  L.pt_ptr.resize((size_t)L.n_pts + 1);
+  for (int64_t p = 0; p <= L.n_pts; ++p) L.pt_ptr[p] = (int32_t)(gptr[p0 + p] - o0);
+  for (int64_t j = 1; j < L.n_obs; ++j)
+    SK_REQUIRE(!(L.obs_pt[j] == L.obs_pt[j - 1] && L.obs_cam[j] == L.obs_cam[j - 1]), SK_ERR_UNSUPPORTED,
+               "a camera observes the same point twice (residual blocks %d and %d): unsupported by the Schur path",
+               L.perm[j - 1], L.perm[j]);
+  // ---- tiles: whole points, at most kTileObs observations -----------------------------------
+  L.tile_obs.clear(); L.tile_pt.clear();
+  L.tile_obs.push_back(0); L.tile_pt.push_back(0);
+  int32_t cur = 0;
+  for (int32_t p = 0; p < L.n_pts; ++p) {
+    const int32_t k = L.pt_ptr[p + 1] - L.pt_ptr[p];
+    SK_REQUIRE(k <= kTileObs, SK_ERR_UNSUPPORTED,
+               "a point is observed by %d cameras; tracks longer than %d observations are not supported yet", k, kTileObs);
+    if (cur + k > kTileObs) { L.tile_obs.push_back(L.pt_ptr[p]); L.tile_pt.push_back(p); cur = 0; }
+    cur += k;
+  }
+  L.tile_obs.push_back(L.n_obs); L.tile_pt.push_back(L.n_pts);
+  L.n_tiles = (int32_t)L.tile_obs.size() - 1;
+  // ---- tile-local camera segments ------------------------------------------------------------
+  L.obs_slot.resize(L.n_obs); L.obs_ptl.resize(L.n_obs); L.seg_perm.resize(L.n_obs);
+  L.tile_seg.assign((size_t)L.n_tiles + 1, 0);
+  L.seg_ptr.clear(); L.seg_cam.clear();
+  L.seg_ptr.reserve((size_t)L.n_obs / 4 + 16); L.seg_cam.reserve((size_t)L.n_obs / 4 + 16);
+  L.max_seg_tile = 0; L.max_pt_tile = 0;
+  std::vector<uint32_t> keys; keys.reserve(kTileObs);
+  for (int32_t t = 0; t < L.n_tiles; ++t) {
+    const int32_t ob = L.tile_obs[t], oe = L.tile_obs[t + 1], pb = L.tile_pt[t];
+    L.max_pt_tile = std::max(L.max_pt_tile, L.tile_pt[t + 1] - pb);
+    keys.clear();
+    for (int32_t j = ob; j < oe; ++j) {
+      L.obs_ptl[j] = (uint16_t)(L.obs_pt[j] - pb);
+      keys.push_back(((uint32_t)L.obs_cam[j] << 8) | (uint32_t)(j - ob));   // kTileObs <= 256, cams < 2^24
+    }
+    std::sort(keys.begin(), keys.end());
+    L.tile_seg[t] = (int32_t)L.seg_cam.size();
+    int32_t prev_cam = -1;
+    for (size_t q = 0; q < keys.size(); ++q) {
+      const int32_t cam = (int32_t)(keys[q] >> 8); const int32_t loc = (int32_t)(keys[q] & 255u);
+      if (cam != prev_cam) { L.seg_ptr.push_back(ob + (int32_t)q); L.seg_cam.push_back(cam); prev_cam = cam; }
+      L.seg_perm[ob + q] = (uint16_t)loc;
+      L.obs_slot[ob + loc] = (uint16_t)((int32_t)L.seg_cam.size() - 1 - L.tile_seg[t]);
+    }
+    L.max_seg_tile = std::max(L.max_seg_tile, (int32_t)L.seg_cam.size() - L.tile_seg[t]);
+  }
+  SK_REQUIRE(L.n_cams < (1 << 24), SK_ERR_UNSUPPORTED, "more than 2^24 cameras");
+  L.n_segs = (int32_t)L.seg_cam.size();
+  L.tile_seg[L.n_tiles] = L.n_segs;
+  L.seg_ptr.push_back(L.n_obs);
+  // ---- camera -> segments (tile order) --------------------------------------------------------
+  L.cam_seg_ptr.assign((size_t)L.n_cams + 1, 0);
+  for (int32_t s = 0; s < L.n_segs; ++s) L.cam_seg_ptr[L.seg_cam[s] + 1]++;
+  for (int32_t c = 0; c < L.n_cams; ++c) L.cam_seg_ptr[c + 1] += L.cam_seg_ptr[c];
+  L.cam_seg.resize(L.n_segs);
+  std::vector<int32_t> fill(L.cam_seg_ptr.begin(), L.cam_seg_ptr.end() - 1);
+  for (int32_t s = 0; s < L.n_segs; ++s) L.cam_seg[fill[L.seg_cam[s]]++] = s;
+}
+
+}  // namespace sk

@@ -1,0 +1,54 @@
+// ba_layout.h — HBM data layout of a bundle-adjustment problem (the SchurEliminator<2,3,9> shape).
+//
+// Observations (SimpleBundleAdjuster.scala:139-145: one residual block per observation, blocks
+// (camera 9, point 3)) are sorted by (point, camera) and cut into TILES of at most kTileObs
+// observations that contain whole points.  One CTA processes one tile:
+//   * per-point reductions (E^T E, E^T r, back-substitution) never leave the tile;
+//   * per-camera reductions are done in two levels without atomics: inside the tile the
+//     observations of one camera form a SEGMENT (tile-local, camera-sorted permutation) that is
+//     summed in a fixed order into one partial per (tile, camera); a second kernel sums the partials
+//     of each camera in tile order (cam_seg CSR).  Deterministic by construction.
+// State vector layout (device): x[9*C + 3*P], cameras first — the BalProblem layout
+// (SimpleBundleAdjuster.scala:28-33), cameras/points ordered by their offset in the user array.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace sk {
+
+constexpr int kTileObs = 256;   // observations per tile == threads per CTA
+
+struct BaLayoutHost {
+  int32_t n_obs = 0, n_pts = 0, n_cams = 0, n_tiles = 0, n_segs = 0;
+  int32_t max_seg_tile = 0, max_pt_tile = 0;
+  bool input_was_sorted = true;
+  std::vector<int64_t> cam_offset;     // [C] offset of each camera block in the user array
+  std::vector<int64_t> pt_offset;      // [P]
+  std::vector<int32_t> perm;           // [O] sorted position -> original residual-block index
+  std::vector<double> obs;             // [2*O] sorted (x, y)
+  std::vector<int32_t> obs_cam;        // [O] camera id (sorted order)
+  std::vector<int32_t> obs_pt;         // [O] point id (sorted order)
+  std::vector<int32_t> pt_ptr;         // [P+1]
+  std::vector<int32_t> tile_obs, tile_pt, tile_seg;  // [T+1]
+  std::vector<uint16_t> obs_slot;      // [O] tile-local segment id
+  std::vector<uint16_t> obs_ptl;       // [O] tile-local point id
+  std::vector<uint16_t> seg_perm;      // [O] tile-local obs ids in (segment, obs) order
+  std::vector<int32_t> seg_ptr;        // [S+1] positions into seg_perm
+  std::vector<int32_t> seg_cam;        // [S]
+  std::vector<int32_t> cam_seg_ptr;    // [C+1]
+  std::vector<int32_t> cam_seg;        // [S]
+};
+
+// cam_off / pt_off: per-observation block offsets inside the user's parameter array.
+// Restricts the layout to the point range [pt_begin_rank, pt_end_rank) of the *sorted* point list
+// when world_size > 1 (point partition balanced by observation count); cameras are replicated.
+// Throws sk::Error on unsupported structure (duplicate (camera, point) pairs, tracks longer than
+// kTileObs, overlapping blocks).
+void build_ba_layout(int64_t n, const int64_t* cam_off, const int64_t* pt_off, const double* obs_xy,
+                     int rank, int world_size, BaLayoutHost* out);
+
+// Contiguous point ranges balanced by observation count (out_begin has world_size + 1 entries).
+void partition_points(int64_t n_points, const int64_t* point_ptr, int world_size, int64_t* out_begin);
+
+}  // namespace sk

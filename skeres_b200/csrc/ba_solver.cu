@@ -1,0 +1,250 @@
+// ba_solver.cu — bundle-adjustment back end: SchurEliminator<2,3,9>-shaped problems solved with
+// ITERATIVE_SCHUR (implicit Schur complement + SCHUR_JACOBI / JACOBI-free IDENTITY PCG) or with the
+// explicit reduced camera system (DENSE_SCHUR / SPARSE_SCHUR, dense Cholesky).
+#include "ba_solver.cuh"
+
+#include <chrono>
+
+#include "dense_kernels.cuh"
+
+namespace sk {
+
+namespace {
+__global__ void k_gather_blocks(int nblocks, int bsize, const long long* __restrict__ offsets, const double* __restrict__ user,
+                                double* __restrict__ x) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nblocks * bsize) return;
+  const int b = idx / bsize, k = idx - b * bsize;
+  x[idx] = user[offsets[b] + k];
+}
+__global__ void k_scatter_blocks(int nblocks, int bsize, const long long* __restrict__ offsets, const double* __restrict__ x,
+                                 double* __restrict__ user) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nblocks * bsize) return;
+  const int b = idx / bsize, k = idx - b * bsize;
+  user[offsets[b] + k] = x[idx];
+}
+}  // namespace
+
+BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHost&& layout, double* user_params,
+                   int64_t user_n, LossSpec loss)
+    : LmSolver(opt, stream), H_(std::move(layout)), user_(user_params), user_n_(user_n), loss_(loss) {
+  const auto& H = H_;
+  cudaStream_t s = stream_;
+  d_tile_obs_.upload(H.tile_obs, s); d_tile_pt_.upload(H.tile_pt, s); d_tile_seg_.upload(H.tile_seg, s);
+  d_pt_ptr_.upload(H.pt_ptr, s); d_obs_slot_.upload(H.obs_slot, s); d_obs_ptl_.upload(H.obs_ptl, s);
+  d_seg_perm_.upload(H.seg_perm, s); d_seg_ptr_.upload(H.seg_ptr, s); d_seg_cam_.upload(H.seg_cam, s);
+  d_cam_seg_ptr_.upload(H.cam_seg_ptr, s); d_cam_seg_.upload(H.cam_seg, s);
+  d_obs_.alloc((size_t)2 * H.n_obs); d_obs_.upload(H.obs.data(), H.obs.size(), s);
+  std::vector<long long> co(H.cam_offset.begin(), H.cam_offset.end()), po(H.pt_offset.begin(), H.pt_offset.end());
+  d_cam_off_.upload(co, s); d_pt_off_.upload(po, s);
+  SK_CUDA(cudaStreamSynchronize(s));   // host vectors above are temporaries / pageable
+  L_.n_obs = H.n_obs; L_.n_pts = H.n_pts; L_.n_cams = H.n_cams; L_.n_tiles = H.n_tiles; L_.n_segs = H.n_segs;
+  L_.max_seg_tile = std::max(H.max_seg_tile, 1); L_.max_pt_tile = std::max(H.max_pt_tile, 1);
+  L_.tile_obs = d_tile_obs_.p; L_.tile_pt = d_tile_pt_.p; L_.tile_seg = d_tile_seg_.p; L_.pt_ptr = d_pt_ptr_.p;
+  L_.obs_slot = d_obs_slot_.p; L_.obs_ptl = d_obs_ptl_.p; L_.seg_perm = d_seg_perm_.p; L_.seg_ptr = d_seg_ptr_.p;
+  L_.seg_cam = d_seg_cam_.p; L_.cam_seg_ptr = d_cam_seg_ptr_.p; L_.cam_seg = d_cam_seg_.p;
+  L_.obs = reinterpret_cast<const double2*>(d_obs_.p);
+  const int64_t nc = (int64_t)9 * H.n_cams, n = nc + (int64_t)3 * H.n_pts;
+  allocate(n, nc);
+  J2_.alloc((size_t)2 * kJPlanes * std::max(H.n_obs, 1)); r2_.alloc((size_t)2 * std::max(H.n_obs, 1));
+  einv_.alloc((size_t)6 * std::max(H.n_pts, 1));
+  seg_a_.alloc((size_t)9 * std::max(H.n_segs, 1)); seg_b_.alloc((size_t)9 * std::max(H.n_segs, 1));
+  tile_cost_.alloc(std::max(H.n_tiles, 1)); tile_mcc_.alloc(std::max(H.n_tiles, 1));
+  tile_cost_.zero(s); tile_mcc_.zero(s);
+  rhs_.alloc(nc); px_.alloc(nc); pr_.alloc(nc); pp_.alloc(nc); pz_.alloc(nc); ybuf_.alloc(nc);
+  pcg_.alloc(1); pcg_h_.alloc(1);
+  pcg_part_.alloc(kMaxPartials);
+  SK_REQUIRE(cdiv(nc, 256) <= kMaxPartials, SK_ERR_UNSUPPORTED, "more than %d cameras", kMaxPartials * 256 / 9);
+  const int lst = opt.linear_solver_type;
+  explicit_schur_ = (lst == SK_DENSE_SCHUR || lst == SK_SPARSE_SCHUR);
+  if (!explicit_schur_) {
+    SK_REQUIRE(opt.preconditioner_type == SK_SCHUR_JACOBI || opt.preconditioner_type == SK_IDENTITY, SK_ERR_UNSUPPORTED,
+               "ITERATIVE_SCHUR supports the SCHUR_JACOBI and IDENTITY preconditioners on the device (got %d)", opt.preconditioner_type);
+    seg_M_.alloc((size_t)45 * std::max(H.n_segs, 1)); M45_.alloc((size_t)45 * H.n_cams); Minv_.alloc((size_t)81 * H.n_cams);
+  } else {
+    SK_REQUIRE(nc <= 16384, SK_ERR_UNSUPPORTED,
+               "DENSE_SCHUR / SPARSE_SCHUR keep the reduced camera matrix dense on the device: at most 1820 cameras (got %d); use ITERATIVE_SCHUR",
+               H.n_cams);
+    SK_REQUIRE(comm_ == nullptr || comm_->world == 1, SK_ERR_UNSUPPORTED, "explicit Schur solvers run on one GPU; use ITERATIVE_SCHUR with a communicator");
+    build_pair_lists();
+    S_.alloc((size_t)nc * nc);
+    seg_M_.alloc((size_t)45 * std::max(H.n_segs, 1)); M45_.alloc((size_t)45 * H.n_cams);
+  }
+}
+
+void BaSolver::load_state() {
+  KScope k(prof_, SK_KF_LM, 2);
+  k_gather_blocks<<<cdiv((int64_t)L_.n_cams * 9, 256), 256, 0, stream_>>>(L_.n_cams, 9, d_cam_off_.p, user_, x_.p);
+  if (L_.n_pts) k_gather_blocks<<<cdiv((int64_t)L_.n_pts * 3, 256), 256, 0, stream_>>>(L_.n_pts, 3, d_pt_off_.p, user_, x_.p + nc_);
+  check_launch("k_gather_blocks");
+}
+
+void BaSolver::store_state() {
+  if (comm_ && comm_->world > 1) {
+    // every rank owns a slice of the points; publish them all through a zero-padded sum
+    DBuf<double> tmp((size_t)user_n_);
+    tmp.zero(stream_);
+    if (comm_->rank == 0) k_scatter_blocks<<<cdiv((int64_t)L_.n_cams * 9, 256), 256, 0, stream_>>>(L_.n_cams, 9, d_cam_off_.p, x_.p, tmp.p);
+    if (L_.n_pts) k_scatter_blocks<<<cdiv((int64_t)L_.n_pts * 3, 256), 256, 0, stream_>>>(L_.n_pts, 3, d_pt_off_.p, x_.p + nc_, tmp.p);
+    comm_allreduce_sum(comm_, tmp.p, (size_t)user_n_, stream_);
+    // only the blocks of this problem are copied back (other entries of the user array are untouched)
+    DBuf<long long> all_pt;   // all point offsets are not known locally: copy the touched ranges rank by rank
+    // cameras
+    k_gather_blocks<<<cdiv((int64_t)L_.n_cams * 9, 256), 256, 0, stream_>>>(L_.n_cams, 9, d_cam_off_.p, tmp.p, x_.p);
+    k_scatter_blocks<<<cdiv((int64_t)L_.n_cams * 9, 256), 256, 0, stream_>>>(L_.n_cams, 9, d_cam_off_.p, x_.p, user_);
+    // points: the global list of point offsets was kept on the host
+    if (!all_pt_off_.empty()) {
+      std::vector<long long> ap(all_pt_off_.begin(), all_pt_off_.end());
+      all_pt.upload(ap, stream_);
+      DBuf<double> buf(ap.size() * 3);
+      k_gather_blocks<<<cdiv((int64_t)ap.size() * 3, 256), 256, 0, stream_>>>((int)ap.size(), 3, all_pt.p, tmp.p, buf.p);
+      k_scatter_blocks<<<cdiv((int64_t)ap.size() * 3, 256), 256, 0, stream_>>>((int)ap.size(), 3, all_pt.p, buf.p, user_);
+      SK_CUDA(cudaStreamSynchronize(stream_));
+    }
+    check_launch("store_state");
+    SK_CUDA(cudaStreamSynchronize(stream_));
+    return;
+  }
+  KScope k(prof_, SK_KF_LM, 2);
+  k_scatter_blocks<<<cdiv((int64_t)L_.n_cams * 9, 256), 256, 0, stream_>>>(L_.n_cams, 9, d_cam_off_.p, x_.p, user_);
+  if (L_.n_pts) k_scatter_blocks<<<cdiv((int64_t)L_.n_pts * 3, 256), 256, 0, stream_>>>(L_.n_pts, 3, d_pt_off_.p, x_.p + nc_, user_);
+  check_launch("k_scatter_blocks");
+}
+
+void BaSolver::fill_summary(sk_solver_summary_data* d) {
+  d->num_parameter_blocks = total_param_blocks_;
+  d->num_parameters = total_params_;
+  d->num_residual_blocks = total_obs_;
+  d->num_residuals = 2 * total_obs_;
+}
+
+ReduceJob BaSolver::cost_job() { return {tile_cost_.p, L_.n_tiles, SB_COST, 0}; }
+
+void BaSolver::eval_jacobian(bool scale_valid, bool store, const int* guard) {
+  {
+    KScope k(prof_, SK_KF_EVALUATE_JACOBIAN, 3);
+    launch_ba_evaluate(L_, x_.p, scale_valid ? scale_.p : nullptr, loss_, true, store, reinterpret_cast<double2*>(J2_.p),
+                       reinterpret_cast<double2*>(r2_.p), grad_.p, cnorm2_.p, seg_a_.p, seg_b_.p, tile_cost_.p,
+                       &st_.p->eval_failed, guard, stream_);
+    launch_cam_reduce(L_, 9, seg_a_.p, grad_.p, guard, stream_);
+    launch_cam_reduce(L_, 9, seg_b_.p, cnorm2_.p, guard, stream_);
+  }
+  if (comm_ && comm_->world > 1) {
+    KScope k(prof_, SK_KF_COMM, 1);
+    comm_group_start(comm_);
+    comm_allreduce_sum(comm_, grad_.p, (size_t)nc_, stream_);
+    comm_allreduce_sum(comm_, cnorm2_.p, (size_t)nc_, stream_);
+    comm_group_end(comm_);
+  }
+}
+
+void BaSolver::eval_cost(const double* xv, const int* guard) {
+  KScope k(prof_, SK_KF_EVALUATE_COST);
+  launch_ba_evaluate(L_, xv, nullptr, loss_, false, false, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, tile_cost_.p,
+                     &st_.p->eval_failed, guard, stream_);
+}
+
+void BaSolver::matvec(const double* in, const int* guard) {
+  {
+    KScope k(prof_, SK_KF_SCHUR_MATVEC);
+    launch_ba_matvec(L_, reinterpret_cast<const double2*>(J2_.p), in, einv_.p, seg_a_.p, guard, stream_);
+  }
+  {
+    KScope k(prof_, SK_KF_PCG_VECTOR);
+    launch_cam_reduce(L_, 9, seg_a_.p, ybuf_.p, guard, stream_);
+  }
+  if (comm_ && comm_->world > 1) {
+    KScope k(prof_, SK_KF_COMM);
+    comm_allreduce_sum(comm_, ybuf_.p, (size_t)nc_, stream_);
+  }
+}
+
+ReduceJob BaSolver::linear_solve(const PcgDev** pcg_out) {
+  const double2* J2 = reinterpret_cast<const double2*>(J2_.p);
+  const double2* r2 = reinterpret_cast<const double2*>(r2_.p);
+  int* lin_error = &st_.p->lin_error;
+  {
+    KScope k(prof_, SK_KF_SCHUR_SETUP, 3);
+    launch_ba_schur_setup(L_, J2, r2, D_.p, einv_.p, seg_b_.p, seg_M_.p, lin_error, stream_);
+    launch_cam_reduce(L_, 9, seg_b_.p, rhs_.p, nullptr, stream_);
+    launch_cam_reduce(L_, 45, seg_M_.p, M45_.p, nullptr, stream_);
+  }
+  if (comm_ && comm_->world > 1) {
+    KScope k(prof_, SK_KF_COMM);
+    comm_group_start(comm_);
+    comm_allreduce_sum(comm_, rhs_.p, (size_t)nc_, stream_);
+    comm_allreduce_sum(comm_, M45_.p, (size_t)45 * L_.n_cams, stream_);
+    comm_group_end(comm_);
+  }
+  if (explicit_schur_) {
+    explicit_schur_solve();
+    *pcg_out = nullptr;
+  } else {
+    const bool schur_jacobi = opt_.preconditioner_type == SK_SCHUR_JACOBI;
+    if (schur_jacobi) {
+      KScope k(prof_, SK_KF_SCHUR_SETUP);
+      launch_ba_precond_invert(L_, M45_.p, D_.p, Minv_.p, lin_error, stream_);
+    }
+    pcg_solve(schur_jacobi ? Minv_.p : nullptr);
+    *pcg_out = pcg_.p;
+  }
+  {
+    KScope k(prof_, SK_KF_BACK_SUBSTITUTE, 2);
+    launch_negate(nc_, px_.p, step_.p, stream_);
+    launch_ba_back_substitute(L_, J2, r2, px_.p, einv_.p, step_.p, tile_mcc_.p, stream_);
+  }
+  return {tile_mcc_.p, L_.n_tiles, SB_MCC, 0};
+}
+
+// ConjugateGradientsSolver::Solve on the implicit Schur complement; all scalars stay on the device.
+void BaSolver::pcg_solve(const double* Minv) {
+  const int nb = vec_blocks(nc_);
+  const int nbp = cdiv(nc_, 256);
+  PcgParams pp{opt_.min_linear_solver_iterations, opt_.max_linear_solver_iterations, opt_.eta};
+  const int* active = &pcg_.p->active;
+  {
+    KScope k(prof_, SK_KF_PCG_VECTOR, 2);
+    launch_pcg_init(nc_, rhs_.p, px_.p, pr_.p, pcg_part_.p, stream_);
+    launch_pcg_start(pcg_.p, pcg_part_.p, nb, &st_.p->lin_error, stream_);
+  }
+  const int kBatch = 8, kResetPeriod = 10;
+  int it = 0;
+  bool done = false;
+  while (!done && it < pp.max_iterations) {
+    for (int b = 0; b < kBatch && it < pp.max_iterations; ++b) {
+      ++it;
+      {
+        KScope k(prof_, SK_KF_PCG_VECTOR, 3);
+        launch_pcg_precond(L_.n_cams, Minv, pr_.p, pz_.p, pcg_part_.p, pcg_.p, stream_);
+        launch_pcg_beta(pcg_.p, pcg_part_.p, nbp, stream_);
+        launch_pcg_p(nc_, pz_.p, pp_.p, pcg_.p, stream_);
+      }
+      matvec(pp_.p, active);
+      const int recompute = (it % kResetPeriod == 0) ? 1 : 0;
+      {
+        KScope k(prof_, SK_KF_PCG_VECTOR, 3);
+        launch_pcg_q(nc_, ybuf_.p, D_.p, pp_.p, pz_.p, pcg_part_.p, pcg_.p, stream_);     // q lives in z (as in Ceres)
+        launch_pcg_alpha(pcg_.p, pcg_part_.p, nb, stream_);
+        launch_pcg_x(nc_, px_.p, pp_.p, pr_.p, pz_.p, rhs_.p, recompute, pcg_part_.p, pcg_.p, stream_);
+      }
+      if (recompute) {
+        matvec(px_.p, active);
+        KScope k(prof_, SK_KF_PCG_VECTOR);
+        launch_pcg_resid(nc_, ybuf_.p, D_.p, px_.p, rhs_.p, pr_.p, pcg_part_.p, pcg_.p, stream_);
+      }
+      KScope k(prof_, SK_KF_PCG_VECTOR);
+      launch_pcg_zeta(pcg_.p, pcg_part_.p, nb, pp, stream_);
+    }
+    SK_CUDA(cudaMemcpyAsync(pcg_h_.p, pcg_.p, sizeof(PcgDev), cudaMemcpyDeviceToHost, stream_));
+    SK_CUDA(cudaStreamSynchronize(stream_));
+    prof_.collect();
+    done = pcg_h_.p->active == 0;
+  }
+}
+
+void BaSolver::fill_totals(int64_t total_obs, int64_t total_blocks, int64_t total_params, std::vector<int64_t>&& all_pt_off) {
+  total_obs_ = total_obs; total_param_blocks_ = total_blocks; total_params_ = total_params; all_pt_off_ = std::move(all_pt_off);
+}
+
+}  // namespace sk

@@ -1,0 +1,54 @@
+// ba_solver.cuh — bundle-adjustment back end of the LM driver (see ba_solver.cu).
+#pragma once
+#include "ba_kernels.cuh"
+#include "lm_solver.cuh"
+
+namespace sk {
+
+class BaSolver : public LmSolver {
+ public:
+  // user_params: device pointer of the user's parameter DoubleArray (all blocks live in it).
+  BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHost&& layout, double* user_params,
+           int64_t user_n, LossSpec loss);
+  void fill_totals(int64_t total_obs, int64_t total_blocks, int64_t total_params, std::vector<int64_t>&& all_pt_off);
+
+  // ---- test / debug access (sk_debug_* entry points) ---------------------------------------------
+  const BaDev& layout() const { return L_; }
+  const BaLayoutHost& host_layout() const { return H_; }
+
+ protected:
+  void eval_jacobian(bool scale_valid, bool store, const int* guard) override;
+  void eval_cost(const double* xv, const int* guard) override;
+  ReduceJob cost_job() override;
+  ReduceJob linear_solve(const PcgDev** pcg_out) override;
+  void load_state() override;
+  void store_state() override;
+  void fill_summary(sk_solver_summary_data* d) override;
+
+ private:
+  void matvec(const double* in, const int* guard);     // ybuf = S_local * in (without the D^2 term)
+  void pcg_solve(const double* Minv);
+  void build_pair_lists();
+  void explicit_schur_solve();
+
+  BaLayoutHost H_;
+  BaDev L_{};
+  double* user_; int64_t user_n_;
+  LossSpec loss_;
+  bool explicit_schur_ = false;
+  int64_t total_obs_ = 0, total_param_blocks_ = 0, total_params_ = 0;
+  std::vector<int64_t> all_pt_off_;
+  DBuf<int> d_tile_obs_, d_tile_pt_, d_tile_seg_, d_pt_ptr_, d_seg_ptr_, d_seg_cam_, d_cam_seg_ptr_, d_cam_seg_;
+  DBuf<unsigned short> d_obs_slot_, d_obs_ptl_, d_seg_perm_;
+  DBuf<double> d_obs_;
+  DBuf<long long> d_cam_off_, d_pt_off_;
+  DBuf<double> J2_, r2_, einv_, seg_a_, seg_b_, seg_M_, M45_, Minv_, tile_cost_, tile_mcc_;
+  DBuf<double> rhs_, px_, pr_, pp_, pz_, ybuf_, pcg_part_, S_;
+  DBuf<PcgDev> pcg_;
+  HBuf<PcgDev> pcg_h_;
+  // explicit Schur: for every camera pair (c1 < c2) sharing points, the list of observation pairs
+  DBuf<int> pair_ptr_, pair_c1_, pair_c2_, pair_o1_, pair_o2_, pair_pt_;
+  int n_pair_groups_ = 0;
+};
+
+}  // namespace sk

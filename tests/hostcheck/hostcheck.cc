@@ -1,0 +1,54 @@
+// tests/hostcheck/hostcheck.cc — TEST HARNESS (not part of the product).
+// Compiles the __host__ __device__ arithmetic of skeres_b200/csrc/jet.cuh and the host-side layout
+// builder (ba_layout.cu has no kernels) with g++ so that they can be checked against the oracle on
+// the CPU-only build host.  The product never runs this code path: libskeres.so calls the same
+// functions from CUDA kernels only.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../skeres_b200/csrc/ba_layout.h"
+#include "../../skeres_b200/csrc/common.cuh"
+#include "../../skeres_b200/csrc/jet.cuh"
+
+extern "C" {
+
+int hc_evaluate(int functor, const double* consts, const double* x, double* res, double* jac) {
+  return sk::evaluate_functor(functor, consts, x, res, jac) ? 1 : 0;
+}
+void hc_snavely_residual(const double* cam, const double* pt, double ox, double oy, double* res) {
+  sk::snavely_residual(cam, pt, ox, oy, res);
+}
+void hc_loss(int type, double a, double s, double* rho) { sk::LossSpec l{type, a}; sk::loss_evaluate(l, s, rho); }
+void hc_correct(int type, double a, int nrow, int ncol, double* res, double* J) {
+  double sq = 0; for (int i = 0; i < nrow; ++i) sq += res[i] * res[i];
+  double rho[3]; sk::LossSpec l{type, a}; sk::loss_evaluate(l, sq, rho);
+  sk::Corrector c(sq, rho);
+  c.correct_jacobian(nrow, ncol, ncol, res, J);
+  c.correct_residuals(nrow, res);
+}
+int hc_invert_spd3(const double* m6, double* inv6) { return sk::invert_spd3(m6, inv6) ? 1 : 0; }
+int hc_invert_spd9(double* A, int n) { return sk::invert_spd<9>(A, n) ? 1 : 0; }
+
+// Layout builder: returns 0 on success, else the sk_status; message in err (256 bytes).
+struct HcLayout { sk::BaLayoutHost L; };
+HcLayout* hc_layout_build(int64_t n, const int64_t* cam_off, const int64_t* pt_off, const double* obs, int rank, int world,
+                          int* status, char* err) {
+  HcLayout* h = new HcLayout;
+  try { sk::build_ba_layout(n, cam_off, pt_off, obs, rank, world, &h->L); *status = 0; }
+  catch (const sk::Error& e) { *status = e.status; std::strncpy(err, e.what(), 255); err[255] = 0; delete h; return nullptr; }
+  return h;
+}
+void hc_layout_free(HcLayout* h) { delete h; }
+void hc_layout_dims(const HcLayout* h, int32_t* out /*8*/) {
+  const auto& L = h->L;
+  out[0] = L.n_obs; out[1] = L.n_pts; out[2] = L.n_cams; out[3] = L.n_tiles; out[4] = L.n_segs; out[5] = L.max_seg_tile; out[6] = L.max_pt_tile;
+  out[7] = L.input_was_sorted ? 1 : 0;
+}
+#define HC_COPY(name, field, T) void hc_layout_##name(const HcLayout* h, T* out) { std::memcpy(out, h->L.field.data(), sizeof(T) * h->L.field.size()); }
+HC_COPY(perm, perm, int32_t) HC_COPY(obs_cam, obs_cam, int32_t) HC_COPY(obs_pt, obs_pt, int32_t) HC_COPY(pt_ptr, pt_ptr, int32_t)
+HC_COPY(tile_obs, tile_obs, int32_t) HC_COPY(tile_pt, tile_pt, int32_t) HC_COPY(tile_seg, tile_seg, int32_t)
+HC_COPY(obs_slot, obs_slot, uint16_t) HC_COPY(obs_ptl, obs_ptl, uint16_t) HC_COPY(seg_perm, seg_perm, uint16_t)
+HC_COPY(seg_ptr, seg_ptr, int32_t) HC_COPY(seg_cam, seg_cam, int32_t) HC_COPY(cam_seg_ptr, cam_seg_ptr, int32_t) HC_COPY(cam_seg, cam_seg, int32_t)
+HC_COPY(cam_offset, cam_offset, int64_t) HC_COPY(pt_offset, pt_offset, int64_t) HC_COPY(obs, obs, double)
+}
