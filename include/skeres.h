@@ -66,6 +66,8 @@ int sk_double_array_upload(sk_double_array* a, int64_t offset, const double* hos
 int sk_double_array_download(const sk_double_array* a, int64_t offset, double* host, int64_t n);
 int sk_double_array_get(const sk_double_array* a, int64_t i, double* out); /* getitem */
 int sk_double_array_set(sk_double_array* a, int64_t i, double value);      /* setitem */
+/* Device-to-device copy between (or inside) DoubleArrays, e.g. to restore a saved start point. */
+int sk_double_array_copy(sk_double_array* dst, int64_t dst_offset, const sk_double_array* src, int64_t src_offset, int64_t n);
 /* Raw device address (for callers that share the CUDA context, e.g. a benchmark harness). */
 void* sk_double_array_device_ptr(sk_double_array* a);
 
@@ -303,6 +305,7 @@ typedef struct sk_solver_summary_data {
   double total_time_in_seconds;      /* host wall clock */
   double preprocessor_time_in_seconds;
   double minimizer_time_in_seconds;
+  double minimizer_device_time_in_seconds; /* CUDA-event time of the minimizer on the solver's stream */
   double kernel_ms[SK_KF_COUNT];     /* profile_kernels only, else 0 */
   int64_t kernel_launches[SK_KF_COUNT];
 } sk_solver_summary_data;
@@ -325,6 +328,16 @@ int sk_solver_summary_is_solution_usable(const sk_solver_summary* s);
  * Runs trust-region Levenberg–Marquardt entirely on the device; on return the parameter arrays
  * hold the solution (when usable), still in device memory. */
 int sk_solve(const sk_solver_options* options, sk_problem* problem, sk_solver_summary* summary);
+
+/* ceres.solve split in its two halves so that a caller can keep the preprocessed problem (Ceres'
+ * Preprocessor: program, Schur ordering, and here the tiled device layout) resident in HBM and run
+ * the minimizer more than once:  sk_solve == create + minimize + destroy.
+ *   max_num_iterations_override < 0 keeps options->max_num_iterations; otherwise it must not exceed it.
+ * Every sk_solver_minimize call starts from the CURRENT contents of the parameter arrays. */
+typedef struct sk_solver sk_solver;
+int sk_solver_create(const sk_solver_options* options, sk_problem* problem, sk_solver** out);
+int sk_solver_minimize(sk_solver* solver, int32_t max_num_iterations_override, sk_solver_summary* summary);
+int sk_solver_destroy(sk_solver* solver);
 
 /* ------------------------------------------------------------------------------------------
  * Batched independent small problems (BASELINE.json configs[3]): n_problems CurveFitting-shaped

@@ -1117,6 +1117,9 @@ struct Minimizer {
     char buf[256];
     while (finalize_iteration_and_check_if_can_continue()) {
       t_iter = wall();
+      if (t_iter - t_start > opt.max_solver_time_in_seconds) {    // MaxSolverTimeReached
+        *message = "Maximum solver time reached."; S->termination_type = SK_NO_CONVERGENCE; return;
+      }
       const int prev_iter = its->back().iteration;
       std::memset(&it, 0, sizeof it);
       it.iteration = prev_iter + 1;

@@ -8,7 +8,7 @@ when it is missing.
 _API = ("DoubleArray", "DoublePointer", "LossFunction", "PredefinedLossFunctions", "CostFunction", "AutoDiffCostFunctor",
         "SnavelyReprojectionError", "ExponentialResidual", "Problem", "Solver", "ceres", "Communicator", "BalProblem",
         "LinearSolverType", "PreconditionerType", "MinimizerType", "TerminationType", "SkeresError", "functor_info",
-        "partition_points", "curve_fit_batch_solve")
+        "partition_points", "curve_fit_batch_solve", "PreparedSolver")
 
 
 def __getattr__(name):

@@ -161,6 +161,7 @@ class SolverSummaryData(C.Structure):
         ("total_time_in_seconds", C.c_double),
         ("preprocessor_time_in_seconds", C.c_double),
         ("minimizer_time_in_seconds", C.c_double),
+        ("minimizer_device_time_in_seconds", C.c_double),
         ("kernel_ms", C.c_double * KF_COUNT),
         ("kernel_launches", C.c_int64 * KF_COUNT),
     ]

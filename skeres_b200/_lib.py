@@ -41,6 +41,7 @@ def _load():
         "sk_double_array_get": (i32, [vp, i64, P(dbl)]),
         "sk_double_array_set": (i32, [vp, i64, dbl]),
         "sk_double_array_device_ptr": (vp, [vp]),
+        "sk_double_array_copy": (i32, [vp, i64, vp, i64, i64]),
         "sk_loss_trivial": (i32, [P(vp)]),
         "sk_loss_huber": (i32, [dbl, P(vp)]),
         "sk_loss_cauchy": (i32, [dbl, P(vp)]),
@@ -73,6 +74,9 @@ def _load():
         "sk_solver_summary_full_report": (C.c_char_p, [vp]),
         "sk_solver_summary_is_solution_usable": (i32, [vp]),
         "sk_solve": (i32, [P(_abi.SolverOptions), vp, vp]),
+        "sk_solver_create": (i32, [P(_abi.SolverOptions), vp, P(vp)]),
+        "sk_solver_minimize": (i32, [vp, i32, vp]),
+        "sk_solver_destroy": (i32, [vp]),
         "sk_curve_fit_batch_solve": (i32, [P(_abi.SolverOptions), i64, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
         "sk_bal_problem_from_file": (i32, [C.c_char_p, P(vp)]),
         "sk_bal_problem_destroy": (i32, [vp]),

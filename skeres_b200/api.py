@@ -114,6 +114,11 @@ class DoubleArray:
     def device_ptr(self):
         return lib.sk_double_array_device_ptr(self._h)
 
+    def copyFromArray(self, src, n=None, dst_offset=0, src_offset=0):
+        """Device-to-device copy from another DoubleArray."""
+        n = min(self.n - dst_offset, src.n - src_offset) if n is None else int(n)
+        check(lib.sk_double_array_copy(self._h, int(dst_offset), src._h, int(src_offset), n))
+
 
 class LossFunction:
     def __init__(self, handle, kind, a=0.0):
@@ -396,6 +401,28 @@ class ceres:
     @staticmethod
     def solve(options, problem, summary):
         check(lib.sk_solve(C.byref(options._o), problem._h, summary._h))
+
+
+class PreparedSolver:
+    """sk_solver: the preprocessed problem kept resident in HBM; minimize() can be called repeatedly
+    and always starts from the current contents of the parameter arrays."""
+
+    def __init__(self, options, problem):
+        h = C.c_void_p()
+        check(lib.sk_solver_create(C.byref(options._o), problem._h, C.byref(h)))
+        self._h, self._keep = h, (options, problem)
+
+    def minimize(self, summary=None, max_num_iterations=-1):
+        summary = summary if summary is not None else Solver.Summary()
+        check(lib.sk_solver_minimize(self._h, int(max_num_iterations), summary._h))
+        return summary
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.sk_solver_destroy(self._h)
+            self._h = None
+
+    __del__ = close
 
 
 class Communicator:

@@ -160,6 +160,15 @@ int sk_double_array_download(const sk_double_array* a, int64_t offset, double* h
 int sk_double_array_get(const sk_double_array* a, int64_t i, double* out) { return sk_double_array_download(a, i, out, 1); }
 int sk_double_array_set(sk_double_array* a, int64_t i, double value) { return sk_double_array_upload(a, i, &value, 1); }
 void* sk_double_array_device_ptr(sk_double_array* a) { return a ? a->d.p : nullptr; }
+int sk_double_array_copy(sk_double_array* dst, int64_t dst_offset, const sk_double_array* src, int64_t src_offset, int64_t n) {
+  SK_API_BEGIN
+  check_block(dst, dst_offset, 0, "sk_double_array_copy");
+  check_block(src, src_offset, 0, "sk_double_array_copy");
+  SK_REQUIRE(n >= 0 && dst_offset + n <= dst->n && src_offset + n <= src->n, SK_ERR_INVALID_ARGUMENT, "sk_double_array_copy: range outside array");
+  ensure_device();
+  if (n) SK_CUDA(cudaMemcpy(dst->d.p + dst_offset, src->d.p + src_offset, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice));
+  SK_API_END
+}
 
 // ---- LossFunction ------------------------------------------------------------------------------------
 static int make_loss(int type, double a, sk_loss_function** out) {
@@ -418,7 +427,7 @@ int sk_solver_summary_is_solution_usable(const sk_solver_summary* s) {
 // ---- Solve -----------------------------------------------------------------------------------------------
 static bool is_schur(int t) { return t == SK_DENSE_SCHUR || t == SK_SPARSE_SCHUR || t == SK_ITERATIVE_SCHUR; }
 
-static void solve_ba(const sk_solver_options& opt, sk_problem* p, sk_solver_summary* S, double t0) {
+static std::unique_ptr<LmSolver> prepare_ba(const sk_solver_options& opt, sk_problem* p, cudaStream_t stream) {
   // All residual blocks must be SnavelyReprojectionError(2; 9, 3) over one DoubleArray with one loss —
   // the SchurEliminator<2, 3, 9> shape (cameras = f-blocks, points = e-blocks).
   sk_double_array* array = nullptr;
@@ -458,18 +467,12 @@ static void solve_ba(const sk_solver_options& opt, sk_problem* p, sk_solver_summ
     total_points = (int64_t)all_pt.size();
   }
   const int64_t n_cams = H.n_cams;
-  cudaStream_t stream;
-  SK_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-  try {
-    BaSolver solver(opt, stream, std::move(H), array->d.p, array->n, loss);
-    solver.fill_totals(n, n_cams + total_points, 9 * n_cams + 3 * total_points, std::move(all_pt));
-    S->data.preprocessor_time_in_seconds = wall() - t0;
-    solver.minimize(S);
-  } catch (...) { cudaStreamDestroy(stream); throw; }
-  cudaStreamDestroy(stream);
+  std::unique_ptr<BaSolver> solver(new BaSolver(opt, stream, std::move(H), array->d.p, array->n, loss));
+  solver->fill_totals(n, n_cams + total_points, 9 * n_cams + 3 * total_points, std::move(all_pt));
+  return solver;
 }
 
-static void solve_dense(const sk_solver_options& opt, sk_problem* p, sk_solver_summary* S, double t0) {
+static std::unique_ptr<LmSolver> prepare_dense(const sk_solver_options& opt, sk_problem* p, cudaStream_t stream) {
   std::map<std::pair<sk_double_array*, int64_t>, std::pair<int, int>> blocks;   // -> (first column, size), program order
   std::vector<std::pair<sk_double_array*, int64_t>> order;
   std::vector<DenseRb> rbs;
@@ -509,33 +512,65 @@ static void solve_dense(const sk_solver_options& opt, sk_problem* p, sk_solver_s
     const auto& cs = blocks[key];
     for (int c = 0; c < cs.second; ++c) ptrs[cs.first + c] = key.first->d.p + key.second + c;
   }
-  cudaStream_t stream;
-  SK_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-  try {
-    DenseSolver solver(opt, stream, rbs, row, ptrs, (int)order.size());
-    S->data.preprocessor_time_in_seconds = wall() - t0;
-    solver.minimize(S);
-  } catch (...) { cudaStreamDestroy(stream); throw; }
-  cudaStreamDestroy(stream);
+  return std::unique_ptr<LmSolver>(new DenseSolver(opt, stream, rbs, row, ptrs, (int)order.size()));
 }
 
-int sk_solve(const sk_solver_options* options, sk_problem* problem, sk_solver_summary* summary) {
+}  // extern "C" (reopened below)
+
+struct sk_solver {
+  cudaStream_t stream = nullptr;
+  std::unique_ptr<LmSolver> impl;
+  double preprocessor_s = 0.0;
+  int device = 0;
+  ~sk_solver() { impl.reset(); if (stream) cudaStreamDestroy(stream); }
+};
+
+extern "C" {
+
+int sk_solver_create(const sk_solver_options* options, sk_problem* problem, sk_solver** out) {
   SK_API_BEGIN
-  SK_REQUIRE(options != nullptr && problem != nullptr && summary != nullptr, SK_ERR_INVALID_ARGUMENT, "sk_solve: null argument");
+  SK_REQUIRE(options != nullptr && problem != nullptr && out != nullptr, SK_ERR_INVALID_ARGUMENT, "sk_solver_create: null argument");
   const double t0 = wall();
-  *summary = sk_solver_summary{};
-  summary->data.termination_type = SK_FAILURE;
   const sk_solver_options& o = *options;
   SK_REQUIRE(o.minimizer_type == SK_TRUST_REGION, SK_ERR_UNSUPPORTED, "only the TRUST_REGION minimizer has a device implementation");
   SK_REQUIRE(o.trust_region_strategy_type == SK_LEVENBERG_MARQUARDT, SK_ERR_UNSUPPORTED, "only the LEVENBERG_MARQUARDT strategy has a device implementation");
   SK_REQUIRE(o.max_num_iterations >= 0 && o.initial_trust_region_radius > 0, SK_ERR_INVALID_ARGUMENT, "invalid solver options");
   ensure_device();
-  if (is_schur(o.linear_solver_type)) solve_ba(o, problem, summary, t0);
-  else if (o.linear_solver_type == SK_DENSE_QR) solve_dense(o, problem, summary, t0);
+  std::unique_ptr<sk_solver> s(new sk_solver);
+  s->device = g_device;
+  SK_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  if (is_schur(o.linear_solver_type)) s->impl = prepare_ba(o, problem, s->stream);
+  else if (o.linear_solver_type == SK_DENSE_QR) s->impl = prepare_dense(o, problem, s->stream);
   else throw Error(SK_ERR_UNSUPPORTED, fmt("linear_solver_type %d has no device implementation (supported: DENSE_QR, DENSE_SCHUR, SPARSE_SCHUR, ITERATIVE_SCHUR)", o.linear_solver_type));
-  summary->data.total_time_in_seconds = wall() - t0;
+  s->preprocessor_s = wall() - t0;
+  *out = s.release();
+  SK_API_END
+}
+
+int sk_solver_minimize(sk_solver* solver, int32_t max_num_iterations_override, sk_solver_summary* summary) {
+  SK_API_BEGIN
+  SK_REQUIRE(solver != nullptr && summary != nullptr, SK_ERR_INVALID_ARGUMENT, "sk_solver_minimize: null argument");
+  const double t0 = wall();
+  SK_CUDA(cudaSetDevice(solver->device));
+  *summary = sk_solver_summary{};
+  summary->data.termination_type = SK_FAILURE;
+  summary->data.preprocessor_time_in_seconds = solver->preprocessor_s;
+  solver->impl->minimize(summary, max_num_iterations_override);
+  summary->data.total_time_in_seconds = wall() - t0 + solver->preprocessor_s;
   format_reports(summary);
   SK_API_END
+}
+
+int sk_solver_destroy(sk_solver* solver) { SK_API_BEGIN delete solver; SK_API_END }
+
+int sk_solve(const sk_solver_options* options, sk_problem* problem, sk_solver_summary* summary) {
+  if (summary == nullptr) return fail(SK_ERR_INVALID_ARGUMENT, "sk_solve: null argument");
+  sk_solver* s = nullptr;
+  int st = sk_solver_create(options, problem, &s);
+  if (st != SK_OK) { summary->data.termination_type = SK_FAILURE; summary->message = g_last_error; return st; }
+  st = sk_solver_minimize(s, -1, summary);
+  sk_solver_destroy(s);
+  return st;
 }
 
 // ---- BAL reader ---------------------------------------------------------------------------------------------

@@ -22,7 +22,7 @@ LmSolver::LmSolver(const sk_solver_options& opt, cudaStream_t stream) : opt_(opt
   prof_.stream = stream;
 }
 
-LmSolver::~LmSolver() {}
+LmSolver::~LmSolver() { if (ev_start_) { cudaEventDestroy(ev_start_); cudaEventDestroy(ev_stop_); } }
 
 void LmSolver::allocate(int64_t n, int64_t nc) {
   n_ = n; nc_ = nc;
@@ -41,9 +41,18 @@ void LmSolver::reduce(std::initializer_list<ReduceJob> jobs, const int* guard) {
   launch_reduce_jobs(v.data(), (int)v.size(), sbuf_.p, guard, stream_);
 }
 
-void LmSolver::minimize(sk_solver_summary* S) {
+void LmSolver::minimize(sk_solver_summary* S, int max_num_iterations_override) {
   const double t_start = wall();
   sk_solver_summary_data& d = S->data;
+  if (max_num_iterations_override >= 0) {
+    SK_REQUIRE(max_num_iterations_override <= opt_.max_num_iterations, SK_ERR_INVALID_ARGUMENT,
+               "max_num_iterations override %d exceeds the %d the solver was created with", max_num_iterations_override, opt_.max_num_iterations);
+    prm_.max_num_iterations = max_num_iterations_override;
+  } else prm_.max_num_iterations = opt_.max_num_iterations;
+  n_res_evals_ = n_jac_evals_ = n_lin_solves_ = n_lin_iters_ = 0;
+  for (int f = 0; f < SK_KF_COUNT; ++f) { prof_.launches[f] = 0; prof_.ms[f] = 0.0; }
+  if (!ev_start_) { SK_CUDA(cudaEventCreate(&ev_start_)); SK_CUDA(cudaEventCreate(&ev_stop_)); }
+  SK_CUDA(cudaEventRecord(ev_start_, stream_));
   const int nb = vec_blocks(n_);
   std::vector<double> t_iter, t_cum;
   auto readback = [&]() -> const LmDev& {
@@ -134,8 +143,10 @@ void LmSolver::minimize(sk_solver_summary* S) {
   d.termination_type = h.termination_type;
   const bool usable = h.termination_type == SK_CONVERGENCE || h.termination_type == SK_NO_CONVERGENCE || h.termination_type == SK_USER_SUCCESS;
   if (usable) store_state();
+  SK_CUDA(cudaEventRecord(ev_stop_, stream_));
   SK_CUDA(cudaStreamSynchronize(stream_));
   prof_.collect();
+  { float ms = 0; cudaEventElapsedTime(&ms, ev_start_, ev_stop_); d.minimizer_device_time_in_seconds = ms * 1e-3; }
   for (int i = 0; i < nrows && i < (int)t_iter.size(); ++i) {
     S->rows[i].iteration_time_in_seconds = t_iter[i];
     S->rows[i].cumulative_time_in_seconds = t_cum[i];

@@ -22,7 +22,7 @@ class LmSolver {
   LmSolver(const sk_solver_options& opt, cudaStream_t stream);
   virtual ~LmSolver();
   // Runs the minimisation; state vector x must have been loaded by the back end.
-  void minimize(sk_solver_summary* summary);
+  void minimize(sk_solver_summary* summary, int max_num_iterations_override = -1);
 
  protected:
   // --- back-end hooks -----------------------------------------------------------------------------
@@ -55,6 +55,7 @@ class LmSolver {
   HBuf<LmDev> st_h_;
   DBuf<sk_iteration_summary> rows_;
   int rows_cap_ = 0;
+  cudaEvent_t ev_start_ = nullptr, ev_stop_ = nullptr;
   int64_t n_res_evals_ = 0, n_jac_evals_ = 0, n_lin_solves_ = 0, n_lin_iters_ = 0;
 };
 

@@ -1,0 +1,311 @@
+"""CPU-side checks of the product's host logic (no GPU, no compute calls on the device):
+  * libskeres.so loads and exports every symbol include/skeres.h declares;
+  * option defaults, functor registry, error behaviour without a device;
+  * the tiled bundle-adjustment layout builder and the point partition (ba_layout.cu) against a numpy restatement;
+  * the __host__ __device__ arithmetic of jet.cuh (built for the host by tests/hostcheck) against the oracle.
+"""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from skeres_b200 import _abi, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# --------------------------------------------------------------------------------------------------- ABI
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "skeres.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sk_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from skeres_b200 import _lib
+    names = declared_functions()
+    assert len(names) > 60
+    for n in names:
+        assert hasattr(_lib.lib, n), f"libskeres.so does not export {n}"
+    assert set(_lib.DECLARED_SYMBOLS) == set(names), set(_lib.DECLARED_SYMBOLS) ^ set(names)
+    assert _lib.lib.sk_abi_version() == _abi.ABI_VERSION
+
+
+def test_no_torch_or_oracle_in_the_product_library():
+    out = subprocess.run(["ldd", os.path.join(ROOT, "skeres_b200", "libskeres.so")], capture_output=True, text=True).stdout
+    assert "torch" not in out and "oracle" not in out and "ceres" not in out
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "skeres_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "liboracle" not in text and "oracle_lib" not in text, f"{f} references the oracle"
+
+
+def test_option_defaults_match_ceres():
+    from skeres_b200 import _lib
+    o = _abi.SolverOptions()
+    _lib.lib.sk_solver_options_init(C.byref(o))
+    d = _abi.default_options()
+    for name, _ in _abi.SolverOptions._fields_:
+        assert getattr(o, name) == getattr(d, name), name
+    assert (o.max_num_iterations, o.initial_trust_region_radius, o.min_relative_decrease) == (50, 1e4, 1e-3)
+    assert (o.function_tolerance, o.gradient_tolerance, o.parameter_tolerance, o.eta) == (1e-6, 1e-10, 1e-8, 1e-1)
+    assert (o.max_linear_solver_iterations, o.min_lm_diagonal, o.max_lm_diagonal) == (500, 1e-6, 1e32)
+
+
+def test_functor_registry_and_unregistered_functor():
+    from skeres_b200 import api
+    assert api.functor_info(_abi.FUNCTOR_SNAVELY_REPROJECTION_ERROR) == (2, [9, 3], 2)      # SimpleBundleAdjuster.scala:79
+    assert api.functor_info(_abi.FUNCTOR_EXPONENTIAL_RESIDUAL) == (1, [1, 1], 2)            # CurveFitting.scala:92
+    assert api.functor_info(_abi.FUNCTOR_TEST_SUM10) == (1, [1] * 10, 0)
+    with pytest.raises(api.SkeresError) as e:
+        api.functor_info(999)
+    assert e.value.status == _abi.ERR_UNSUPPORTED and "no CPU fallback" in str(e.value)
+
+    class Arbitrary(api.AutoDiffCostFunctor):        # an arbitrary closure cannot run on the device
+        pass
+    with pytest.raises(api.SkeresError):
+        Arbitrary(1, 2).toAutoDiffCostFunction()
+    for factory in (lambda: api.PredefinedLossFunctions.tukeyLoss(1.0), lambda: api.PredefinedLossFunctions.softLOneLoss(1.0),
+                    lambda: api.PredefinedLossFunctions.tolerantLoss(1.0, 2.0)):
+        with pytest.raises(api.SkeresError) as e:
+            factory()
+        assert e.value.status == _abi.ERR_UNSUPPORTED
+
+
+def test_fails_loudly_without_a_gpu():
+    from skeres_b200 import api
+    if api.lib.sk_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(api.SkeresError) as e:
+        api.DoubleArray(8)
+    assert e.value.status == _abi.ERR_CUDA and "no CPU fallback" in str(e.value)
+
+
+# --------------------------------------------------------------------------------------------------- host check harness
+@pytest.fixture(scope="module")
+def hc():
+    d = os.path.join(ROOT, "tests", "hostcheck")
+    subprocess.run(["make", "-C", d], check=True, capture_output=True)
+    L = C.CDLL(os.path.join(d, "libhostcheck.so"))
+    L.hc_layout_build.restype = C.c_void_p
+    L.hc_layout_build.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_char_p]
+    L.hc_layout_free.argtypes = [C.c_void_p]
+    L.hc_evaluate.argtypes = [C.c_int] + [C.c_void_p] * 4
+    L.hc_snavely_residual.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p]
+    L.hc_loss.argtypes = [C.c_int, C.c_double, C.c_double, C.c_void_p]
+    L.hc_correct.argtypes = [C.c_int, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.hc_invert_spd3.argtypes = [C.c_void_p, C.c_void_p]
+    L.hc_invert_spd9.argtypes = [C.c_void_p, C.c_int]
+    return L
+
+
+def p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Layout:
+    FIELDS = {"perm": np.int32, "obs_cam": np.int32, "obs_pt": np.int32, "pt_ptr": np.int32, "tile_obs": np.int32, "tile_pt": np.int32,
+              "tile_seg": np.int32, "obs_slot": np.uint16, "obs_ptl": np.uint16, "seg_perm": np.uint16, "seg_ptr": np.int32,
+              "seg_cam": np.int32, "cam_seg_ptr": np.int32, "cam_seg": np.int32, "cam_offset": np.int64, "pt_offset": np.int64, "obs": np.float64}
+
+    def __init__(self, L, cam_off, pt_off, obs, rank=0, world=1):
+        cam_off = np.ascontiguousarray(cam_off, dtype=np.int64); pt_off = np.ascontiguousarray(pt_off, dtype=np.int64)
+        obs = np.ascontiguousarray(obs, dtype=np.float64)
+        st = C.c_int(); err = C.create_string_buffer(256)
+        h = L.hc_layout_build(cam_off.size, p(cam_off), p(pt_off), p(obs), rank, world, C.byref(st), err)
+        self.status, self.error = st.value, err.value.decode()
+        if not h:
+            return
+        dims = np.zeros(8, dtype=np.int32)
+        L.hc_layout_dims(C.c_void_p(h), p(dims))
+        self.n_obs, self.n_pts, self.n_cams, self.n_tiles, self.n_segs, self.max_seg_tile, self.max_pt_tile, self.sorted = dims.tolist()
+        size = {"perm": self.n_obs, "obs_cam": self.n_obs, "obs_pt": self.n_obs, "pt_ptr": self.n_pts + 1, "tile_obs": self.n_tiles + 1,
+                "tile_pt": self.n_tiles + 1, "tile_seg": self.n_tiles + 1, "obs_slot": self.n_obs, "obs_ptl": self.n_obs, "seg_perm": self.n_obs,
+                "seg_ptr": self.n_segs + 1, "seg_cam": self.n_segs, "cam_seg_ptr": self.n_cams + 1, "cam_seg": self.n_segs,
+                "cam_offset": self.n_cams, "pt_offset": self.n_pts, "obs": 2 * self.n_obs}
+        for name, dt in self.FIELDS.items():
+            a = np.zeros(size[name], dtype=dt)
+            fn = getattr(L, "hc_layout_" + name)
+            fn.argtypes = [C.c_void_p, C.c_void_p]
+            fn(C.c_void_p(h), p(a))
+            setattr(self, name, a)
+        L.hc_layout_free(C.c_void_p(h))
+
+
+def check_layout(lay, cam_off, pt_off, obs, pt_range=None):
+    """Every invariant the tile kernels rely on."""
+    cams = np.unique(cam_off); pts_all = np.unique(pt_off)
+    pts = pts_all if pt_range is None else pts_all[pt_range[0]:pt_range[1]]
+    assert lay.n_cams == cams.size and np.array_equal(lay.cam_offset, cams)
+    assert lay.n_pts == pts.size and np.array_equal(lay.pt_offset, pts)
+    # sorted by (point, camera); perm maps back to the original residual blocks
+    key = lay.obs_pt.astype(np.int64) * (lay.n_cams + 1) + lay.obs_cam
+    assert np.all(np.diff(key) > 0)
+    assert np.array_equal(cam_off[lay.perm], cams[lay.obs_cam]) and np.array_equal(pt_off[lay.perm], pts[lay.obs_pt])
+    assert np.array_equal(obs.reshape(-1, 2)[lay.perm].ravel(), lay.obs)
+    assert np.array_equal(np.bincount(lay.obs_pt, minlength=lay.n_pts), np.diff(lay.pt_ptr))
+    # tiles: whole points, <= 256 observations, consistent point / segment ranges
+    assert lay.tile_obs[0] == 0 and lay.tile_obs[-1] == lay.n_obs and lay.tile_pt[-1] == lay.n_pts and lay.tile_seg[-1] == lay.n_segs
+    assert np.all(np.diff(lay.tile_obs) <= 256) and np.all(np.diff(lay.tile_obs) > 0)
+    assert np.array_equal(lay.pt_ptr[lay.tile_pt], lay.tile_obs)
+    assert lay.max_pt_tile == np.diff(lay.tile_pt).max() and lay.max_seg_tile == np.diff(lay.tile_seg).max()
+    for t in range(lay.n_tiles):
+        ob, oe, pb, sb, se = lay.tile_obs[t], lay.tile_obs[t + 1], lay.tile_pt[t], lay.tile_seg[t], lay.tile_seg[t + 1]
+        assert np.array_equal(lay.obs_ptl[ob:oe], lay.obs_pt[ob:oe] - pb)
+        assert np.array_equal(lay.seg_cam[sb:se], np.unique(lay.obs_cam[ob:oe]))          # one segment per distinct camera, ascending
+        assert np.array_equal(lay.seg_cam[sb + lay.obs_slot[ob:oe].astype(int)], lay.obs_cam[ob:oe])
+        assert lay.seg_ptr[sb] == ob and lay.seg_ptr[se] == oe
+        assert sorted(lay.seg_perm[ob:oe].tolist()) == list(range(oe - ob))              # a permutation of the tile's observations
+        for s in range(sb, se):
+            loc = lay.seg_perm[lay.seg_ptr[s]:lay.seg_ptr[s + 1]].astype(int)
+            assert np.all(lay.obs_cam[ob + loc] == lay.seg_cam[s]) and np.all(np.diff(loc) > 0)   # fixed (point) order inside a segment
+    # camera -> segments in tile order, every segment exactly once
+    assert sorted(lay.cam_seg.tolist()) == list(range(lay.n_segs))
+    for c in range(lay.n_cams):
+        segs = lay.cam_seg[lay.cam_seg_ptr[c]:lay.cam_seg_ptr[c + 1]]
+        assert np.all(lay.seg_cam[segs] == c) and np.all(np.diff(segs) > 0)
+
+
+@pytest.mark.parametrize("shape,seed", [("tiny", 1), ("small", 2), ("ladybug-49", 1)])
+def test_layout_invariants(hc, shape, seed):
+    d = synth.make_bal(shape, seed=seed)
+    off = d.block_offsets()
+    lay = Layout(hc, off[:, 0], off[:, 1], d.observations)
+    assert lay.status == 0 and lay.sorted == 1
+    check_layout(lay, off[:, 0], off[:, 1], d.observations)
+
+
+def test_layout_sorts_shuffled_input_and_handles_arbitrary_offsets(hc):
+    d = synth.make_bal("small", seed=5)
+    off = d.block_offsets()
+    perm = np.random.default_rng(1).permutation(d.num_observations)
+    cam_off = off[perm, 0] * 7 + 1000003            # sparse, non-BAL offsets -> exercises the sort + binary-search id path
+    pt_off = off[perm, 1] * 5 + 900000007
+    obs = d.observations.reshape(-1, 2)[perm].ravel()
+    lay = Layout(hc, cam_off, pt_off, obs)
+    assert lay.status == 0 and lay.sorted == 0
+    check_layout(lay, cam_off, pt_off, obs)
+
+
+def test_layout_rejects_bad_structure(hc):
+    d = synth.make_bal("tiny", seed=1)
+    off = d.block_offsets()
+    dup = np.concatenate([off, off[:1]])                               # same (camera, point) twice
+    lay = Layout(hc, dup[:, 0], dup[:, 1], np.concatenate([d.observations, d.observations[:2]]))
+    assert lay.status == _abi.ERR_UNSUPPORTED and "twice" in lay.error
+    bad = off.copy(); bad[0, 0] += 4                                   # overlapping camera blocks
+    lay = Layout(hc, bad[:, 0], bad[:, 1], d.observations)
+    assert lay.status == _abi.ERR_INVALID_ARGUMENT and "overlap" in lay.error
+    n = 300                                                           # a 300-observation track exceeds the tile size
+    lay = Layout(hc, np.arange(n) * 9, np.full(n, 9 * n), np.zeros(2 * n))
+    assert lay.status == _abi.ERR_UNSUPPORTED and "tracks longer" in lay.error
+
+
+def test_ragged_tracks_fill_tiles(hc):
+    """Tracks of very different lengths (1 .. 256 observations) still give whole-point tiles."""
+    rng = np.random.default_rng(3)
+    n_cam = 300
+    lens = np.concatenate([[256, 1, 255, 2], rng.integers(1, 40, 200), [256]])
+    cam, pt = [], []
+    for j, k in enumerate(lens):
+        cam.extend(sorted(rng.choice(n_cam, size=k, replace=False))); pt.extend([j] * k)
+    cam_off = np.array(cam, dtype=np.int64) * 9; pt_off = 9 * n_cam + np.array(pt, dtype=np.int64) * 3
+    obs = rng.normal(size=2 * cam_off.size)
+    lay = Layout(hc, cam_off, pt_off, obs)
+    assert lay.status == 0
+    check_layout(lay, cam_off, pt_off, obs)
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_point_partition(hc, world):
+    from skeres_b200 import api
+    d = synth.make_bal("ladybug-49", seed=1)
+    off = d.block_offsets()
+    ptr = np.concatenate([[0], np.cumsum(np.bincount(d.point_index))]).astype(np.int64)
+    begin = api.partition_points(ptr, world)
+    assert begin[0] == 0 and begin[-1] == d.num_points and np.all(np.diff(begin) >= 0)
+    per_rank = np.diff(ptr[begin])
+    assert per_rank.sum() == d.num_observations
+    assert per_rank.max() - per_rank.min() <= 2 * np.diff(ptr).max()          # balanced by observation count
+    seen = []
+    for r in range(world):                                                     # the per-rank layouts tile the problem exactly
+        lay = Layout(hc, off[:, 0], off[:, 1], d.observations, rank=r, world=world)
+        assert lay.status == 0 and lay.n_cams == d.num_cameras                 # cameras are replicated
+        check_layout(lay, off[:, 0], off[:, 1], d.observations, pt_range=(begin[r], begin[r + 1]))
+        seen.append(lay.perm)
+    assert sorted(np.concatenate(seen).tolist()) == list(range(d.num_observations))
+
+
+# --------------------------------------------------------------------------------------------------- device arithmetic on the host
+def test_device_functors_match_the_oracle(hc, oracle):
+    """jet.cuh (two-stage 6-wide duals for Snavely, full-width duals elsewhere) vs the 12-wide spire-style oracle."""
+    d = synth.make_bal("small", seed=7)
+    rng = np.random.default_rng(0)
+    worst = 0.0
+    for i in list(rng.integers(0, d.num_observations, 300)) + list(np.nonzero(d.camera_index == 0)[0][:20]):   # camera 0 = Taylor branch
+        cam = d.parameters[9 * d.camera_index[i]:9 * d.camera_index[i] + 9]
+        pt = d.parameters[9 * d.num_cameras + 3 * d.point_index[i]:][:3]
+        obs = d.observations[2 * i:2 * i + 2]
+        ok, res, (F, E) = oracle.evaluate(_abi.FUNCTOR_SNAVELY_REPROJECTION_ERROR, obs, [cam, pt])
+        x = np.ascontiguousarray(np.concatenate([cam, pt])); r2 = np.zeros(2); jac = np.zeros(24)
+        assert hc.hc_evaluate(_abi.FUNCTOR_SNAVELY_REPROJECTION_ERROR, p(np.ascontiguousarray(obs)), p(x), p(r2), p(jac)) == 1
+        J = np.concatenate([F, E], axis=1)
+        assert np.allclose(r2, res, rtol=1e-13, atol=1e-10)
+        worst = max(worst, np.max(np.abs(jac.reshape(2, 12) - J) / np.abs(J).max()))
+        r3 = np.zeros(2)
+        hc.hc_snavely_residual(p(np.ascontiguousarray(cam)), p(np.ascontiguousarray(pt)), obs[0], obs[1], p(r3))
+        assert np.allclose(r3, res, rtol=1e-13, atol=1e-10)
+    assert worst < 1e-13
+    import json
+    for case in json.load(open(os.path.join(ROOT, "tests", "golden", "autodiff_spec_vectors.json")))["cases"]:
+        x = np.ascontiguousarray(np.concatenate(case["parameters"]), dtype=np.float64)
+        consts = np.ascontiguousarray(case["consts"] + [0.0], dtype=np.float64)
+        nres = len(case["residuals"]); res = np.zeros(nres); jac = np.zeros(nres * x.size)
+        assert hc.hc_evaluate(case["functor"], p(consts), p(x), p(res), p(jac)) == 1
+        assert res.tolist() == case["residuals"]
+        jac = jac.reshape(nres, x.size); col = 0
+        for blk, want in zip(case["parameters"], case["jacobians"]):
+            assert jac[:, col:col + len(blk)].ravel().tolist() == want
+            col += len(blk)
+
+
+def test_device_loss_and_corrector_match_the_oracle(hc, oracle):
+    rng = np.random.default_rng(1)
+    for kind, a in [(_abi.LOSS_TRIVIAL, 0.0), (_abi.LOSS_HUBER, 0.7), (_abi.LOSS_CAUCHY, 0.5)]:
+        for s in [0.0, 0.2, 3.0, 40.0]:
+            rho = np.zeros(3)
+            hc.hc_loss(kind, a, s, p(rho))
+            assert np.allclose(rho, oracle.loss(kind, a, s), rtol=1e-15, atol=0)
+    # Corrector through a one-block solve: compare the corrected residual/Jacobian implied by the oracle's gradient
+    d = synth.make_bal("tiny", seed=3)
+    for kind, a in [(_abi.LOSS_HUBER, 1.0), (_abi.LOSS_CAUCHY, 2.0)]:
+        op = oracle.OracleProblem(d.parameters)
+        op.add_residual_blocks(_abi.FUNCTOR_SNAVELY_REPROJECTION_ERROR, d.observations.reshape(-1, 2), d.block_offsets(), kind, a)
+        cost, r, g, Jv = op.evaluate()
+        op0 = oracle.OracleProblem(d.parameters)
+        op0.add_residual_blocks(_abi.FUNCTOR_SNAVELY_REPROJECTION_ERROR, d.observations.reshape(-1, 2), d.block_offsets())
+        _, r0, _, J0 = op0.evaluate()
+        for i in rng.integers(0, d.num_observations, 25):
+            res = r0[2 * i:2 * i + 2].copy(); J = J0[24 * i:24 * i + 18].copy()
+            hc.hc_correct(kind, a, 2, 9, p(res), p(J))
+            assert np.allclose(res, r[2 * i:2 * i + 2], rtol=1e-14, atol=1e-14)
+            assert np.allclose(J, Jv[24 * i:24 * i + 18], rtol=1e-13, atol=1e-13)
+
+
+def test_small_spd_inverses(hc):
+    rng = np.random.default_rng(2)
+    for _ in range(50):
+        A = rng.normal(size=(5, 3)); M = A.T @ A + 1e-3 * np.eye(3)
+        m6 = np.array([M[0, 0], M[0, 1], M[0, 2], M[1, 1], M[1, 2], M[2, 2]]); inv6 = np.zeros(6)
+        assert hc.hc_invert_spd3(p(m6), p(inv6)) == 1
+        W = np.linalg.inv(M)
+        assert np.allclose(inv6, [W[0, 0], W[0, 1], W[0, 2], W[1, 1], W[1, 2], W[2, 2]], rtol=1e-10)
+        B = rng.normal(size=(20, 9)); S = np.ascontiguousarray(B.T @ B + 1e-3 * np.eye(9))
+        want = np.linalg.inv(S)
+        assert hc.hc_invert_spd9(p(S), 9) == 1 and np.allclose(S, want, rtol=1e-9, atol=1e-12)
+    bad = np.array([1.0, 2.0, 0.0, 1.0, 0.0, 1.0]); out = np.zeros(6)
+    assert hc.hc_invert_spd3(p(bad), p(out)) == 0            # not positive definite -> reported, not NaN-propagated
