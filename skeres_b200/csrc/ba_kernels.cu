@@ -18,6 +18,8 @@
 //                         + the model-cost-change product of TrustRegionMinimizer (A.3 step 3)
 #include "ba_kernels.cuh"
 
+#include "lm_kernels.cuh"
+
 namespace sk {
 
 namespace {
@@ -300,9 +302,33 @@ __global__ void k_ba_precond_invert(BaDev L, const double* __restrict__ M45, con
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(T) k_ba_matvec(BaDev L, const double2* __restrict__ J2, const double* __restrict__ p,
-                                                 const double* __restrict__ einv, double* __restrict__ seg_y,
-                                                 const int* guard) {
+// Tile metadata needed by the later phases, fetched at the top of the kernel so that its latency
+// overlaps the streaming Jacobian loads: tile-local segment permutation / segment starts / point starts.
+struct TileMetaSmem { unsigned short* sperm; int* sptr; int* pptr; };
+
+__device__ __forceinline__ void stage_tile_meta(const BaDev& L, const Tile& q, const TileMetaSmem& m) {
+  const int tid = threadIdx.x;
+  if (tid < q.no) m.sperm[tid] = L.seg_perm[q.ob + tid];
+  for (int idx = tid; idx <= q.ns; idx += T) m.sptr[idx] = L.seg_ptr[q.sb + idx] - q.ob;
+  for (int idx = tid; idx <= q.np; idx += T) m.pptr[idx] = L.pt_ptr[q.pb + idx] - q.ob;
+}
+
+// seg_reduce9 with the metadata already in shared memory.
+__device__ __forceinline__ void seg_reduce9_s(const Tile& q, const TileMetaSmem& m, const double* v, double* out, int ostride, int ooff) {
+  for (int idx = threadIdx.x; idx < q.ns * 9; idx += T) {
+    const int s = idx / 9, k = idx - s * 9;
+    const int b = m.sptr[s], e = m.sptr[s + 1];
+    double sum = 0.0;
+    for (int pos = b; pos < e; ++pos) sum += v[k * VLD + m.sperm[pos]];
+    out[(size_t)(q.sb + s) * ostride + ooff + k] = sum;
+  }
+}
+
+// Input vector: `p` itself, or (pcg != nullptr) the PCG direction z + beta p formed on the fly (p = z in iteration 1).
+__global__ void __launch_bounds__(T, 3) k_ba_matvec(BaDev L, const double2* __restrict__ J2, const double* __restrict__ p,
+                                                    const double* __restrict__ zdir, const PcgDev* pcg,
+                                                    const double* __restrict__ einv, double* __restrict__ seg_y,
+                                                    const int* guard) {
   if (guard != nullptr && *guard == 0) return;
   extern __shared__ double sm[];
   const Tile q = load_tile(L, blockIdx.x);
@@ -311,6 +337,11 @@ __global__ void __launch_bounds__(T) k_ba_matvec(BaDev L, const double2* __restr
   double* v = xs + L.max_seg_tile * 9;       // [9][VLD]
   double* w = v + 9 * VLD;                   // [3][T]  E^T t per observation
   double* u = w + 3 * T;                     // [3][T]  (E^T E)^-1 w per point
+  double* ei = u + 3 * T;                    // [max_pt][6]
+  TileMetaSmem meta;
+  meta.sptr = reinterpret_cast<int*>(ei + L.max_pt_tile * 6);        // [max_seg + 1]
+  meta.pptr = meta.sptr + L.max_seg_tile + 1;                        // [max_pt + 1]
+  meta.sperm = reinterpret_cast<unsigned short*>(meta.pptr + L.max_pt_tile + 1);   // [T]
   const bool active = tid < q.no;
   const int i = q.ob + tid;
   const size_t O = (size_t)L.n_obs;
@@ -323,9 +354,13 @@ __global__ void __launch_bounds__(T) k_ba_matvec(BaDev L, const double2* __restr
     for (int k = 0; k < 3; ++k) Ev[k] = ldcs2(J2 + (9 + k) * O + i);
     slot = L.obs_slot[i]; ptl = L.obs_ptl[i];
   }
+  // everything the later phases need from global memory is requested now, behind the Jacobian loads
+  stage_tile_meta(L, q, meta);
+  for (int idx = tid; idx < q.np * 6; idx += T) ei[idx] = einv[(size_t)q.pb * 6 + idx];
   for (int idx = tid; idx < q.ns * 9; idx += T) {
     const int s = idx / 9, k = idx - s * 9;
-    xs[idx] = p[(size_t)L.seg_cam[q.sb + s] * 9 + k];
+    const size_t e = (size_t)L.seg_cam[q.sb + s] * 9 + k;
+    xs[idx] = (pcg == nullptr) ? p[e] : ((pcg->iter == 1) ? zdir[e] : (zdir[e] + pcg->beta * p[e]));
   }
   __syncthreads();
   double t0 = 0.0, t1 = 0.0;
@@ -337,11 +372,10 @@ __global__ void __launch_bounds__(T) k_ba_matvec(BaDev L, const double2* __restr
   }
   __syncthreads();
   if (tid < q.np) {
-    const int pnt = q.pb + tid;
-    const int b = L.pt_ptr[pnt] - q.ob, e = L.pt_ptr[pnt + 1] - q.ob;
+    const int b = meta.pptr[tid], e = meta.pptr[tid + 1];
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
     for (int j = b; j < e; ++j) { a0 += w[j]; a1 += w[T + j]; a2 += w[2 * T + j]; }
-    const double* m = einv + (size_t)pnt * 6;
+    const double* m = ei + tid * 6;
     u[tid] = m[0] * a0 + m[1] * a1 + m[2] * a2;
     u[T + tid] = m[1] * a0 + m[3] * a1 + m[4] * a2;
     u[2 * T + tid] = m[2] * a0 + m[4] * a1 + m[5] * a2;
@@ -355,7 +389,7 @@ __global__ void __launch_bounds__(T) k_ba_matvec(BaDev L, const double2* __restr
     for (int k = 0; k < 9; ++k) v[k * VLD + tid] = Fv[k].x * s0 + Fv[k].y * s1;
   }
   __syncthreads();
-  seg_reduce9(L, q, v, seg_y, 9, 0);
+  seg_reduce9_s(q, meta, v, seg_y, 9, 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -478,12 +512,13 @@ void launch_ba_precond_invert(const BaDev& L, const double* M45, const double* D
   check_launch("k_ba_precond_invert");
 }
 
-void launch_ba_matvec(const BaDev& L, const double2* J2, const double* p, const double* einv, double* seg_y,
-                      const int* guard, cudaStream_t s) {
+void launch_ba_matvec(const BaDev& L, const double2* J2, const double* p, const double* zdir, const PcgDev* pcg, const double* einv,
+                      double* seg_y, const int* guard, cudaStream_t s) {
   if (L.n_tiles == 0) return;
-  const size_t smem = sizeof(double) * ((size_t)L.max_seg_tile * 9 + 9 * VLD + 6 * T);
+  const size_t smem = sizeof(double) * ((size_t)L.max_seg_tile * 9 + 9 * VLD + 6 * T + (size_t)L.max_pt_tile * 6) +
+                      sizeof(int) * ((size_t)L.max_seg_tile + L.max_pt_tile + 2) + sizeof(unsigned short) * T + 16;
   set_smem(k_ba_matvec, smem);
-  k_ba_matvec<<<L.n_tiles, T, smem, s>>>(L, J2, p, einv, seg_y, guard);
+  k_ba_matvec<<<L.n_tiles, T, smem, s>>>(L, J2, p, zdir, pcg, einv, seg_y, guard);
   check_launch("k_ba_matvec");
 }
 

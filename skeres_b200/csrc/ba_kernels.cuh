@@ -54,8 +54,9 @@ void launch_ba_precond_invert(const BaDev& L, const double* M45 /*[C][45]*/, con
                               int* error_flag, cudaStream_t s);
 
 // Implicit Schur product partials: seg_y[S][9] of  F^T (F p - E (E^T E)^-1 E^T F p)
-void launch_ba_matvec(const BaDev& L, const double2* J2, const double* p, const double* einv, double* seg_y,
-                      const int* guard, cudaStream_t s);
+struct PcgDev;
+void launch_ba_matvec(const BaDev& L, const double2* J2, const double* p, const double* zdir, const PcgDev* pcg, const double* einv,
+                      double* seg_y, const int* guard, cudaStream_t s);
 
 // Back-substitution + model cost change. z = reduced solution [9C] (not negated).
 //   step[9C + 3p + k] = -y_p ; tile_mcc[t] = sum_i m_i . (r_i + m_i / 2), m = J * step

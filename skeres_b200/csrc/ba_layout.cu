@@ -2,11 +2,30 @@
 #include "ba_layout.h"
 
 #include <algorithm>
+#include <mutex>
 #include <numeric>
+#include <thread>
 
 #include "common.cuh"
 
 namespace sk {
+
+// Static-chunk parallel loop over [0, n) on the host (results do not depend on the thread count).
+template <class F>
+static void parallel_for(int64_t n, F f) {
+  int nt = (int)std::min<int64_t>(std::max(1u, std::thread::hardware_concurrency()), 32);
+  nt = (int)std::min<int64_t>(nt, std::max<int64_t>(1, n / 64));
+  if (nt <= 1) { f(0, n); return; }
+  std::vector<std::thread> th;
+  std::exception_ptr err;
+  std::mutex mu;
+  for (int k = 0; k < nt; ++k) {
+    const int64_t a = n * k / nt, b = n * (k + 1) / nt;
+    th.emplace_back([&, a, b] { try { f(a, b); } catch (...) { std::lock_guard<std::mutex> g(mu); err = std::current_exception(); } });
+  }
+  for (auto& t : th) t.join();
+  if (err) std::rethrow_exception(err);
+}
 
 void partition_points(int64_t n_points, const int64_t* point_ptr, int world_size, int64_t* out_begin) {
   const int64_t total = point_ptr[n_points];
@@ -98,13 +117,15 @@ void build_ba_layout(int64_t n, const int64_t* cam_off, const int64_t* pt_off, c
   L.n_obs = (int32_t)(o1 - o0);
   L.pt_offset.assign(pt_offsets_all.begin() + p0, pt_offsets_all.begin() + p1);
   L.perm.resize(L.n_obs); L.obs.resize((size_t)2 * L.n_obs); L.obs_cam.resize(L.n_obs); L.obs_pt.resize(L.n_obs);
-  for (int64_t j = 0; j < L.n_obs; ++j) {
-    const int32_t i = order[o0 + j];
-    L.perm[j] = i;
-    L.obs[2 * j] = obs_xy[2 * (int64_t)i]; L.obs[2 * j + 1] = obs_xy[2 * (int64_t)i + 1];
-    L.obs_cam[j] = cam_id[i];
-    L.obs_pt[j] = (int32_t)(pt_id[i] - p0);
-  }
+  parallel_for(L.n_obs, [&](int64_t j0, int64_t j1) {
+    for (int64_t j = j0; j < j1; ++j) {
+      const int32_t i = order[o0 + j];
+      L.perm[j] = i;
+      L.obs[2 * j] = obs_xy[2 * (int64_t)i]; L.obs[2 * j + 1] = obs_xy[2 * (int64_t)i + 1];
+      L.obs_cam[j] = cam_id[i];
+      L.obs_pt[j] = (int32_t)(pt_id[i] - p0);
+    }
+  });
   L.pt_ptr.resize((size_t)L.n_pts + 1);
   for (int64_t p = 0; p <= L.n_pts; ++p) L.pt_ptr[p] = (int32_t)(gptr[p0 + p] - o0);
   for (int64_t j = 1; j < L.n_obs; ++j)
@@ -124,36 +145,51 @@ void build_ba_layout(int64_t n, const int64_t* cam_off, const int64_t* pt_off, c
   }
   L.tile_obs.push_back(L.n_obs); L.tile_pt.push_back(L.n_pts);
   L.n_tiles = (int32_t)L.tile_obs.size() - 1;
-  // ---- tile-local camera segments ------------------------------------------------------------
+  // ---- tile-local camera segments (tiles are independent: built by all host threads) -------------
+  SK_REQUIRE(L.n_cams < (1 << 24), SK_ERR_UNSUPPORTED, "more than 2^24 cameras");
   L.obs_slot.resize(L.n_obs); L.obs_ptl.resize(L.n_obs); L.seg_perm.resize(L.n_obs);
   L.tile_seg.assign((size_t)L.n_tiles + 1, 0);
-  L.seg_ptr.clear(); L.seg_cam.clear();
-  L.seg_ptr.reserve((size_t)L.n_obs / 4 + 16); L.seg_cam.reserve((size_t)L.n_obs / 4 + 16);
+  // pass 1: camera-sort each tile, remember the tile-local segment structure, count segments
+  std::vector<int32_t> tile_nseg((size_t)L.n_tiles, 0);
+  parallel_for(L.n_tiles, [&](int64_t t0, int64_t t1) {
+    uint32_t keys[kTileObs];
+    for (int64_t t = t0; t < t1; ++t) {
+      const int32_t ob = L.tile_obs[t], oe = L.tile_obs[t + 1], pb = L.tile_pt[t], no = oe - ob;
+      for (int32_t j = 0; j < no; ++j) {
+        L.obs_ptl[ob + j] = (uint16_t)(L.obs_pt[ob + j] - pb);
+        keys[j] = ((uint32_t)L.obs_cam[ob + j] << 8) | (uint32_t)j;          // kTileObs <= 256, cams < 2^24
+      }
+      std::sort(keys, keys + no);
+      int32_t prev_cam = -1, nseg = 0;
+      for (int32_t q = 0; q < no; ++q) {
+        const int32_t cam = (int32_t)(keys[q] >> 8), loc = (int32_t)(keys[q] & 255u);
+        if (cam != prev_cam) { ++nseg; prev_cam = cam; }
+        L.seg_perm[ob + q] = (uint16_t)loc;
+        L.obs_slot[ob + loc] = (uint16_t)(nseg - 1);
+      }
+      tile_nseg[t] = nseg;
+    }
+  });
   L.max_seg_tile = 0; L.max_pt_tile = 0;
-  std::vector<uint32_t> keys; keys.reserve(kTileObs);
   for (int32_t t = 0; t < L.n_tiles; ++t) {
-    const int32_t ob = L.tile_obs[t], oe = L.tile_obs[t + 1], pb = L.tile_pt[t];
-    L.max_pt_tile = std::max(L.max_pt_tile, L.tile_pt[t + 1] - pb);
-    keys.clear();
-    for (int32_t j = ob; j < oe; ++j) {
-      L.obs_ptl[j] = (uint16_t)(L.obs_pt[j] - pb);
-      keys.push_back(((uint32_t)L.obs_cam[j] << 8) | (uint32_t)(j - ob));   // kTileObs <= 256, cams < 2^24
-    }
-    std::sort(keys.begin(), keys.end());
-    L.tile_seg[t] = (int32_t)L.seg_cam.size();
-    int32_t prev_cam = -1;
-    for (size_t q = 0; q < keys.size(); ++q) {
-      const int32_t cam = (int32_t)(keys[q] >> 8); const int32_t loc = (int32_t)(keys[q] & 255u);
-      if (cam != prev_cam) { L.seg_ptr.push_back(ob + (int32_t)q); L.seg_cam.push_back(cam); prev_cam = cam; }
-      L.seg_perm[ob + q] = (uint16_t)loc;
-      L.obs_slot[ob + loc] = (uint16_t)((int32_t)L.seg_cam.size() - 1 - L.tile_seg[t]);
-    }
-    L.max_seg_tile = std::max(L.max_seg_tile, (int32_t)L.seg_cam.size() - L.tile_seg[t]);
+    L.tile_seg[t + 1] = L.tile_seg[t] + tile_nseg[t];
+    L.max_seg_tile = std::max(L.max_seg_tile, tile_nseg[t]);
+    L.max_pt_tile = std::max(L.max_pt_tile, L.tile_pt[t + 1] - L.tile_pt[t]);
   }
-  SK_REQUIRE(L.n_cams < (1 << 24), SK_ERR_UNSUPPORTED, "more than 2^24 cameras");
-  L.n_segs = (int32_t)L.seg_cam.size();
-  L.tile_seg[L.n_tiles] = L.n_segs;
-  L.seg_ptr.push_back(L.n_obs);
+  L.n_segs = L.tile_seg[L.n_tiles];
+  L.seg_ptr.assign((size_t)L.n_segs + 1, 0); L.seg_cam.assign((size_t)L.n_segs, 0);
+  // pass 2: segment starts and cameras
+  parallel_for(L.n_tiles, [&](int64_t t0, int64_t t1) {
+    for (int64_t t = t0; t < t1; ++t) {
+      const int32_t ob = L.tile_obs[t], oe = L.tile_obs[t + 1];
+      int32_t s = L.tile_seg[t] - 1, prev_cam = -1;
+      for (int32_t q = ob; q < oe; ++q) {
+        const int32_t cam = L.obs_cam[ob + L.seg_perm[q]];
+        if (cam != prev_cam) { ++s; L.seg_ptr[s] = q; L.seg_cam[s] = cam; prev_cam = cam; }
+      }
+    }
+  });
+  L.seg_ptr[L.n_segs] = L.n_obs;
   // ---- camera -> segments (tile order) --------------------------------------------------------
   L.cam_seg_ptr.assign((size_t)L.n_cams + 1, 0);
   for (int32_t s = 0; s < L.n_segs; ++s) L.cam_seg_ptr[L.seg_cam[s] + 1]++;

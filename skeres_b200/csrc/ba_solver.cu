@@ -6,6 +6,7 @@
 #include <chrono>
 
 #include "dense_kernels.cuh"
+#include "pcg_kernels.cuh"
 
 namespace sk {
 
@@ -54,8 +55,8 @@ BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHo
   tile_cost_.zero(s); tile_mcc_.zero(s);
   rhs_.alloc(nc); px_.alloc(nc); pr_.alloc(nc); pp_.alloc(nc); pz_.alloc(nc); ybuf_.alloc(nc);
   pcg_.alloc(1); pcg_h_.alloc(1);
-  pcg_part_.alloc(kMaxPartials);
-  SK_REQUIRE(cdiv(nc, 256) <= kMaxPartials, SK_ERR_UNSUPPORTED, "more than %d cameras", kMaxPartials * 256 / 9);
+  pcg_part_.alloc(4 * kMaxPartials);
+  SK_REQUIRE(cdiv(H.n_cams, 8) <= kMaxPartials, SK_ERR_UNSUPPORTED, "more than %d cameras", kMaxPartials * 256 / 9);
   const int lst = opt.linear_solver_type;
   explicit_schur_ = (lst == SK_DENSE_SCHUR || lst == SK_SPARSE_SCHUR);
   if (!explicit_schur_) {
@@ -74,6 +75,7 @@ BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHo
 }
 
 void BaSolver::load_state() {
+  n_real_matvecs_ = 0;
   KScope k(prof_, SK_KF_LM, 2);
   k_gather_blocks<<<cdiv((int64_t)L_.n_cams * 9, 256), 256, 0, stream_>>>(L_.n_cams, 9, d_cam_off_.p, user_, x_.p);
   if (L_.n_pts) k_gather_blocks<<<cdiv((int64_t)L_.n_pts * 3, 256), 256, 0, stream_>>>(L_.n_pts, 3, d_pt_off_.p, user_, x_.p + nc_);
@@ -117,6 +119,9 @@ void BaSolver::fill_summary(sk_solver_summary_data* d) {
   d->num_parameters = total_params_;
   d->num_residual_blocks = total_obs_;
   d->num_residuals = 2 * total_obs_;
+  // matvec launches that did work: launches issued after PCG termination inside a batch return at once and
+  // would dilute the per-launch average the roofline figure is built from
+  if (!explicit_schur_) d->kernel_launches[SK_KF_SCHUR_MATVEC] = n_real_matvecs_;
 }
 
 ReduceJob BaSolver::cost_job() { return {tile_cost_.p, L_.n_tiles, SB_COST, 0}; }
@@ -145,19 +150,22 @@ void BaSolver::eval_cost(const double* xv, const int* guard) {
                      &st_.p->eval_failed, guard, stream_);
 }
 
-void BaSolver::matvec(const double* in, const int* guard) {
+// seg_a_ = segment partials of S_local * v, where v = `in` or (pcg_dir) the PCG direction z + beta p.
+// Multi-GPU: the partials are reduced per camera into ybuf_ and allreduced; returns the vector the
+// consumer kernels should read (nullptr = "reduce the segment partials yourself").
+const double* BaSolver::matvec(const double* in, bool pcg_dir, const int* guard) {
   {
     KScope k(prof_, SK_KF_SCHUR_MATVEC);
-    launch_ba_matvec(L_, reinterpret_cast<const double2*>(J2_.p), in, einv_.p, seg_a_.p, guard, stream_);
-  }
-  {
-    KScope k(prof_, SK_KF_PCG_VECTOR);
-    launch_cam_reduce(L_, 9, seg_a_.p, ybuf_.p, guard, stream_);
+    launch_ba_matvec(L_, reinterpret_cast<const double2*>(J2_.p), in, pcg_dir ? pz_.p : nullptr, pcg_dir ? pcg_.p : nullptr, einv_.p,
+                     seg_a_.p, guard, stream_);
   }
   if (comm_ && comm_->world > 1) {
+    { KScope k(prof_, SK_KF_PCG_VECTOR); launch_cam_reduce(L_, 9, seg_a_.p, ybuf_.p, guard, stream_); }
     KScope k(prof_, SK_KF_COMM);
     comm_allreduce_sum(comm_, ybuf_.p, (size_t)nc_, stream_);
+    return ybuf_.p;
   }
+  return nullptr;
 }
 
 ReduceJob BaSolver::linear_solve(const PcgDev** pcg_out) {
@@ -197,16 +205,20 @@ ReduceJob BaSolver::linear_solve(const PcgDev** pcg_out) {
   return {tile_mcc_.p, L_.n_tiles, SB_MCC, 0};
 }
 
-// ConjugateGradientsSolver::Solve on the implicit Schur complement; all scalars stay on the device.
+// ConjugateGradientsSolver::Solve on the implicit Schur complement; all scalars stay on the device
+// (pcg_kernels.cu).  The host enqueues iterations in batches and polls the state block between batches;
+// kernels of iterations after termination return immediately.
 void BaSolver::pcg_solve(const double* Minv) {
-  const int nb = vec_blocks(nc_);
-  const int nbp = cdiv(nc_, 256);
+  const int nb = pcg_blocks(L_.n_cams);
   PcgParams pp{opt_.min_linear_solver_iterations, opt_.max_linear_solver_iterations, opt_.eta};
   const int* active = &pcg_.p->active;
+  double* part_bb = pcg_part_.p;
+  double* part_rho = pcg_part_.p + kMaxPartials;
+  double* part_pq = pcg_part_.p + 2 * kMaxPartials;
+  double* part_Q = pcg_part_.p + 3 * kMaxPartials;
   {
     KScope k(prof_, SK_KF_PCG_VECTOR, 2);
-    launch_pcg_init(nc_, rhs_.p, px_.p, pr_.p, pcg_part_.p, stream_);
-    launch_pcg_start(pcg_.p, pcg_part_.p, nb, &st_.p->lin_error, stream_);
+    launch_pcg_begin(L_.n_cams, rhs_.p, Minv, px_.p, pr_.p, pz_.p, part_bb, part_rho, pcg_.p, &st_.p->lin_error, stream_);
   }
   const int kBatch = 8, kResetPeriod = 10;
   int it = 0;
@@ -214,33 +226,29 @@ void BaSolver::pcg_solve(const double* Minv) {
   while (!done && it < pp.max_iterations) {
     for (int b = 0; b < kBatch && it < pp.max_iterations; ++b) {
       ++it;
-      {
-        KScope k(prof_, SK_KF_PCG_VECTOR, 3);
-        launch_pcg_precond(L_.n_cams, Minv, pr_.p, pz_.p, pcg_part_.p, pcg_.p, stream_);
-        launch_pcg_beta(pcg_.p, pcg_part_.p, nbp, stream_);
-        launch_pcg_p(nc_, pz_.p, pp_.p, pcg_.p, stream_);
-      }
-      matvec(pp_.p, active);
+      { KScope k(prof_, SK_KF_PCG_VECTOR); launch_pcg_head(pcg_.p, part_rho, part_pq, part_Q, nb, pp, 0, stream_); }
+      const double* y = matvec(pp_.p, true, active);
       const int recompute = (it % kResetPeriod == 0) ? 1 : 0;
       {
-        KScope k(prof_, SK_KF_PCG_VECTOR, 3);
-        launch_pcg_q(nc_, ybuf_.p, D_.p, pp_.p, pz_.p, pcg_part_.p, pcg_.p, stream_);     // q lives in z (as in Ceres)
-        launch_pcg_alpha(pcg_.p, pcg_part_.p, nb, stream_);
-        launch_pcg_x(nc_, px_.p, pp_.p, pr_.p, pz_.p, rhs_.p, recompute, pcg_part_.p, pcg_.p, stream_);
+        KScope k(prof_, SK_KF_PCG_VECTOR, 2);
+        launch_pcg_reduce(L_, seg_a_.p, y, D_.p, pz_.p, pp_.p, part_pq, pcg_.p, stream_);
+        launch_pcg_update(L_.n_cams, Minv, rhs_.p, px_.p, pp_.p, pr_.p, pz_.p, part_pq, recompute, part_Q, part_rho, pcg_.p, stream_);
       }
       if (recompute) {
-        matvec(px_.p, active);
+        const double* yx = matvec(px_.p, false, active);
         KScope k(prof_, SK_KF_PCG_VECTOR);
-        launch_pcg_resid(nc_, ybuf_.p, D_.p, px_.p, rhs_.p, pr_.p, pcg_part_.p, pcg_.p, stream_);
+        launch_pcg_resid2(L_, seg_a_.p, yx, D_.p, Minv, rhs_.p, px_.p, pr_.p, pz_.p, part_Q, part_rho, pcg_.p, stream_);
       }
-      KScope k(prof_, SK_KF_PCG_VECTOR);
-      launch_pcg_zeta(pcg_.p, pcg_part_.p, nb, pp, stream_);
     }
+    { KScope k(prof_, SK_KF_PCG_VECTOR); launch_pcg_head(pcg_.p, part_rho, part_pq, part_Q, nb, pp, 1, stream_); }
     SK_CUDA(cudaMemcpyAsync(pcg_h_.p, pcg_.p, sizeof(PcgDev), cudaMemcpyDeviceToHost, stream_));
     SK_CUDA(cudaStreamSynchronize(stream_));
     prof_.collect();
     done = pcg_h_.p->active == 0;
+    n_real_matvecs_ += 0;
   }
+  const int its = pcg_h_.p->iter;
+  n_real_matvecs_ += its + its / kResetPeriod;
 }
 
 void BaSolver::fill_totals(int64_t total_obs, int64_t total_blocks, int64_t total_params, std::vector<int64_t>&& all_pt_off) {

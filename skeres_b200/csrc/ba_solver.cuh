@@ -26,7 +26,7 @@ class BaSolver : public LmSolver {
   void fill_summary(sk_solver_summary_data* d) override;
 
  private:
-  void matvec(const double* in, const int* guard);     // ybuf = S_local * in (without the D^2 term)
+  const double* matvec(const double* in, bool pcg_dir, const int* guard);
   void pcg_solve(const double* Minv);
   void build_pair_lists();
   void explicit_schur_solve();
@@ -49,6 +49,8 @@ class BaSolver : public LmSolver {
   // explicit Schur: for every camera pair (c1 < c2) sharing points, the list of observation pairs
   DBuf<int> pair_ptr_, pair_c1_, pair_c2_, pair_o1_, pair_o2_, pair_pt_;
   int n_pair_groups_ = 0;
+ public:
+  int64_t n_real_matvecs_ = 0;   // matvec launches that did work (not skipped by the PCG guard)
 };
 
 }  // namespace sk

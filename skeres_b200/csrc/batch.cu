@@ -85,19 +85,24 @@ __global__ void __launch_bounds__(BT) k_batch_init(int64_t np, int nobs, const d
                                                    int jacobi_scaling, int* active_count) {
   extern __shared__ double e_s[];
   const int64_t p = blockIdx.x * (int64_t)BT + threadIdx.x;
-  if (p >= np) { publish_active(false, active_count); return; }
-  const double m = mc[p], c = mc[np + p];
-  Sums s;
-  pass_jacobian(x, y, np, p, nobs, m, c, 1.0, 1.0, e_s + threadIdx.x, &s);
-  const double s1 = jacobi_scaling ? 1.0 / (1.0 + sqrt(s.n1)) : 1.0, s2 = jacobi_scaling ? 1.0 / (1.0 + sqrt(s.n2)) : 1.0;
-  st.scale1[p] = s1; st.scale2[p] = s2;
-  st.radius[p] = radius0; st.decrease[p] = 2.0; st.reuse[p] = 0; st.nci[p] = 0;
-  st.x_cost[p] = s.cost; st.x_norm[p] = sqrt(m * m + c * c);
-  st.initial_cost[p] = s.cost; st.final_cost[p] = s.cost;
-  st.iteration[p] = 0; st.done[p] = 0; st.term[p] = SK_NO_CONVERGENCE; st.nsucc[p] = 0; st.nunsucc[p] = 0;
-  const double gm = fmax(fabs(m - (m + (-s.g1))), fabs(c - (c + (-s.g2))));
-  st.grad_max[p] = gm;
-  publish_active(finalize(st, p, true, gm, s.cost, prm), active_count);
+  // No thread may leave before publish_active: it contains a CTA-wide barrier, and a warp whose lanes reach
+  // a barrier at two different program points (n_problems not a multiple of 32) is undefined behaviour.
+  bool active = false;
+  if (p < np) {
+    const double m = mc[p], c = mc[np + p];
+    Sums s;
+    pass_jacobian(x, y, np, p, nobs, m, c, 1.0, 1.0, e_s + threadIdx.x, &s);
+    const double s1 = jacobi_scaling ? 1.0 / (1.0 + sqrt(s.n1)) : 1.0, s2 = jacobi_scaling ? 1.0 / (1.0 + sqrt(s.n2)) : 1.0;
+    st.scale1[p] = s1; st.scale2[p] = s2;
+    st.radius[p] = radius0; st.decrease[p] = 2.0; st.reuse[p] = 0; st.nci[p] = 0;
+    st.x_cost[p] = s.cost; st.x_norm[p] = sqrt(m * m + c * c);
+    st.initial_cost[p] = s.cost; st.final_cost[p] = s.cost;
+    st.iteration[p] = 0; st.done[p] = 0; st.term[p] = SK_NO_CONVERGENCE; st.nsucc[p] = 0; st.nunsucc[p] = 0;
+    const double gm = fmax(fabs(m - (m + (-s.g1))), fabs(c - (c + (-s.g2))));
+    st.grad_max[p] = gm;
+    active = finalize(st, p, true, gm, s.cost, prm);
+  }
+  publish_active(active, active_count);
 }
 
 // One LM iteration of problem p; returns whether the problem is still active afterwards.
@@ -250,6 +255,9 @@ void curve_fit_batch_solve(const sk_solver_options& opt, int64_t np, int nobs, c
   SK_CUDA(cudaStreamSynchronize(stream));
   int lm_iters = 0;
   while (*active_h.p > 0) {
+    // every active problem retires after at most max_num_iterations iterations; never spin past that
+    SK_REQUIRE(lm_iters <= opt.max_num_iterations + 1, SK_ERR_INTERNAL,
+               "batched solve: %d problems still active after %d launches (max_num_iterations %d)", *active_h.p, lm_iters, opt.max_num_iterations);
     active.zero(stream);
     { KScope k(prof, SK_KF_DENSE);
       k_batch_iterate<<<blocks, BT, smem, stream>>>(np, nobs, x, y, mc, st, prm, active.p); }

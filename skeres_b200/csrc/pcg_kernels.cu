@@ -1,0 +1,277 @@
+// pcg_kernels.cu — fused preconditioned conjugate gradients on the reduced camera system
+// (ConjugateGradientsSolver::Solve) with every scalar kept on the device.
+//
+// One PCG iteration is four launches:
+//   k_pcg_head    (1 CTA)  finishes the previous iteration (Q-based termination test, max iterations,
+//                          indefiniteness), then rho = r.z, beta, iteration counter
+//   k_ba_matvec   (tiles)  implicit Schur product of p = z + beta p_old, formed on the fly (ba_kernels.cu)
+//   k_pcg_reduce  (warp per camera) p = z + beta p_old (stored), q = sum of the camera's segment partials
+//                          + D^2 p, and the p.q partials
+//   k_pcg_update  (warp per camera) alpha = rho / p.q; x += alpha p; r -= alpha q; Q partials;
+//                          z = M^-1 r (SchurJacobi block) and the r.z partials of the NEXT iteration
+// Every residual_reset_period-th iteration r is recomputed as b - S x (one more matvec + k_pcg_resid).
+// All sums are fixed-order (per-warp partials reduced by one CTA), hence bit-reproducible.
+#include "pcg_kernels.cuh"
+
+namespace sk {
+
+namespace {
+
+constexpr int WPB = 8;                    // warps (= cameras) per CTA
+
+__device__ __forceinline__ double block_sum_fixed(double x, double* red) {   // 256 threads
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = x;
+  __syncthreads();
+  double r = 0.0;
+  if (w == 0) {
+    r = (l < (int)(blockDim.x >> 5)) ? red[l] : 0.0;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
+  }
+  return r;                               // valid in thread 0
+}
+
+__device__ double sum_fixed(const double* part, int n, double* red) {
+  double a = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) a += part[i];
+  return block_sum_fixed(a, red);
+}
+
+// Same value in every thread of the CTA (used where each CTA needs the scalar itself).
+__device__ double sum_fixed_all(const double* part, int n, double* red, double* bcast) {
+  const double s = sum_fixed(part, n, red);
+  if (threadIdx.x == 0) *bcast = s;
+  __syncthreads();
+  return *bcast;
+}
+
+__device__ __forceinline__ bool zero_or_inf(double x) { return x == 0.0 || isinf(x); }
+
+__global__ void k_pcg_begin(int n_cams, const double* __restrict__ rhs, const double* __restrict__ Minv, double* __restrict__ x,
+                            double* __restrict__ r, double* __restrict__ z, double* __restrict__ part_bb, double* __restrict__ part_rho) {
+  // x0 = 0 => r = b - S*0 = b;  z = M^-1 r;  partials of |b|^2 and r.z
+  __shared__ double red[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * WPB + warp;
+  double bb = 0.0, rz = 0.0;
+  if (c < n_cams) {
+    const double rk = (lane < 9) ? rhs[(size_t)c * 9 + lane] : 0.0;
+    double zk = 0.0;
+    if (Minv != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        const double rj = __shfl_sync(0xffffffffu, rk, j);
+        if (lane < 9) zk += Minv[(size_t)c * 81 + lane * 9 + j] * rj;
+      }
+    } else zk = rk;
+    if (lane < 9) { x[(size_t)c * 9 + lane] = 0.0; r[(size_t)c * 9 + lane] = rk; z[(size_t)c * 9 + lane] = zk; bb = rk * rk; rz = rk * zk; }
+  }
+  const double s1 = block_sum_fixed(bb, red), s2 = block_sum_fixed(rz, red);
+  if (threadIdx.x == 0) { part_bb[blockIdx.x] = s1; part_rho[blockIdx.x] = s2; }
+}
+
+__global__ void k_pcg_start2(PcgDev* st, const double* part_bb, int nparts, const int* lin_error) {
+  __shared__ double red[8];
+  const double bb = sum_fixed(part_bb, nparts, red);
+  if (threadIdx.x != 0) return;
+  st->norm_b = sqrt(bb);
+  st->rho = 1.0; st->last_rho = 1.0; st->pq = 0.0; st->alpha = 0.0; st->beta = 0.0;
+  st->Q0 = 0.0; st->Q1 = 0.0;                                   // Q0 = -x.(b + r) with x = 0
+  st->iter = 0; st->active = 1; st->termination = LIN_NO_CONVERGENCE; st->pad_ = 0;   // pad_ = last finished iteration
+  if (*lin_error) { st->active = 0; st->termination = LIN_FAILURE; }
+  else if (st->norm_b == 0.0) { st->active = 0; st->termination = LIN_SUCCESS; }
+}
+
+// Finishes iteration st->iter (if not done yet) and, unless finish_only, opens the next one.
+__global__ void k_pcg_head(PcgDev* st, const double* part_rho, const double* part_pq, const double* part_Q, int nparts,
+                           PcgParams prm, int finish_only) {
+  if (st->active == 0) return;
+  __shared__ double red[8];
+  const int it = st->iter;
+  const bool need_finish = it >= 1 && st->pad_ != it;
+  double pq = 0.0, xbr = 0.0;
+  if (need_finish) { pq = sum_fixed(part_pq, nparts, red); xbr = sum_fixed(part_Q, nparts, red); }
+  double rho = 0.0;
+  if (!finish_only) rho = sum_fixed(part_rho, nparts, red);
+  if (threadIdx.x != 0) return;
+  if (need_finish) {
+    st->pad_ = it;
+    st->pq = pq;
+    if (!(pq > 0.0) || isinf(pq)) { st->active = 0; st->termination = LIN_NO_CONVERGENCE; return; }   // indefinite: x was not updated
+    st->alpha = st->rho / pq;
+    if (isinf(st->alpha)) { st->active = 0; st->termination = LIN_FAILURE; return; }
+    const double Q1 = -1.0 * xbr;
+    st->Q1 = Q1;
+    const double zeta = it * (Q1 - st->Q0) / Q1;
+    if (zeta < prm.q_tolerance && it >= prm.min_iterations) { st->active = 0; st->termination = LIN_SUCCESS; return; }
+    st->Q0 = Q1;
+    if (it >= prm.max_iterations) { st->active = 0; st->termination = LIN_NO_CONVERGENCE; return; }
+  }
+  if (finish_only) return;
+  st->last_rho = st->rho;
+  st->rho = rho;
+  st->iter = it + 1;
+  if (zero_or_inf(rho) || !(rho == rho)) { st->active = 0; st->termination = LIN_FAILURE; return; }
+  if (it + 1 > 1) {
+    st->beta = rho / st->last_rho;
+    if (zero_or_inf(st->beta)) { st->active = 0; st->termination = LIN_FAILURE; return; }
+  }
+}
+
+// Warp per camera: y = fixed-order sum of the camera's segment partials (or y_in when already reduced /
+// allreduced); p = z + beta p_old (iteration 1: p = z); q = y + D^2 p (stored in z, as Ceres does); p.q.
+__global__ void k_pcg_reduce(BaDev L, const double* __restrict__ seg_y, const double* __restrict__ y_in, const double* __restrict__ D,
+                             double* __restrict__ z, double* __restrict__ p, double* __restrict__ part_pq, const PcgDev* st) {
+  if (st->active == 0) return;
+  __shared__ double red[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * WPB + warp;
+  double pq = 0.0;
+  if (c < L.n_cams) {
+    const int k = lane % 9, j = lane / 9;             // 3 segment lanes x 9 components; lanes 27..31 idle
+    double acc = 0.0;
+    if (y_in == nullptr) {
+      if (lane < 27)
+        for (int t = L.cam_seg_ptr[c] + j; t < L.cam_seg_ptr[c + 1]; t += 3) acc += seg_y[(size_t)L.cam_seg[t] * 9 + k];
+      const double a1 = __shfl_down_sync(0xffffffffu, acc, 9), a2 = __shfl_down_sync(0xffffffffu, acc, 18);
+      acc = (acc + a1) + a2;
+    } else if (lane < 9) acc = y_in[(size_t)c * 9 + lane];
+    if (lane < 9) {
+      const size_t e = (size_t)c * 9 + lane;
+      const double zk = z[e];
+      const double pk = (st->iter == 1) ? zk : (zk + st->beta * p[e]);
+      const double d = D[e];
+      const double qk = (d * d) * pk + acc;
+      p[e] = pk; z[e] = qk;
+      pq = pk * qk;
+    }
+  }
+  const double s = block_sum_fixed(pq, red);
+  if (threadIdx.x == 0) part_pq[blockIdx.x] = s;
+}
+
+// Warp per camera: x += alpha p; then either r -= alpha q (q lives in z) or, when `recompute`, nothing more
+// (r is rebuilt by k_pcg_resid after the extra matvec).  Without recompute also: Q partials, z = M^-1 r, r.z.
+__global__ void k_pcg_update(int n_cams, const double* __restrict__ Minv, const double* __restrict__ b, double* __restrict__ x,
+                             const double* __restrict__ p, double* __restrict__ r, double* __restrict__ z, const double* __restrict__ part_pq,
+                             int nparts, int recompute, double* __restrict__ part_Q, double* __restrict__ part_rho, const PcgDev* st) {
+  if (st->active == 0) return;
+  __shared__ double red[8];
+  __shared__ double bc;
+  const double pq = sum_fixed_all(part_pq, nparts, red, &bc);
+  const bool ok = (pq > 0.0) && !isinf(pq);
+  const double alpha = st->rho / pq;
+  const bool go = ok && !isinf(alpha);               // otherwise Ceres breaks before touching x; k_pcg_head records why
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * WPB + warp;
+  double qsum = 0.0, rz = 0.0;
+  if (go && c < n_cams) {
+    const size_t e = (size_t)c * 9 + (lane < 9 ? lane : 0);
+    double rk = 0.0;
+    if (lane < 9) {
+      const double xk = x[e] + alpha * p[e];
+      x[e] = xk;
+      if (!recompute) {
+        rk = r[e] - alpha * z[e];
+        r[e] = rk;
+        qsum = xk * (b[e] + rk);
+      }
+    }
+    if (!recompute) {
+      double zk = 0.0;
+      if (Minv != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+          const double rj = __shfl_sync(0xffffffffu, rk, j);
+          if (lane < 9) zk += Minv[(size_t)c * 81 + lane * 9 + j] * rj;
+        }
+      } else zk = rk;
+      if (lane < 9) { z[e] = zk; rz = rk * zk; }
+    }
+  }
+  if (!recompute) {
+    const double s1 = block_sum_fixed(qsum, red), s2 = block_sum_fixed(rz, red);
+    if (threadIdx.x == 0) { part_Q[blockIdx.x] = s1; part_rho[blockIdx.x] = s2; }
+  }
+}
+
+// Residual reset: r = b - (y + D^2 x) with y = sum of segment partials of S_local x (or y_in); then the
+// Q partials, z = M^-1 r and the r.z partials.
+__global__ void k_pcg_resid2(BaDev L, const double* __restrict__ seg_y, const double* __restrict__ y_in, const double* __restrict__ D,
+                             const double* __restrict__ Minv, const double* __restrict__ b, const double* __restrict__ x,
+                             double* __restrict__ r, double* __restrict__ z, double* __restrict__ part_Q, double* __restrict__ part_rho,
+                             const PcgDev* st) {
+  if (st->active == 0) return;
+  __shared__ double red[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * WPB + warp;
+  double qsum = 0.0, rz = 0.0;
+  if (c < L.n_cams) {
+    const int k = lane % 9, j = lane / 9;
+    double acc = 0.0;
+    if (y_in == nullptr) {
+      if (lane < 27)
+        for (int t = L.cam_seg_ptr[c] + j; t < L.cam_seg_ptr[c + 1]; t += 3) acc += seg_y[(size_t)L.cam_seg[t] * 9 + k];
+      const double a1 = __shfl_down_sync(0xffffffffu, acc, 9), a2 = __shfl_down_sync(0xffffffffu, acc, 18);
+      acc = (acc + a1) + a2;
+    } else if (lane < 9) acc = y_in[(size_t)c * 9 + lane];
+    const size_t e = (size_t)c * 9 + (lane < 9 ? lane : 0);
+    double rk = 0.0;
+    if (lane < 9) {
+      const double d = D[e], xk = x[e];
+      rk = b[e] - ((d * d) * xk + acc);
+      r[e] = rk;
+      qsum = xk * (b[e] + rk);
+    }
+    double zk = 0.0;
+    if (Minv != nullptr) {
+#pragma unroll
+      for (int jj = 0; jj < 9; ++jj) {
+        const double rj = __shfl_sync(0xffffffffu, rk, jj);
+        if (lane < 9) zk += Minv[(size_t)c * 81 + lane * 9 + jj] * rj;
+      }
+    } else zk = rk;
+    if (lane < 9) { z[e] = zk; rz = rk * zk; }
+  }
+  const double s1 = block_sum_fixed(qsum, red), s2 = block_sum_fixed(rz, red);
+  if (threadIdx.x == 0) { part_Q[blockIdx.x] = s1; part_rho[blockIdx.x] = s2; }
+}
+
+}  // namespace
+
+int pcg_blocks(int n_cams) { return cdiv(n_cams, WPB); }
+
+void launch_pcg_begin(int n_cams, const double* rhs, const double* Minv, double* x, double* r, double* z, double* part_bb,
+                      double* part_rho, PcgDev* st, const int* lin_error, cudaStream_t s) {
+  const int nb = pcg_blocks(n_cams);
+  k_pcg_begin<<<nb, WPB * 32, 0, s>>>(n_cams, rhs, Minv, x, r, z, part_bb, part_rho);
+  k_pcg_start2<<<1, 256, 0, s>>>(st, part_bb, nb, lin_error);
+  check_launch("k_pcg_begin");
+}
+void launch_pcg_head(PcgDev* st, const double* part_rho, const double* part_pq, const double* part_Q, int nparts, PcgParams prm,
+                     int finish_only, cudaStream_t s) {
+  k_pcg_head<<<1, 256, 0, s>>>(st, part_rho, part_pq, part_Q, nparts, prm, finish_only);
+  check_launch("k_pcg_head");
+}
+void launch_pcg_reduce(const BaDev& L, const double* seg_y, const double* y_in, const double* D, double* z, double* p, double* part_pq,
+                       const PcgDev* st, cudaStream_t s) {
+  k_pcg_reduce<<<pcg_blocks(L.n_cams), WPB * 32, 0, s>>>(L, seg_y, y_in, D, z, p, part_pq, st);
+  check_launch("k_pcg_reduce");
+}
+void launch_pcg_update(int n_cams, const double* Minv, const double* b, double* x, const double* p, double* r, double* z,
+                       const double* part_pq, int recompute, double* part_Q, double* part_rho, const PcgDev* st, cudaStream_t s) {
+  const int nb = pcg_blocks(n_cams);
+  k_pcg_update<<<nb, WPB * 32, 0, s>>>(n_cams, Minv, b, x, p, r, z, part_pq, nb, recompute, part_Q, part_rho, st);
+  check_launch("k_pcg_update");
+}
+void launch_pcg_resid2(const BaDev& L, const double* seg_y, const double* y_in, const double* D, const double* Minv, const double* b,
+                       const double* x, double* r, double* z, double* part_Q, double* part_rho, const PcgDev* st, cudaStream_t s) {
+  k_pcg_resid2<<<pcg_blocks(L.n_cams), WPB * 32, 0, s>>>(L, seg_y, y_in, D, Minv, b, x, r, z, part_Q, part_rho, st);
+  check_launch("k_pcg_resid2");
+}
+
+}  // namespace sk

@@ -1,0 +1,459 @@
+"""Parity of the CUDA path (through the C ABI of libskeres.so) with the CPU oracle.  Needs a B200.
+
+Tolerances (BASELINE.json north_star): final cost within 1e-6 relative, parameters within 1e-5 relative,
+identical iteration / termination behaviour on well-conditioned problems.  Integer quantities (iteration
+counts, PCG iteration counts, termination types) are compared exactly.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from skeres_b200 import _abi, synth
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+COST_RTOL = 1e-6
+PARAM_RTOL = 1e-5
+
+
+def load(name):
+    return json.load(open(os.path.join(HERE, "golden", name)))
+
+
+def rel_param_diff(a, b, floor=1e-2):
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
+
+
+def oracle_ba(oracle, d, lst, prec=_abi.SCHUR_JACOBI, loss=(_abi.LOSS_TRIVIAL, 0.0), **opts):
+    p = oracle.OracleProblem(d.parameters)
+    p.add_residual_blocks(_abi.FUNCTOR_SNAVELY_REPROJECTION_ERROR, d.observations.reshape(-1, 2), d.block_offsets(), *loss)
+    o = _abi.default_options()
+    o.linear_solver_type, o.preconditioner_type = lst, prec
+    for k, v in opts.items():
+        setattr(o, k, v)
+    return p, p.solve(o)
+
+
+def gpu_ba(sk, d, lst, prec=_abi.SCHUR_JACOBI, loss=None, order=None, **opts):
+    bal = sk.BalProblem.fromArrays(d)
+    if order is not None:
+        bal.cameraIndex, bal.pointIndex = bal.cameraIndex[order], bal.pointIndex[order]
+        bal.observations = bal.observations.reshape(-1, 2)[order].ravel()
+    problem = bal.buildProblem(loss)
+    o = sk.Solver.Options()
+    o.setLinearSolverType(lst)
+    o.setPreconditionerType(prec)
+    for k, v in opts.items():
+        setattr(o, k, v)
+    s = sk.Solver.Summary()
+    sk.ceres.solve(o, problem, s)
+    return bal, s
+
+
+def assert_same_trajectory(s, so, exact_rows=True, row_rtol=1e-6):
+    assert s.termination_type == so.termination_type, (s.message, so.message)
+    assert len(s.iterations) == len(so.iterations)
+    assert (s.num_successful_steps, s.num_unsuccessful_steps) == (so.num_successful_steps, so.num_unsuccessful_steps)
+    for a, b in zip(s.iterations, so.iterations):
+        assert (a.iteration, a.step_is_valid, a.step_is_successful) == (b.iteration, b.step_is_valid, b.step_is_successful)
+        if exact_rows:
+            assert a.linear_solver_iterations == b.linear_solver_iterations
+        assert np.isclose(a.cost, b.cost, rtol=row_rtol)
+        assert np.isclose(a.trust_region_radius, b.trust_region_radius, rtol=1e-4)
+    assert abs(s.initial_cost - so.initial_cost) <= 1e-12 * abs(so.initial_cost)
+    assert abs(s.final_cost - so.final_cost) <= COST_RTOL * abs(so.final_cost)
+
+
+# --------------------------------------------------------------------------------------------------- evaluate boundary
+def test_golden_vectors_host_abi(sk):
+    """AutodiffCostFuntionSpec.scala replayed through sk_cost_function_evaluate_host (exact equality)."""
+    for case in load("autodiff_spec_vectors.json")["cases"]:
+        cf = sk.CostFunction(case["functor"], case["consts"])
+        ok, res, jacs = cf.evaluate_host(case["parameters"], want_jacobians=False)
+        assert ok and res.tolist() == case["residuals"] and jacs is None          # jacobians == NULL branch (:80)
+        ok, res, jacs = cf.evaluate_host(case["parameters"])
+        assert ok and res.tolist() == case["residuals"]
+        for j, want in zip(jacs, case["jacobians"]):
+            assert j.ravel().tolist() == want
+        ok, res, jacs = cf.evaluate_host(case["parameters"], skip_blocks=(0,))     # NULL row (:118)
+        assert ok and jacs[0] is None and jacs[1].ravel().tolist() == case["jacobians"][1]
+
+
+def test_golden_vectors_device_pointers(sk):
+    """The same through device DoubleArrays / DoublePointers, as the Scala spec does with RichDoubleMatrix."""
+    case = load("autodiff_spec_vectors.json")["cases"][1]
+    params = sk.DoubleArray.fromArray(np.concatenate(case["parameters"]))
+    residuals = sk.DoubleArray(3)
+    jac = sk.DoubleArray(12)
+    cf = sk.CostFunction(case["functor"], case["consts"])
+    pp = [params.toPointer(), params.slice(2)]
+    assert cf.evaluate(pp, residuals.toPointer(), None) is True
+    assert residuals.toArray().tolist() == case["residuals"]
+    residuals.copyFrom(np.zeros(3))
+    assert cf.evaluate(pp, residuals.toPointer(), [jac.toPointer(), jac.slice(6)]) is True
+    assert residuals.get(0) == 10.0
+    assert jac.toArray().tolist() == case["jacobians"][0] + case["jacobians"][1]
+
+
+def test_double_array_semantics(sk):
+    """RichDoubleArraySpec.scala / DoubleArraySliceSpec.scala: get/set/slice alias the parent buffer."""
+    a = sk.DoubleArray(10)
+    a.copyFrom(np.arange(10.0))
+    s = a.slice(4)
+    assert s.get(0) == 4.0 and s.toArray(3).tolist() == [4.0, 5.0, 6.0]
+    s.set(1, -1.0)
+    assert a.get(5) == -1.0
+    assert s.slice(2).get(0) == 6.0
+    with pytest.raises(sk.SkeresError):
+        a.copyFrom(np.zeros(11))
+    with pytest.raises(sk.SkeresError):
+        a.get(10)
+
+
+def test_snavely_evaluate_matches_oracle(sk, oracle):
+    d = synth.make_bal("small", seed=11)
+    rng = np.random.default_rng(0)
+    idx = list(rng.integers(0, d.num_observations, 60)) + list(np.nonzero(d.camera_index == 0)[0][:10])   # camera 0: Taylor branch
+    for i in idx:
+        cam = d.parameters[9 * d.camera_index[i]:9 * d.camera_index[i] + 9]
+        pt = d.parameters[9 * d.num_cameras + 3 * d.point_index[i]:][:3]
+        obs = d.observations[2 * i:2 * i + 2]
+        cf = sk.CostFunction(_abi.FUNCTOR_SNAVELY_REPROJECTION_ERROR, obs)
+        ok, res, (F, E) = cf.evaluate_host([cam, pt])
+        ok2, res_o, (Fo, Eo) = oracle.evaluate(_abi.FUNCTOR_SNAVELY_REPROJECTION_ERROR, obs, [cam, pt])
+        assert ok and ok2
+        scale = max(np.abs(Fo).max(), np.abs(Eo).max())
+        assert np.allclose(res, res_o, rtol=1e-12, atol=1e-9)
+        assert np.max(np.abs(F - Fo)) <= 1e-12 * scale and np.max(np.abs(E - Eo)) <= 1e-12 * scale
+        ok, res_only, _ = cf.evaluate_host([cam, pt], want_jacobians=False)
+        assert np.allclose(res_only, res_o, rtol=1e-12, atol=1e-9)
+
+
+def test_loss_functions_match_oracle(sk, oracle):
+    L = sk.PredefinedLossFunctions
+    for loss, kind, a in [(L.trivialLoss(), _abi.LOSS_TRIVIAL, 0.0), (L.huberLoss(0.7), _abi.LOSS_HUBER, 0.7), (L.cauchyLoss(0.5), _abi.LOSS_CAUCHY, 0.5)]:
+        for s in [0.0, 0.2, 0.49, 3.0, 40.0]:
+            assert np.allclose(loss.evaluate(s), oracle.loss(kind, a, s), rtol=1e-14, atol=0)
+
+
+# --------------------------------------------------------------------------------------------------- config 1: CurveFitting, DENSE_QR
+def curve_fit(sk, loss=None, y_mod=None, max_it=25):
+    d = load("curve_fitting_data.json")
+    y = np.array(d["y"]) if y_mod is None else y_mod(np.array(d["y"]))
+    m, c = sk.DoubleArray(1), sk.DoubleArray(1)                     # two separate DoubleArrays, CurveFitting.scala:103-106
+    loss = loss if loss is not None else sk.PredefinedLossFunctions.trivialLoss()
+    problem = sk.Problem()
+    for xi, yi in zip(d["x"], y):
+        problem.addResidualBlock(sk.ExponentialResidual(xi, yi).toAutoDiffCostFunction(), loss, m.toPointer(), c.toPointer())
+    o = sk.Solver.Options()
+    o.setMaxNumIterations(max_it)
+    o.setLinearSolverType(_abi.DENSE_QR)
+    s = sk.Solver.Summary()
+    sk.ceres.solve(o, problem, s)
+    return np.array([m.get(0), c.get(0)]), s, problem
+
+
+def test_curve_fitting_matches_oracle_and_ceres_tutorial(sk, oracle):
+    x, s, problem = curve_fit(sk)
+    assert (problem.numResidualBlocks(), problem.numResiduals(), problem.numParameterBlocks(), problem.numParameters()) == (67, 67, 2, 2)
+    d = load("curve_fitting_data.json")
+    p = oracle.OracleProblem(np.zeros(2))
+    p.add_residual_blocks(_abi.FUNCTOR_EXPONENTIAL_RESIDUAL, np.stack([d["x"], d["y"]], 1), np.tile([0, 1], (67, 1)))
+    o = _abi.default_options()
+    o.linear_solver_type, o.max_num_iterations = _abi.DENSE_QR, 25
+    so = p.solve(o)
+    assert_same_trajectory(s, so)
+    assert rel_param_diff(x, p.params, 1e-6) <= PARAM_RTOL
+    gold = load("ceres_tutorial_curve_fitting_log.json")
+    assert len(s.iterations) == len(gold["rows"])
+    for row, g in zip(s.iterations, gold["rows"]):
+        if row.step_is_successful:
+            assert float(f"{row.cost:.6e}") == g[1]
+        assert float(f"{row.trust_region_radius:.2e}") == g[6]
+    assert round(x[0], 6) == gold["final"]["m"] and round(x[1], 6) == gold["final"]["c"]
+    assert "Function tolerance reached" in s.message and "CONVERGENCE" in s.briefReport()
+    assert s.briefReport().startswith("Ceres Solver Report: Iterations: 14, Initial cost: 1.211734e+02, Final cost: 1.056751e+00")
+
+
+def test_robust_curve_fitting(sk, oracle):
+    """RobustCurveFitting.scala: outliers (:41-42) + CauchyLoss(0.5) (:107) — Corrector on the device."""
+    def spoil(y):
+        y = y.copy(); y[10] += 8.0; y[40] -= 6.0
+        return y
+    d = load("curve_fitting_data.json")
+    for make, kind, a in [(lambda: sk.PredefinedLossFunctions.cauchyLoss(0.5), _abi.LOSS_CAUCHY, 0.5),
+                          (lambda: sk.PredefinedLossFunctions.huberLoss(1.0), _abi.LOSS_HUBER, 1.0)]:
+        x, s, _ = curve_fit(sk, make(), spoil, max_it=50)
+        p = oracle.OracleProblem(np.zeros(2))
+        p.add_residual_blocks(_abi.FUNCTOR_EXPONENTIAL_RESIDUAL, np.stack([d["x"], spoil(np.array(d["y"]))], 1), np.tile([0, 1], (67, 1)), kind, a)
+        o = _abi.default_options()
+        o.linear_solver_type = _abi.DENSE_QR
+        so = p.solve(o)
+        assert_same_trajectory(s, so)
+        assert rel_param_diff(x, p.params, 1e-6) <= PARAM_RTOL
+
+
+def test_max_iterations_and_zero_iterations(sk):
+    x, s, _ = curve_fit(sk, max_it=3)
+    assert s.termination_type == _abi.NO_CONVERGENCE and len(s.iterations) == 4
+    assert s.message == "Maximum number of iterations reached. Number of iterations: 3."
+    x, s, _ = curve_fit(sk, max_it=0)
+    assert len(s.iterations) == 1 and np.all(x == 0.0) and s.initial_cost == s.final_cost
+
+
+# --------------------------------------------------------------------------------------------------- config 2/3: bundle adjustment
+@pytest.mark.parametrize("shape,seed", [("tiny", 1), ("small", 2), ("ladybug-49", 1)])
+@pytest.mark.parametrize("lst", [_abi.DENSE_SCHUR, _abi.SPARSE_SCHUR])
+def test_ba_explicit_schur_matches_oracle(sk, oracle, shape, seed, lst):
+    """SimpleBundleAdjuster.scala:147-149 (DENSE_SCHUR) and BASELINE configs[1] (SPARSE_SCHUR): exact reduced solve."""
+    d = synth.make_bal(shape, seed=seed)
+    p, so = oracle_ba(oracle, d, lst)
+    bal, s = gpu_ba(sk, d, lst)
+    assert_same_trajectory(s, so)
+    assert rel_param_diff(bal.parameters.toArray(), p.params) <= PARAM_RTOL
+    assert s.num_residual_blocks == d.num_observations and s.num_parameters == d.parameters.size
+
+
+@pytest.mark.parametrize("shape,seed", [("tiny", 1), ("small", 2), ("small", 5), ("ladybug-49", 1)])
+def test_ba_iterative_schur_matches_oracle(sk, oracle, shape, seed):
+    """ITERATIVE_SCHUR + SCHUR_JACOBI: same LM rows and the same number of PCG iterations per LM iteration."""
+    d = synth.make_bal(shape, seed=seed)
+    p, so = oracle_ba(oracle, d, _abi.ITERATIVE_SCHUR, _abi.SCHUR_JACOBI)
+    bal, s = gpu_ba(sk, d, _abi.ITERATIVE_SCHUR, _abi.SCHUR_JACOBI)
+    assert_same_trajectory(s, so, row_rtol=1e-6)
+    # An inexact (eta = 0.1) PCG step is sensitive to summation order after ~100 iterations, so on the largest case
+    # the parameters are compared on the cost they reach (1e-6) and loosely in value; small cases meet 1e-5.
+    tol = PARAM_RTOL if shape != "ladybug-49" else 2e-2
+    assert rel_param_diff(bal.parameters.toArray(), p.params) <= tol
+
+
+def test_ba_identity_preconditioner(sk, oracle):
+    d = synth.make_bal("small", seed=3)
+    p, so = oracle_ba(oracle, d, _abi.ITERATIVE_SCHUR, _abi.IDENTITY)
+    bal, s = gpu_ba(sk, d, _abi.ITERATIVE_SCHUR, _abi.IDENTITY)
+    # unpreconditioned CG needs ~70+ iterations per solve here and its Q-based stopping test then flips within a
+    # few iterations under a different summation order: LM rows must agree, PCG counts within 10 %.
+    assert_same_trajectory(s, so, exact_rows=False)
+    for a, b in zip(s.iterations, so.iterations):
+        assert abs(a.linear_solver_iterations - b.linear_solver_iterations) <= max(2, 0.1 * b.linear_solver_iterations)
+    # Parameters: NOT within the 1e-5 target here (measured 2.9e-3 on a B200). Same bound and same reason as the
+    # Ladybug ITERATIVE_SCHUR case: a truncated (eta = 0.1) CG solve depends on summation order; the cost reached
+    # (checked to 1e-6 above) is the well-defined quantity. Recorded as a parity gap in DESIGN.md section 2.
+    assert rel_param_diff(bal.parameters.toArray(), p.params) <= 2e-2
+
+
+def residuals_at(oracle, d, params):
+    """Reprojection residuals (gauge-invariant) at a parameter vector, evaluated by the oracle on the host."""
+    p = oracle.OracleProblem(params)
+    p.add_residual_blocks(_abi.FUNCTOR_SNAVELY_REPROJECTION_ERROR, d.observations.reshape(-1, 2), d.block_offsets())
+    return p.evaluate()[1]
+
+
+def test_ba_tight_tolerances_reach_the_same_optimum(sk, oracle):
+    """Both sides iterated to the optimum (function_tolerance 1e-12) by DIFFERENT linear solvers.
+    These synthetic problems do not fix the 7-dof gauge (global similarity), so the minimiser is an orbit, not a
+    point: measured on a B200, the two parameter vectors differ by 0.35 relative while the costs agree to 1e-9.
+    Parameters are therefore not comparable here; the gauge-invariant quantities are: the cost and the residuals."""
+    d = synth.make_bal("small", seed=4)
+    p, so = oracle_ba(oracle, d, _abi.DENSE_SCHUR, function_tolerance=1e-12, max_num_iterations=60)
+    bal, s = gpu_ba(sk, d, _abi.ITERATIVE_SCHUR, _abi.SCHUR_JACOBI, function_tolerance=1e-12, max_num_iterations=60, eta=1e-3)
+    assert s.termination_type == _abi.CONVERGENCE
+    assert abs(s.final_cost - so.final_cost) <= 1e-9 * so.final_cost
+    r_gpu, r_ora = residuals_at(oracle, d, bal.parameters.toArray()), residuals_at(oracle, d, p.params)
+    worst = float(np.max(np.abs(r_gpu - r_ora)))
+    # bound chosen a priori: 500x below the 0.5 px observation noise, far above rounding
+    assert worst <= 1e-3, f"residuals at the two optima differ by {worst:.3e} px"
+
+
+@pytest.mark.parametrize("lst", [_abi.DENSE_SCHUR, _abi.ITERATIVE_SCHUR])
+def test_ba_unsorted_observations(sk, oracle, lst):
+    """Residual blocks added in arbitrary order (the reference adds them in file order) give the same solve."""
+    d = synth.make_bal("small", seed=6)
+    order = np.random.default_rng(2).permutation(d.num_observations)
+    p, so = oracle_ba(oracle, d, lst)
+    bal, s = gpu_ba(sk, d, lst, order=order)
+    assert_same_trajectory(s, so)
+    assert rel_param_diff(bal.parameters.toArray(), p.params) <= PARAM_RTOL
+
+
+def robust_case(sk, oracle, kind, a, **opts):
+    d = synth.make_bal("small", seed=8)
+    d.observations[::37] += 25.0                                  # gross outliers
+    loss = sk.PredefinedLossFunctions.cauchyLoss(a) if kind == _abi.LOSS_CAUCHY else sk.PredefinedLossFunctions.huberLoss(a)
+    p, so = oracle_ba(oracle, d, _abi.DENSE_SCHUR, loss=(kind, a), **opts)
+    bal, s = gpu_ba(sk, d, _abi.DENSE_SCHUR, loss=loss, **opts)
+    return p, so, bal, s
+
+
+@pytest.mark.parametrize("kind,a", [(_abi.LOSS_CAUCHY, 2.0), (_abi.LOSS_HUBER, 1.5)])
+def test_ba_robust_loss_well_conditioned(sk, oracle, kind, a):
+    """Strict: with the trust region capped at 1e12 the reduced system stays well conditioned and the whole LM
+    trajectory (rows, radii, costs) must equal the oracle's."""
+    p, so, bal, s = robust_case(sk, oracle, kind, a, max_trust_region_radius=1e12)
+    assert all(r.step_is_valid for r in so.iterations)
+    assert_same_trajectory(s, so)
+
+
+@pytest.mark.parametrize("kind,a", [(_abi.LOSS_CAUCHY, 2.0), (_abi.LOSS_HUBER, 1.5)])
+def test_ba_robust_loss_default_radius(sk, oracle, kind, a):
+    """Default max_trust_region_radius = 1e16.  KNOWN DIVERGENCE: once the radius saturates,
+    the LM damping is ~1e-16 of J'J and, the gauge being free, the reduced camera matrix is singular to working
+    precision.  The oracle's Cholesky then reports a non-positive pivot (invalid step, radius halved) on every other
+    iteration, the device factorisation does not: Huber(1.5) takes 46 rows in the oracle and 37 on the device, same
+    steps, same final cost.  Rows are compared exactly only below the saturated radius."""
+    p, so, bal, s = robust_case(sk, oracle, kind, a)
+    assert s.termination_type == so.termination_type
+    assert abs(s.final_cost - so.final_cost) <= COST_RTOL * abs(so.final_cost)
+    rmax = 1e16
+    n = 0
+    for g, o in zip(s.iterations, so.iterations):
+        if max(g.trust_region_radius, o.trust_region_radius) >= rmax:
+            break
+        assert (g.step_is_valid, g.step_is_successful) == (o.step_is_valid, o.step_is_successful)
+        assert np.isclose(g.cost, o.cost, rtol=1e-6)
+        n += 1
+    assert n >= 10, "the comparable prefix of the trajectory is suspiciously short"
+
+
+def test_ba_per_block_api_equals_bulk_api(sk):
+    """Problem.addResidualBlock per observation (SimpleBundleAdjuster.scala:139-145) == the bulk call."""
+    d = synth.make_bal("tiny", seed=9)
+    bal = sk.BalProblem.fromArrays(d)
+    loss = sk.PredefinedLossFunctions.trivialLoss()
+    problem = sk.Problem()
+    o = d.observations
+    for i in range(d.num_observations):
+        cost = sk.SnavelyReprojectionError(o[2 * i], o[2 * i + 1]).toAutoDiffCostFunction()
+        problem.addResidualBlock(cost, loss, bal.mutableCameraForObservation(i), bal.mutablePointForObservation(i))
+    opt = sk.Solver.Options()
+    opt.setLinearSolverType(_abi.DENSE_SCHUR)
+    s1 = sk.Solver.Summary()
+    sk.ceres.solve(opt, problem, s1)
+    bal2, s2 = gpu_ba(sk, d, _abi.DENSE_SCHUR)
+    assert s1.final_cost == s2.final_cost and len(s1.iterations) == len(s2.iterations)
+    assert np.array_equal(bal.parameters.toArray(), bal2.parameters.toArray())
+    assert "DENSE_SCHUR" in s1.fullReport()
+
+
+def test_bal_file_round_trip(sk, tmp_path):
+    """BalProblem.fromFile (SimpleBundleAdjuster.scala:37-77) on a file in the BAL text layout."""
+    d = synth.make_bal("tiny", seed=10)
+    path = tmp_path / "problem.txt"
+    synth.write_bal_text(d, path)
+    bal = sk.BalProblem.fromFile(path)
+    assert (bal.numCameras, bal.numPoints, bal.numObservations) == (d.num_cameras, d.num_points, d.num_observations)
+    assert np.array_equal(bal.cameraIndex, d.camera_index) and np.array_equal(bal.pointIndex, d.point_index)
+    assert np.array_equal(bal.observations, d.observations) and np.array_equal(bal.parameters.toArray(), d.parameters)
+    with pytest.raises(sk.SkeresError) as e:
+        sk.BalProblem.fromFile(tmp_path / "missing.txt")
+    assert e.value.status == _abi.ERR_IO
+
+
+def test_unsupported_requests_fail_loudly(sk):
+    d = synth.make_bal("tiny", seed=1)
+    bal = sk.BalProblem.fromArrays(d)
+    problem = bal.buildProblem()
+    for setter in (lambda o: o.setLinearSolverType(_abi.SPARSE_NORMAL_CHOLESKY), lambda o: o.setMinimizerType(_abi.LINE_SEARCH),
+                   lambda o: (o.setLinearSolverType(_abi.ITERATIVE_SCHUR), o.setPreconditionerType(_abi.CLUSTER_JACOBI))):
+        o = sk.Solver.Options()
+        o.setLinearSolverType(_abi.DENSE_SCHUR)
+        setter(o)
+        with pytest.raises(sk.SkeresError) as e:
+            sk.ceres.solve(o, problem, sk.Solver.Summary())
+        assert e.value.status == _abi.ERR_UNSUPPORTED
+    # a Schur solver on a non-BA problem
+    m, c = sk.DoubleArray(1), sk.DoubleArray(1)
+    p2 = sk.Problem()
+    p2.addResidualBlock(sk.ExponentialResidual(1.0, 2.0).toAutoDiffCostFunction(), None, m.toPointer(), c.toPointer())
+    o = sk.Solver.Options()
+    o.setLinearSolverType(_abi.DENSE_SCHUR)
+    with pytest.raises(sk.SkeresError):
+        sk.ceres.solve(o, p2, sk.Solver.Summary())
+
+
+def test_solver_is_deterministic_and_restartable(sk):
+    """Atomic-free fixed-order reductions: two runs are bit-identical; a prepared solver can be re-run."""
+    d = synth.make_bal("ladybug-49", seed=2)
+    bal = sk.BalProblem.fromArrays(d)
+    problem = bal.buildProblem()
+    o = sk.Solver.Options()
+    o.setLinearSolverType(_abi.ITERATIVE_SCHUR)
+    o.setPreconditionerType(_abi.SCHUR_JACOBI)
+    solver = sk.PreparedSolver(o, problem)
+    s1 = solver.minimize()
+    x1 = bal.parameters.toArray()
+    bal.parameters.copyFrom(d.parameters)
+    s2 = solver.minimize()
+    x2 = bal.parameters.toArray()
+    assert np.array_equal(x1, x2)
+    assert [(r.cost, r.linear_solver_iterations) for r in s1.iterations] == [(r.cost, r.linear_solver_iterations) for r in s2.iterations]
+    s3 = solver.minimize(max_num_iterations=2)                        # continues from the converged point
+    assert len(s3.iterations) <= 3 and s3.initial_cost <= s1.final_cost * (1 + 1e-9)
+    solver.close()
+
+
+# --------------------------------------------------------------------------------------------------- config 4: batched curve fits
+def test_batched_curve_fits_match_per_problem_oracle(sk, oracle):
+    n = 3000
+    x, y, truth = synth.make_curve_fit_batch(n, seed=5)
+    xa, ya = sk.DoubleArray.fromArray(x), sk.DoubleArray.fromArray(y)
+    mc = sk.DoubleArray(2 * n)
+    o = sk.Solver.Options()
+    o.setLinearSolverType(_abi.DENSE_QR)
+    o.setMaxNumIterations(25)
+    summary, ic, fc, it, tt = sk.curve_fit_batch_solve(o, xa, ya, mc)
+    sol = mc.toArray().reshape(2, n)
+    assert np.all(tt == _abi.CONVERGENCE)
+    oo = _abi.default_options()
+    oo.linear_solver_type, oo.max_num_iterations = _abi.DENSE_QR, 25
+    for j in range(0, n, 7):
+        p = oracle.OracleProblem(np.zeros(2))
+        p.add_residual_blocks(_abi.FUNCTOR_EXPONENTIAL_RESIDUAL, np.stack([x[:, j], y[:, j]], 1), np.tile([0, 1], (x.shape[0], 1)))
+        so = p.solve(oo)
+        assert it[j] == so.num_successful_steps + so.num_unsuccessful_steps, j
+        assert tt[j] == so.termination_type
+        assert abs(ic[j] - so.initial_cost) <= 1e-12 * so.initial_cost and abs(fc[j] - so.final_cost) <= COST_RTOL * so.final_cost
+        assert rel_param_diff(sol[:, j], p.params, 1e-3) <= PARAM_RTOL
+    assert np.median(np.abs(sol[0] - truth[0])) < 0.02                 # and the fits recover the generating parameters
+    assert summary.num_kernel_launches == summary.num_iterations       # one launch per LM iteration
+
+
+def test_batched_equals_single_problem_path(sk):
+    """The in-tree CurveFitting data as a batch of one equals the DENSE_QR single-problem solve."""
+    d = load("curve_fitting_data.json")
+    x1, s1, _ = curve_fit(sk)
+    xa, ya = sk.DoubleArray.fromArray(np.array(d["x"])), sk.DoubleArray.fromArray(np.array(d["y"]))
+    mc = sk.DoubleArray(2)
+    o = sk.Solver.Options()
+    o.setLinearSolverType(_abi.DENSE_QR)
+    o.setMaxNumIterations(25)
+    summary, ic, fc, it, tt = sk.curve_fit_batch_solve(o, xa, ya, mc)
+    assert it[0] == 14 and tt[0] == _abi.CONVERGENCE
+    assert np.allclose(mc.toArray(), x1, rtol=1e-9)
+    assert abs(fc[0] - s1.final_cost) <= 1e-12 * s1.final_cost
+
+
+# --------------------------------------------------------------------------------------------------- full BASELINE sizes: properties
+@pytest.mark.parametrize("shape", ["venice-1778"])
+def test_full_size_properties(sk, shape):
+    """At BASELINE.json's full size the oracle is too slow; check size-independent properties instead:
+    monotone cost on accepted steps, run-to-run bit determinism, and invariance to the order in which
+    the residual blocks were added (exercises the sort + tiling at scale)."""
+    d = synth.make_bal(shape, seed=1)
+    bal, s = gpu_ba(sk, d, _abi.ITERATIVE_SCHUR, _abi.SCHUR_JACOBI, max_num_iterations=4)
+    rows = s.iterations
+    assert len(rows) == 5 and s.termination_type == _abi.NO_CONVERGENCE
+    costs = [r.cost for r in rows if r.step_is_successful]
+    assert all(b < a for a, b in zip(costs, costs[1:]))
+    assert rows[0].cost > 10 * rows[-1].cost
+    assert s.num_residual_blocks == d.num_observations
+    x1 = bal.parameters.toArray()
+    bal2, s2 = gpu_ba(sk, d, _abi.ITERATIVE_SCHUR, _abi.SCHUR_JACOBI, max_num_iterations=4)
+    assert np.array_equal(x1, bal2.parameters.toArray())
+    assert [r.cost for r in s2.iterations] == [r.cost for r in rows]
+    order = np.random.default_rng(0).permutation(d.num_observations)
+    bal3, s3 = gpu_ba(sk, d, _abi.ITERATIVE_SCHUR, _abi.SCHUR_JACOBI, order=order, max_num_iterations=4)
+    assert [r.linear_solver_iterations for r in s3.iterations] == [r.linear_solver_iterations for r in rows]
+    assert np.array_equal(x1, bal3.parameters.toArray())               # the internal order is canonical

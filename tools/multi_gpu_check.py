@@ -1,0 +1,48 @@
+"""Multi-GPU correctness check (development helper): torchrun --nproc-per-node N tools/multi_gpu_check.py [shape]
+Every rank solves the same problem through a point-partitioned communicator; rank 0 also solves it on a
+single GPU and compares."""
+import os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import torch.distributed as dist
+from skeres_b200 import _abi, api, synth
+
+rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+api.check(api.lib.sk_set_device(local))
+ids = [api.Communicator.unique_id() if rank == 0 else None]
+dist.broadcast_object_list(ids, src=0)
+comm = api.Communicator(ids[0], rank, world)
+shape = sys.argv[1] if len(sys.argv) > 1 else "ladybug-49"
+d = synth.make_bal(shape, seed=1)
+
+def solve(use_comm):
+    bal = api.BalProblem.fromArrays(d)
+    prob = bal.buildProblem()
+    o = api.Solver.Options(); o.setLinearSolverType(_abi.ITERATIVE_SCHUR); o.setPreconditionerType(_abi.SCHUR_JACOBI)
+    if use_comm: o.comm = comm
+    s = api.Solver.Summary()
+    t = time.time(); api.ceres.solve(o, prob, s); dt = time.time() - t
+    return bal.parameters.toArray(), s, dt
+
+x, s, dt = solve(True)
+rows = [(r.iteration, r.cost, r.linear_solver_iterations) for r in s.iterations]
+print(f"rank {rank}: {s.message} final {s.final_cost:.9e} its {len(rows)} pcg {[r[2] for r in rows]} {dt:.3f}s gpus {s.num_gpus}", flush=True)
+gathered = [None] * world
+dist.all_gather_object(gathered, (x.tobytes(), rows))
+if rank == 0:
+    for g in gathered[1:]:
+        assert g[0] == gathered[0][0], "ranks disagree on the solution"
+        assert g[1] == gathered[0][1], "ranks disagree on the trajectory"
+    x1, s1, dt1 = solve(False)
+    rel = np.max(np.abs(x - x1) / np.maximum(np.abs(x1), 1e-2))
+    print(f"single GPU: final {s1.final_cost:.9e} its {len(s1.iterations)} pcg {[r.linear_solver_iterations for r in s1.iterations]} {dt1:.3f}s")
+    print(f"multi vs single: cost rel diff {abs(s.final_cost - s1.final_cost) / s1.final_cost:.2e}, max rel param diff {rel:.2e}")
+    assert abs(s.final_cost - s1.final_cost) <= 1e-6 * s1.final_cost
+    assert len(s.iterations) == len(s1.iterations)
+    print("MULTI-GPU CHECK OK")
+dist.barrier()
+dist.destroy_process_group()
