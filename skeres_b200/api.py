@@ -42,6 +42,13 @@ def _vp(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
+def _destroy(name, handle):
+    """Handle destructor usable from __del__: at interpreter shutdown the module globals are already None."""
+    L = lib
+    if L is not None and handle:
+        getattr(L, name)(handle)
+
+
 class DoublePointer:
     """SWIGTYPE_p_double (package.scala:11): an interior pointer = (array, offset)."""
 
@@ -74,7 +81,7 @@ class DoubleArray:
 
     def __del__(self):
         if getattr(self, "_h", None):
-            lib.sk_double_array_destroy(self._h)
+            _destroy("sk_double_array_destroy", self._h)
             self._h = None
 
     @classmethod
@@ -126,7 +133,7 @@ class LossFunction:
 
     def __del__(self):
         if getattr(self, "_h", None):
-            lib.sk_loss_destroy(self._h)
+            _destroy("sk_loss_destroy", self._h)
             self._h = None
 
     def evaluate(self, s):
@@ -190,7 +197,7 @@ class CostFunction:
 
     def __del__(self):
         if getattr(self, "_h", None):
-            lib.sk_cost_function_destroy(self._h)
+            _destroy("sk_cost_function_destroy", self._h)
             self._h = None
 
     def evaluate(self, parameters, residuals, jacobians):
@@ -276,7 +283,7 @@ class Problem:
 
     def __del__(self):
         if getattr(self, "_h", None):
-            lib.sk_problem_destroy(self._h)
+            _destroy("sk_problem_destroy", self._h)
             self._h = None
 
     def addResidualBlock(self, cost, loss, *x):
@@ -351,7 +358,7 @@ class Solver:
 
         def __del__(self):
             if getattr(self, "_h", None):
-                lib.sk_solver_summary_destroy(self._h)
+                _destroy("sk_solver_summary_destroy", self._h)
                 self._h = None
 
         @property
@@ -419,7 +426,7 @@ class PreparedSolver:
 
     def close(self):
         if getattr(self, "_h", None):
-            lib.sk_solver_destroy(self._h)
+            _destroy("sk_solver_destroy", self._h)
             self._h = None
 
     __del__ = close
@@ -442,7 +449,7 @@ class Communicator:
 
     def __del__(self):
         if getattr(self, "_h", None):
-            lib.sk_comm_destroy(self._h)
+            _destroy("sk_comm_destroy", self._h)
             self._h = None
 
 
