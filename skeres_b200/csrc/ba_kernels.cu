@@ -18,6 +18,9 @@
 //                         + the model-cost-change product of TrustRegionMinimizer (A.3 step 3)
 #include "ba_kernels.cuh"
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "lm_kernels.cuh"
 
 namespace sk {
@@ -393,6 +396,113 @@ __global__ void __launch_bounds__(T, 3) k_ba_matvec(BaDev L, const double2* __re
 }
 
 // ------------------------------------------------------------------------------------------------
+// Persistent variant of k_ba_matvec: identical arithmetic and identical partial-sum layout (results are bitwise
+// equal), but each CTA walks a strided list of tiles and, while it computes tile i from registers, cp.async
+// (LDGSTS) streams the 12 Jacobian planes of tile i+1 into shared memory.  Each thread copies and later reads back
+// only its own 12 vectors, so the Jacobian needs no barrier of its own; cp.async.wait_group orders it.  With two
+// CTAs per SM this keeps ~96 KB per SM in flight all the time instead of only during a CTA's first phase.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+__global__ void __launch_bounds__(T, 2) k_ba_matvec_persistent(BaDev L, const double2* __restrict__ J2, const double* __restrict__ p,
+                                                               const double* __restrict__ zdir, const PcgDev* pcg,
+                                                               const double* __restrict__ einv, double* __restrict__ seg_y,
+                                                               const int* guard, int max_tiles_per_cta) {
+  if (guard != nullptr && *guard == 0) return;
+  extern __shared__ double sm[];
+  const int tid = threadIdx.x;
+  double2* Jbuf = reinterpret_cast<double2*>(sm);            // [12][T] next tile's Jacobian (16-byte aligned)
+  double* xs = sm + 2 * kJPlanes * T;                        // [max_seg][9]
+  double* v = xs + L.max_seg_tile * 9;                       // [9][VLD]
+  double* w = v + 9 * VLD;                                   // [3][T]
+  double* u = w + 3 * T;                                     // [3][T]
+  double* ei = u + 3 * T;                                    // [max_pt][6]
+  TileMetaSmem meta;
+  meta.sptr = reinterpret_cast<int*>(ei + L.max_pt_tile * 6);
+  meta.pptr = meta.sptr + L.max_seg_tile + 1;
+  int* hdr = meta.pptr + L.max_pt_tile + 1;                  // [max_tiles_per_cta][6] this CTA's tile headers
+  meta.sperm = reinterpret_cast<unsigned short*>(hdr + max_tiles_per_cta * 6);
+  const size_t O = (size_t)L.n_obs;
+  const int my_tiles = (L.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  for (int idx = tid; idx < my_tiles; idx += T) {
+    const int t = blockIdx.x + idx * gridDim.x;
+    hdr[idx * 6 + 0] = L.tile_obs[t]; hdr[idx * 6 + 1] = L.tile_obs[t + 1] - L.tile_obs[t];
+    hdr[idx * 6 + 2] = L.tile_pt[t];  hdr[idx * 6 + 3] = L.tile_pt[t + 1] - L.tile_pt[t];
+    hdr[idx * 6 + 4] = L.tile_seg[t]; hdr[idx * 6 + 5] = L.tile_seg[t + 1] - L.tile_seg[t];
+  }
+  __syncthreads();
+  auto prefetch = [&](int it) {                              // this thread's 12 vectors of tile `it`
+    if (it < my_tiles && tid < hdr[it * 6 + 1]) {
+      const size_t i = (size_t)hdr[it * 6 + 0] + tid;
+#pragma unroll
+      for (int k = 0; k < kJPlanes; ++k) cp_async16(Jbuf + k * T + tid, J2 + k * O + i);
+    }
+    cp_async_commit();
+  };
+  prefetch(0);
+  for (int it = 0; it < my_tiles; ++it) {
+    Tile q;
+    q.ob = hdr[it * 6 + 0]; q.no = hdr[it * 6 + 1]; q.pb = hdr[it * 6 + 2]; q.np = hdr[it * 6 + 3]; q.sb = hdr[it * 6 + 4]; q.ns = hdr[it * 6 + 5];
+    const bool active = tid < q.no;
+    const int i = q.ob + tid;
+    double2 Fv[9], Ev[3];
+    int slot = 0, ptl = 0;
+    cp_async_wait_all();                                     // my own copies of this tile have landed
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) Fv[k] = Jbuf[k * T + tid];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) Ev[k] = Jbuf[(9 + k) * T + tid];
+      slot = L.obs_slot[i]; ptl = L.obs_ptl[i];
+    }
+    stage_tile_meta(L, q, meta);
+    for (int idx = tid; idx < q.np * 6; idx += T) ei[idx] = einv[(size_t)q.pb * 6 + idx];
+    for (int idx = tid; idx < q.ns * 9; idx += T) {
+      const int s = idx / 9, k = idx - s * 9;
+      const size_t e = (size_t)L.seg_cam[q.sb + s] * 9 + k;
+      xs[idx] = (pcg == nullptr) ? p[e] : ((pcg->iter == 1) ? zdir[e] : (zdir[e] + pcg->beta * p[e]));
+    }
+    __syncthreads();
+    double t0 = 0.0, t1 = 0.0;
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) { const double xk = xs[slot * 9 + k]; t0 += Fv[k].x * xk; t1 += Fv[k].y * xk; }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) w[k * T + tid] = Ev[k].x * t0 + Ev[k].y * t1;
+    }
+    // Every thread reads back only the 12 slots it copied itself, and phase 1 has consumed all of them (t0, t1 use
+    // every Fv, w every Ev), so those shared-memory loads have completed: the slots can be refilled now.  The next
+    // tile streams in during the remaining three phases and the staging of the next iteration.
+    prefetch(it + 1);
+    __syncthreads();
+    if (tid < q.np) {
+      const int b = meta.pptr[tid], e = meta.pptr[tid + 1];
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+      for (int j = b; j < e; ++j) { a0 += w[j]; a1 += w[T + j]; a2 += w[2 * T + j]; }
+      const double* m = ei + tid * 6;
+      u[tid] = m[0] * a0 + m[1] * a1 + m[2] * a2;
+      u[T + tid] = m[1] * a0 + m[3] * a1 + m[4] * a2;
+      u[2 * T + tid] = m[2] * a0 + m[4] * a1 + m[5] * a2;
+    }
+    __syncthreads();
+    if (active) {
+      const double u0 = u[ptl], u1 = u[T + ptl], u2 = u[2 * T + ptl];
+      const double s0 = t0 - (Ev[0].x * u0 + Ev[1].x * u1 + Ev[2].x * u2);
+      const double s1 = t1 - (Ev[0].y * u0 + Ev[1].y * u1 + Ev[2].y * u2);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) v[k * VLD + tid] = Fv[k].x * s0 + Fv[k].y * s1;
+    }
+    __syncthreads();
+    seg_reduce9_s(q, meta, v, seg_y, 9, 0);
+    __syncthreads();                                         // v / meta / xs are rewritten by the next tile
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(T) k_ba_back_substitute(BaDev L, const double2* __restrict__ J2,
                                                           const double2* __restrict__ r2, const double* __restrict__ z,
                                                           const double* __restrict__ einv, double* __restrict__ step,
@@ -517,6 +627,19 @@ void launch_ba_matvec(const BaDev& L, const double2* J2, const double* p, const 
   if (L.n_tiles == 0) return;
   const size_t smem = sizeof(double) * ((size_t)L.max_seg_tile * 9 + 9 * VLD + 6 * T + (size_t)L.max_pt_tile * 6) +
                       sizeof(int) * ((size_t)L.max_seg_tile + L.max_pt_tile + 2) + sizeof(unsigned short) * T + 16;
+  static const int mode = [] { const char* e = getenv("SKERES_MATVEC"); return (e && e[0] == 'p') ? 1 : 0; }();
+  if (mode == 1) {           // experimental persistent kernel (profiles/r01_v3_*): SKERES_MATVEC=persistent
+    static int sms = 0;
+    if (sms == 0) { int dev = 0; SK_CUDA(cudaGetDevice(&dev)); SK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)); }
+    const int grid = std::min(L.n_tiles, 2 * sms);
+    const int max_tiles = (L.n_tiles + grid - 1) / grid;
+    const size_t smem_p = smem + sizeof(double2) * kJPlanes * T + sizeof(int) * 6 * (size_t)max_tiles;
+    set_smem(k_ba_matvec_persistent, smem_p);
+    SK_CUDA(cudaFuncSetAttribute(k_ba_matvec_persistent, cudaFuncAttributePreferredSharedMemoryCarveout, 100));   // 2 CTAs x ~86 KB per SM
+    k_ba_matvec_persistent<<<grid, T, smem_p, s>>>(L, J2, p, zdir, pcg, einv, seg_y, guard, max_tiles);
+    check_launch("k_ba_matvec_persistent");
+    return;
+  }
   set_smem(k_ba_matvec, smem);
   k_ba_matvec<<<L.n_tiles, T, smem, s>>>(L, J2, p, zdir, pcg, einv, seg_y, guard);
   check_launch("k_ba_matvec");
