@@ -640,8 +640,12 @@ void launch_ba_matvec(const BaDev& L, const double2* J2, const double* p, const 
     check_launch("k_ba_matvec_persistent");
     return;
   }
-  set_smem(k_ba_matvec, smem);
-  k_ba_matvec<<<L.n_tiles, T, smem, s>>>(L, J2, p, zdir, pcg, einv, seg_y, guard);
+  // development probe: SKERES_MATVEC_PAD_KB=<n> pads the dynamic shared memory (unused) to lower the CTAs per SM
+  static const size_t pad = [] { const char* e = getenv("SKERES_MATVEC_PAD_KB"); return e ? (size_t)atoi(e) * 1024 : (size_t)0; }();
+  const size_t smem_v2 = smem + pad;
+  set_smem(k_ba_matvec, smem_v2);
+  if (pad) SK_CUDA(cudaFuncSetAttribute(k_ba_matvec, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  k_ba_matvec<<<L.n_tiles, T, smem_v2, s>>>(L, J2, p, zdir, pcg, einv, seg_y, guard);
   check_launch("k_ba_matvec");
 }
 
