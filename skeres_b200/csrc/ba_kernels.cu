@@ -338,7 +338,8 @@ __global__ void __launch_bounds__(T, 3) k_ba_matvec(BaDev L, const double2* __re
   const int tid = threadIdx.x;
   double* xs = sm;                           // [max_seg][9]
   double* v = xs + L.max_seg_tile * 9;       // [9][VLD]
-  double* w = v + 9 * VLD;                   // [3][T]  E^T t per observation
+  double* w = v + 9 * VLD;                   // [3][T]  E^T t per observation.  (Aliasing w onto planes 0..2 of v saves 6 KB per
+                                             // CTA and is bitwise-equivalent, but measured 5 % SLOWER on a B200: profiles/r01_v3_*.)
   double* u = w + 3 * T;                     // [3][T]  (E^T E)^-1 w per point
   double* ei = u + 3 * T;                    // [max_pt][6]
   TileMetaSmem meta;
@@ -625,8 +626,9 @@ void launch_ba_precond_invert(const BaDev& L, const double* M45, const double* D
 void launch_ba_matvec(const BaDev& L, const double2* J2, const double* p, const double* zdir, const PcgDev* pcg, const double* einv,
                       double* seg_y, const int* guard, cudaStream_t s) {
   if (L.n_tiles == 0) return;
-  const size_t smem = sizeof(double) * ((size_t)L.max_seg_tile * 9 + 9 * VLD + 6 * T + (size_t)L.max_pt_tile * 6) +
-                      sizeof(int) * ((size_t)L.max_seg_tile + L.max_pt_tile + 2) + sizeof(unsigned short) * T + 16;
+  const size_t smem_tail = sizeof(double) * ((size_t)L.max_pt_tile * 6) + sizeof(int) * ((size_t)L.max_seg_tile + L.max_pt_tile + 2) +
+                           sizeof(unsigned short) * T + 16;
+  const size_t smem = sizeof(double) * ((size_t)L.max_seg_tile * 9 + 9 * VLD + 6 * T) + smem_tail;       // persistent kernel layout
   static const int mode = [] { const char* e = getenv("SKERES_MATVEC"); return (e && e[0] == 'p') ? 1 : 0; }();
   if (mode == 1) {           // experimental persistent kernel (profiles/r01_v3_*): SKERES_MATVEC=persistent
     static int sms = 0;
@@ -644,7 +646,10 @@ void launch_ba_matvec(const BaDev& L, const double2* J2, const double* p, const 
   static const size_t pad = [] { const char* e = getenv("SKERES_MATVEC_PAD_KB"); return e ? (size_t)atoi(e) * 1024 : (size_t)0; }();
   const size_t smem_v2 = smem + pad;
   set_smem(k_ba_matvec, smem_v2);
-  if (pad) SK_CUDA(cudaFuncSetAttribute(k_ba_matvec, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  // development probe: SKERES_MATVEC_CARVEOUT=<percent> sets the shared-memory carveout hint (L1 gets the rest)
+  static const int carve = [] { const char* e = getenv("SKERES_MATVEC_CARVEOUT"); return e ? atoi(e) : -1; }();
+  if (carve >= 0) SK_CUDA(cudaFuncSetAttribute(k_ba_matvec, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+  else if (pad) SK_CUDA(cudaFuncSetAttribute(k_ba_matvec, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   k_ba_matvec<<<L.n_tiles, T, smem_v2, s>>>(L, J2, p, zdir, pcg, einv, seg_y, guard);
   check_launch("k_ba_matvec");
 }
