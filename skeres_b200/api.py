@@ -42,11 +42,12 @@ def _vp(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
-def _destroy(name, handle):
-    """Handle destructor usable from __del__: at interpreter shutdown the module globals are already None."""
-    L = lib
-    if L is not None and handle:
-        getattr(L, name)(handle)
+def _destroy(name, handle, _lib=lib):
+    """Handle destructor usable from __del__.  At interpreter shutdown module globals (including this function's own
+    name and `lib`) are set to None, so everything needed is bound as a default argument at definition time; the
+    __del__ methods below bind `_destroy` the same way."""
+    if _lib is not None and handle:
+        getattr(_lib, name)(handle)
 
 
 class DoublePointer:
@@ -79,7 +80,7 @@ class DoubleArray:
         check(lib.sk_double_array_create(int(n), C.byref(h)))
         self._h, self.n = h, int(n)
 
-    def __del__(self):
+    def __del__(self, _destroy=_destroy):
         if getattr(self, "_h", None):
             _destroy("sk_double_array_destroy", self._h)
             self._h = None
@@ -131,7 +132,7 @@ class LossFunction:
     def __init__(self, handle, kind, a=0.0):
         self._h, self.kind, self.a = handle, kind, a
 
-    def __del__(self):
+    def __del__(self, _destroy=_destroy):
         if getattr(self, "_h", None):
             _destroy("sk_loss_destroy", self._h)
             self._h = None
@@ -195,7 +196,7 @@ class CostFunction:
         check(lib.sk_cost_function_create(self.functor_id, _vp(self.consts), self.consts.size, C.byref(h)))
         self._h = h
 
-    def __del__(self):
+    def __del__(self, _destroy=_destroy):
         if getattr(self, "_h", None):
             _destroy("sk_cost_function_destroy", self._h)
             self._h = None
@@ -281,7 +282,7 @@ class Problem:
         self._h = h
         self._keep = []          # Problem.scala:29-32: keep cost/loss/arrays alive
 
-    def __del__(self):
+    def __del__(self, _destroy=_destroy):
         if getattr(self, "_h", None):
             _destroy("sk_problem_destroy", self._h)
             self._h = None
@@ -356,7 +357,7 @@ class Solver:
             check(lib.sk_solver_summary_create(C.byref(h)))
             self._h = h
 
-        def __del__(self):
+        def __del__(self, _destroy=_destroy):
             if getattr(self, "_h", None):
                 _destroy("sk_solver_summary_destroy", self._h)
                 self._h = None
@@ -424,7 +425,7 @@ class PreparedSolver:
         check(lib.sk_solver_minimize(self._h, int(max_num_iterations), summary._h))
         return summary
 
-    def close(self):
+    def close(self, _destroy=_destroy):
         if getattr(self, "_h", None):
             _destroy("sk_solver_destroy", self._h)
             self._h = None
@@ -447,7 +448,7 @@ class Communicator:
         check(lib.sk_comm_get_unique_id(buf))
         return buf.raw
 
-    def __del__(self):
+    def __del__(self, _destroy=_destroy):
         if getattr(self, "_h", None):
             _destroy("sk_comm_destroy", self._h)
             self._h = None

@@ -460,10 +460,8 @@ static std::unique_ptr<LmSolver> prepare_ba(const sk_solver_options& opt, sk_pro
   build_ba_layout(n, cam_off.data(), pt_off.data(), obs.data(), rank, world, &H);
   std::vector<int64_t> all_pt;
   int64_t total_points = H.n_pts;
-  if (world > 1) {
-    all_pt = pt_off;
-    std::sort(all_pt.begin(), all_pt.end());
-    all_pt.erase(std::unique(all_pt.begin(), all_pt.end()), all_pt.end());
+  if (world > 1) {                 // computed once by the layout builder (was: a second O(n log n) sort of all observations)
+    all_pt = std::move(H.all_pt_offset);
     total_points = (int64_t)all_pt.size();
   }
   const int64_t n_cams = H.n_cams;

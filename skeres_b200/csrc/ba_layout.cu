@@ -46,7 +46,15 @@ void partition_points(int64_t n_points, const int64_t* point_ptr, int world_size
 static void dense_ids(int64_t n, const int64_t* off, int block_size, std::vector<int64_t>* uniq,
                       std::vector<int32_t>* ids) {
   int64_t lo = off[0], hi = off[0];
-  for (int64_t i = 1; i < n; ++i) { lo = std::min(lo, off[i]); hi = std::max(hi, off[i]); }
+  {
+    std::mutex mu;
+    parallel_for(n, [&](int64_t a, int64_t b) {
+      int64_t l = off[a], h = off[a];
+      for (int64_t i = a + 1; i < b; ++i) { l = std::min(l, off[i]); h = std::max(h, off[i]); }
+      std::lock_guard<std::mutex> g(mu);
+      lo = std::min(lo, l); hi = std::max(hi, h);
+    });
+  }
   const int64_t range = hi - lo + 1;
   ids->resize(n);
   if (range <= std::max<int64_t>(64 * n, 1 << 20)) {           // direct table
@@ -60,7 +68,7 @@ static void dense_ids(int64_t n, const int64_t* off, int block_size, std::vector
                  (long long)(last + lo), (long long)(k + lo));
       table[k] = next++; uniq->push_back(k + lo); last = k;
     }
-    for (int64_t i = 0; i < n; ++i) (*ids)[i] = table[off[i] - lo];
+    parallel_for(n, [&](int64_t a, int64_t b) { for (int64_t i = a; i < b; ++i) (*ids)[i] = table[off[i] - lo]; });
   } else {                                                       // sort + binary search
     std::vector<int64_t> u(off, off + n);
     std::sort(u.begin(), u.end());
@@ -116,6 +124,7 @@ void build_ba_layout(int64_t n, const int64_t* cam_off, const int64_t* pt_off, c
   L.n_pts = (int32_t)(p1 - p0);
   L.n_obs = (int32_t)(o1 - o0);
   L.pt_offset.assign(pt_offsets_all.begin() + p0, pt_offsets_all.begin() + p1);
+  if (world_size > 1) L.all_pt_offset = pt_offsets_all;   // the caller needs them to publish the full solution
   L.perm.resize(L.n_obs); L.obs.resize((size_t)2 * L.n_obs); L.obs_cam.resize(L.n_obs); L.obs_pt.resize(L.n_obs);
   parallel_for(L.n_obs, [&](int64_t j0, int64_t j1) {
     for (int64_t j = j0; j < j1; ++j) {

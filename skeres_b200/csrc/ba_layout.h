@@ -24,7 +24,8 @@ struct BaLayoutHost {
   int32_t max_seg_tile = 0, max_pt_tile = 0;
   bool input_was_sorted = true;
   std::vector<int64_t> cam_offset;     // [C] offset of each camera block in the user array
-  std::vector<int64_t> pt_offset;      // [P]
+  std::vector<int64_t> pt_offset;      // [P]   this rank's points
+  std::vector<int64_t> all_pt_offset;  // every point of the problem, sorted (filled only when world_size > 1)
   std::vector<int32_t> perm;           // [O] sorted position -> original residual-block index
   std::vector<double> obs;             // [2*O] sorted (x, y)
   std::vector<int32_t> obs_cam;        // [O] camera id (sorted order)

@@ -160,7 +160,7 @@ const double* BaSolver::matvec(const double* in, bool pcg_dir, const int* guard)
                      seg_a_.p, guard, stream_);
   }
   if (comm_ && comm_->world > 1) {
-    { KScope k(prof_, SK_KF_PCG_VECTOR); launch_cam_reduce(L_, 9, seg_a_.p, ybuf_.p, guard, stream_); }
+    { KScope k(prof_, SK_KF_PCG_VECTOR); launch_cam_reduce9_warp(L_, seg_a_.p, ybuf_.p, guard, stream_); }
     KScope k(prof_, SK_KF_COMM);
     comm_allreduce_sum(comm_, ybuf_.p, (size_t)nc_, stream_);
     return ybuf_.p;

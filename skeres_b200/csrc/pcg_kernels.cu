@@ -241,9 +241,30 @@ __global__ void k_pcg_resid2(BaDev L, const double* __restrict__ seg_y, const do
   if (threadIdx.x == 0) { part_Q[blockIdx.x] = s1; part_rho[blockIdx.x] = s2; }
 }
 
+// Warp per camera: y[c] = fixed-order sum of the camera's segment partials, in exactly the order k_pcg_reduce uses
+// (three interleaved segment lanes, combined (a0 + a1) + a2).  Used before the allreduce of the multi-GPU path.
+__global__ void k_cam_reduce9_warp(BaDev L, const double* __restrict__ seg_y, double* __restrict__ y, const int* guard) {
+  if (guard != nullptr && *guard == 0) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * WPB + warp;
+  if (c >= L.n_cams) return;                       // warp-uniform
+  const int k = lane % 9, j = lane / 9;
+  double acc = 0.0;
+  if (lane < 27)
+    for (int t = L.cam_seg_ptr[c] + j; t < L.cam_seg_ptr[c + 1]; t += 3) acc += seg_y[(size_t)L.cam_seg[t] * 9 + k];
+  const double a1 = __shfl_down_sync(0xffffffffu, acc, 9), a2 = __shfl_down_sync(0xffffffffu, acc, 18);
+  acc = (acc + a1) + a2;
+  if (lane < 9) y[(size_t)c * 9 + lane] = acc;
+}
+
 }  // namespace
 
 int pcg_blocks(int n_cams) { return cdiv(n_cams, WPB); }
+
+void launch_cam_reduce9_warp(const BaDev& L, const double* seg_y, double* y, const int* guard, cudaStream_t s) {
+  k_cam_reduce9_warp<<<pcg_blocks(L.n_cams), WPB * 32, 0, s>>>(L, seg_y, y, guard);
+  check_launch("k_cam_reduce9_warp");
+}
 
 void launch_pcg_begin(int n_cams, const double* rhs, const double* Minv, double* x, double* r, double* z, double* part_bb,
                       double* part_rho, PcgDev* st, const int* lin_error, cudaStream_t s) {

@@ -6,6 +6,7 @@
 namespace sk {
 
 int pcg_blocks(int n_cams);   // CTAs (= partial sums) of the warp-per-camera kernels
+void launch_cam_reduce9_warp(const BaDev& L, const double* seg_y, double* y, const int* guard, cudaStream_t s);
 void launch_pcg_begin(int n_cams, const double* rhs, const double* Minv, double* x, double* r, double* z, double* part_bb,
                       double* part_rho, PcgDev* st, const int* lin_error, cudaStream_t s);
 void launch_pcg_head(PcgDev* st, const double* part_rho, const double* part_pq, const double* part_Q, int nparts, PcgParams prm,
