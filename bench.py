@@ -130,6 +130,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the Venice-1778 shape per GPU (development only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-profile", action="store_true", help="development: no per-kernel CUDA events in the timed region (roofline keys become meaningless)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -185,7 +186,9 @@ def main():
     opt.setLinearSolverType(_abi.ITERATIVE_SCHUR)
     opt.setPreconditionerType(_abi.SCHUR_JACOBI)
     opt.setMaxNumIterations(max(K, W, 1))
-    opt.profile_kernels = 1
+    # Events around EVERY launch cost ~10 % of the step at N = 2 (profiles/r01_multigpu_first_run.md), so the timed region
+    # records them only around the dominant kernel (what the roofline needs); the full breakdown comes from a separate pass.
+    opt.profile_kernels = 0 if args.no_profile else 2
     if comm is not None:
         opt.comm = comm
     solver = api.PreparedSolver(opt, problem)
@@ -222,6 +225,14 @@ def main():
     barrier()
     t_wall = time.time() - t_wall
     clocks = sampler.stop() if rank == 0 else None
+    # separate, NOT-timed-for-value pass with events around every family (same K steps) for the breakdown
+    fam_ms, fam_launches = None, None
+    if not args.no_profile:
+        solver.close()
+        opt.profile_kernels = 1
+        solver = api.PreparedSolver(opt, problem)
+        _, _, _, fam_ms, fam_launches, _ = run_steps(K)
+        barrier()
     if dist is not None:
         import torch
         t = torch.tensor([dev_s], dtype=torch.float64, device="cuda")
@@ -238,8 +249,10 @@ def main():
                 "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": mv_bytes, "avg_launch_ms": mv_ms, "launches": int(kl[3]),
                 "share_of_step_device_time": float(kms[3] / (dev_s * 1e3)) if dev_s > 0 else None,
-                "kernel_family_ms": {_abi.KF_NAMES[i]: float(kms[i]) for i in range(_abi.KF_COUNT)},
-                "kernel_family_launches": {_abi.KF_NAMES[i]: int(kl[i]) for i in range(_abi.KF_COUNT)}}
+                "events_in_timed_region": "k_ba_matvec only",
+                "kernel_family_ms": None if fam_ms is None else {_abi.KF_NAMES[i]: float(fam_ms[i]) for i in range(_abi.KF_COUNT)},
+                "kernel_family_launches": None if fam_launches is None else {_abi.KF_NAMES[i]: int(fam_launches[i]) for i in range(_abi.KF_COUNT)},
+                "kernel_family_note": "from a separate pass of the same K steps with events around every launch (not the pass `value` is timed on)"}
 
     # ------------------------------------------------------------------ end-to-end through the public API, host buffers
     e2e = None

@@ -4,6 +4,7 @@
 
 #include <dlfcn.h>
 
+#include <chrono>
 #include <mutex>
 
 namespace sk {
@@ -81,9 +82,15 @@ void comm_destroy(sk_comm* c) {
   delete c;
 }
 
+double g_comm_host_seconds = 0.0;   // development trace: host wall time spent enqueuing collectives
+long g_comm_calls = 0;
+static double host_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 void comm_allreduce_sum(sk_comm* c, double* buf, size_t count, cudaStream_t stream) {
   if (!c || c->world == 1 || count == 0) return;
+  const double t0 = host_now();
   check(api().AllReduce(buf, buf, count, kNcclFloat64, kNcclSum, c->nccl_comm, stream), "ncclAllReduce(sum)");
+  g_comm_host_seconds += host_now() - t0; ++g_comm_calls;
 }
 void comm_allreduce_max(sk_comm* c, double* buf, size_t count, cudaStream_t stream) {
   if (!c || c->world == 1 || count == 0) return;

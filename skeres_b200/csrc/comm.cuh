@@ -17,6 +17,8 @@ void comm_destroy(sk_comm* c);
 // In-place sum / max allreduce of `count` doubles on `stream`; no-op when c == nullptr or world == 1.
 void comm_allreduce_sum(sk_comm* c, double* buf, size_t count, cudaStream_t stream);
 void comm_allreduce_max(sk_comm* c, double* buf, size_t count, cudaStream_t stream);
+extern double g_comm_host_seconds;   // development trace (SKERES_TRACE_HOST)
+extern long g_comm_calls;
 void comm_group_start(sk_comm* c);
 void comm_group_end(sk_comm* c);
 

@@ -72,6 +72,7 @@ struct HBuf {
 // Per-solve launch accounting + optional CUDA-event timing per kernel family.
 struct Profiler {
   bool enabled = false;
+  unsigned family_mask = ~0u;   // which kernel families get CUDA events when enabled (profile_kernels = 2: matvec only)
   cudaStream_t stream = nullptr;
   int64_t launches[SK_KF_COUNT] = {0};
   double ms[SK_KF_COUNT] = {0};
@@ -98,10 +99,10 @@ struct KScope {
   Profiler& pr; int family; cudaEvent_t a = nullptr;
   KScope(Profiler& p, int fam, int count = 1) : pr(p), family(fam) {
     pr.launches[fam] += count;
-    if (pr.enabled) { a = pr.get(); cudaEventRecord(a, pr.stream); }
+    if (pr.enabled && ((pr.family_mask >> fam) & 1u)) { a = pr.get(); cudaEventRecord(a, pr.stream); }
   }
   ~KScope() {
-    if (pr.enabled) { cudaEvent_t b = pr.get(); cudaEventRecord(b, pr.stream); pr.pending.push_back({family, a, b}); }
+    if (a != nullptr) { cudaEvent_t b = pr.get(); cudaEventRecord(b, pr.stream); pr.pending.push_back({family, a, b}); }
   }
 };
 

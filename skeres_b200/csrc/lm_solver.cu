@@ -3,6 +3,7 @@
 
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 
 namespace sk {
 
@@ -19,6 +20,7 @@ LmSolver::LmSolver(const sk_solver_options& opt, cudaStream_t stream) : opt_(opt
   prm_.function_tolerance = opt.function_tolerance; prm_.gradient_tolerance = opt.gradient_tolerance;
   prm_.parameter_tolerance = opt.parameter_tolerance; prm_.eta = opt.eta; prm_.fixed_cost = 0.0;
   prof_.enabled = opt.profile_kernels != 0;
+  prof_.family_mask = (opt.profile_kernels == 2) ? (1u << SK_KF_SCHUR_MATVEC) : ~0u;
   prof_.stream = stream;
 }
 
@@ -165,6 +167,11 @@ void LmSolver::minimize(sk_solver_summary* S, int max_num_iterations_override) {
   fill_summary(&d);
   S->message = termination_message(h, opt_);
   d.minimizer_time_in_seconds = wall() - t_start;
+  if (getenv("SKERES_TRACE_HOST")) {
+    std::fprintf(stderr, "[skeres trace] minimize: host %.1f ms, device %.1f ms, launches %lld, nccl enqueue host %.1f ms over %ld calls (cumulative)\n",
+                 1e3 * d.minimizer_time_in_seconds, 1e3 * d.minimizer_device_time_in_seconds, (long long)d.num_kernel_launches,
+                 1e3 * g_comm_host_seconds, g_comm_calls);
+  }
 }
 
 std::string termination_message(const LmDev& st, const sk_solver_options& opt) {
