@@ -297,10 +297,16 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": max(world, 1), "steps": K, "warmup": W,
                 "ms_per_step": 1e3 * dev_s / max(done, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": cfg, "lm_iterations_per_s": done / dev_s, "steps_timed": done,
-                # Weak scaling changes the PROBLEM with N, and with it the PCG iterations an LM iteration needs, so
-                # `value` at different N mixes hardware scaling with a change of work per step.  This key does not:
-                # observations x executed implicit-Schur products per second (hot kernel + its collective only).
+                # CAUTION for scaling efficiency: weak scaling changes the PROBLEM with N and with it the number of PCG
+                # iterations an LM iteration needs (measured: 742 executed matvecs per 10 LM iterations at N=1, 283 at
+                # N=4), so value(N) / (N value(1)) mixes hardware scaling with a change of work per step (1.68 at N=4).
+                # matvec_obs_per_s is affected too (the fixed per-LM-iteration work is amortised over fewer matvecs).
+                # The quantity that IS comparable across N is the device time of one PCG iteration, pcg_iteration_ms.
                 "matvec_obs_per_s": n_obs * float(kl[3]) / dev_s, "pcg_matvecs_timed": int(kl[3]),
+                "pcg_iteration_ms": None if fam_ms is None or fam_launches[3] == 0 else
+                    float((fam_ms[3] + fam_ms[4] + fam_ms[8]) / fam_launches[3]),
+                "pcg_iteration_ms_note": "(k_ba_matvec + PCG vector kernels + allreduce) device time / executed matvecs, from the "
+                                         "instrumented pass; N=1 reference 0.324 ms",
                 "wall_s_timed_region": t_wall, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "clocks": clocks, "final_cost_last_solve": last.final_cost if last is not None else None,
                 "pcg_iterations_last_solve": [r.linear_solver_iterations for r in last.iterations] if last is not None else None}
