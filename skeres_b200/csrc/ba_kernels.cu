@@ -30,14 +30,38 @@ namespace {
 constexpr int T = kTileObs;
 constexpr int VLD = T + 1;   // padded leading dimension of the per-observation staging planes
 
-struct Tile { int ob, no, pb, np, sb, ns; };
+struct Tile { int ob, no, pb, np, sb, ns, chunk; };   // chunk >= 0: chunk tile of a long track (np == 1), else -1
 
 __device__ __forceinline__ Tile load_tile(const BaDev& L, int t) {
   Tile q;
   q.ob = L.tile_obs[t]; q.no = L.tile_obs[t + 1] - q.ob;
-  q.pb = L.tile_pt[t];  q.np = L.tile_pt[t + 1] - q.pb;
+  q.pb = L.tile_pt[t];
+  const int np = L.tile_np[t];
+  q.np = np < 0 ? 1 : np; q.chunk = np < 0 ? -np - 1 : -1;
   q.sb = L.tile_seg[t]; q.ns = L.tile_seg[t + 1] - q.sb;
   return q;
+}
+
+// Sums of N per-thread values over the CTA, returned to EVERY thread (fixed shuffle tree, then the 8 warp totals in
+// warp order): used by the long-track kernels, which accumulate per-point sums chunk by chunk.  red: [N][8] doubles.
+template <int N>
+__device__ __forceinline__ void block_sum_all(double (&x)[N], double* red) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x[n] += __shfl_down_sync(0xffffffffu, x[n], o);
+    if (l == 0) red[n * 8 + w] = x[n];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    double r = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r += red[n * 8 + k];
+    x[n] = r;
+  }
+  __syncthreads();   // red may be rewritten by the next call
 }
 
 // out[(sb+s)*ostride + ooff + k] = sum over segment s of v[k][local obs], fixed (point) order.
@@ -77,7 +101,7 @@ __global__ void __launch_bounds__(T) k_ba_evaluate(BaDev L, const double* __rest
                                                    double2* __restrict__ r2, double* __restrict__ grad,
                                                    double* __restrict__ cnorm2, double* __restrict__ seg_g,
                                                    double* __restrict__ seg_n, double* __restrict__ tile_cost,
-                                                   int* fail_flag, const int* guard) {
+                                                   double* __restrict__ chunk_pt, int* fail_flag, const int* guard) {
   if (guard != nullptr && *guard == 0) return;
   extern __shared__ double sm[];
   const Tile q = load_tile(L, blockIdx.x);
@@ -139,7 +163,14 @@ __global__ void __launch_bounds__(T) k_ba_evaluate(BaDev L, const double* __rest
     if (write_j) r2[i] = make_double2(res[0], res[1]);
   }
   __syncthreads();
-  if (tid < q.np) {
+  if (q.chunk >= 0) {
+    // chunk of a long track: this tile's share of the point sums; k_ba_giant_point_combine adds the chunks in order
+    if (tid < 6) {
+      double sum = 0.0;
+      for (int j = 0; j < q.no; ++j) sum += v[tid * VLD + j];
+      chunk_pt[(size_t)q.chunk * 6 + tid] = sum;
+    }
+  } else if (tid < q.np) {
     const int p = q.pb + tid;
     const int b = L.pt_ptr[p] - q.ob, e = L.pt_ptr[p + 1] - q.ob;
     double s6[6] = {0, 0, 0, 0, 0, 0};
@@ -198,9 +229,12 @@ __host__ __device__ constexpr int upper_col(int idx) {
 __global__ void __launch_bounds__(T) k_ba_schur_setup(BaDev L, const double2* __restrict__ J2, const double2* __restrict__ r2,
                                                       const double* __restrict__ D, double* __restrict__ einv,
                                                       double* __restrict__ seg_rhs, double* __restrict__ seg_M,
-                                                      int* error_flag) {
+                                                      int* error_flag, int ftf_only) {
+  // ftf_only: the diagonal blocks keep only F^T F (JACOBI preconditioner = block_diagonal_FtF_inverse of the implicit
+  // Schur complement) instead of F^T F - G^T (E^T E)^-1 G (SCHUR_JACOBI / the explicit reduced matrix).
   extern __shared__ double sm[];
   const Tile q = load_tile(L, blockIdx.x);
+  if (q.chunk >= 0) return;            // long tracks: k_ba_schur_setup_giant
   const int tid = threadIdx.x;
   double* v = sm;                      // [9][VLD]
   double* pinv = v + 9 * VLD;          // [max_pt][9]: inverse (6, upper) + inverse * g (3)
@@ -280,7 +314,8 @@ __global__ void __launch_bounds__(T) k_ba_schur_setup(BaDev L, const double2* __
 #pragma unroll
       for (int j = 0; j < 9; ++j) {
         const int k = upper_row(round * 9 + j), l = upper_col(round * 9 + j);
-        v[j * VLD + tid] = (Fv[k].x * Fv[l].x + Fv[k].y * Fv[l].y) - (G[0][k] * H[0][l] + G[1][k] * H[1][l] + G[2][k] * H[2][l]);
+        const double ftf = Fv[k].x * Fv[l].x + Fv[k].y * Fv[l].y;
+        v[j * VLD + tid] = ftf_only ? ftf : (ftf - (G[0][k] * H[0][l] + G[1][k] * H[1][l] + G[2][k] * H[2][l]));
       }
     }
     __syncthreads();
@@ -335,6 +370,7 @@ __global__ void __launch_bounds__(T, 3) k_ba_matvec(BaDev L, const double2* __re
   if (guard != nullptr && *guard == 0) return;
   extern __shared__ double sm[];
   const Tile q = load_tile(L, blockIdx.x);
+  if (q.chunk >= 0) return;                  // long tracks: k_ba_matvec_giant
   const int tid = threadIdx.x;
   double* xs = sm;                           // [max_seg][9]
   double* v = xs + L.max_seg_tile * 9;       // [9][VLD]
@@ -431,9 +467,10 @@ __global__ void __launch_bounds__(T, 2) k_ba_matvec_persistent(BaDev L, const do
   const int my_tiles = (L.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   for (int idx = tid; idx < my_tiles; idx += T) {
     const int t = blockIdx.x + idx * gridDim.x;
-    hdr[idx * 6 + 0] = L.tile_obs[t]; hdr[idx * 6 + 1] = L.tile_obs[t + 1] - L.tile_obs[t];
-    hdr[idx * 6 + 2] = L.tile_pt[t];  hdr[idx * 6 + 3] = L.tile_pt[t + 1] - L.tile_pt[t];
-    hdr[idx * 6 + 4] = L.tile_seg[t]; hdr[idx * 6 + 5] = L.tile_seg[t + 1] - L.tile_seg[t];
+    const bool chunk = L.tile_np[t] < 0;       // long tracks are left to k_ba_matvec_giant: an empty work item here
+    hdr[idx * 6 + 0] = L.tile_obs[t]; hdr[idx * 6 + 1] = chunk ? 0 : L.tile_obs[t + 1] - L.tile_obs[t];
+    hdr[idx * 6 + 2] = L.tile_pt[t];  hdr[idx * 6 + 3] = chunk ? 0 : L.tile_np[t];
+    hdr[idx * 6 + 4] = L.tile_seg[t]; hdr[idx * 6 + 5] = chunk ? 0 : L.tile_seg[t + 1] - L.tile_seg[t];
   }
   __syncthreads();
   auto prefetch = [&](int it) {                              // this thread's 12 vectors of tile `it`
@@ -447,7 +484,7 @@ __global__ void __launch_bounds__(T, 2) k_ba_matvec_persistent(BaDev L, const do
   prefetch(0);
   for (int it = 0; it < my_tiles; ++it) {
     Tile q;
-    q.ob = hdr[it * 6 + 0]; q.no = hdr[it * 6 + 1]; q.pb = hdr[it * 6 + 2]; q.np = hdr[it * 6 + 3]; q.sb = hdr[it * 6 + 4]; q.ns = hdr[it * 6 + 5];
+    q.ob = hdr[it * 6 + 0]; q.no = hdr[it * 6 + 1]; q.pb = hdr[it * 6 + 2]; q.np = hdr[it * 6 + 3]; q.sb = hdr[it * 6 + 4]; q.ns = hdr[it * 6 + 5]; q.chunk = -1;
     const bool active = tid < q.no;
     const int i = q.ob + tid;
     double2 Fv[9], Ev[3];
@@ -510,6 +547,7 @@ __global__ void __launch_bounds__(T) k_ba_back_substitute(BaDev L, const double2
                                                           double* __restrict__ tile_mcc) {
   extern __shared__ double sm[];
   const Tile q = load_tile(L, blockIdx.x);
+  if (q.chunk >= 0) return;                  // long tracks: k_ba_back_substitute_giant
   const int tid = threadIdx.x;
   double* zs = sm;                           // [max_seg][9]
   double* w = zs + L.max_seg_tile * 9;       // [3][T]
@@ -569,6 +607,262 @@ __global__ void __launch_bounds__(T) k_ba_back_substitute(BaDev L, const double2
   if (tid == 0) tile_mcc[blockIdx.x] = tot;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Long tracks (more observations than one tile holds).  One CTA per long track g walks the chunk tiles
+// [gp_tile_begin[g], +gp_tile_count[g]) of point gp_point[g] twice: pass 0 accumulates the per-point sums chunk by
+// chunk (fixed order: block tree inside a chunk, chunks in tile order), pass 1 re-reads the chunk (48 KB, an L2 hit)
+// and finishes exactly like the second half of the regular kernel.  The camera side (segments, k_cam_reduce) is the
+// same as for regular tiles, so results stay atomic-free and bit-reproducible.  Real BAL files have a handful of
+// such tracks; these kernels are about correctness on them, not about the roofline.
+struct Giant { int pnt, tb, nc; };
+__device__ __forceinline__ Giant load_giant(const BaDev& L, int g) { return {L.gp_point[g], L.gp_tile_begin[g], L.gp_tile_count[g]}; }
+
+__global__ void k_ba_giant_point_combine(BaDev L, const double* __restrict__ chunk_pt, double* __restrict__ grad,
+                                         double* __restrict__ cnorm2, const int* guard) {
+  if (guard != nullptr && *guard == 0) return;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= L.n_giant) return;
+  const Giant G = load_giant(L, g);
+  const int c0 = -L.tile_np[G.tb] - 1;
+  double s6[6] = {0, 0, 0, 0, 0, 0};
+  for (int c = 0; c < G.nc; ++c)
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s6[k] += chunk_pt[(size_t)(c0 + c) * 6 + k];
+  const size_t o = (size_t)9 * L.n_cams + (size_t)G.pnt * 3;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { grad[o + k] = s6[k]; cnorm2[o + k] = s6[3 + k]; }
+}
+
+__global__ void __launch_bounds__(T) k_ba_schur_setup_giant(BaDev L, const double2* __restrict__ J2, const double2* __restrict__ r2,
+                                                            const double* __restrict__ D, double* __restrict__ einv,
+                                                            double* __restrict__ seg_rhs, double* __restrict__ seg_M,
+                                                            int* error_flag, int ftf_only) {
+  extern __shared__ double sm[];
+  const Giant G = load_giant(L, blockIdx.x);
+  const int tid = threadIdx.x;
+  double* v = sm;                      // [9][VLD]
+  double* red = v + 9 * VLD;           // [9][8]
+  const size_t O = (size_t)L.n_obs;
+  // pass 0: E^T E (upper: 00 01 02 11 12 22) and E^T r over the whole track
+  double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int c = 0; c < G.nc; ++c) {
+    const Tile q = load_tile(L, G.tb + c);
+    double x[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (tid < q.no) {
+      const int i = q.ob + tid;
+      double2 Ev[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) Ev[k] = J2[(9 + k) * O + i];
+      const double2 r = r2[i];
+      x[0] = Ev[0].x * Ev[0].x + Ev[0].y * Ev[0].y;
+      x[1] = Ev[0].x * Ev[1].x + Ev[0].y * Ev[1].y;
+      x[2] = Ev[0].x * Ev[2].x + Ev[0].y * Ev[2].y;
+      x[3] = Ev[1].x * Ev[1].x + Ev[1].y * Ev[1].y;
+      x[4] = Ev[1].x * Ev[2].x + Ev[1].y * Ev[2].y;
+      x[5] = Ev[2].x * Ev[2].x + Ev[2].y * Ev[2].y;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) x[6 + k] = Ev[k].x * r.x + Ev[k].y * r.y;
+    }
+    block_sum_all<9>(x, red);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[k] += x[k];
+  }
+  // every thread holds the same sums: invert redundantly, thread 0 publishes
+  const double* Dp = D + (size_t)9 * L.n_cams + (size_t)G.pnt * 3;
+  double m[6] = {acc[0] + Dp[0] * Dp[0], acc[1], acc[2], acc[3] + Dp[1] * Dp[1], acc[4], acc[5] + Dp[2] * Dp[2]};
+  double pi[9];
+  if (!invert_spd3(m, pi)) {
+    if (tid == 0) atomicOr(error_flag, 1);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) pi[k] = 0.0;
+  }
+  if (tid < 6) einv[(size_t)G.pnt * 6 + tid] = pi[tid];
+  pi[6] = pi[0] * acc[6] + pi[1] * acc[7] + pi[2] * acc[8];
+  pi[7] = pi[1] * acc[6] + pi[3] * acc[7] + pi[4] * acc[8];
+  pi[8] = pi[2] * acc[6] + pi[4] * acc[7] + pi[5] * acc[8];
+  // pass 1: reduced rhs and diagonal-block partials of every chunk
+  for (int c = 0; c < G.nc; ++c) {
+    const Tile q = load_tile(L, G.tb + c);
+    const bool active = tid < q.no;
+    const int i = q.ob + tid;
+    double2 Fv[9], Ev[3], r = make_double2(0.0, 0.0);
+    double Gm[3][9], H[3][9];
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) Fv[k] = J2[k * O + i];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) Ev[k] = J2[(9 + k) * O + i];
+      r = r2[i];
+      const double q0 = r.x - (Ev[0].x * pi[6] + Ev[1].x * pi[7] + Ev[2].x * pi[8]);
+      const double q1 = r.y - (Ev[0].y * pi[6] + Ev[1].y * pi[7] + Ev[2].y * pi[8]);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) v[k * VLD + tid] = Fv[k].x * q0 + Fv[k].y * q1;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) Gm[a][k] = Ev[a].x * Fv[k].x + Ev[a].y * Fv[k].y;
+        H[0][k] = pi[0] * Gm[0][k] + pi[1] * Gm[1][k] + pi[2] * Gm[2][k];
+        H[1][k] = pi[1] * Gm[0][k] + pi[3] * Gm[1][k] + pi[4] * Gm[2][k];
+        H[2][k] = pi[2] * Gm[0][k] + pi[4] * Gm[1][k] + pi[5] * Gm[2][k];
+      }
+    }
+    __syncthreads();
+    seg_reduce9(L, q, v, seg_rhs, 9, 0);
+#pragma unroll
+    for (int round = 0; round < 5; ++round) {
+      __syncthreads();
+      if (active) {
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+          const int k = upper_row(round * 9 + j), l = upper_col(round * 9 + j);
+          const double ftf = Fv[k].x * Fv[l].x + Fv[k].y * Fv[l].y;
+          v[j * VLD + tid] = ftf_only ? ftf : (ftf - (Gm[0][k] * H[0][l] + Gm[1][k] * H[1][l] + Gm[2][k] * H[2][l]));
+        }
+      }
+      __syncthreads();
+      seg_reduce9(L, q, v, seg_M, 45, round * 9);
+    }
+    __syncthreads();                   // v is rewritten by the next chunk
+  }
+}
+
+// Input vector exactly as in k_ba_matvec (p, or the PCG direction z + beta p).
+__global__ void __launch_bounds__(T) k_ba_matvec_giant(BaDev L, const double2* __restrict__ J2, const double* __restrict__ p,
+                                                       const double* __restrict__ zdir, const PcgDev* pcg,
+                                                       const double* __restrict__ einv, double* __restrict__ seg_y,
+                                                       const int* guard) {
+  if (guard != nullptr && *guard == 0) return;
+  extern __shared__ double sm[];
+  const Giant G = load_giant(L, blockIdx.x);
+  const int tid = threadIdx.x;
+  double* xs = sm;                           // [max_seg][9]
+  double* v = xs + L.max_seg_tile * 9;       // [9][VLD]
+  double* red = v + 9 * VLD;                 // [3][8]
+  const size_t O = (size_t)L.n_obs;
+  double a[3] = {0, 0, 0}, u[3] = {0, 0, 0};
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int c = 0; c < G.nc; ++c) {
+      const Tile q = load_tile(L, G.tb + c);
+      const bool active = tid < q.no;
+      const int i = q.ob + tid;
+      double2 Fv[9], Ev[3];
+      int slot = 0;
+      if (active) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Fv[k] = J2[k * O + i];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) Ev[k] = J2[(9 + k) * O + i];
+        slot = L.obs_slot[i];
+      }
+      for (int idx = tid; idx < q.ns * 9; idx += T) {
+        const int s = idx / 9, k = idx - s * 9;
+        const size_t e = (size_t)L.seg_cam[q.sb + s] * 9 + k;
+        xs[idx] = (pcg == nullptr) ? p[e] : ((pcg->iter == 1) ? zdir[e] : (zdir[e] + pcg->beta * p[e]));
+      }
+      __syncthreads();
+      double t0 = 0.0, t1 = 0.0;
+      if (active) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { const double xk = xs[slot * 9 + k]; t0 += Fv[k].x * xk; t1 += Fv[k].y * xk; }
+      }
+      if (pass == 0) {
+        double w[3] = {0, 0, 0};
+        if (active) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) w[k] = Ev[k].x * t0 + Ev[k].y * t1;
+        }
+        block_sum_all<3>(w, red);            // ends with a barrier: xs may be restaged
+#pragma unroll
+        for (int k = 0; k < 3; ++k) a[k] += w[k];
+      } else {
+        if (active) {
+          const double s0 = t0 - (Ev[0].x * u[0] + Ev[1].x * u[1] + Ev[2].x * u[2]);
+          const double s1 = t1 - (Ev[0].y * u[0] + Ev[1].y * u[1] + Ev[2].y * u[2]);
+#pragma unroll
+          for (int k = 0; k < 9; ++k) v[k * VLD + tid] = Fv[k].x * s0 + Fv[k].y * s1;
+        }
+        __syncthreads();
+        seg_reduce9(L, q, v, seg_y, 9, 0);
+        __syncthreads();
+      }
+    }
+    if (pass == 0) {
+      const double* m = einv + (size_t)G.pnt * 6;
+      u[0] = m[0] * a[0] + m[1] * a[1] + m[2] * a[2];
+      u[1] = m[1] * a[0] + m[3] * a[1] + m[4] * a[2];
+      u[2] = m[2] * a[0] + m[4] * a[1] + m[5] * a[2];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(T) k_ba_back_substitute_giant(BaDev L, const double2* __restrict__ J2, const double2* __restrict__ r2,
+                                                                const double* __restrict__ z, const double* __restrict__ einv,
+                                                                double* __restrict__ step, double* __restrict__ tile_mcc) {
+  extern __shared__ double sm[];
+  const Giant G = load_giant(L, blockIdx.x);
+  const int tid = threadIdx.x;
+  double* zs = sm;                           // [max_seg][9]
+  double* red = zs + L.max_seg_tile * 9;     // [3][8]
+  const size_t O = (size_t)L.n_obs;
+  double a[3] = {0, 0, 0}, u[3] = {0, 0, 0};
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int c = 0; c < G.nc; ++c) {
+      const Tile q = load_tile(L, G.tb + c);
+      const bool active = tid < q.no;
+      const int i = q.ob + tid;
+      double2 Fv[9], Ev[3], r = make_double2(0.0, 0.0);
+      int slot = 0;
+      if (active) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Fv[k] = J2[k * O + i];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) Ev[k] = J2[(9 + k) * O + i];
+        r = r2[i];
+        slot = L.obs_slot[i];
+      }
+      for (int idx = tid; idx < q.ns * 9; idx += T) {
+        const int s = idx / 9, k = idx - s * 9;
+        zs[idx] = z[(size_t)L.seg_cam[q.sb + s] * 9 + k];
+      }
+      __syncthreads();
+      double s0 = 0.0, s1 = 0.0;
+      if (active) {
+        double f0 = 0.0, f1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { const double zk = zs[slot * 9 + k]; f0 += Fv[k].x * zk; f1 += Fv[k].y * zk; }
+        s0 = r.x - f0; s1 = r.y - f1;
+      }
+      if (pass == 0) {
+        double w[3] = {0, 0, 0};
+        if (active) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) w[k] = Ev[k].x * s0 + Ev[k].y * s1;
+        }
+        block_sum_all<3>(w, red);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) a[k] += w[k];
+      } else {
+        double mc[1] = {0.0};
+        if (active) {
+          const double m0 = (s0 - r.x) + (Ev[0].x * u[0] + Ev[1].x * u[1] + Ev[2].x * u[2]);
+          const double m1 = (s1 - r.y) + (Ev[0].y * u[0] + Ev[1].y * u[1] + Ev[2].y * u[2]);
+          mc[0] = m0 * (r.x + m0 / 2.0) + m1 * (r.y + m1 / 2.0);
+        }
+        block_sum_all<1>(mc, red);
+        if (tid == 0) tile_mcc[G.tb + c] = mc[0];
+      }
+    }
+    if (pass == 0) {
+      const double* m = einv + (size_t)G.pnt * 6;
+      const double y0 = m[0] * a[0] + m[1] * a[1] + m[2] * a[2];
+      const double y1 = m[1] * a[0] + m[3] * a[1] + m[4] * a[2];
+      const double y2 = m[2] * a[0] + m[4] * a[1] + m[5] * a[2];
+      u[0] = -y0; u[1] = -y1; u[2] = -y2;
+      if (tid < 3) step[(size_t)9 * L.n_cams + (size_t)G.pnt * 3 + tid] = u[tid];
+    }
+  }
+}
+
 __global__ void k_ba_export_jacobian(BaDev L, const double2* __restrict__ J2, double* __restrict__ F, double* __restrict__ E) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= L.n_obs) return;
@@ -586,18 +880,19 @@ void set_smem(K kernel, size_t bytes) {
 
 void launch_ba_evaluate(const BaDev& L, const double* x, const double* scale, LossSpec loss, bool with_jacobian,
                         bool write_jacobian, double2* J2, double2* r2, double* grad, double* cnorm2, double* seg_g,
-                        double* seg_n, double* tile_cost, int* fail_flag, const int* guard, cudaStream_t s) {
+                        double* seg_n, double* tile_cost, double* chunk_pt, int* fail_flag, const int* guard, cudaStream_t s) {
   if (L.n_tiles == 0) return;
   if (with_jacobian) {
     const size_t smem = sizeof(double) * ((size_t)2 * (L.max_seg_tile * 9 + L.max_pt_tile * 3) + 9 * VLD + 8);
     set_smem(k_ba_evaluate<true>, smem);
     k_ba_evaluate<true><<<L.n_tiles, T, smem, s>>>(L, x, scale, loss, write_jacobian ? 1 : 0, J2, r2, grad, cnorm2, seg_g,
-                                                   seg_n, tile_cost, fail_flag, guard);
+                                                   seg_n, tile_cost, chunk_pt, fail_flag, guard);
+    if (L.n_giant) k_ba_giant_point_combine<<<cdiv(L.n_giant, 64), 64, 0, s>>>(L, chunk_pt, grad, cnorm2, guard);
   } else {
     const size_t smem = sizeof(double) * ((size_t)(L.max_seg_tile * 9 + L.max_pt_tile * 3) + 8);
     set_smem(k_ba_evaluate<false>, smem);
     k_ba_evaluate<false><<<L.n_tiles, T, smem, s>>>(L, x, scale, loss, 0, J2, r2, grad, cnorm2, seg_g, seg_n, tile_cost,
-                                                    fail_flag, guard);
+                                                    chunk_pt, fail_flag, guard);
   }
   check_launch("k_ba_evaluate");
 }
@@ -609,11 +904,16 @@ void launch_cam_reduce(const BaDev& L, int K, const double* seg, double* out, co
 }
 
 void launch_ba_schur_setup(const BaDev& L, const double2* J2, const double2* r2, const double* D, double* einv,
-                           double* seg_rhs, double* seg_M, int* error_flag, cudaStream_t s) {
+                           double* seg_rhs, double* seg_M, int* error_flag, bool ftf_only, cudaStream_t s) {
   if (L.n_tiles == 0) return;
   const size_t smem = sizeof(double) * ((size_t)9 * VLD + (size_t)L.max_pt_tile * 9);
   set_smem(k_ba_schur_setup, smem);
-  k_ba_schur_setup<<<L.n_tiles, T, smem, s>>>(L, J2, r2, D, einv, seg_rhs, seg_M, error_flag);
+  k_ba_schur_setup<<<L.n_tiles, T, smem, s>>>(L, J2, r2, D, einv, seg_rhs, seg_M, error_flag, ftf_only ? 1 : 0);
+  if (L.n_giant) {
+    const size_t smem_g = sizeof(double) * ((size_t)9 * VLD + 9 * 8);
+    set_smem(k_ba_schur_setup_giant, smem_g);
+    k_ba_schur_setup_giant<<<L.n_giant, T, smem_g, s>>>(L, J2, r2, D, einv, seg_rhs, seg_M, error_flag, ftf_only ? 1 : 0);
+  }
   check_launch("k_ba_schur_setup");
 }
 
@@ -626,6 +926,12 @@ void launch_ba_precond_invert(const BaDev& L, const double* M45, const double* D
 void launch_ba_matvec(const BaDev& L, const double2* J2, const double* p, const double* zdir, const PcgDev* pcg, const double* einv,
                       double* seg_y, const int* guard, cudaStream_t s) {
   if (L.n_tiles == 0) return;
+  if (L.n_giant) {             // long tracks first (any order works: the two kernels write disjoint segments)
+    const size_t smem_g = sizeof(double) * ((size_t)L.max_seg_tile * 9 + 9 * VLD + 3 * 8);
+    set_smem(k_ba_matvec_giant, smem_g);
+    k_ba_matvec_giant<<<L.n_giant, T, smem_g, s>>>(L, J2, p, zdir, pcg, einv, seg_y, guard);
+    check_launch("k_ba_matvec_giant");
+  }
   const size_t smem_tail = sizeof(double) * ((size_t)L.max_pt_tile * 6) + sizeof(int) * ((size_t)L.max_seg_tile + L.max_pt_tile + 2) +
                            sizeof(unsigned short) * T + 16;
   const size_t smem = sizeof(double) * ((size_t)L.max_seg_tile * 9 + 9 * VLD + 6 * T) + smem_tail;       // persistent kernel layout
@@ -660,6 +966,11 @@ void launch_ba_back_substitute(const BaDev& L, const double2* J2, const double2*
   const size_t smem = sizeof(double) * ((size_t)L.max_seg_tile * 9 + 6 * T + 8);
   set_smem(k_ba_back_substitute, smem);
   k_ba_back_substitute<<<L.n_tiles, T, smem, s>>>(L, J2, r2, z, einv, step, tile_mcc);
+  if (L.n_giant) {
+    const size_t smem_g = sizeof(double) * ((size_t)L.max_seg_tile * 9 + 3 * 8);
+    set_smem(k_ba_back_substitute_giant, smem_g);
+    k_ba_back_substitute_giant<<<L.n_giant, T, smem_g, s>>>(L, J2, r2, z, einv, step, tile_mcc);
+  }
   check_launch("k_ba_back_substitute");
 }
 

@@ -9,7 +9,10 @@ namespace sk {
 // Device view of BaLayoutHost (plain pointers, passed to kernels by value).
 struct BaDev {
   int n_obs, n_pts, n_cams, n_tiles, n_segs, max_seg_tile, max_pt_tile;
+  int n_giant, n_chunks;               // tracks longer than one tile and the chunk tiles they are cut into (ba_layout.h)
   const int* tile_obs; const int* tile_pt; const int* tile_seg; const int* pt_ptr;
+  const int* tile_np;                  // [T] > 0: points of a regular tile;  < 0: chunk tile, ordinal = -tile_np - 1
+  const int* gp_tile_begin; const int* gp_tile_count; const int* gp_point;   // [n_giant]
   const unsigned short* obs_slot; const unsigned short* obs_ptl; const unsigned short* seg_perm;
   const int* seg_ptr; const int* seg_cam; const int* cam_seg_ptr; const int* cam_seg;
   const double2* obs;   // [n_obs] observed (x, y)
@@ -33,10 +36,11 @@ struct Flags {           // device-resident control block shared by the LM / PCG
 //   grad, cnorm2 outputs for the POINT part [9C .. 9C+3P) written directly; camera part goes to
 //                seg_g / seg_n partials [S][9] (only when with_jacobian)
 //   tile_cost    [n_tiles] partial costs
+//   chunk_pt     [n_chunks][6] scratch: point-part partials of the chunk tiles of long tracks (with_jacobian)
 //   guard        kernel returns immediately when *guard == 0 (nullptr = always run)
 void launch_ba_evaluate(const BaDev& L, const double* x, const double* scale, LossSpec loss, bool with_jacobian,
                         bool write_jacobian, double2* J2, double2* r2, double* grad, double* cnorm2,
-                        double* seg_g, double* seg_n, double* tile_cost, int* fail_flag, const int* guard,
+                        double* seg_g, double* seg_n, double* tile_cost, double* chunk_pt, int* fail_flag, const int* guard,
                         cudaStream_t s);
 
 // out[c*K + k] = sum over the camera's segments of seg[s*K + k]   (deterministic, tile order)
@@ -46,7 +50,7 @@ void launch_cam_reduce(const BaDev& L, int K, const double* seg, double* out, co
 // solver needs): per point (E^T E + D_p^2)^-1 -> einv [P][6]; per (tile, camera) partials of the
 // reduced right-hand side [S][9] and of the diagonal blocks of S (upper triangle, [S][45]).
 void launch_ba_schur_setup(const BaDev& L, const double2* J2, const double2* r2, const double* D, double* einv,
-                           double* seg_rhs, double* seg_M, int* error_flag, cudaStream_t s);
+                           double* seg_rhs, double* seg_M, int* error_flag, bool ftf_only, cudaStream_t s);
 
 // Minv[c] = (sum of seg_M + D_c^2)^-1 as a full 9x9 row-major block (SchurJacobiPreconditioner).
 // diag_only_identity: IDENTITY preconditioner (Minv = I).

@@ -142,18 +142,37 @@ void build_ba_layout(int64_t n, const int64_t* cam_off, const int64_t* pt_off, c
                "a camera observes the same point twice (residual blocks %d and %d): unsupported by the Schur path",
                L.perm[j - 1], L.perm[j]);
   // ---- tiles: whole points, at most kTileObs observations -----------------------------------
-  L.tile_obs.clear(); L.tile_pt.clear();
-  L.tile_obs.push_back(0); L.tile_pt.push_back(0);
-  int32_t cur = 0;
+  // tile t covers observations [tile_obs[t], tile_obs[t+1]) and points [tile_pt[t], tile_pt[t] + tile_np[t])
+  L.tile_obs.clear(); L.tile_pt.clear(); L.tile_np.clear(); L.tile_chunk.clear();
+  L.gp_tile_begin.clear(); L.gp_tile_count.clear(); L.gp_point.clear();
+  int32_t cur = 0, cur_first_pt = 0, cur_first_obs = 0;
+  L.n_chunks = 0;
+  auto close_regular = [&](int32_t p_end) {          // emit the pending regular tile [cur_first_pt, p_end)
+    if (cur == 0) return;
+    L.tile_obs.push_back(cur_first_obs); L.tile_pt.push_back(cur_first_pt); L.tile_np.push_back(p_end - cur_first_pt); L.tile_chunk.push_back(-1);
+    cur = 0;
+  };
   for (int32_t p = 0; p < L.n_pts; ++p) {
     const int32_t k = L.pt_ptr[p + 1] - L.pt_ptr[p];
-    SK_REQUIRE(k <= kTileObs, SK_ERR_UNSUPPORTED,
-               "a point is observed by %d cameras; tracks longer than %d observations are not supported yet", k, kTileObs);
-    if (cur + k > kTileObs) { L.tile_obs.push_back(L.pt_ptr[p]); L.tile_pt.push_back(p); cur = 0; }
+    if (k > kTileObs) {                              // long track: its own chain of chunk tiles
+      close_regular(p);
+      const int32_t nch = (k + kTileObs - 1) / kTileObs;
+      L.gp_point.push_back(p); L.gp_tile_begin.push_back((int32_t)L.tile_obs.size()); L.gp_tile_count.push_back(nch);
+      for (int32_t c = 0; c < nch; ++c) {
+        L.tile_obs.push_back(L.pt_ptr[p] + (int32_t)((int64_t)k * c / nch));
+        L.tile_pt.push_back(p); L.tile_np.push_back(1); L.tile_chunk.push_back(L.n_chunks++);
+      }
+      cur_first_pt = p + 1; cur_first_obs = L.pt_ptr[p + 1];
+      continue;
+    }
+    if (cur + k > kTileObs) close_regular(p);
+    if (cur == 0) { cur_first_pt = p; cur_first_obs = L.pt_ptr[p]; }
     cur += k;
   }
+  close_regular(L.n_pts);
+  L.n_tiles = (int32_t)L.tile_obs.size();
   L.tile_obs.push_back(L.n_obs); L.tile_pt.push_back(L.n_pts);
-  L.n_tiles = (int32_t)L.tile_obs.size() - 1;
+  L.n_giant = (int32_t)L.gp_point.size();
   // ---- tile-local camera segments (tiles are independent: built by all host threads) -------------
   SK_REQUIRE(L.n_cams < (1 << 24), SK_ERR_UNSUPPORTED, "more than 2^24 cameras");
   L.obs_slot.resize(L.n_obs); L.obs_ptl.resize(L.n_obs); L.seg_perm.resize(L.n_obs);
@@ -183,7 +202,7 @@ void build_ba_layout(int64_t n, const int64_t* cam_off, const int64_t* pt_off, c
   for (int32_t t = 0; t < L.n_tiles; ++t) {
     L.tile_seg[t + 1] = L.tile_seg[t] + tile_nseg[t];
     L.max_seg_tile = std::max(L.max_seg_tile, tile_nseg[t]);
-    L.max_pt_tile = std::max(L.max_pt_tile, L.tile_pt[t + 1] - L.tile_pt[t]);
+    L.max_pt_tile = std::max(L.max_pt_tile, L.tile_np[t]);
   }
   L.n_segs = L.tile_seg[L.n_tiles];
   L.seg_ptr.assign((size_t)L.n_segs + 1, 0); L.seg_cam.assign((size_t)L.n_segs, 0);

@@ -31,7 +31,16 @@ struct BaLayoutHost {
   std::vector<int32_t> obs_cam;        // [O] camera id (sorted order)
   std::vector<int32_t> obs_pt;         // [O] point id (sorted order)
   std::vector<int32_t> pt_ptr;         // [P+1]
-  std::vector<int32_t> tile_obs, tile_pt, tile_seg;  // [T+1]
+  std::vector<int32_t> tile_obs, tile_pt, tile_seg;  // [T+1]  (tile_pt[t] = first point of tile t)
+  std::vector<int32_t> tile_np;        // [T] points of tile t (regular: whole points; chunk of a long track: 1)
+  // Tracks longer than kTileObs are cut into consecutive CHUNK tiles (tile_chunk >= 0). Chunk tiles behave like any
+  // tile on the camera side (segments, slots); their per-point sums are formed by one CTA per long track that walks
+  // the chunk tiles [gp_tile_begin[g], gp_tile_begin[g] + gp_tile_count[g]) of point gp_point[g].
+  std::vector<int32_t> tile_chunk;     // [T] -1 for a regular tile, else the ordinal of the chunk among all chunk tiles
+  std::vector<int32_t> gp_tile_begin;  // [G]
+  std::vector<int32_t> gp_tile_count;  // [G]
+  std::vector<int32_t> gp_point;       // [G]
+  int32_t n_giant = 0, n_chunks = 0;
   std::vector<uint16_t> obs_slot;      // [O] tile-local segment id
   std::vector<uint16_t> obs_ptl;       // [O] tile-local point id
   std::vector<uint16_t> seg_perm;      // [O] tile-local obs ids in (segment, obs) order
@@ -45,7 +54,7 @@ struct BaLayoutHost {
 // Restricts the layout to the point range [pt_begin_rank, pt_end_rank) of the *sorted* point list
 // when world_size > 1 (point partition balanced by observation count); cameras are replicated.
 // Throws sk::Error on unsupported structure (duplicate (camera, point) pairs, tracks longer than
-// kTileObs, overlapping blocks).
+// overlapping blocks).
 void build_ba_layout(int64_t n, const int64_t* cam_off, const int64_t* pt_off, const double* obs_xy,
                      int rank, int world_size, BaLayoutHost* out);
 

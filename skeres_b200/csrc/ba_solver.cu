@@ -37,6 +37,12 @@ BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHo
   d_seg_perm_.upload(H.seg_perm, s); d_seg_ptr_.upload(H.seg_ptr, s); d_seg_cam_.upload(H.seg_cam, s);
   d_cam_seg_ptr_.upload(H.cam_seg_ptr, s); d_cam_seg_.upload(H.cam_seg, s);
   d_obs_.alloc((size_t)2 * H.n_obs); d_obs_.upload(H.obs.data(), H.obs.size(), s);
+  // device encoding of the tile kind: > 0 points of a regular tile, < 0 chunk tile of a long track (ordinal = -v - 1)
+  std::vector<int> tile_np_enc((size_t)H.n_tiles);
+  for (int t = 0; t < H.n_tiles; ++t) tile_np_enc[t] = H.tile_chunk[t] >= 0 ? -(H.tile_chunk[t] + 1) : H.tile_np[t];
+  d_tile_np_.upload(tile_np_enc, s);
+  d_gp_begin_.upload(H.gp_tile_begin, s); d_gp_count_.upload(H.gp_tile_count, s); d_gp_point_.upload(H.gp_point, s);
+  chunk_pt_.alloc((size_t)6 * std::max(H.n_chunks, 1));
   std::vector<long long> co(H.cam_offset.begin(), H.cam_offset.end()), po(H.pt_offset.begin(), H.pt_offset.end());
   d_cam_off_.upload(co, s); d_pt_off_.upload(po, s);
   SK_CUDA(cudaStreamSynchronize(s));   // host vectors above are temporaries / pageable
@@ -46,6 +52,8 @@ BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHo
   L_.obs_slot = d_obs_slot_.p; L_.obs_ptl = d_obs_ptl_.p; L_.seg_perm = d_seg_perm_.p; L_.seg_ptr = d_seg_ptr_.p;
   L_.seg_cam = d_seg_cam_.p; L_.cam_seg_ptr = d_cam_seg_ptr_.p; L_.cam_seg = d_cam_seg_.p;
   L_.obs = reinterpret_cast<const double2*>(d_obs_.p);
+  L_.n_giant = H.n_giant; L_.n_chunks = H.n_chunks; L_.tile_np = d_tile_np_.p;
+  L_.gp_tile_begin = d_gp_begin_.p; L_.gp_tile_count = d_gp_count_.p; L_.gp_point = d_gp_point_.p;
   const int64_t nc = (int64_t)9 * H.n_cams, n = nc + (int64_t)3 * H.n_pts;
   allocate(n, nc);
   J2_.alloc((size_t)2 * kJPlanes * std::max(H.n_obs, 1)); r2_.alloc((size_t)2 * std::max(H.n_obs, 1));
@@ -60,8 +68,9 @@ BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHo
   const int lst = opt.linear_solver_type;
   explicit_schur_ = (lst == SK_DENSE_SCHUR || lst == SK_SPARSE_SCHUR);
   if (!explicit_schur_) {
-    SK_REQUIRE(opt.preconditioner_type == SK_SCHUR_JACOBI || opt.preconditioner_type == SK_IDENTITY, SK_ERR_UNSUPPORTED,
-               "ITERATIVE_SCHUR supports the SCHUR_JACOBI and IDENTITY preconditioners on the device (got %d)", opt.preconditioner_type);
+    SK_REQUIRE(opt.preconditioner_type == SK_SCHUR_JACOBI || opt.preconditioner_type == SK_JACOBI || opt.preconditioner_type == SK_IDENTITY,
+               SK_ERR_UNSUPPORTED, "ITERATIVE_SCHUR supports the JACOBI, SCHUR_JACOBI and IDENTITY preconditioners on the device (got %d)",
+               opt.preconditioner_type);
     seg_M_.alloc((size_t)45 * std::max(H.n_segs, 1)); M45_.alloc((size_t)45 * H.n_cams); Minv_.alloc((size_t)81 * H.n_cams);
   } else {
     SK_REQUIRE(nc <= 16384, SK_ERR_UNSUPPORTED,
@@ -128,10 +137,10 @@ ReduceJob BaSolver::cost_job() { return {tile_cost_.p, L_.n_tiles, SB_COST, 0}; 
 
 void BaSolver::eval_jacobian(bool scale_valid, bool store, const int* guard) {
   {
-    KScope k(prof_, SK_KF_EVALUATE_JACOBIAN, 3);
+    KScope k(prof_, SK_KF_EVALUATE_JACOBIAN, 3 + (L_.n_giant ? 1 : 0));
     launch_ba_evaluate(L_, x_.p, scale_valid ? scale_.p : nullptr, loss_, true, store, reinterpret_cast<double2*>(J2_.p),
                        reinterpret_cast<double2*>(r2_.p), grad_.p, cnorm2_.p, seg_a_.p, seg_b_.p, tile_cost_.p,
-                       &st_.p->eval_failed, guard, stream_);
+                       chunk_pt_.p, &st_.p->eval_failed, guard, stream_);
     launch_cam_reduce(L_, 9, seg_a_.p, grad_.p, guard, stream_);
     launch_cam_reduce(L_, 9, seg_b_.p, cnorm2_.p, guard, stream_);
   }
@@ -147,7 +156,7 @@ void BaSolver::eval_jacobian(bool scale_valid, bool store, const int* guard) {
 void BaSolver::eval_cost(const double* xv, const int* guard) {
   KScope k(prof_, SK_KF_EVALUATE_COST);
   launch_ba_evaluate(L_, xv, nullptr, loss_, false, false, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, tile_cost_.p,
-                     &st_.p->eval_failed, guard, stream_);
+                     nullptr, &st_.p->eval_failed, guard, stream_);
 }
 
 // seg_a_ = segment partials of S_local * v, where v = `in` or (pcg_dir) the PCG direction z + beta p.
@@ -155,7 +164,7 @@ void BaSolver::eval_cost(const double* xv, const int* guard) {
 // consumer kernels should read (nullptr = "reduce the segment partials yourself").
 const double* BaSolver::matvec(const double* in, bool pcg_dir, const int* guard) {
   {
-    KScope k(prof_, SK_KF_SCHUR_MATVEC);
+    KScope k(prof_, SK_KF_SCHUR_MATVEC, 1 + (L_.n_giant ? 1 : 0));
     launch_ba_matvec(L_, reinterpret_cast<const double2*>(J2_.p), in, pcg_dir ? pz_.p : nullptr, pcg_dir ? pcg_.p : nullptr, einv_.p,
                      seg_a_.p, guard, stream_);
   }
@@ -173,8 +182,9 @@ ReduceJob BaSolver::linear_solve(const PcgDev** pcg_out) {
   const double2* r2 = reinterpret_cast<const double2*>(r2_.p);
   int* lin_error = &st_.p->lin_error;
   {
-    KScope k(prof_, SK_KF_SCHUR_SETUP, 3);
-    launch_ba_schur_setup(L_, J2, r2, D_.p, einv_.p, seg_b_.p, seg_M_.p, lin_error, stream_);
+    KScope k(prof_, SK_KF_SCHUR_SETUP, 3 + (L_.n_giant ? 1 : 0));
+    const bool jacobi = !explicit_schur_ && opt_.preconditioner_type == SK_JACOBI;
+    launch_ba_schur_setup(L_, J2, r2, D_.p, einv_.p, seg_b_.p, seg_M_.p, lin_error, jacobi, stream_);
     launch_cam_reduce(L_, 9, seg_b_.p, rhs_.p, nullptr, stream_);
     launch_cam_reduce(L_, 45, seg_M_.p, M45_.p, nullptr, stream_);
   }
@@ -189,7 +199,7 @@ ReduceJob BaSolver::linear_solve(const PcgDev** pcg_out) {
     explicit_schur_solve();
     *pcg_out = nullptr;
   } else {
-    const bool schur_jacobi = opt_.preconditioner_type == SK_SCHUR_JACOBI;
+    const bool schur_jacobi = opt_.preconditioner_type == SK_SCHUR_JACOBI || opt_.preconditioner_type == SK_JACOBI;   // block preconditioner
     if (schur_jacobi) {
       KScope k(prof_, SK_KF_SCHUR_SETUP);
       launch_ba_precond_invert(L_, M45_.p, D_.p, Minv_.p, lin_error, stream_);
@@ -198,7 +208,7 @@ ReduceJob BaSolver::linear_solve(const PcgDev** pcg_out) {
     *pcg_out = pcg_.p;
   }
   {
-    KScope k(prof_, SK_KF_BACK_SUBSTITUTE, 2);
+    KScope k(prof_, SK_KF_BACK_SUBSTITUTE, 2 + (L_.n_giant ? 1 : 0));
     launch_negate(nc_, px_.p, step_.p, stream_);
     launch_ba_back_substitute(L_, J2, r2, px_.p, einv_.p, step_.p, tile_mcc_.p, stream_);
   }
@@ -245,10 +255,9 @@ void BaSolver::pcg_solve(const double* Minv) {
     SK_CUDA(cudaStreamSynchronize(stream_));
     prof_.collect();
     done = pcg_h_.p->active == 0;
-    n_real_matvecs_ += 0;
   }
   const int its = pcg_h_.p->iter;
-  n_real_matvecs_ += its + its / kResetPeriod;
+  n_real_matvecs_ += (its + its / kResetPeriod) * (L_.n_giant ? 2 : 1);
 }
 
 void BaSolver::fill_totals(int64_t total_obs, int64_t total_blocks, int64_t total_params, std::vector<int64_t>&& all_pt_off) {

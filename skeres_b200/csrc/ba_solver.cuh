@@ -39,6 +39,8 @@ class BaSolver : public LmSolver {
   int64_t total_obs_ = 0, total_param_blocks_ = 0, total_params_ = 0;
   std::vector<int64_t> all_pt_off_;
   DBuf<int> d_tile_obs_, d_tile_pt_, d_tile_seg_, d_pt_ptr_, d_seg_ptr_, d_seg_cam_, d_cam_seg_ptr_, d_cam_seg_;
+  DBuf<int> d_tile_np_, d_gp_begin_, d_gp_count_, d_gp_point_;   // long tracks (ba_layout.h)
+  DBuf<double> chunk_pt_;                                        // [n_chunks][6] point partials of chunk tiles
   DBuf<unsigned short> d_obs_slot_, d_obs_ptl_, d_seg_perm_;
   DBuf<double> d_obs_;
   DBuf<long long> d_cam_off_, d_pt_off_;

@@ -97,7 +97,9 @@ def _track_lengths(rng, n_pt, n_obs, kmax):
 
 
 def make_bal(shape="ladybug-49", seed=1, noise_px=0.5, point_sigma=0.05, rot_sigma=1e-3,
-             trans_sigma=1e-2, n_cam=None, n_pt=None, n_obs=None) -> BalData:
+             trans_sigma=1e-2, n_cam=None, n_pt=None, n_obs=None, long_tracks=()) -> BalData:
+    """long_tracks: track lengths (<= n_cam) forced onto evenly spaced points, on top of n_obs -- real BAL files hold a
+    few points seen by hundreds of cameras, which the device layout cuts into chunk tiles (ba_layout.h)."""
     if n_cam is None:
         n_cam, n_pt, n_obs = SHAPES[shape]
     rng = np.random.default_rng(seed)
@@ -124,6 +126,10 @@ def make_bal(shape="ladybug-49", seed=1, noise_px=0.5, point_sigma=0.05, rot_sig
     # --- visibility: a run of consecutive cameras around the nearest one --------------------------
     kmax = int(min(n_cam, max(6, np.ceil(3.0 * n_obs / n_pt))))
     k = _track_lengths(rng, n_pt, n_obs, kmax)
+    for j, length in enumerate(long_tracks):
+        assert 2 <= length <= n_cam
+        k[(j + 1) * n_pt // (len(long_tracks) + 1)] = length
+    n_obs = int(k.sum())
     nearest = np.floor(phi / (2.0 * np.pi) * n_cam + 0.5).astype(np.int64)
     base = nearest + rng.integers(-2, 3, n_pt) - k // 2
     base = np.clip(base, 0, n_cam - k)

@@ -45,10 +45,14 @@ void hc_layout_dims(const HcLayout* h, int32_t* out /*8*/) {
   out[0] = L.n_obs; out[1] = L.n_pts; out[2] = L.n_cams; out[3] = L.n_tiles; out[4] = L.n_segs; out[5] = L.max_seg_tile; out[6] = L.max_pt_tile;
   out[7] = L.input_was_sorted ? 1 : 0;
 }
+int32_t hc_layout_n_giant(const HcLayout* h) { return h->L.n_giant; }
+int32_t hc_layout_n_chunks(const HcLayout* h) { return h->L.n_chunks; }
 #define HC_COPY(name, field, T) void hc_layout_##name(const HcLayout* h, T* out) { std::memcpy(out, h->L.field.data(), sizeof(T) * h->L.field.size()); }
 HC_COPY(perm, perm, int32_t) HC_COPY(obs_cam, obs_cam, int32_t) HC_COPY(obs_pt, obs_pt, int32_t) HC_COPY(pt_ptr, pt_ptr, int32_t)
 HC_COPY(tile_obs, tile_obs, int32_t) HC_COPY(tile_pt, tile_pt, int32_t) HC_COPY(tile_seg, tile_seg, int32_t)
 HC_COPY(obs_slot, obs_slot, uint16_t) HC_COPY(obs_ptl, obs_ptl, uint16_t) HC_COPY(seg_perm, seg_perm, uint16_t)
 HC_COPY(seg_ptr, seg_ptr, int32_t) HC_COPY(seg_cam, seg_cam, int32_t) HC_COPY(cam_seg_ptr, cam_seg_ptr, int32_t) HC_COPY(cam_seg, cam_seg, int32_t)
+HC_COPY(tile_np, tile_np, int32_t) HC_COPY(tile_chunk, tile_chunk, int32_t) HC_COPY(gp_tile_begin, gp_tile_begin, int32_t)
+HC_COPY(gp_tile_count, gp_tile_count, int32_t) HC_COPY(gp_point, gp_point, int32_t)
 HC_COPY(cam_offset, cam_offset, int64_t) HC_COPY(pt_offset, pt_offset, int64_t) HC_COPY(obs, obs, double)
 }

@@ -229,6 +229,28 @@ def test_ba_iterative_schur_matches_oracle(sk, oracle, shape, seed):
     assert rel_param_diff(bal.parameters.toArray(), p.params) <= tol
 
 
+@pytest.mark.parametrize("shape,seed", [("tiny", 1), ("small", 2)])
+def test_ba_jacobi_preconditioner(sk, oracle, shape, seed):
+    """JACOBI is Ceres' DEFAULT preconditioner_type: a caller who only sets ITERATIVE_SCHUR gets it.  For the implicit
+    Schur complement it is the inverse of the block diagonal of F'F + D^2 (block_diagonal_FtF_inverse)."""
+    d = synth.make_bal(shape, seed=seed)
+    p, so = oracle_ba(oracle, d, _abi.ITERATIVE_SCHUR, _abi.JACOBI)
+    bal, s = gpu_ba(sk, d, _abi.ITERATIVE_SCHUR, _abi.JACOBI)
+    assert_same_trajectory(s, so)
+    assert rel_param_diff(bal.parameters.toArray(), p.params) <= PARAM_RTOL
+
+
+def test_ba_default_preconditioner_is_accepted(sk):
+    d = synth.make_bal("tiny", seed=1)
+    bal = sk.BalProblem.fromArrays(d)
+    o = sk.Solver.Options()                       # preconditioner_type left at the Ceres default (JACOBI)
+    o.setLinearSolverType(_abi.ITERATIVE_SCHUR)
+    assert o.preconditioner_type == _abi.JACOBI
+    s = sk.Solver.Summary()
+    sk.ceres.solve(o, bal.buildProblem(), s)
+    assert s.termination_type == _abi.CONVERGENCE and s.preconditioner_type_used == _abi.JACOBI
+
+
 def test_ba_identity_preconditioner(sk, oracle):
     d = synth.make_bal("small", seed=3)
     p, so = oracle_ba(oracle, d, _abi.ITERATIVE_SCHUR, _abi.IDENTITY)
@@ -242,6 +264,58 @@ def test_ba_identity_preconditioner(sk, oracle):
     # Ladybug ITERATIVE_SCHUR case: a truncated (eta = 0.1) CG solve depends on summation order; the cost reached
     # (checked to 1e-6 above) is the well-defined quantity. Recorded as a parity gap in DESIGN.md section 2.
     assert rel_param_diff(bal.parameters.toArray(), p.params) <= 2e-2
+
+
+LONG_TRACK_CASE = dict(n_cam=600, n_pt=1500, n_obs=12000, seed=5, long_tracks=(257, 600, 513))     # chunk tiles: 2, 3, 3
+LONG_TRACK_SMALL = dict(n_cam=270, n_pt=220, n_obs=2200, seed=11, long_tracks=(257, 270, 264))     # the DENSE_SCHUR fixture's case
+
+
+@pytest.mark.parametrize("case,prec", [(LONG_TRACK_CASE, _abi.SCHUR_JACOBI), (LONG_TRACK_SMALL, _abi.SCHUR_JACOBI),
+                                       (LONG_TRACK_SMALL, _abi.JACOBI)])
+def test_ba_long_tracks_iterative_schur(sk, oracle, case, prec):
+    """Points seen by more cameras than one tile holds (257 / 513 / 600 observations: 2 and 3 chunk tiles) go through
+    the k_ba_*_giant kernels; everything the LM loop derives from them must still follow the oracle row by row."""
+    d = synth.make_bal(**case)
+    assert np.sort(np.bincount(d.point_index))[-3:].tolist() == sorted(case["long_tracks"])
+    p, so = oracle_ba(oracle, d, _abi.ITERATIVE_SCHUR, prec)
+    bal, s = gpu_ba(sk, d, _abi.ITERATIVE_SCHUR, prec)
+    # rows and cost to 1e-6; PCG counts may differ by a few where a solve runs for ~100 iterations (summation order)
+    assert_same_trajectory(s, so, exact_rows=False)
+    for a, b in zip(s.iterations, so.iterations):
+        assert abs(a.linear_solver_iterations - b.linear_solver_iterations) <= max(2, 0.1 * b.linear_solver_iterations)
+        assert np.isclose(a.gradient_max_norm, b.gradient_max_norm, rtol=1e-5, atol=1e-9)
+    r_gpu, r_ora = residuals_at(oracle, d, bal.parameters.toArray()), residuals_at(oracle, d, p.params)
+    assert float(np.max(np.abs(r_gpu - r_ora))) <= 1e-3        # px; the long tracks' residuals included
+
+
+def test_ba_long_tracks_first_iteration_is_exact(sk, oracle):
+    """One LM iteration with a tight PCG (eta 1e-8): gradient, Jacobi scaling, Schur set-up, implicit product and
+    back-substitution of the long tracks all enter the step, and the step is unique, so parameters must agree to 1e-5."""
+    d = synth.make_bal(**LONG_TRACK_CASE)
+    kw = dict(max_num_iterations=1, eta=1e-8, max_linear_solver_iterations=2000)
+    p, so = oracle_ba(oracle, d, _abi.ITERATIVE_SCHUR, _abi.SCHUR_JACOBI, **kw)
+    bal, s = gpu_ba(sk, d, _abi.ITERATIVE_SCHUR, _abi.SCHUR_JACOBI, **kw)
+    assert len(s.iterations) == len(so.iterations) == 2
+    assert np.isclose(s.iterations[1].cost, so.iterations[1].cost, rtol=1e-9)
+    assert np.isclose(s.iterations[1].trust_region_radius, so.iterations[1].trust_region_radius, rtol=1e-6)
+    assert rel_param_diff(bal.parameters.toArray(), p.params) <= PARAM_RTOL
+
+
+def test_ba_long_tracks_dense_schur_matches_oracle_fixture(sk):
+    """DENSE_SCHUR on long tracks against the oracle's committed output (tests/golden/make_oracle_long_tracks.py; the
+    oracle's dense reduced solve needs minutes of CPU at 270 cameras, so it is not re-run here)."""
+    g = load("oracle_long_tracks_dense_schur.json")
+    case = dict(g["case"]); case["long_tracks"] = tuple(case["long_tracks"])
+    d = synth.make_bal(**case)
+    assert float(np.sum(d.parameters) + np.sum(d.observations)) == g["input_checksum"]      # same synthetic input
+    bal, s = gpu_ba(sk, d, _abi.DENSE_SCHUR)
+    assert s.termination_type == g["termination_type"] and len(s.iterations) == len(g["iterations"])
+    assert (s.num_successful_steps, s.num_unsuccessful_steps) == (g["num_successful_steps"], g["num_unsuccessful_steps"])
+    for a, b in zip(s.iterations, g["iterations"]):
+        assert (a.iteration, int(a.step_is_valid), int(a.step_is_successful)) == (b["iteration"], b["step_is_valid"], b["step_is_successful"])
+        assert np.isclose(a.cost, b["cost"], rtol=1e-6) and np.isclose(a.trust_region_radius, b["trust_region_radius"], rtol=1e-4)
+    assert abs(s.final_cost - g["final_cost"]) <= COST_RTOL * abs(g["final_cost"])
+    assert rel_param_diff(bal.parameters.toArray(), np.array(g["params"])) <= PARAM_RTOL
 
 
 def residuals_at(oracle, d, params):

@@ -110,7 +110,8 @@ def p(a):
 class Layout:
     FIELDS = {"perm": np.int32, "obs_cam": np.int32, "obs_pt": np.int32, "pt_ptr": np.int32, "tile_obs": np.int32, "tile_pt": np.int32,
               "tile_seg": np.int32, "obs_slot": np.uint16, "obs_ptl": np.uint16, "seg_perm": np.uint16, "seg_ptr": np.int32,
-              "seg_cam": np.int32, "cam_seg_ptr": np.int32, "cam_seg": np.int32, "cam_offset": np.int64, "pt_offset": np.int64, "obs": np.float64}
+              "seg_cam": np.int32, "cam_seg_ptr": np.int32, "cam_seg": np.int32, "cam_offset": np.int64, "pt_offset": np.int64, "obs": np.float64,
+              "tile_np": np.int32, "tile_chunk": np.int32, "gp_tile_begin": np.int32, "gp_tile_count": np.int32, "gp_point": np.int32}
 
     def __init__(self, L, cam_off, pt_off, obs, rank=0, world=1):
         cam_off = np.ascontiguousarray(cam_off, dtype=np.int64); pt_off = np.ascontiguousarray(pt_off, dtype=np.int64)
@@ -123,10 +124,15 @@ class Layout:
         dims = np.zeros(8, dtype=np.int32)
         L.hc_layout_dims(C.c_void_p(h), p(dims))
         self.n_obs, self.n_pts, self.n_cams, self.n_tiles, self.n_segs, self.max_seg_tile, self.max_pt_tile, self.sorted = dims.tolist()
+        L.hc_layout_n_giant.argtypes = [C.c_void_p]
+        self.n_giant = L.hc_layout_n_giant(C.c_void_p(h))
+        L.hc_layout_n_chunks.argtypes = [C.c_void_p]
+        self.n_chunks = L.hc_layout_n_chunks(C.c_void_p(h))
         size = {"perm": self.n_obs, "obs_cam": self.n_obs, "obs_pt": self.n_obs, "pt_ptr": self.n_pts + 1, "tile_obs": self.n_tiles + 1,
                 "tile_pt": self.n_tiles + 1, "tile_seg": self.n_tiles + 1, "obs_slot": self.n_obs, "obs_ptl": self.n_obs, "seg_perm": self.n_obs,
                 "seg_ptr": self.n_segs + 1, "seg_cam": self.n_segs, "cam_seg_ptr": self.n_cams + 1, "cam_seg": self.n_segs,
-                "cam_offset": self.n_cams, "pt_offset": self.n_pts, "obs": 2 * self.n_obs}
+                "cam_offset": self.n_cams, "pt_offset": self.n_pts, "obs": 2 * self.n_obs, "tile_np": self.n_tiles, "tile_chunk": self.n_tiles,
+                "gp_tile_begin": self.n_giant, "gp_tile_count": self.n_giant, "gp_point": self.n_giant}
         for name, dt in self.FIELDS.items():
             a = np.zeros(size[name], dtype=dt)
             fn = getattr(L, "hc_layout_" + name)
@@ -148,11 +154,32 @@ def check_layout(lay, cam_off, pt_off, obs, pt_range=None):
     assert np.array_equal(cam_off[lay.perm], cams[lay.obs_cam]) and np.array_equal(pt_off[lay.perm], pts[lay.obs_pt])
     assert np.array_equal(obs.reshape(-1, 2)[lay.perm].ravel(), lay.obs)
     assert np.array_equal(np.bincount(lay.obs_pt, minlength=lay.n_pts), np.diff(lay.pt_ptr))
-    # tiles: whole points, <= 256 observations, consistent point / segment ranges
+    # tiles: <= 256 observations, consistent point / segment ranges; regular tiles hold whole points, a track longer
+    # than 256 observations is a chain of consecutive chunk tiles that together cover exactly that point
     assert lay.tile_obs[0] == 0 and lay.tile_obs[-1] == lay.n_obs and lay.tile_pt[-1] == lay.n_pts and lay.tile_seg[-1] == lay.n_segs
     assert np.all(np.diff(lay.tile_obs) <= 256) and np.all(np.diff(lay.tile_obs) > 0)
-    assert np.array_equal(lay.pt_ptr[lay.tile_pt], lay.tile_obs)
-    assert lay.max_pt_tile == np.diff(lay.tile_pt).max() and lay.max_seg_tile == np.diff(lay.tile_seg).max()
+    assert lay.max_pt_tile == lay.tile_np.max() and lay.max_seg_tile == np.diff(lay.tile_seg).max()
+    track = np.diff(lay.pt_ptr)
+    assert np.array_equal(np.sort(lay.gp_point), np.nonzero(track > 256)[0]) and lay.n_giant == int((track > 256).sum())
+    covered = np.zeros(lay.n_pts, dtype=int)
+    for t in range(lay.n_tiles):
+        if lay.tile_chunk[t] >= 0:
+            assert lay.tile_np[t] == 1 and track[lay.tile_pt[t]] > 256
+            assert np.all(lay.obs_pt[lay.tile_obs[t]:lay.tile_obs[t + 1]] == lay.tile_pt[t])
+        else:
+            pts = np.arange(lay.tile_pt[t], lay.tile_pt[t] + lay.tile_np[t])
+            covered[pts] += 1
+            assert np.all(track[pts] <= 256)
+            assert lay.pt_ptr[pts[0]] == lay.tile_obs[t] and lay.pt_ptr[pts[-1] + 1] == lay.tile_obs[t + 1]      # whole points
+    for g in range(lay.n_giant):
+        p_, b_, c_ = lay.gp_point[g], lay.gp_tile_begin[g], lay.gp_tile_count[g]
+        covered[p_] += 1
+        assert c_ == -(-track[p_] // 256) and np.all(lay.tile_chunk[b_:b_ + c_] >= 0) and np.all(lay.tile_pt[b_:b_ + c_] == p_)
+        assert lay.tile_obs[b_] == lay.pt_ptr[p_] and lay.tile_obs[b_ + c_] == lay.pt_ptr[p_ + 1]                  # chunks tile the track
+        assert np.diff(lay.tile_obs[b_:b_ + c_ + 1]).max() - np.diff(lay.tile_obs[b_:b_ + c_ + 1]).min() <= 1      # balanced
+    chunk_ids = lay.tile_chunk[lay.tile_chunk >= 0]
+    assert np.array_equal(chunk_ids, np.arange(lay.n_chunks)) and lay.n_chunks == int(lay.gp_tile_count.sum())   # compact, in tile order
+    assert np.all(covered == 1)                                                                                   # every point exactly once
     for t in range(lay.n_tiles):
         ob, oe, pb, sb, se = lay.tile_obs[t], lay.tile_obs[t + 1], lay.tile_pt[t], lay.tile_seg[t], lay.tile_seg[t + 1]
         assert np.array_equal(lay.obs_ptl[ob:oe], lay.obs_pt[ob:oe] - pb)
@@ -200,9 +227,30 @@ def test_layout_rejects_bad_structure(hc):
     bad = off.copy(); bad[0, 0] += 4                                   # overlapping camera blocks
     lay = Layout(hc, bad[:, 0], bad[:, 1], d.observations)
     assert lay.status == _abi.ERR_INVALID_ARGUMENT and "overlap" in lay.error
-    n = 300                                                           # a 300-observation track exceeds the tile size
-    lay = Layout(hc, np.arange(n) * 9, np.full(n, 9 * n), np.zeros(2 * n))
-    assert lay.status == _abi.ERR_UNSUPPORTED and "tracks longer" in lay.error
+
+
+def test_long_tracks_become_chunk_tiles(hc):
+    """Tracks longer than one tile (real BAL files have them) are cut into balanced chunk tiles; everything else about
+    the layout (segments, slots, camera lists) holds for chunk tiles exactly as for regular ones."""
+    rng = np.random.default_rng(7)
+    n_cam = 700
+    lens = np.concatenate([rng.integers(2, 9, 40), [257], rng.integers(2, 9, 30), [256, 700, 513], rng.integers(2, 9, 50), [300]])
+    cam, pt = [], []
+    for j, k in enumerate(lens):
+        cam.extend(sorted(rng.choice(n_cam, size=k, replace=False))); pt.extend([j] * k)
+    cam_off = np.array(cam, dtype=np.int64) * 9; pt_off = 9 * n_cam + np.array(pt, dtype=np.int64) * 3
+    obs = rng.normal(size=2 * cam_off.size)
+    lay = Layout(hc, cam_off, pt_off, obs)
+    assert lay.status == 0 and lay.n_giant == 4                            # 256 still fits one regular tile
+    assert sorted(lay.gp_tile_count.tolist()) == [2, 2, 3, 3]             # 257 -> 2, 300 -> 2, 513 -> 3, 700 -> 3
+    check_layout(lay, cam_off, pt_off, obs)
+    for world in (2, 3):                                                  # long tracks are never split across ranks
+        total = 0
+        for r in range(world):
+            sub_ = Layout(hc, cam_off, pt_off, obs, rank=r, world=world)
+            assert sub_.status == 0
+            total += sub_.n_giant
+        assert total == 4
 
 
 def test_ragged_tracks_fill_tiles(hc):
