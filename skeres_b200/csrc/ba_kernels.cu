@@ -51,14 +51,14 @@ __device__ __forceinline__ void block_sum_all(double (&x)[N], double* red) {
   for (int n = 0; n < N; ++n) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x[n] += __shfl_down_sync(0xffffffffu, x[n], o);
-    if (l == 0) red[n * 8 + w] = x[n];
+    if (l == 0) red[n * (T / 32) + w] = x[n];
   }
   __syncthreads();
 #pragma unroll
   for (int n = 0; n < N; ++n) {
     double r = 0.0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) r += red[n * 8 + k];
+    for (int k = 0; k < T / 32; ++k) r += red[n * (T / 32) + k];
     x[n] = r;
   }
   __syncthreads();   // red may be rewritten by the next call
@@ -363,7 +363,7 @@ __device__ __forceinline__ void seg_reduce9_s(const Tile& q, const TileMetaSmem&
 }
 
 // Input vector: `p` itself, or (pcg != nullptr) the PCG direction z + beta p formed on the fly (p = z in iteration 1).
-__global__ void __launch_bounds__(T, 3) k_ba_matvec(BaDev L, const double2* __restrict__ J2, const double* __restrict__ p,
+__global__ void __launch_bounds__(T, 768 / T) k_ba_matvec(BaDev L, const double2* __restrict__ J2, const double* __restrict__ p,
                                                     const double* __restrict__ zdir, const PcgDev* pcg,
                                                     const double* __restrict__ einv, double* __restrict__ seg_y,
                                                     const int* guard) {
@@ -433,78 +433,117 @@ __global__ void __launch_bounds__(T, 3) k_ba_matvec(BaDev L, const double2* __re
 }
 
 // ------------------------------------------------------------------------------------------------
-// Persistent variant of k_ba_matvec: identical arithmetic and identical partial-sum layout (results are bitwise
-// equal), but each CTA walks a strided list of tiles and, while it computes tile i from registers, cp.async
-// (LDGSTS) streams the 12 Jacobian planes of tile i+1 into shared memory.  Each thread copies and later reads back
-// only its own 12 vectors, so the Jacobian needs no barrier of its own; cp.async.wait_group orders it.  With two
-// CTAs per SM this keeps ~96 KB per SM in flight all the time instead of only during a CTA's first phase.
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+// Persistent, fully prefetching variant of k_ba_matvec.  Same arithmetic in the same order (results agree with
+// k_ba_matvec up to the compiler's choice of multiply-add contraction), but each CTA walks a strided list of tiles and,
+// while it computes tile i from registers, the TMA engine streams EVERYTHING tile i+1 needs into shared memory:
+// the 12 Jacobian planes (12 bulk copies of <= 4 KB), the tile's metadata record (one bulk copy; packed per tile by
+// BaSolver::build_tile_records, layout: RecView) and the (E^T E)^-1 blocks of its points (one bulk copy).  One thread
+// issues the 14 copies; completion is tracked by mbarriers, so the copy costs no LSU issue slots -- with per-thread
+// cp.async the issue of the copies and the read-back took a third of a tile's time (profiles/r01_v5_matvec_*.md).
+// The gather of the input vector for tile i+1 is started into registers while tile i runs its segment sums.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(count));
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::
+               "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
 
-__global__ void __launch_bounds__(T, 2) k_ba_matvec_persistent(BaDev L, const double2* __restrict__ J2, const double* __restrict__ p,
-                                                               const double* __restrict__ zdir, const PcgDev* pcg,
-                                                               const double* __restrict__ einv, double* __restrict__ seg_y,
-                                                               const int* guard, int max_tiles_per_cta) {
+// Per-tile metadata record (device only; all sub-arrays 16-byte aligned, starts relative to the tile's first observation):
+//   u16 slot[T] | u16 ptl[T] | u16 sperm[T] | u16 pad[T] | i32 sptr[rec_sp] | i32 pptr[rec_pp] | i32 scam[rec_sp]
+struct RecView { const unsigned short* slot; const unsigned short* ptl; const unsigned short* sperm; const int* sptr; const int* pptr; const int* scam; };
+__device__ __forceinline__ RecView rec_view(const BaDev& L, const unsigned char* base) {
+  RecView r;
+  r.slot = reinterpret_cast<const unsigned short*>(base);
+  r.ptl = r.slot + T; r.sperm = r.ptl + T;
+  r.sptr = reinterpret_cast<const int*>(base + 8 * T);
+  r.pptr = r.sptr + L.rec_sp; r.scam = r.pptr + L.rec_pp;
+  return r;
+}
+
+__global__ void __launch_bounds__(T, 512 / T) k_ba_matvec_tma(BaDev L, const double2* __restrict__ J2, const double* __restrict__ p,
+                                                              const double* __restrict__ zdir, const PcgDev* pcg,
+                                                              const double* __restrict__ einv, double* __restrict__ seg_y,
+                                                              const int* guard) {
   if (guard != nullptr && *guard == 0) return;
-  extern __shared__ double sm[];
+  extern __shared__ __align__(128) double sm[];
   const int tid = threadIdx.x;
-  double2* Jbuf = reinterpret_cast<double2*>(sm);            // [12][T] next tile's Jacobian (16-byte aligned)
+  double2* Jbuf = reinterpret_cast<double2*>(sm);            // [12][T] next tile's Jacobian
   double* xs = sm + 2 * kJPlanes * T;                        // [max_seg][9]
-  double* v = xs + L.max_seg_tile * 9;                       // [9][VLD]
+  double* v = xs + ((L.max_seg_tile * 9 + 1) & ~1);          // [9][VLD]   (xs padded to an even count: 16-byte alignment below)
   double* w = v + 9 * VLD;                                   // [3][T]
   double* u = w + 3 * T;                                     // [3][T]
-  double* ei = u + 3 * T;                                    // [max_pt][6]
-  TileMetaSmem meta;
-  meta.sptr = reinterpret_cast<int*>(ei + L.max_pt_tile * 6);
-  meta.pptr = meta.sptr + L.max_seg_tile + 1;
-  int* hdr = meta.pptr + L.max_pt_tile + 1;                  // [max_tiles_per_cta][6] this CTA's tile headers
-  meta.sperm = reinterpret_cast<unsigned short*>(hdr + max_tiles_per_cta * 6);
+  double* eibuf = u + 3 * T + 1;                             // 2 x [max_pt][6]   (+1: 9 * VLD is odd)
+  unsigned char* recbuf = reinterpret_cast<unsigned char*>(eibuf + 2 * (size_t)L.max_pt_tile * 6);   // 2 x rec_stride bytes
+  unsigned long long* bar_full = reinterpret_cast<unsigned long long*>(recbuf + 2 * (size_t)L.rec_stride);   // [2] Jacobian + einv
+  unsigned long long* bar_rec = bar_full + 2;                                                                // [2] record
   const size_t O = (size_t)L.n_obs;
-  const int my_tiles = (L.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  for (int idx = tid; idx < my_tiles; idx += T) {
-    const int t = blockIdx.x + idx * gridDim.x;
-    const bool chunk = L.tile_np[t] < 0;       // long tracks are left to k_ba_matvec_giant: an empty work item here
-    hdr[idx * 6 + 0] = L.tile_obs[t]; hdr[idx * 6 + 1] = chunk ? 0 : L.tile_obs[t + 1] - L.tile_obs[t];
-    hdr[idx * 6 + 2] = L.tile_pt[t];  hdr[idx * 6 + 3] = chunk ? 0 : L.tile_np[t];
-    hdr[idx * 6 + 4] = L.tile_seg[t]; hdr[idx * 6 + 5] = chunk ? 0 : L.tile_seg[t + 1] - L.tile_seg[t];
+  const int my_tiles = ((int)blockIdx.x < L.n_tiles) ? (L.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  if (my_tiles == 0) return;
+  if (tid == 0) {
+    mbar_init(bar_full, 1); mbar_init(bar_full + 1, 1); mbar_init(bar_rec, 1); mbar_init(bar_rec + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
-  auto prefetch = [&](int it) {                              // this thread's 12 vectors of tile `it`
-    if (it < my_tiles && tid < hdr[it * 6 + 1]) {
-      const size_t i = (size_t)hdr[it * 6 + 0] + tid;
-#pragma unroll
-      for (int k = 0; k < kJPlanes; ++k) cp_async16(Jbuf + k * T + tid, J2 + k * O + i);
-    }
-    cp_async_commit();
+  auto header = [&](int it) {                                // chunk tiles of long tracks are empty work items here
+    Tile q = load_tile(L, blockIdx.x + it * gridDim.x);
+    if (q.chunk >= 0) { q.no = 0; q.np = 0; q.ns = 0; }
+    return q;
   };
-  prefetch(0);
+  auto issue = [&](const Tile& q, int t, int buf) {          // thread 0: everything tile t needs, into ring slot `buf`
+    mbar_expect_tx(bar_rec + buf, (unsigned)L.rec_stride);
+    bulk_g2s(recbuf + (size_t)buf * L.rec_stride, L.tile_rec + (size_t)t * L.rec_stride, (unsigned)L.rec_stride, bar_rec + buf);
+    mbar_expect_tx(bar_full + buf, (unsigned)(q.no * kJPlanes * 16 + q.np * 48));
+    if (q.no > 0) {
+#pragma unroll
+      for (int k = 0; k < kJPlanes; ++k) bulk_g2s(Jbuf + k * T, J2 + k * O + q.ob, (unsigned)q.no * 16u, bar_full + buf);
+    }
+    if (q.np > 0) bulk_g2s(eibuf + (size_t)buf * L.max_pt_tile * 6, einv + (size_t)q.pb * 6, (unsigned)q.np * 48u, bar_full + buf);
+  };
+  auto gather = [&](const RecView& R, int idx) {             // element idx of the tile's input vector [ns][9]
+    const int s = idx / 9, k = idx - s * 9;
+    const size_t e = (size_t)R.scam[s] * 9 + k;
+    return (pcg == nullptr) ? p[e] : ((pcg->iter == 1) ? zdir[e] : (zdir[e] + pcg->beta * p[e]));
+  };
+  Tile q = header(0);
+  Tile qn = q;
+  if (my_tiles > 1) qn = header(1);
+  if (tid == 0) issue(q, blockIdx.x, 0);
+  mbar_wait(bar_rec, 0);
+  double xpre = 0.0;                                         // element `tid` of the current tile's input vector
+  if (tid < q.ns * 9) xpre = gather(rec_view(L, recbuf), tid);
   for (int it = 0; it < my_tiles; ++it) {
-    Tile q;
-    q.ob = hdr[it * 6 + 0]; q.no = hdr[it * 6 + 1]; q.pb = hdr[it * 6 + 2]; q.np = hdr[it * 6 + 3]; q.sb = hdr[it * 6 + 4]; q.ns = hdr[it * 6 + 5]; q.chunk = -1;
+    const int cur = it & 1;
+    const unsigned par = (unsigned)((it >> 1) & 1);
+    Tile qnn = qn;
+    if (it + 2 < my_tiles) qnn = header(it + 2);             // plain loads, consumed in the next iteration
+    const RecView R = rec_view(L, recbuf + (size_t)cur * L.rec_stride);
+    const double* ei = eibuf + (size_t)cur * L.max_pt_tile * 6;
     const bool active = tid < q.no;
-    const int i = q.ob + tid;
+    mbar_wait(bar_full + cur, par);                          // this tile's Jacobian and (E^T E)^-1 have landed
     double2 Fv[9], Ev[3];
     int slot = 0, ptl = 0;
-    cp_async_wait_all();                                     // my own copies of this tile have landed
     if (active) {
 #pragma unroll
       for (int k = 0; k < 9; ++k) Fv[k] = Jbuf[k * T + tid];
 #pragma unroll
       for (int k = 0; k < 3; ++k) Ev[k] = Jbuf[(9 + k) * T + tid];
-      slot = L.obs_slot[i]; ptl = L.obs_ptl[i];
+      slot = R.slot[tid]; ptl = R.ptl[tid];
     }
-    stage_tile_meta(L, q, meta);
-    for (int idx = tid; idx < q.np * 6; idx += T) ei[idx] = einv[(size_t)q.pb * 6 + idx];
-    for (int idx = tid; idx < q.ns * 9; idx += T) {
-      const int s = idx / 9, k = idx - s * 9;
-      const size_t e = (size_t)L.seg_cam[q.sb + s] * 9 + k;
-      xs[idx] = (pcg == nullptr) ? p[e] : ((pcg->iter == 1) ? zdir[e] : (zdir[e] + pcg->beta * p[e]));
-    }
-    __syncthreads();
+    if (tid < q.ns * 9) xs[tid] = xpre;
+    for (int idx = tid + T; idx < q.ns * 9; idx += T) xs[idx] = gather(R, idx);   // more than 28 segments: the rest, not prefetched
+    __syncthreads();                                         // xs complete; everyone has taken its Jacobian out of Jbuf
+    if (tid == 0 && it + 1 < my_tiles) issue(qn, blockIdx.x + (it + 1) * gridDim.x, cur ^ 1);
     double t0 = 0.0, t1 = 0.0;
     if (active) {
 #pragma unroll
@@ -512,13 +551,9 @@ __global__ void __launch_bounds__(T, 2) k_ba_matvec_persistent(BaDev L, const do
 #pragma unroll
       for (int k = 0; k < 3; ++k) w[k * T + tid] = Ev[k].x * t0 + Ev[k].y * t1;
     }
-    // Every thread reads back only the 12 slots it copied itself, and phase 1 has consumed all of them (t0, t1 use
-    // every Fv, w every Ev), so those shared-memory loads have completed: the slots can be refilled now.  The next
-    // tile streams in during the remaining three phases and the staging of the next iteration.
-    prefetch(it + 1);
     __syncthreads();
     if (tid < q.np) {
-      const int b = meta.pptr[tid], e = meta.pptr[tid + 1];
+      const int b = R.pptr[tid], e = R.pptr[tid + 1];
       double a0 = 0.0, a1 = 0.0, a2 = 0.0;
       for (int j = b; j < e; ++j) { a0 += w[j]; a1 += w[T + j]; a2 += w[2 * T + j]; }
       const double* m = ei + tid * 6;
@@ -535,8 +570,25 @@ __global__ void __launch_bounds__(T, 2) k_ba_matvec_persistent(BaDev L, const do
       for (int k = 0; k < 9; ++k) v[k * VLD + tid] = Fv[k].x * s0 + Fv[k].y * s1;
     }
     __syncthreads();
-    seg_reduce9_s(q, meta, v, seg_y, 9, 0);
-    __syncthreads();                                         // v / meta / xs are rewritten by the next tile
+    if (it + 1 < my_tiles) {                                 // start the next tile's input gather behind the segment sums
+      mbar_wait(bar_rec + (cur ^ 1), (unsigned)(((it + 1) >> 1) & 1));
+      if (tid < qn.ns * 9) xpre = gather(rec_view(L, recbuf + (size_t)(cur ^ 1) * L.rec_stride), tid);
+    }
+    for (int idx = tid; idx < q.ns * 9; idx += T) {
+      const int s = idx / 9, k = idx - s * 9;
+      const int b = R.sptr[s], e = R.sptr[s + 1];
+      const double* vk = v + k * VLD;
+      double sum = 0.0;
+      int pos = b;
+      for (; pos + 4 <= e; pos += 4) {
+        const int i0 = R.sperm[pos], i1 = R.sperm[pos + 1], i2 = R.sperm[pos + 2], i3 = R.sperm[pos + 3];
+        const double x0 = vk[i0], x1 = vk[i1], x2 = vk[i2], x3 = vk[i3];
+        sum += x0; sum += x1; sum += x2; sum += x3;
+      }
+      for (; pos < e; ++pos) sum += vk[R.sperm[pos]];
+      seg_y[(size_t)(q.sb + s) * 9 + k] = sum;
+    }
+    q = qn; qn = qnn;
   }
 }
 
@@ -934,18 +986,19 @@ void launch_ba_matvec(const BaDev& L, const double2* J2, const double* p, const 
   }
   const size_t smem_tail = sizeof(double) * ((size_t)L.max_pt_tile * 6) + sizeof(int) * ((size_t)L.max_seg_tile + L.max_pt_tile + 2) +
                            sizeof(unsigned short) * T + 16;
-  const size_t smem = sizeof(double) * ((size_t)L.max_seg_tile * 9 + 9 * VLD + 6 * T) + smem_tail;       // persistent kernel layout
+  const size_t smem = sizeof(double) * ((size_t)L.max_seg_tile * 9 + 9 * VLD + 6 * T) + smem_tail;
   static const int mode = [] { const char* e = getenv("SKERES_MATVEC"); return (e && e[0] == 'p') ? 1 : 0; }();
-  if (mode == 1) {           // experimental persistent kernel (profiles/r01_v3_*): SKERES_MATVEC=persistent
+  if (mode == 1) {           // persistent TMA-prefetching kernel: SKERES_MATVEC=p...
+    SK_REQUIRE(L.tile_rec != nullptr, SK_ERR_INTERNAL, "k_ba_matvec_tma needs the per-tile metadata records");
     static int sms = 0;
     if (sms == 0) { int dev = 0; SK_CUDA(cudaGetDevice(&dev)); SK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)); }
-    const int grid = std::min(L.n_tiles, 2 * sms);
-    const int max_tiles = (L.n_tiles + grid - 1) / grid;
-    const size_t smem_p = smem + sizeof(double2) * kJPlanes * T + sizeof(int) * 6 * (size_t)max_tiles;
-    set_smem(k_ba_matvec_persistent, smem_p);
-    SK_CUDA(cudaFuncSetAttribute(k_ba_matvec_persistent, cudaFuncAttributePreferredSharedMemoryCarveout, 100));   // 2 CTAs x ~86 KB per SM
-    k_ba_matvec_persistent<<<grid, T, smem_p, s>>>(L, J2, p, zdir, pcg, einv, seg_y, guard, max_tiles);
-    check_launch("k_ba_matvec_persistent");
+    const int grid = std::min(L.n_tiles, (512 / T) * sms);
+    const size_t smem_p = sizeof(double2) * kJPlanes * T + sizeof(double) * ((size_t)((L.max_seg_tile * 9 + 1) & ~1) + 9 * VLD + 6 * T + 1 +
+                          2 * (size_t)L.max_pt_tile * 6) + 2 * (size_t)L.rec_stride + 4 * sizeof(unsigned long long);
+    set_smem(k_ba_matvec_tma, smem_p);
+    SK_CUDA(cudaFuncSetAttribute(k_ba_matvec_tma, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    k_ba_matvec_tma<<<grid, T, smem_p, s>>>(L, J2, p, zdir, pcg, einv, seg_y, guard);
+    check_launch("k_ba_matvec_tma");
     return;
   }
   // development probe: SKERES_MATVEC_PAD_KB=<n> pads the dynamic shared memory (unused) to lower the CTAs per SM

@@ -13,6 +13,8 @@ struct BaDev {
   const int* tile_obs; const int* tile_pt; const int* tile_seg; const int* pt_ptr;
   const int* tile_np;                  // [T] > 0: points of a regular tile;  < 0: chunk tile, ordinal = -tile_np - 1
   const int* gp_tile_begin; const int* gp_tile_count; const int* gp_point;   // [n_giant]
+  // per-tile metadata records for the prefetching matvec (ba_kernels.cu: RecView); nullptr when not built
+  const unsigned char* tile_rec; int rec_stride, rec_sp, rec_pp;
   const unsigned short* obs_slot; const unsigned short* obs_ptl; const unsigned short* seg_perm;
   const int* seg_ptr; const int* seg_cam; const int* cam_seg_ptr; const int* cam_seg;
   const double2* obs;   // [n_obs] observed (x, y)

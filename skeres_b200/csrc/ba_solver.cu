@@ -54,6 +54,7 @@ BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHo
   L_.obs = reinterpret_cast<const double2*>(d_obs_.p);
   L_.n_giant = H.n_giant; L_.n_chunks = H.n_chunks; L_.tile_np = d_tile_np_.p;
   L_.gp_tile_begin = d_gp_begin_.p; L_.gp_tile_count = d_gp_count_.p; L_.gp_point = d_gp_point_.p;
+  L_.tile_rec = nullptr; L_.rec_stride = L_.rec_sp = L_.rec_pp = 0;
   const int64_t nc = (int64_t)9 * H.n_cams, n = nc + (int64_t)3 * H.n_pts;
   allocate(n, nc);
   J2_.alloc((size_t)2 * kJPlanes * std::max(H.n_obs, 1)); r2_.alloc((size_t)2 * std::max(H.n_obs, 1));
@@ -67,6 +68,7 @@ BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHo
   SK_REQUIRE(cdiv(H.n_cams, 8) <= kMaxPartials, SK_ERR_UNSUPPORTED, "more than %d cameras", kMaxPartials * 256 / 9);
   const int lst = opt.linear_solver_type;
   explicit_schur_ = (lst == SK_DENSE_SCHUR || lst == SK_SPARSE_SCHUR);
+  if (!explicit_schur_) build_tile_records();
   if (!explicit_schur_) {
     SK_REQUIRE(opt.preconditioner_type == SK_SCHUR_JACOBI || opt.preconditioner_type == SK_JACOBI || opt.preconditioner_type == SK_IDENTITY,
                SK_ERR_UNSUPPORTED, "ITERATIVE_SCHUR supports the JACOBI, SCHUR_JACOBI and IDENTITY preconditioners on the device (got %d)",
@@ -81,6 +83,30 @@ BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHo
     S_.alloc((size_t)nc * nc);
     seg_M_.alloc((size_t)45 * std::max(H.n_segs, 1)); M45_.alloc((size_t)45 * H.n_cams);
   }
+}
+
+// Per-tile metadata records for k_ba_matvec_pf: everything a tile needs besides the Jacobian and (E^T E)^-1, packed so
+// that it can be streamed into shared memory with 16-byte cp.async copies (layout: RecView in ba_kernels.cu).
+void BaSolver::build_tile_records() {
+  const auto& H = H_;
+  const int T = kTileObs;
+  const int sp = (std::max(H.max_seg_tile, 1) + 1 + 3) & ~3, pp = (std::max(H.max_pt_tile, 1) + 1 + 3) & ~3;
+  const size_t stride = (size_t)8 * T + 4 * ((size_t)2 * sp + pp);
+  std::vector<unsigned char> rec((size_t)std::max(H.n_tiles, 1) * stride, 0);
+  for (int t = 0; t < H.n_tiles; ++t) {
+    unsigned char* base = rec.data() + (size_t)t * stride;
+    uint16_t* slot = reinterpret_cast<uint16_t*>(base); uint16_t* ptl = slot + T; uint16_t* sperm = ptl + T;
+    int32_t* sptr = reinterpret_cast<int32_t*>(base + 8 * T); int32_t* pptr = sptr + sp; int32_t* scam = pptr + pp;
+    const int ob = H.tile_obs[t], no = H.tile_obs[t + 1] - ob, pb = H.tile_pt[t], np = H.tile_np[t];
+    const int sb = H.tile_seg[t], ns = H.tile_seg[t + 1] - sb;
+    for (int j = 0; j < no; ++j) { slot[j] = H.obs_slot[ob + j]; ptl[j] = H.obs_ptl[ob + j]; sperm[j] = H.seg_perm[ob + j]; }
+    for (int s = 0; s <= ns; ++s) sptr[s] = H.seg_ptr[sb + s] - ob;
+    for (int s = 0; s < ns; ++s) scam[s] = H.seg_cam[sb + s];
+    if (H.tile_chunk[t] < 0) for (int q = 0; q <= np; ++q) pptr[q] = H.pt_ptr[pb + q] - ob;
+  }
+  d_tile_rec_.upload(rec, stream_);
+  SK_CUDA(cudaStreamSynchronize(stream_));
+  L_.tile_rec = d_tile_rec_.p; L_.rec_stride = (int)stride; L_.rec_sp = sp; L_.rec_pp = pp;
 }
 
 void BaSolver::load_state() {

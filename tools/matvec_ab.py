@@ -1,4 +1,4 @@
-"""Development helper: matvec kernel A/B. Run once per kernel (SKERES_MATVEC unset / =persistent); prints costs with
+"""Development helper: matvec kernel A/B. Run once per kernel (SKERES_MATVEC unset / =pf); prints costs with
 full precision (the two kernels must agree bitwise), PCG counts and the matvec time per executed launch."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -7,7 +7,7 @@ from skeres_b200 import _abi, api, synth
 d = synth.make_bal("venice-1778", seed=1)
 bal = api.BalProblem.fromArrays(d); prob = bal.buildProblem()
 o = api.Solver.Options(); o.setLinearSolverType(_abi.ITERATIVE_SCHUR); o.setPreconditionerType(_abi.SCHUR_JACOBI)
-o.setMaxNumIterations(8); o.profile_kernels = 1
+o.setMaxNumIterations(8); o.profile_kernels = 2
 solver = api.PreparedSolver(o, prob)
 x0 = api.DoubleArray.fromArray(d.parameters)
 solver.minimize()                      # warm-up
