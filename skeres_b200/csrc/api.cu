@@ -447,6 +447,8 @@ static std::unique_ptr<LmSolver> prepare_ba(const sk_solver_options& opt, sk_pro
     n += g.n;
   }
   SK_REQUIRE(n > 0, SK_ERR_INVALID_ARGUMENT, "problem has no residual blocks");
+  const bool trace = getenv("SKERES_TRACE_HOST") != nullptr;   // development: where the preprocessor's time goes
+  const double tp0 = wall();
   std::vector<int64_t> cam_off((size_t)n), pt_off((size_t)n);
   std::vector<double> obs((size_t)2 * n);
   int64_t at = 0;
@@ -457,7 +459,9 @@ static std::unique_ptr<LmSolver> prepare_ba(const sk_solver_options& opt, sk_pro
     }
   BaLayoutHost H;
   const int rank = opt.comm ? opt.comm->rank : 0, world = opt.comm ? opt.comm->world : 1;
+  const double tp1 = wall();
   build_ba_layout(n, cam_off.data(), pt_off.data(), obs.data(), rank, world, &H);
+  const double tp2 = wall();
   std::vector<int64_t> all_pt;
   int64_t total_points = H.n_pts;
   if (world > 1) {                 // computed once by the layout builder (was: a second O(n log n) sort of all observations)
@@ -467,6 +471,7 @@ static std::unique_ptr<LmSolver> prepare_ba(const sk_solver_options& opt, sk_pro
   const int64_t n_cams = H.n_cams;
   std::unique_ptr<BaSolver> solver(new BaSolver(opt, stream, std::move(H), array->d.p, array->n, loss));
   solver->fill_totals(n, n_cams + total_points, 9 * n_cams + 3 * total_points, std::move(all_pt));
+  if (trace) fprintf(stderr, "[skeres] preprocess: flatten %.3f s, layout %.3f s, device set-up %.3f s\n", tp1 - tp0, tp2 - tp1, wall() - tp2);
   return solver;
 }
 

@@ -363,10 +363,14 @@ __device__ __forceinline__ void seg_reduce9_s(const Tile& q, const TileMetaSmem&
 }
 
 // Input vector: `p` itself, or (pcg != nullptr) the PCG direction z + beta p formed on the fly (p = z in iteration 1).
+__device__ __forceinline__ void l2_prefetch(const void* gsrc, unsigned bytes) {   // TMA prefetch into L2: no registers, no smem
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+
 __global__ void __launch_bounds__(T, 768 / T) k_ba_matvec(BaDev L, const double2* __restrict__ J2, const double* __restrict__ p,
                                                     const double* __restrict__ zdir, const PcgDev* pcg,
                                                     const double* __restrict__ einv, double* __restrict__ seg_y,
-                                                    const int* guard) {
+                                                    const int* guard, int pf_dist) {
   if (guard != nullptr && *guard == 0) return;
   extern __shared__ double sm[];
   const Tile q = load_tile(L, blockIdx.x);
@@ -393,6 +397,13 @@ __global__ void __launch_bounds__(T, 768 / T) k_ba_matvec(BaDev L, const double2
 #pragma unroll
     for (int k = 0; k < 3; ++k) Ev[k] = ldcs2(J2 + (9 + k) * O + i);
     slot = L.obs_slot[i]; ptl = L.obs_ptl[i];
+  }
+  // The tile that a CTA `pf_dist` places further down the grid will stream (about one wave of resident CTAs ahead) is
+  // pulled into L2 now: 12 lanes issue one bulk prefetch each.  That CTA's loads then see L2 latency, not DRAM latency.
+  if (pf_dist > 0 && tid < kJPlanes && (int)blockIdx.x + pf_dist < L.n_tiles) {
+    const int tn = blockIdx.x + pf_dist;
+    const int obn = L.tile_obs[tn], non = L.tile_obs[tn + 1] - obn;
+    if (non > 0) l2_prefetch(J2 + tid * O + obn, (unsigned)non * 16u);
   }
   // everything the later phases need from global memory is requested now, behind the Jacobian loads
   stage_tile_meta(L, q, meta);
@@ -471,7 +482,10 @@ __device__ __forceinline__ RecView rec_view(const BaDev& L, const unsigned char*
   return r;
 }
 
-__global__ void __launch_bounds__(T, 512 / T) k_ba_matvec_tma(BaDev L, const double2* __restrict__ J2, const double* __restrict__ p,
+#ifndef SK_TMA_CTAS
+#define SK_TMA_CTAS (512 / T)
+#endif
+__global__ void __launch_bounds__(T, SK_TMA_CTAS) k_ba_matvec_tma(BaDev L, const double2* __restrict__ J2, const double* __restrict__ p,
                                                               const double* __restrict__ zdir, const PcgDev* pcg,
                                                               const double* __restrict__ einv, double* __restrict__ seg_y,
                                                               const int* guard) {
@@ -482,8 +496,9 @@ __global__ void __launch_bounds__(T, 512 / T) k_ba_matvec_tma(BaDev L, const dou
   double* xs = sm + 2 * kJPlanes * T;                        // [max_seg][9]
   double* v = xs + ((L.max_seg_tile * 9 + 1) & ~1);          // [9][VLD]   (xs padded to an even count: 16-byte alignment below)
   double* w = v + 9 * VLD;                                   // [3][T]
-  double* u = w + 3 * T;                                     // [3][T]
-  double* eibuf = u + 3 * T + 1;                             // 2 x [max_pt][6]   (+1: 9 * VLD is odd)
+  const int UP = (L.max_pt_tile + 1) & ~1;
+  double* u = w + 3 * T;                                     // [3][UP]
+  double* eibuf = u + 3 * UP + 1;                            // 2 x [max_pt][6]   (+1: 9 * VLD is odd)
   unsigned char* recbuf = reinterpret_cast<unsigned char*>(eibuf + 2 * (size_t)L.max_pt_tile * 6);   // 2 x rec_stride bytes
   unsigned long long* bar_full = reinterpret_cast<unsigned long long*>(recbuf + 2 * (size_t)L.rec_stride);   // [2] Jacobian + einv
   unsigned long long* bar_rec = bar_full + 2;                                                                // [2] record
@@ -510,10 +525,13 @@ __global__ void __launch_bounds__(T, 512 / T) k_ba_matvec_tma(BaDev L, const dou
     }
     if (q.np > 0) bulk_g2s(eibuf + (size_t)buf * L.max_pt_tile * 6, einv + (size_t)q.pb * 6, (unsigned)q.np * 48u, bar_full + buf);
   };
+  // PCG direction z + beta p formed on the fly (p = z in iteration 1); the two scalars are read once, not per tile
+  const bool dir_is_z = pcg != nullptr && pcg->iter == 1;
+  const double beta = (pcg != nullptr && !dir_is_z) ? pcg->beta : 0.0;
   auto gather = [&](const RecView& R, int idx) {             // element idx of the tile's input vector [ns][9]
     const int s = idx / 9, k = idx - s * 9;
     const size_t e = (size_t)R.scam[s] * 9 + k;
-    return (pcg == nullptr) ? p[e] : ((pcg->iter == 1) ? zdir[e] : (zdir[e] + pcg->beta * p[e]));
+    return (pcg == nullptr) ? p[e] : (dir_is_z ? zdir[e] : (zdir[e] + beta * p[e]));
   };
   Tile q = header(0);
   Tile qn = q;
@@ -558,12 +576,12 @@ __global__ void __launch_bounds__(T, 512 / T) k_ba_matvec_tma(BaDev L, const dou
       for (int j = b; j < e; ++j) { a0 += w[j]; a1 += w[T + j]; a2 += w[2 * T + j]; }
       const double* m = ei + tid * 6;
       u[tid] = m[0] * a0 + m[1] * a1 + m[2] * a2;
-      u[T + tid] = m[1] * a0 + m[3] * a1 + m[4] * a2;
-      u[2 * T + tid] = m[2] * a0 + m[4] * a1 + m[5] * a2;
+      u[UP + tid] = m[1] * a0 + m[3] * a1 + m[4] * a2;
+      u[2 * UP + tid] = m[2] * a0 + m[4] * a1 + m[5] * a2;
     }
     __syncthreads();
     if (active) {
-      const double u0 = u[ptl], u1 = u[T + ptl], u2 = u[2 * T + ptl];
+      const double u0 = u[ptl], u1 = u[UP + ptl], u2 = u[2 * UP + ptl];
       const double s0 = t0 - (Ev[0].x * u0 + Ev[1].x * u1 + Ev[2].x * u2);
       const double s1 = t1 - (Ev[0].y * u0 + Ev[1].y * u1 + Ev[2].y * u2);
 #pragma unroll
@@ -987,29 +1005,39 @@ void launch_ba_matvec(const BaDev& L, const double2* J2, const double* p, const 
   const size_t smem_tail = sizeof(double) * ((size_t)L.max_pt_tile * 6) + sizeof(int) * ((size_t)L.max_seg_tile + L.max_pt_tile + 2) +
                            sizeof(unsigned short) * T + 16;
   const size_t smem = sizeof(double) * ((size_t)L.max_seg_tile * 9 + 9 * VLD + 6 * T) + smem_tail;
-  static const int mode = [] { const char* e = getenv("SKERES_MATVEC"); return (e && e[0] == 'p') ? 1 : 0; }();
-  if (mode == 1) {           // persistent TMA-prefetching kernel: SKERES_MATVEC=p...
-    SK_REQUIRE(L.tile_rec != nullptr, SK_ERR_INTERNAL, "k_ba_matvec_tma needs the per-tile metadata records");
-    static int sms = 0;
-    if (sms == 0) { int dev = 0; SK_CUDA(cudaGetDevice(&dev)); SK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)); }
-    const int grid = std::min(L.n_tiles, (512 / T) * sms);
-    const size_t smem_p = sizeof(double2) * kJPlanes * T + sizeof(double) * ((size_t)((L.max_seg_tile * 9 + 1) & ~1) + 9 * VLD + 6 * T + 1 +
+  if (!L.matvec_classic && L.tile_rec != nullptr) {
+    // Default: persistent TMA-prefetching kernel, one wave of as many CTAs per SM as its shared memory allows.
+    const size_t smem_p = sizeof(double2) * kJPlanes * T + sizeof(double) * ((size_t)((L.max_seg_tile * 9 + 1) & ~1) + 9 * VLD + 3 * T + 3 * (size_t)((L.max_pt_tile + 1) & ~1) + 1 +
                           2 * (size_t)L.max_pt_tile * 6) + 2 * (size_t)L.rec_stride + 4 * sizeof(unsigned long long);
-    set_smem(k_ba_matvec_tma, smem_p);
-    SK_CUDA(cudaFuncSetAttribute(k_ba_matvec_tma, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    k_ba_matvec_tma<<<grid, T, smem_p, s>>>(L, J2, p, zdir, pcg, einv, seg_y, guard);
-    check_launch("k_ba_matvec_tma");
-    return;
+    static int sms = 0, smem_max = 0;
+    if (sms == 0) {
+      int dev = 0; SK_CUDA(cudaGetDevice(&dev));
+      SK_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+      SK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    if (smem_p <= (size_t)smem_max) {
+      static size_t cfg_smem = 0; static int per_sm = 0;       // function attributes / occupancy, redone when the size changes
+      if (smem_p != cfg_smem) {
+        set_smem(k_ba_matvec_tma, smem_p);
+        SK_CUDA(cudaFuncSetAttribute(k_ba_matvec_tma, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        SK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ba_matvec_tma, T, smem_p));
+        cfg_smem = smem_p;
+      }
+      if (per_sm > 0) {
+        const int grid = std::min(L.n_tiles, per_sm * sms);
+        k_ba_matvec_tma<<<grid, T, smem_p, s>>>(L, J2, p, zdir, pcg, einv, seg_y, guard);
+        check_launch("k_ba_matvec_tma");
+        return;
+      }
+    }
   }
-  // development probe: SKERES_MATVEC_PAD_KB=<n> pads the dynamic shared memory (unused) to lower the CTAs per SM
-  static const size_t pad = [] { const char* e = getenv("SKERES_MATVEC_PAD_KB"); return e ? (size_t)atoi(e) * 1024 : (size_t)0; }();
-  const size_t smem_v2 = smem + pad;
+  // Classic kernel (one CTA per tile, Jacobian straight into registers): SKERES_MATVEC=classic, or when the per-tile
+  // maxima of a problem make the prefetching kernel's shared memory exceed what one CTA may have.
+  const size_t smem_v2 = smem;
   set_smem(k_ba_matvec, smem_v2);
-  // development probe: SKERES_MATVEC_CARVEOUT=<percent> sets the shared-memory carveout hint (L1 gets the rest)
-  static const int carve = [] { const char* e = getenv("SKERES_MATVEC_CARVEOUT"); return e ? atoi(e) : -1; }();
-  if (carve >= 0) SK_CUDA(cudaFuncSetAttribute(k_ba_matvec, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-  else if (pad) SK_CUDA(cudaFuncSetAttribute(k_ba_matvec, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  k_ba_matvec<<<L.n_tiles, T, smem_v2, s>>>(L, J2, p, zdir, pcg, einv, seg_y, guard);
+  // development knob: SKERES_MATVEC_PFDIST=<tiles> L2 prefetch distance (0 = off; measured +5 %, profiles/r01_v5_*)
+  static const int pf_dist = [] { const char* e = getenv("SKERES_MATVEC_PFDIST"); return e ? atoi(e) : 0; }();
+  k_ba_matvec<<<L.n_tiles, T, smem_v2, s>>>(L, J2, p, zdir, pcg, einv, seg_y, guard, pf_dist);
   check_launch("k_ba_matvec");
 }
 

@@ -15,6 +15,7 @@ struct BaDev {
   const int* gp_tile_begin; const int* gp_tile_count; const int* gp_point;   // [n_giant]
   // per-tile metadata records for the prefetching matvec (ba_kernels.cu: RecView); nullptr when not built
   const unsigned char* tile_rec; int rec_stride, rec_sp, rec_pp;
+  int matvec_classic;                  // 1: use k_ba_matvec instead of k_ba_matvec_tma (SKERES_MATVEC=classic, read per solver)
   const unsigned short* obs_slot; const unsigned short* obs_ptl; const unsigned short* seg_perm;
   const int* seg_ptr; const int* seg_cam; const int* cam_seg_ptr; const int* cam_seg;
   const double2* obs;   // [n_obs] observed (x, y)

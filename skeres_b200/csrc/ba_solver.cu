@@ -4,6 +4,7 @@
 #include "ba_solver.cuh"
 
 #include <chrono>
+#include <cstdlib>
 
 #include "dense_kernels.cuh"
 #include "pcg_kernels.cuh"
@@ -55,6 +56,7 @@ BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHo
   L_.n_giant = H.n_giant; L_.n_chunks = H.n_chunks; L_.tile_np = d_tile_np_.p;
   L_.gp_tile_begin = d_gp_begin_.p; L_.gp_tile_count = d_gp_count_.p; L_.gp_point = d_gp_point_.p;
   L_.tile_rec = nullptr; L_.rec_stride = L_.rec_sp = L_.rec_pp = 0;
+  { const char* e = getenv("SKERES_MATVEC"); L_.matvec_classic = (e != nullptr && e[0] == 'c') ? 1 : 0; }
   const int64_t nc = (int64_t)9 * H.n_cams, n = nc + (int64_t)3 * H.n_pts;
   allocate(n, nc);
   J2_.alloc((size_t)2 * kJPlanes * std::max(H.n_obs, 1)); r2_.alloc((size_t)2 * std::max(H.n_obs, 1));
@@ -68,7 +70,11 @@ BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHo
   SK_REQUIRE(cdiv(H.n_cams, 8) <= kMaxPartials, SK_ERR_UNSUPPORTED, "more than %d cameras", kMaxPartials * 256 / 9);
   const int lst = opt.linear_solver_type;
   explicit_schur_ = (lst == SK_DENSE_SCHUR || lst == SK_SPARSE_SCHUR);
-  if (!explicit_schur_) build_tile_records();
+  if (!explicit_schur_) {
+    const auto t0 = std::chrono::steady_clock::now();
+    build_tile_records();
+    if (getenv("SKERES_TRACE_HOST")) fprintf(stderr, "[skeres] tile records: %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+  }
   if (!explicit_schur_) {
     SK_REQUIRE(opt.preconditioner_type == SK_SCHUR_JACOBI || opt.preconditioner_type == SK_JACOBI || opt.preconditioner_type == SK_IDENTITY,
                SK_ERR_UNSUPPORTED, "ITERATIVE_SCHUR supports the JACOBI, SCHUR_JACOBI and IDENTITY preconditioners on the device (got %d)",

@@ -337,6 +337,20 @@ def test_ba_long_tracks_dense_schur_matches_oracle_fixture(sk):
     assert rel_param_diff(bal.parameters.toArray(), np.array(g["params"])) <= PARAM_RTOL
 
 
+@pytest.mark.parametrize("case", [dict(shape="small", seed=2), LONG_TRACK_SMALL])
+def test_matvec_kernels_agree_bitwise(sk, monkeypatch, case):
+    """The default implicit-Schur product (persistent TMA-prefetching k_ba_matvec_tma) and the classic one-CTA-per-tile
+    kernel add in the same order: every LM row and every parameter must be identical, not merely close."""
+    d = synth.make_bal(**case)
+    runs = []
+    for mode in ("classic", "tma"):
+        monkeypatch.setenv("SKERES_MATVEC", mode)          # read when a solver is constructed
+        bal, s = gpu_ba(sk, d, _abi.ITERATIVE_SCHUR, _abi.SCHUR_JACOBI)
+        runs.append(([r.cost for r in s.iterations], [r.linear_solver_iterations for r in s.iterations], bal.parameters.toArray()))
+    assert runs[0][0] == runs[1][0] and runs[0][1] == runs[1][1]
+    assert np.array_equal(runs[0][2], runs[1][2])
+
+
 def residuals_at(oracle, d, params):
     """Reprojection residuals (gauge-invariant) at a parameter vector, evaluated by the oracle on the host."""
     p = oracle.OracleProblem(params)

@@ -123,6 +123,30 @@ __global__ void __launch_bounds__(T) k_tile_tma(const double2* __restrict__ J, s
   sink(s, out, tid);
 }
 
+
+// Latency probes (one warp): dependent chains of N operations, cycles per operation by clock64().
+__global__ void k_latency(double* out, long long* cyc, int N) {
+  __shared__ double sh[1024];
+  __shared__ unsigned short perm[1024];
+  for (int i = threadIdx.x; i < 1024; i += 32) { sh[i] = 1.0 + i * 1e-9; perm[i] = (unsigned short)((i * 37) & 1023); }
+  __syncwarp();
+  double a = out[0], b = out[1];
+  long long t0 = clock64();
+  for (int i = 0; i < N; ++i) a += b;                                   // DADD chain
+  long long t1 = clock64();
+  for (int i = 0; i < N; ++i) a = fma(a, b, b);                         // DFMA chain
+  long long t2 = clock64();
+  for (int i = 0; i < N; ++i) a += sh[(i + threadIdx.x) & 1023];        // independent LDS feeding a DADD chain (no unroll hints)
+  long long t3 = clock64();
+  for (int i = 0; i < N; ++i) a += sh[perm[(i + threadIdx.x) & 1023]];  // LDS index -> LDS value -> DADD (segment-sum pattern)
+  long long t4 = clock64();
+  float f = (float)out[2], g = (float)out[3];
+  for (int i = 0; i < N; ++i) f += g;                                   // FADD chain for comparison
+  long long t5 = clock64();
+  if (threadIdx.x == 0) { cyc[0] = t1 - t0; cyc[1] = t2 - t1; cyc[2] = t3 - t2; cyc[3] = t4 - t3; cyc[4] = t5 - t4; }
+  out[4 + threadIdx.x] = a + f;
+}
+
 template <class F>
 static double time_ms(F launch, int reps = 20) {
   cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
@@ -141,6 +165,15 @@ int main() {
   double2* J; double* out; CK(cudaMalloc(&J, n * sizeof(double2))); CK(cudaMalloc(&out, O * sizeof(double)));
   CK(cudaMemset(J, 0, n * sizeof(double2)));
   int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+  {
+    long long* cyc; CK(cudaMalloc(&cyc, 8 * sizeof(long long))); CK(cudaMemset(out, 0, 64 * sizeof(double)));
+    const int N = 4096;
+    k_latency<<<1, 32>>>(out, cyc, N); CK(cudaDeviceSynchronize());
+    long long h[5]; CK(cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost));
+    printf("latency per dependent op (cycles): DADD %.1f  DFMA %.1f  LDS+DADD %.1f  LDS->LDS->DADD %.1f  FADD %.1f\n",
+           h[0] / (double)N, h[1] / (double)N, h[2] / (double)N, h[3] / (double)N, h[4] / (double)N);
+    if (getenv("MVPROBE_LATENCY_ONLY")) return 0;
+  }
   const double gb = n * sizeof(double2) / 1e9;
   printf("bytes per pass %.3f GB, %d SMs\n", gb, sms);
   auto report = [&](const char* name, double ms) { printf("%-44s %8.4f ms  %7.1f GB/s\n", name, ms, gb / ms * 1e3); fflush(stdout); };
