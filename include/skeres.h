@@ -391,6 +391,12 @@ int sk_comm_world_size(const sk_comm* c);
 int sk_partition_points(int64_t n_points, const int64_t* point_ptr, int world_size,
                         int64_t* out_begin);
 
+/* Device memory freed by destroyed solvers / arrays is cached for the next allocation of the same size (cudaMalloc and
+ * cudaFree of GB-sized buffers cost 0.1-0.4 s per solver otherwise).  sk_release_cached_memory returns it to the driver --
+ * the counterpart of what a JVM host does with a native arena (no reference equivalent: libceres uses malloc). */
+int sk_release_cached_memory(void);
+int64_t sk_cached_memory_bytes(void);
+
 #ifdef __cplusplus
 }
 #endif

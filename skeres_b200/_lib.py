@@ -94,6 +94,8 @@ def _load():
         "sk_comm_rank": (i32, [vp]),
         "sk_comm_world_size": (i32, [vp]),
         "sk_partition_points": (i32, [i64, vp, i32, vp]),
+        "sk_release_cached_memory": (i32, []),
+        "sk_cached_memory_bytes": (i64, []),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)          # AttributeError here == the .so does not export a declared symbol

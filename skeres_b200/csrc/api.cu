@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "ba_solver.cuh"
+#include "host_parallel.h"
 #include "batch.cuh"
 #include "comm.cuh"
 #include "dense_solver.cuh"
@@ -342,19 +343,30 @@ int sk_problem_add_residual_blocks(sk_problem* p, int functor_id, int64_t n, con
   SK_REQUIRE(functor_info(functor_id, &fi), SK_ERR_UNSUPPORTED,
              "functor id %d is not a registered device functor (arbitrary JVM functors cannot run on the GPU; there is no CPU fallback)", functor_id);
   SK_REQUIRE(consts != nullptr || fi.nconsts == 0 || n == 0, SK_ERR_INVALID_ARGUMENT, "missing constants");
-  for (int64_t i = 0; i < n; ++i)
-    for (int k = 0; k < fi.nblk; ++k) {
-      const int64_t off = block_offsets[i * fi.nblk + k];
-      if (off < 0 || off + fi.sizes[k] > array->n)
-        throw Error(SK_ERR_INVALID_ARGUMENT, fmt("residual block %lld: parameter block %d at offset %lld is outside the array of %lld doubles",
-                                                 (long long)i, k, (long long)off, (long long)array->n));
-    }
+  {
+    int64_t bad = -1;                                          // lowest offending residual block, whatever the thread count
+    std::mutex mu;
+    parallel_for(n, [&](int64_t a, int64_t b) {
+      for (int64_t i = a; i < b; ++i)
+        for (int k = 0; k < fi.nblk; ++k) {
+          const int64_t off = block_offsets[i * fi.nblk + k];
+          if (off < 0 || off + fi.sizes[k] > array->n) { std::lock_guard<std::mutex> g(mu); if (bad < 0 || i < bad) bad = i; return; }
+        }
+    });
+    if (bad >= 0)
+      for (int k = 0; k < fi.nblk; ++k) {
+        const int64_t off = block_offsets[bad * fi.nblk + k];
+        if (off < 0 || off + fi.sizes[k] > array->n)
+          throw Error(SK_ERR_INVALID_ARGUMENT, fmt("residual block %lld: parameter block %d at offset %lld is outside the array of %lld doubles",
+                                                   (long long)bad, k, (long long)off, (long long)array->n));
+      }
+  }
   const LossSpec ls = loss ? loss->spec : LossSpec{SK_LOSS_TRIVIAL, 0.0};
   p->groups.emplace_back();
   ResidualGroup& g = p->groups.back();
   g.functor_id = functor_id; g.info = fi; g.loss = ls; g.n = n;
   g.arrays.assign(1, array);            // size-1 == "all blocks in this one array"
-  g.offsets.assign(block_offsets, block_offsets + n * fi.nblk);
+  g.offsets.assign(block_offsets, block_offsets + n * fi.nblk);        // the problem owns copies (the caller may reuse its arrays)
   if (fi.nconsts) g.consts.assign(consts, consts + n * fi.nconsts);
   if (first_id) *first_id = p->num_residual_blocks;
   p->num_residual_blocks += n; p->num_residuals += n * fi.nres;
@@ -449,18 +461,25 @@ static std::unique_ptr<LmSolver> prepare_ba(const sk_solver_options& opt, sk_pro
   SK_REQUIRE(n > 0, SK_ERR_INVALID_ARGUMENT, "problem has no residual blocks");
   const bool trace = getenv("SKERES_TRACE_HOST") != nullptr;   // development: where the preprocessor's time goes
   const double tp0 = wall();
-  std::vector<int64_t> cam_off((size_t)n), pt_off((size_t)n);
-  std::vector<double> obs((size_t)2 * n);
-  int64_t at = 0;
-  for (auto& g : p->groups)
-    for (int64_t i = 0; i < g.n; ++i, ++at) {
-      cam_off[at] = g.offsets[2 * i]; pt_off[at] = g.offsets[2 * i + 1];
-      obs[2 * at] = g.consts[2 * i]; obs[2 * at + 1] = g.consts[2 * i + 1];
-    }
   BaLayoutHost H;
   const int rank = opt.comm ? opt.comm->rank : 0, world = opt.comm ? opt.comm->world : 1;
-  const double tp1 = wall();
-  build_ba_layout(n, cam_off.data(), pt_off.data(), obs.data(), rank, world, &H);
+  const ResidualGroup* single = nullptr;                    // one bulk group (the usual case): read its arrays in place
+  for (auto& g : p->groups) if (g.n == n) single = &g;
+  double tp1 = tp0;
+  if (single != nullptr) {
+    build_ba_layout(n, single->offsets.data(), single->offsets.data() + 1, single->consts.data(), rank, world, &H, 2);
+  } else {
+    std::vector<int64_t> cam_off((size_t)n), pt_off((size_t)n);
+    std::vector<double> obs((size_t)2 * n);
+    int64_t at = 0;
+    for (auto& g : p->groups)
+      for (int64_t i = 0; i < g.n; ++i, ++at) {
+        cam_off[at] = g.offsets[2 * i]; pt_off[at] = g.offsets[2 * i + 1];
+        obs[2 * at] = g.consts[2 * i]; obs[2 * at + 1] = g.consts[2 * i + 1];
+      }
+    tp1 = wall();
+    build_ba_layout(n, cam_off.data(), pt_off.data(), obs.data(), rank, world, &H);
+  }
   const double tp2 = wall();
   std::vector<int64_t> all_pt;
   int64_t total_points = H.n_pts;
@@ -661,5 +680,7 @@ int sk_partition_points(int64_t n_points, const int64_t* point_ptr, int world_si
   partition_points(n_points, point_ptr, world_size, out_begin);
   SK_API_END
 }
+int sk_release_cached_memory(void) { SK_API_BEGIN DevicePool::get().release_all(); SK_API_END }
+int64_t sk_cached_memory_bytes(void) { return (int64_t)DevicePool::get().cached_bytes(); }
 
 }  // extern "C"

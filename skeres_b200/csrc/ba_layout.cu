@@ -2,30 +2,29 @@
 #include "ba_layout.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <numeric>
 #include <thread>
 
 #include "common.cuh"
+#include "host_parallel.h"
 
 namespace sk {
 
-// Static-chunk parallel loop over [0, n) on the host (results do not depend on the thread count).
-template <class F>
-static void parallel_for(int64_t n, F f) {
-  int nt = (int)std::min<int64_t>(std::max(1u, std::thread::hardware_concurrency()), 32);
-  nt = (int)std::min<int64_t>(nt, std::max<int64_t>(1, n / 64));
-  if (nt <= 1) { f(0, n); return; }
-  std::vector<std::thread> th;
-  std::exception_ptr err;
-  std::mutex mu;
-  for (int k = 0; k < nt; ++k) {
-    const int64_t a = n * k / nt, b = n * (k + 1) / nt;
-    th.emplace_back([&, a, b] { try { f(a, b); } catch (...) { std::lock_guard<std::mutex> g(mu); err = std::current_exception(); } });
+// development: SKERES_TRACE_HOST prints where the builder's time goes
+struct Lap {
+  bool on = std::getenv("SKERES_TRACE_HOST") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void operator()(const char* what) {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[skeres] layout: %-28s %.3f s\n", what, std::chrono::duration<double>(now - t).count());
+    t = now;
   }
-  for (auto& t : th) t.join();
-  if (err) std::rethrow_exception(err);
-}
+};
 
 void partition_points(int64_t n_points, const int64_t* point_ptr, int world_size, int64_t* out_begin) {
   const int64_t total = point_ptr[n_points];
@@ -43,8 +42,9 @@ void partition_points(int64_t n_points, const int64_t* point_ptr, int world_size
 }
 
 // Maps arbitrary block offsets to dense ids ordered by offset.
-static void dense_ids(int64_t n, const int64_t* off, int block_size, std::vector<int64_t>* uniq,
+static void dense_ids(int64_t n, const int64_t* off_base, int64_t stride, int block_size, std::vector<int64_t>* uniq,
                       std::vector<int32_t>* ids) {
+  struct Strided { const int64_t* p; int64_t s; int64_t operator[](int64_t i) const { return p[i * s]; } } off{off_base, stride};
   int64_t lo = off[0], hi = off[0];
   {
     std::mutex mu;
@@ -59,7 +59,8 @@ static void dense_ids(int64_t n, const int64_t* off, int block_size, std::vector
   ids->resize(n);
   if (range <= std::max<int64_t>(64 * n, 1 << 20)) {           // direct table
     std::vector<int32_t> table((size_t)range, -1);
-    for (int64_t i = 0; i < n; ++i) table[off[i] - lo] = 0;
+    // every thread stores the same value: relaxed atomic stores keep that defined
+    parallel_for(n, [&](int64_t a, int64_t b) { for (int64_t i = a; i < b; ++i) __atomic_store_n(&table[off[i] - lo], 0, __ATOMIC_RELAXED); });
     int32_t next = 0;
     int64_t last = -(int64_t)block_size;
     uniq->clear();
@@ -70,7 +71,8 @@ static void dense_ids(int64_t n, const int64_t* off, int block_size, std::vector
     }
     parallel_for(n, [&](int64_t a, int64_t b) { for (int64_t i = a; i < b; ++i) (*ids)[i] = table[off[i] - lo]; });
   } else {                                                       // sort + binary search
-    std::vector<int64_t> u(off, off + n);
+    std::vector<int64_t> u((size_t)n);
+    for (int64_t i = 0; i < n; ++i) u[i] = off[i];
     std::sort(u.begin(), u.end());
     u.erase(std::unique(u.begin(), u.end()), u.end());
     for (size_t k = 1; k < u.size(); ++k)
@@ -81,42 +83,61 @@ static void dense_ids(int64_t n, const int64_t* off, int block_size, std::vector
 }
 
 void build_ba_layout(int64_t n, const int64_t* cam_off, const int64_t* pt_off, const double* obs_xy,
-                     int rank, int world_size, BaLayoutHost* out) {
+                     int rank, int world_size, BaLayoutHost* out, int64_t offset_stride) {
   BaLayoutHost& L = *out;
   SK_REQUIRE(n > 0, SK_ERR_INVALID_ARGUMENT, "bundle adjustment problem without observations");
   SK_REQUIRE(n < (int64_t)2000000000, SK_ERR_UNSUPPORTED, "more than 2e9 observations");
   std::vector<int32_t> cam_id, pt_id;
   std::vector<int64_t> pt_offsets_all;
-  dense_ids(n, cam_off, 9, &L.cam_offset, &cam_id);
-  dense_ids(n, pt_off, 3, &pt_offsets_all, &pt_id);
+  Lap lap;
+  dense_ids(n, cam_off, offset_stride, 9, &L.cam_offset, &cam_id);
+  dense_ids(n, pt_off, offset_stride, 3, &pt_offsets_all, &pt_id);
+  lap("dense ids");
   L.n_cams = (int32_t)L.cam_offset.size();
   const int64_t n_pts_all = (int64_t)pt_offsets_all.size();
-  {  // camera and point blocks must not overlap each other
-    std::vector<std::pair<int64_t, int>> all;
-    all.reserve(L.cam_offset.size() + pt_offsets_all.size());
-    for (auto o : L.cam_offset) all.push_back({o, 9});
-    for (auto o : pt_offsets_all) all.push_back({o, 3});
-    std::sort(all.begin(), all.end());
-    for (size_t k = 1; k < all.size(); ++k)
-      SK_REQUIRE(all[k].first >= all[k - 1].first + all[k - 1].second, SK_ERR_INVALID_ARGUMENT,
-                 "camera and point parameter blocks overlap at offset %lld", (long long)all[k].first);
+  {  // camera and point blocks must not overlap each other: one merge pass over the two sorted offset lists
+    size_t ic = 0, ip = 0;
+    int64_t prev_end = INT64_MIN;
+    while (ic < L.cam_offset.size() || ip < pt_offsets_all.size()) {
+      const bool take_cam = ip >= pt_offsets_all.size() || (ic < L.cam_offset.size() && L.cam_offset[ic] <= pt_offsets_all[ip]);
+      const int64_t o = take_cam ? L.cam_offset[ic++] : pt_offsets_all[ip++];
+      SK_REQUIRE(o >= prev_end, SK_ERR_INVALID_ARGUMENT, "camera and point parameter blocks overlap at offset %lld", (long long)o);
+      prev_end = o + (take_cam ? 9 : 3);
+    }
   }
+  lap("overlap check");
   // ---- sort by (point, camera) -------------------------------------------------------------
   bool sorted = true;
-  for (int64_t i = 1; i < n && sorted; ++i)
-    sorted = (pt_id[i] > pt_id[i - 1]) || (pt_id[i] == pt_id[i - 1] && cam_id[i] >= cam_id[i - 1]);
+  {
+    std::mutex mu;
+    parallel_for(n, [&](int64_t a, int64_t b) {
+      bool ok = true;
+      for (int64_t i = std::max<int64_t>(a, 1); i < b && ok; ++i)
+        ok = (pt_id[i] > pt_id[i - 1]) || (pt_id[i] == pt_id[i - 1] && cam_id[i] >= cam_id[i - 1]);
+      if (!ok) { std::lock_guard<std::mutex> g(mu); sorted = false; }
+    });
+  }
   L.input_was_sorted = sorted;
-  std::vector<int32_t> order((size_t)n);
-  std::iota(order.begin(), order.end(), 0);
+  std::vector<int32_t> order;                                   // sorted position -> input index; empty = identity
   if (!sorted) {
+    order.resize((size_t)n);
+    std::iota(order.begin(), order.end(), 0);
     std::vector<uint64_t> key((size_t)n);
     for (int64_t i = 0; i < n; ++i) key[i] = ((uint64_t)(uint32_t)pt_id[i] << 32) | (uint32_t)cam_id[i];
     std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
   }
-  // global point CSR over the sorted list, then this rank's point range
-  std::vector<int64_t> gptr((size_t)n_pts_all + 1, 0);
-  for (int64_t i = 0; i < n; ++i) gptr[pt_id[i] + 1]++;
-  for (int64_t p = 0; p < n_pts_all; ++p) gptr[p + 1] += gptr[p];
+  auto src = [&](int64_t j) -> int64_t { return sorted ? j : (int64_t)order[j]; };
+  lap("sort / sortedness");
+  // global point CSR over the sorted list (every dense point id occurs, so the run boundaries ARE the CSR), then
+  // this rank's point range
+  std::vector<int64_t> gptr((size_t)n_pts_all + 1);
+  gptr[0] = 0; gptr[n_pts_all] = n;
+  parallel_for(n, [&](int64_t a, int64_t b) {
+    for (int64_t j = std::max<int64_t>(a, 1); j < b; ++j) {
+      const int32_t pj = pt_id[src(j)];
+      if (pj != pt_id[src(j - 1)]) gptr[pj] = j;
+    }
+  });
   std::vector<int64_t> begin((size_t)world_size + 1);
   partition_points(n_pts_all, gptr.data(), world_size, begin.data());
   const int64_t p0 = begin[rank], p1 = begin[rank + 1];
@@ -125,22 +146,43 @@ void build_ba_layout(int64_t n, const int64_t* cam_off, const int64_t* pt_off, c
   L.n_obs = (int32_t)(o1 - o0);
   L.pt_offset.assign(pt_offsets_all.begin() + p0, pt_offsets_all.begin() + p1);
   if (world_size > 1) L.all_pt_offset = pt_offsets_all;   // the caller needs them to publish the full solution
-  L.perm.resize(L.n_obs); L.obs.resize((size_t)2 * L.n_obs); L.obs_cam.resize(L.n_obs); L.obs_pt.resize(L.n_obs);
-  parallel_for(L.n_obs, [&](int64_t j0, int64_t j1) {
-    for (int64_t j = j0; j < j1; ++j) {
-      const int32_t i = order[o0 + j];
-      L.perm[j] = i;
-      L.obs[2 * j] = obs_xy[2 * (int64_t)i]; L.obs[2 * j + 1] = obs_xy[2 * (int64_t)i + 1];
-      L.obs_cam[j] = cam_id[i];
-      L.obs_pt[j] = (int32_t)(pt_id[i] - p0);
-    }
-  });
+  L.perm.resize(L.n_obs);
+  if (sorted && world_size == 1) {                        // the common case (BAL files): ids and observations are already in place
+    L.obs_cam = std::move(cam_id); L.obs_pt = std::move(pt_id);
+    L.obs.clear(); L.obs_src = obs_xy;
+    parallel_for(L.n_obs, [&](int64_t j0, int64_t j1) { for (int64_t j = j0; j < j1; ++j) L.perm[j] = (int32_t)j; });
+  } else {
+    L.obs.resize((size_t)2 * L.n_obs); L.obs_src = L.obs.data();
+    L.obs_cam.resize(L.n_obs); L.obs_pt.resize(L.n_obs);
+    parallel_for(L.n_obs, [&](int64_t j0, int64_t j1) {
+      for (int64_t j = j0; j < j1; ++j) {
+        const int64_t i = src(o0 + j);
+        L.perm[j] = (int32_t)i;
+        L.obs[2 * j] = obs_xy[2 * i]; L.obs[2 * j + 1] = obs_xy[2 * i + 1];
+        L.obs_cam[j] = cam_id[i];
+        L.obs_pt[j] = (int32_t)(pt_id[i] - p0);
+      }
+    });
+  }
+  lap("point CSR + gather");
   L.pt_ptr.resize((size_t)L.n_pts + 1);
   for (int64_t p = 0; p <= L.n_pts; ++p) L.pt_ptr[p] = (int32_t)(gptr[p0 + p] - o0);
-  for (int64_t j = 1; j < L.n_obs; ++j)
-    SK_REQUIRE(!(L.obs_pt[j] == L.obs_pt[j - 1] && L.obs_cam[j] == L.obs_cam[j - 1]), SK_ERR_UNSUPPORTED,
+  {
+    int64_t first_dup = -1;                                  // lowest index, so the message does not depend on the thread count
+    std::mutex mu;
+    parallel_for(L.n_obs, [&](int64_t a, int64_t b) {
+      for (int64_t j = std::max<int64_t>(a, 1); j < b; ++j)
+        if (L.obs_pt[j] == L.obs_pt[j - 1] && L.obs_cam[j] == L.obs_cam[j - 1]) {
+          std::lock_guard<std::mutex> g(mu);
+          if (first_dup < 0 || j < first_dup) first_dup = j;
+          break;
+        }
+    });
+    SK_REQUIRE(first_dup < 0, SK_ERR_UNSUPPORTED,
                "a camera observes the same point twice (residual blocks %d and %d): unsupported by the Schur path",
-               L.perm[j - 1], L.perm[j]);
+               L.perm[std::max<int64_t>(first_dup, 1) - 1], L.perm[std::max<int64_t>(first_dup, 0)]);
+  }
+  lap("pt_ptr + duplicate check");
   // ---- tiles: whole points, at most kTileObs observations -----------------------------------
   // tile t covers observations [tile_obs[t], tile_obs[t+1]) and points [tile_pt[t], tile_pt[t] + tile_np[t])
   L.tile_obs.clear(); L.tile_pt.clear(); L.tile_np.clear(); L.tile_chunk.clear();
@@ -173,6 +215,7 @@ void build_ba_layout(int64_t n, const int64_t* cam_off, const int64_t* pt_off, c
   L.n_tiles = (int32_t)L.tile_obs.size();
   L.tile_obs.push_back(L.n_obs); L.tile_pt.push_back(L.n_pts);
   L.n_giant = (int32_t)L.gp_point.size();
+  lap("tiles");
   // ---- tile-local camera segments (tiles are independent: built by all host threads) -------------
   SK_REQUIRE(L.n_cams < (1 << 24), SK_ERR_UNSUPPORTED, "more than 2^24 cameras");
   L.obs_slot.resize(L.n_obs); L.obs_ptl.resize(L.n_obs); L.seg_perm.resize(L.n_obs);
@@ -218,6 +261,7 @@ void build_ba_layout(int64_t n, const int64_t* cam_off, const int64_t* pt_off, c
     }
   });
   L.seg_ptr[L.n_segs] = L.n_obs;
+  lap("segments");
   // ---- camera -> segments (tile order) --------------------------------------------------------
   L.cam_seg_ptr.assign((size_t)L.n_cams + 1, 0);
   for (int32_t s = 0; s < L.n_segs; ++s) L.cam_seg_ptr[L.seg_cam[s] + 1]++;
@@ -225,6 +269,7 @@ void build_ba_layout(int64_t n, const int64_t* cam_off, const int64_t* pt_off, c
   L.cam_seg.resize(L.n_segs);
   std::vector<int32_t> fill(L.cam_seg_ptr.begin(), L.cam_seg_ptr.end() - 1);
   for (int32_t s = 0; s < L.n_segs; ++s) L.cam_seg[fill[L.seg_cam[s]]++] = s;
+  lap("camera -> segments");
 }
 
 }  // namespace sk

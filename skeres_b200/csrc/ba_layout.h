@@ -28,6 +28,8 @@ struct BaLayoutHost {
   std::vector<int64_t> all_pt_offset;  // every point of the problem, sorted (filled only when world_size > 1)
   std::vector<int32_t> perm;           // [O] sorted position -> original residual-block index
   std::vector<double> obs;             // [2*O] sorted (x, y)
+  const double* obs_src = nullptr;     // sorted (x, y): obs.data(), or -- input already sorted, one rank -- the CALLER's array
+                                       // (no copy; valid only while the caller's array lives: BaSolver uploads it at once)
   std::vector<int32_t> obs_cam;        // [O] camera id (sorted order)
   std::vector<int32_t> obs_pt;         // [O] point id (sorted order)
   std::vector<int32_t> pt_ptr;         // [P+1]
@@ -56,7 +58,9 @@ struct BaLayoutHost {
 // Throws sk::Error on unsupported structure (duplicate (camera, point) pairs, tracks longer than
 // overlapping blocks).
 void build_ba_layout(int64_t n, const int64_t* cam_off, const int64_t* pt_off, const double* obs_xy,
-                     int rank, int world_size, BaLayoutHost* out);
+                     int rank, int world_size, BaLayoutHost* out, int64_t offset_stride = 1);
+// offset_stride: cam_off[i * stride] / pt_off[i * stride] -- 2 lets the builder read a problem's interleaved
+// (camera, point) offset pairs in place.
 
 // Contiguous point ranges balanced by observation count (out_begin has world_size + 1 entries).
 void partition_points(int64_t n_points, const int64_t* point_ptr, int world_size, int64_t* out_begin);

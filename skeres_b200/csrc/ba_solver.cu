@@ -37,7 +37,7 @@ BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHo
   d_pt_ptr_.upload(H.pt_ptr, s); d_obs_slot_.upload(H.obs_slot, s); d_obs_ptl_.upload(H.obs_ptl, s);
   d_seg_perm_.upload(H.seg_perm, s); d_seg_ptr_.upload(H.seg_ptr, s); d_seg_cam_.upload(H.seg_cam, s);
   d_cam_seg_ptr_.upload(H.cam_seg_ptr, s); d_cam_seg_.upload(H.cam_seg, s);
-  d_obs_.alloc((size_t)2 * H.n_obs); d_obs_.upload(H.obs.data(), H.obs.size(), s);
+  d_obs_.alloc((size_t)2 * H.n_obs); d_obs_.upload(H.obs_src, (size_t)2 * H.n_obs, s);   // possibly the caller's own array
   // device encoding of the tile kind: > 0 points of a regular tile, < 0 chunk tile of a long track (ordinal = -v - 1)
   std::vector<int> tile_np_enc((size_t)H.n_tiles);
   for (int t = 0; t < H.n_tiles; ++t) tile_np_enc[t] = H.tile_chunk[t] >= 0 ? -(H.tile_chunk[t] + 1) : H.tile_np[t];

@@ -54,5 +54,6 @@ HC_COPY(obs_slot, obs_slot, uint16_t) HC_COPY(obs_ptl, obs_ptl, uint16_t) HC_COP
 HC_COPY(seg_ptr, seg_ptr, int32_t) HC_COPY(seg_cam, seg_cam, int32_t) HC_COPY(cam_seg_ptr, cam_seg_ptr, int32_t) HC_COPY(cam_seg, cam_seg, int32_t)
 HC_COPY(tile_np, tile_np, int32_t) HC_COPY(tile_chunk, tile_chunk, int32_t) HC_COPY(gp_tile_begin, gp_tile_begin, int32_t)
 HC_COPY(gp_tile_count, gp_tile_count, int32_t) HC_COPY(gp_point, gp_point, int32_t)
-HC_COPY(cam_offset, cam_offset, int64_t) HC_COPY(pt_offset, pt_offset, int64_t) HC_COPY(obs, obs, double)
+HC_COPY(cam_offset, cam_offset, int64_t) HC_COPY(pt_offset, pt_offset, int64_t)
+void hc_layout_obs(const HcLayout* h, double* out) { std::memcpy(out, h->L.obs_src, sizeof(double) * 2 * (size_t)h->L.n_obs); }   // caller's array still alive
 }
