@@ -512,8 +512,10 @@ class BalProblem:
 
     def blockOffsets(self):
         off = np.empty((self.numObservations, 2), dtype=np.int64)
-        off[:, 0] = self.cameraIndex.astype(np.int64) * 9
-        off[:, 1] = 9 * self.numCameras + self.pointIndex.astype(np.int64) * 3
+        # written straight into the interleaved array, in int64, without temporaries (this is on the e2e path)
+        np.multiply(self.cameraIndex, 9, out=off[:, 0], dtype=np.int64)
+        np.multiply(self.pointIndex, 3, out=off[:, 1], dtype=np.int64)
+        off[:, 1] += 9 * self.numCameras
         return off
 
     def buildProblem(self, loss=None):

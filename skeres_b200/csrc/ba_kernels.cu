@@ -465,6 +465,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
       "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(smem_u32(b)), "r"(parity) : "memory");
 }
+// One box of a 2-D tensor map (inner coordinate c0, outer c1) into shared memory, completion on an mbarrier.
+__device__ __forceinline__ void tma_box_2d(void* dst, const CUtensorMap* map, int c0, int c1, unsigned long long* b) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::
+               "r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(smem_u32(b)) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* b) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::
                "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
@@ -485,7 +490,10 @@ __device__ __forceinline__ RecView rec_view(const BaDev& L, const unsigned char*
 #ifndef SK_TMA_CTAS
 #define SK_TMA_CTAS (512 / T)
 #endif
-__global__ void __launch_bounds__(T, SK_TMA_CTAS) k_ba_matvec_tma(BaDev L, const double2* __restrict__ J2, const double* __restrict__ p,
+// TMAP: the Jacobian of a tile arrives as two [12 planes][128 observations] boxes of a 2-D tensor map over the plane-major
+// array (2 TMA instructions per tile) instead of 12 one-plane bulk copies; Jbuf is then [2][12][T/2].
+template <bool TMAP>
+__global__ void __launch_bounds__(T, SK_TMA_CTAS) k_ba_matvec_tma(const __grid_constant__ CUtensorMap tmapJ, BaDev L, const double2* __restrict__ J2, const double* __restrict__ p,
                                                               const double* __restrict__ zdir, const PcgDev* pcg,
                                                               const double* __restrict__ einv, double* __restrict__ seg_y,
                                                               const int* guard) {
@@ -518,10 +526,17 @@ __global__ void __launch_bounds__(T, SK_TMA_CTAS) k_ba_matvec_tma(BaDev L, const
   auto issue = [&](const Tile& q, int t, int buf) {          // thread 0: everything tile t needs, into ring slot `buf`
     mbar_expect_tx(bar_rec + buf, (unsigned)L.rec_stride);
     bulk_g2s(recbuf + (size_t)buf * L.rec_stride, L.tile_rec + (size_t)t * L.rec_stride, (unsigned)L.rec_stride, bar_rec + buf);
-    mbar_expect_tx(bar_full + buf, (unsigned)(q.no * kJPlanes * 16 + q.np * 48));
-    if (q.no > 0) {
+    if (TMAP) {
+      static_assert(T == 256, "the tensor-map box is 128 observations: two boxes per tile");
+      const int boxes = (q.no + T / 2 - 1) / (T / 2);          // a box past the tile's end only brings the next tile's data
+      mbar_expect_tx(bar_full + buf, (unsigned)(boxes * kJPlanes * (T / 2) * 16 + q.np * 48));
+      for (int h = 0; h < boxes; ++h) tma_box_2d(Jbuf + h * kJPlanes * (T / 2), &tmapJ, 2 * (q.ob + h * (T / 2)), 0, bar_full + buf);
+    } else {
+      mbar_expect_tx(bar_full + buf, (unsigned)(q.no * kJPlanes * 16 + q.np * 48));
+      if (q.no > 0) {
 #pragma unroll
-      for (int k = 0; k < kJPlanes; ++k) bulk_g2s(Jbuf + k * T, J2 + k * O + q.ob, (unsigned)q.no * 16u, bar_full + buf);
+        for (int k = 0; k < kJPlanes; ++k) bulk_g2s(Jbuf + k * T, J2 + k * O + q.ob, (unsigned)q.no * 16u, bar_full + buf);
+      }
     }
     if (q.np > 0) bulk_g2s(eibuf + (size_t)buf * L.max_pt_tile * 6, einv + (size_t)q.pb * 6, (unsigned)q.np * 48u, bar_full + buf);
   };
@@ -553,9 +568,9 @@ __global__ void __launch_bounds__(T, SK_TMA_CTAS) k_ba_matvec_tma(BaDev L, const
     int slot = 0, ptl = 0;
     if (active) {
 #pragma unroll
-      for (int k = 0; k < 9; ++k) Fv[k] = Jbuf[k * T + tid];
+      for (int k = 0; k < 9; ++k) Fv[k] = TMAP ? Jbuf[(tid >> 7) * kJPlanes * (T / 2) + k * (T / 2) + (tid & 127)] : Jbuf[k * T + tid];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) Ev[k] = Jbuf[(9 + k) * T + tid];
+      for (int k = 0; k < 3; ++k) Ev[k] = TMAP ? Jbuf[(tid >> 7) * kJPlanes * (T / 2) + (9 + k) * (T / 2) + (tid & 127)] : Jbuf[(9 + k) * T + tid];
       slot = R.slot[tid]; ptl = R.ptl[tid];
     }
     if (tid < q.ns * 9) xs[tid] = xpre;
@@ -994,7 +1009,7 @@ void launch_ba_precond_invert(const BaDev& L, const double* M45, const double* D
 }
 
 void launch_ba_matvec(const BaDev& L, const double2* J2, const double* p, const double* zdir, const PcgDev* pcg, const double* einv,
-                      double* seg_y, const int* guard, cudaStream_t s) {
+                      double* seg_y, const int* guard, cudaStream_t s, const CUtensorMap* tmapJ) {
   if (L.n_tiles == 0) return;
   if (L.n_giant) {             // long tracks first (any order works: the two kernels write disjoint segments)
     const size_t smem_g = sizeof(double) * ((size_t)L.max_seg_tile * 9 + 9 * VLD + 3 * 8);
@@ -1016,16 +1031,19 @@ void launch_ba_matvec(const BaDev& L, const double2* J2, const double* p, const 
       SK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     }
     if (smem_p <= (size_t)smem_max) {
-      static size_t cfg_smem = 0; static int per_sm = 0;       // function attributes / occupancy, redone when the size changes
-      if (smem_p != cfg_smem) {
-        set_smem(k_ba_matvec_tma, smem_p);
-        SK_CUDA(cudaFuncSetAttribute(k_ba_matvec_tma, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        SK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ba_matvec_tma, T, smem_p));
-        cfg_smem = smem_p;
+      static size_t cfg_smem[2] = {0, 0}; static int per_sm[2] = {0, 0};   // function attributes / occupancy, redone when the size changes
+      const int v = tmapJ != nullptr ? 1 : 0;
+      auto kernel = v ? k_ba_matvec_tma<true> : k_ba_matvec_tma<false>;
+      if (smem_p != cfg_smem[v]) {
+        set_smem(kernel, smem_p);
+        SK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        SK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[v], kernel, T, smem_p));
+        cfg_smem[v] = smem_p;
       }
-      if (per_sm > 0) {
-        const int grid = std::min(L.n_tiles, per_sm * sms);
-        k_ba_matvec_tma<<<grid, T, smem_p, s>>>(L, J2, p, zdir, pcg, einv, seg_y, guard);
+      if (per_sm[v] > 0) {
+        const int grid = std::min(L.n_tiles, per_sm[v] * sms);
+        static const CUtensorMap no_map{};
+        kernel<<<grid, T, smem_p, s>>>(v ? *tmapJ : no_map, L, J2, p, zdir, pcg, einv, seg_y, guard);
         check_launch("k_ba_matvec_tma");
         return;
       }
@@ -1039,6 +1057,29 @@ void launch_ba_matvec(const BaDev& L, const double2* J2, const double* p, const 
   static const int pf_dist = [] { const char* e = getenv("SKERES_MATVEC_PFDIST"); return e ? atoi(e) : 0; }();
   k_ba_matvec<<<L.n_tiles, T, smem_v2, s>>>(L, J2, p, zdir, pcg, einv, seg_y, guard, pf_dist);
   check_launch("k_ba_matvec");
+}
+
+// 2-D view of the plane-major Jacobian for TMA: inner dimension = the 2 * n_obs doubles of one plane, outer = 12 planes.
+// A box is [12 planes][128 observations] = 24 KB.  The encoder lives in libcuda; it is fetched through the runtime so that
+// the library keeps no link-time dependency on the driver library.
+bool make_jacobian_tensor_map(const double2* J2, int n_obs, CUtensorMap* out) {
+  if (n_obs < T / 2) return false;                              // the box would exceed the tensor
+  using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = [] {
+    void* fn = nullptr; cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &st) != cudaSuccess || st != cudaDriverEntryPointSuccess) fn = nullptr;
+    return reinterpret_cast<EncodeFn>(fn);
+  }();
+  if (encode == nullptr) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)2 * (cuuint64_t)n_obs, (cuuint64_t)kJPlanes};
+  const cuuint64_t strides[1] = {(cuuint64_t)n_obs * 16};      // bytes between planes
+  const cuuint32_t box[2] = {(cuuint32_t)T, (cuuint32_t)kJPlanes};   // 256 doubles = 128 observations
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double2*>(J2), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
 }
 
 void launch_ba_back_substitute(const BaDev& L, const double2* J2, const double2* r2, const double* z, const double* einv,

@@ -1,5 +1,7 @@
 // ba_kernels.cuh — launch wrappers of the bundle-adjustment tile kernels (ba_kernels.cu).
 #pragma once
+#include <cuda.h>   // CUtensorMap (type only; the encoder is fetched with cudaGetDriverEntryPoint, no libcuda link)
+
 #include "ba_layout.h"
 #include "common.cuh"
 #include "jet.cuh"
@@ -63,7 +65,9 @@ void launch_ba_precond_invert(const BaDev& L, const double* M45 /*[C][45]*/, con
 // Implicit Schur product partials: seg_y[S][9] of  F^T (F p - E (E^T E)^-1 E^T F p)
 struct PcgDev;
 void launch_ba_matvec(const BaDev& L, const double2* J2, const double* p, const double* zdir, const PcgDev* pcg, const double* einv,
-                      double* seg_y, const int* guard, cudaStream_t s);
+                      double* seg_y, const int* guard, cudaStream_t s, const CUtensorMap* tmapJ = nullptr);
+// tmapJ: 2-D tensor map over the stored Jacobian (make_jacobian_tensor_map), or nullptr = one bulk copy per plane.
+bool make_jacobian_tensor_map(const double2* J2, int n_obs, CUtensorMap* out);   // false when the problem is too small for the box
 
 // Back-substitution + model cost change. z = reduced solution [9C] (not negated).
 //   step[9C + 3p + k] = -y_p ; tile_mcc[t] = sum_i m_i . (r_i + m_i / 2), m = J * step

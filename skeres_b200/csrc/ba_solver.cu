@@ -73,6 +73,8 @@ BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHo
   if (!explicit_schur_) {
     const auto t0 = std::chrono::steady_clock::now();
     build_tile_records();
+    { const char* e = getenv("SKERES_MATVEC_TMAP");   // development: SKERES_MATVEC_TMAP=0 keeps one bulk copy per plane
+      if (!(e && e[0] == '0')) have_tmapJ_ = make_jacobian_tensor_map(reinterpret_cast<const double2*>(J2_.p), H_.n_obs, &tmapJ_); }
     if (getenv("SKERES_TRACE_HOST")) fprintf(stderr, "[skeres] tile records: %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
   }
   if (!explicit_schur_) {
@@ -198,7 +200,7 @@ const double* BaSolver::matvec(const double* in, bool pcg_dir, const int* guard)
   {
     KScope k(prof_, SK_KF_SCHUR_MATVEC, 1 + (L_.n_giant ? 1 : 0));
     launch_ba_matvec(L_, reinterpret_cast<const double2*>(J2_.p), in, pcg_dir ? pz_.p : nullptr, pcg_dir ? pcg_.p : nullptr, einv_.p,
-                     seg_a_.p, guard, stream_);
+                     seg_a_.p, guard, stream_, have_tmapJ_ ? &tmapJ_ : nullptr);
   }
   if (comm_ && comm_->world > 1) {
     { KScope k(prof_, SK_KF_PCG_VECTOR); launch_cam_reduce9_warp(L_, seg_a_.p, ybuf_.p, guard, stream_); }
