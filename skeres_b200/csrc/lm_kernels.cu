@@ -275,156 +275,6 @@ __global__ void k_lm_finalize(LmDev* st, sk_iteration_summary* rows, int cap, Lm
   }
 }
 
-// ---------------- PCG ------------------------------------------------------------------------------
-__device__ __forceinline__ bool zero_or_inf(double x) { return x == 0.0 || isinf(x); }
-
-__global__ void k_pcg_init(int64_t nc, const double* __restrict__ rhs, double* __restrict__ x, double* __restrict__ r,
-                           double* __restrict__ part) {
-  __shared__ double red[8];
-  double a = 0.0;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nc; i += (int64_t)gridDim.x * blockDim.x) {
-    const double b = rhs[i]; x[i] = 0.0; r[i] = b; a += b * b;     // x0 = 0  =>  r = b - S*0 = b
-  }
-  a = block_sum256(a, red);
-  if (threadIdx.x == 0) part[blockIdx.x] = a;
-}
-
-__global__ void k_pcg_start(PcgDev* st, const double* part, int nparts, const int* lin_error) {
-  __shared__ double red[8];
-  const double bb = sum_partials(part, nparts, red);
-  if (threadIdx.x != 0) return;
-  st->norm_b = sqrt(bb);
-  st->rho = 1.0; st->last_rho = 1.0; st->pq = 0.0; st->alpha = 0.0; st->beta = 0.0;
-  st->Q0 = 0.0; st->Q1 = 0.0;                       // Q0 = -x.(b + r) with x = 0
-  st->iter = 0; st->active = 1; st->termination = LIN_NO_CONVERGENCE;
-  if (*lin_error) { st->active = 0; st->termination = LIN_FAILURE; }
-  else if (st->norm_b == 0.0) { st->active = 0; st->termination = LIN_SUCCESS; }
-}
-
-__global__ void k_pcg_precond(int n_cams, const double* __restrict__ Minv, const double* __restrict__ r,
-                              double* __restrict__ z, double* __restrict__ part, const PcgDev* st) {
-  if (st->active == 0) return;
-  __shared__ double red[8];
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  double a = 0.0;
-  if (idx < n_cams * 9) {
-    const int c = idx / 9, i = idx - c * 9;
-    double zi;
-    if (Minv != nullptr) {
-      const double* m = Minv + (size_t)c * 81 + i * 9;
-      const double* rc = r + (size_t)c * 9;
-      zi = 0.0;
-#pragma unroll
-      for (int j = 0; j < 9; ++j) zi += m[j] * rc[j];
-    } else zi = r[idx];
-    z[idx] = zi;
-    a = r[idx] * zi;
-  }
-  a = block_sum256(a, red);
-  if (threadIdx.x == 0) part[blockIdx.x] = a;
-}
-
-__global__ void k_pcg_beta(PcgDev* st, const double* part, int nparts) {
-  if (st->active == 0) return;
-  __shared__ double red[8];
-  const double rho = sum_partials(part, nparts, red);
-  if (threadIdx.x != 0) return;
-  st->iter += 1;
-  st->last_rho = st->rho;
-  st->rho = rho;
-  if (zero_or_inf(rho) || !(rho == rho)) { st->active = 0; st->termination = LIN_FAILURE; return; }
-  if (st->iter > 1) {
-    st->beta = rho / st->last_rho;
-    if (zero_or_inf(st->beta)) { st->active = 0; st->termination = LIN_FAILURE; return; }
-  }
-}
-
-__global__ void k_pcg_p(int64_t nc, const double* __restrict__ z, double* __restrict__ p, const PcgDev* st) {
-  if (st->active == 0) return;
-  const bool first = st->iter == 1;
-  const double beta = st->beta;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nc; i += (int64_t)gridDim.x * blockDim.x)
-    p[i] = first ? z[i] : (z[i] + beta * p[i]);
-}
-
-__global__ void k_pcg_q(int64_t nc, const double* __restrict__ y, const double* __restrict__ D, const double* __restrict__ p,
-                        double* __restrict__ q, double* __restrict__ part, const PcgDev* st) {
-  if (st->active == 0) return;
-  __shared__ double red[8];
-  double a = 0.0;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nc; i += (int64_t)gridDim.x * blockDim.x) {
-    const double d = D[i], pi = p[i];
-    const double qi = (d * d) * pi + y[i];           // y5 = D^2 x ; y = y5 + F'y1   (A.6)
-    q[i] = qi; a += pi * qi;
-  }
-  a = block_sum256(a, red);
-  if (threadIdx.x == 0) part[blockIdx.x] = a;
-}
-
-__global__ void k_pcg_alpha(PcgDev* st, const double* part, int nparts) {
-  if (st->active == 0) return;
-  __shared__ double red[8];
-  const double pq = sum_partials(part, nparts, red);
-  if (threadIdx.x != 0) return;
-  st->pq = pq;
-  if (!(pq > 0.0) || isinf(pq)) { st->active = 0; st->termination = LIN_NO_CONVERGENCE; return; }   // indefinite
-  st->alpha = st->rho / pq;
-  if (isinf(st->alpha)) { st->active = 0; st->termination = LIN_FAILURE; return; }
-}
-
-__global__ void k_pcg_x(int64_t nc, double* __restrict__ x, const double* __restrict__ p, double* __restrict__ r,
-                        const double* __restrict__ q, const double* __restrict__ b, int recompute, double* __restrict__ part,
-                        const PcgDev* st) {
-  if (st->active == 0) return;
-  __shared__ double red[8];
-  const double alpha = st->alpha;
-  double a = 0.0;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nc; i += (int64_t)gridDim.x * blockDim.x) {
-    const double xi = x[i] + alpha * p[i];
-    x[i] = xi;
-    if (!recompute) {
-      const double ri = r[i] - alpha * q[i];
-      r[i] = ri;
-      a += xi * (b[i] + ri);
-    }
-  }
-  if (!recompute) {
-    a = block_sum256(a, red);
-    if (threadIdx.x == 0) part[blockIdx.x] = a;
-  }
-}
-
-__global__ void k_pcg_resid(int64_t nc, const double* __restrict__ y, const double* __restrict__ D, const double* __restrict__ x,
-                            const double* __restrict__ b, double* __restrict__ r, double* __restrict__ part, const PcgDev* st) {
-  if (st->active == 0) return;
-  __shared__ double red[8];
-  double a = 0.0;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nc; i += (int64_t)gridDim.x * blockDim.x) {
-    const double d = D[i], xi = x[i];
-    const double ri = b[i] - ((d * d) * xi + y[i]);
-    r[i] = ri;
-    a += xi * (b[i] + ri);
-  }
-  a = block_sum256(a, red);
-  if (threadIdx.x == 0) part[blockIdx.x] = a;
-}
-
-__global__ void k_pcg_zeta(PcgDev* st, const double* part, int nparts, PcgParams prm) {
-  if (st->active == 0) return;
-  __shared__ double red[8];
-  const double xbr = sum_partials(part, nparts, red);
-  if (threadIdx.x != 0) return;
-  const double Q1 = -1.0 * xbr;                      // Q = x'Ax - 2 b'x = -x.(b + r)
-  st->Q1 = Q1;
-  const double zeta = st->iter * (Q1 - st->Q0) / Q1;
-  if (zeta < prm.q_tolerance && st->iter >= prm.min_iterations) { st->active = 0; st->termination = LIN_SUCCESS; return; }
-  st->Q0 = Q1;
-  // residual-based termination is disabled by the LM strategy (r_tolerance = -1)
-  if (st->iter >= prm.max_iterations) { st->active = 0; st->termination = LIN_NO_CONVERGENCE; }
-}
-
-__global__ void k_pcg_finish(const PcgDev* pcg, LmDev* lm) { lm->lin_iterations = pcg->iter; lm->lin_termination = pcg->termination; }
-
 }  // namespace
 
 int vec_blocks(int64_t n) { return (int)std::min<int64_t>((n + VT - 1) / VT, 1184); }
@@ -462,29 +312,5 @@ void launch_lm_decide_a(LmDev* st, const PcgDev* pcg, const double* sbuf, LmPara
 void launch_lm_decide_b(LmDev* st, const double* sbuf, LmParams prm, cudaStream_t s) { k_lm_decide_b<<<1, 1, 0, s>>>(st, sbuf, prm); check_launch("k_lm_decide_b"); }
 void launch_lm_post_accept(LmDev* st, const double* sbuf, LmParams prm, cudaStream_t s) { k_lm_post_accept<<<1, 1, 0, s>>>(st, sbuf, prm); check_launch("k_lm_post_accept"); }
 void launch_lm_finalize(LmDev* st, sk_iteration_summary* rows, int cap, LmParams prm, cudaStream_t s) { k_lm_finalize<<<1, 1, 0, s>>>(st, rows, cap, prm); check_launch("k_lm_finalize"); }
-
-void launch_pcg_init(int64_t nc, const double* rhs, double* x, double* r, double* part, cudaStream_t s) {
-  k_pcg_init<<<vec_blocks(nc), VT, 0, s>>>(nc, rhs, x, r, part); check_launch("k_pcg_init");
-}
-void launch_pcg_start(PcgDev* st, const double* part, int nparts, const int* lin_error, cudaStream_t s) {
-  k_pcg_start<<<1, VT, 0, s>>>(st, part, nparts, lin_error); check_launch("k_pcg_start");
-}
-void launch_pcg_precond(int n_cams, const double* Minv, const double* r, double* z, double* part, const PcgDev* st, cudaStream_t s) {
-  k_pcg_precond<<<cdiv((int64_t)n_cams * 9, VT), VT, 0, s>>>(n_cams, Minv, r, z, part, st); check_launch("k_pcg_precond");
-}
-void launch_pcg_beta(PcgDev* st, const double* part, int nparts, cudaStream_t s) { k_pcg_beta<<<1, VT, 0, s>>>(st, part, nparts); check_launch("k_pcg_beta"); }
-void launch_pcg_p(int64_t nc, const double* z, double* p, const PcgDev* st, cudaStream_t s) { k_pcg_p<<<vec_blocks(nc), VT, 0, s>>>(nc, z, p, st); check_launch("k_pcg_p"); }
-void launch_pcg_q(int64_t nc, const double* y, const double* D, const double* p, double* q, double* part, const PcgDev* st, cudaStream_t s) {
-  k_pcg_q<<<vec_blocks(nc), VT, 0, s>>>(nc, y, D, p, q, part, st); check_launch("k_pcg_q");
-}
-void launch_pcg_alpha(PcgDev* st, const double* part, int nparts, cudaStream_t s) { k_pcg_alpha<<<1, VT, 0, s>>>(st, part, nparts); check_launch("k_pcg_alpha"); }
-void launch_pcg_x(int64_t nc, double* x, const double* p, double* r, const double* q, const double* b, int recompute, double* part, const PcgDev* st, cudaStream_t s) {
-  k_pcg_x<<<vec_blocks(nc), VT, 0, s>>>(nc, x, p, r, q, b, recompute, part, st); check_launch("k_pcg_x");
-}
-void launch_pcg_resid(int64_t nc, const double* y, const double* D, const double* x, const double* b, double* r, double* part, const PcgDev* st, cudaStream_t s) {
-  k_pcg_resid<<<vec_blocks(nc), VT, 0, s>>>(nc, y, D, x, b, r, part, st); check_launch("k_pcg_resid");
-}
-void launch_pcg_zeta(PcgDev* st, const double* part, int nparts, PcgParams prm, cudaStream_t s) { k_pcg_zeta<<<1, VT, 0, s>>>(st, part, nparts, prm); check_launch("k_pcg_zeta"); }
-void launch_pcg_finish(const PcgDev* pcg, LmDev* lm, cudaStream_t s) { k_pcg_finish<<<1, 1, 0, s>>>(pcg, lm); check_launch("k_pcg_finish"); }
 
 }  // namespace sk

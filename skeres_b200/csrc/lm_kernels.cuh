@@ -88,19 +88,6 @@ void launch_lm_decide_b(LmDev* st, const double* sbuf, LmParams prm, cudaStream_
 void launch_lm_post_accept(LmDev* st, const double* sbuf, LmParams prm, cudaStream_t s);
 void launch_lm_finalize(LmDev* st, sk_iteration_summary* rows, int rows_capacity, LmParams prm, cudaStream_t s);
 
-// ---- PCG on camera vectors (nc = 9C) ------------------------------------------------------------
-void launch_pcg_init(int64_t nc, const double* rhs, double* x, double* r, double* part, cudaStream_t s);
-void launch_pcg_start(PcgDev* st, const double* part, int nparts, const int* lin_error, cudaStream_t s);
-void launch_pcg_precond(int n_cams, const double* Minv /*[C][81] or nullptr = identity*/, const double* r, double* z, double* part, const PcgDev* st, cudaStream_t s);
-void launch_pcg_beta(PcgDev* st, const double* part, int nparts, cudaStream_t s);
-void launch_pcg_p(int64_t nc, const double* z, double* p, const PcgDev* st, cudaStream_t s);
-void launch_pcg_q(int64_t nc, const double* y, const double* D, const double* p, double* q, double* part, const PcgDev* st, cudaStream_t s);
-void launch_pcg_alpha(PcgDev* st, const double* part, int nparts, cudaStream_t s);
-// x += alpha p; when !recompute also r -= alpha q and the Q partials
-void launch_pcg_x(int64_t nc, double* x, const double* p, double* r, const double* q, const double* b, int recompute, double* part, const PcgDev* st, cudaStream_t s);
-// r = b - (y + D^2 x) and the Q partials (residual reset every residual_reset_period iterations)
-void launch_pcg_resid(int64_t nc, const double* y, const double* D, const double* x, const double* b, double* r, double* part, const PcgDev* st, cudaStream_t s);
-void launch_pcg_zeta(PcgDev* st, const double* part, int nparts, PcgParams prm, cudaStream_t s);
-void launch_pcg_finish(const PcgDev* pcg, LmDev* lm, cudaStream_t s);
+// The PCG kernels on camera vectors live in pcg_kernels.cu (fused: four launches per iteration).
 
 }  // namespace sk
