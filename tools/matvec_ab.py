@@ -7,7 +7,7 @@ from skeres_b200 import _abi, api, synth
 d = synth.make_bal("venice-1778", seed=1)
 bal = api.BalProblem.fromArrays(d); prob = bal.buildProblem()
 o = api.Solver.Options(); o.setLinearSolverType(_abi.ITERATIVE_SCHUR); o.setPreconditionerType(_abi.SCHUR_JACOBI)
-o.setMaxNumIterations(8); o.profile_kernels = 2
+o.setMaxNumIterations(8); o.profile_kernels = int(os.environ.get("AB_PROFILE", "2"))
 solver = api.PreparedSolver(o, prob)
 x0 = api.DoubleArray.fromArray(d.parameters)
 solver.minimize()                      # warm-up
