@@ -226,7 +226,7 @@ __host__ __device__ constexpr int upper_col(int idx) {
   return k + (idx - start);
 }
 
-__global__ void __launch_bounds__(T) k_ba_schur_setup(BaDev L, const double2* __restrict__ J2, const double2* __restrict__ r2,
+__global__ void __launch_bounds__(T, 2) k_ba_schur_setup(BaDev L, const double2* __restrict__ J2, const double2* __restrict__ r2,
                                                       const double* __restrict__ D, double* __restrict__ einv,
                                                       double* __restrict__ seg_rhs, double* __restrict__ seg_M,
                                                       int* error_flag, int ftf_only) {

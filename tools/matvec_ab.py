@@ -19,3 +19,4 @@ print("kernel", os.environ.get("SKERES_MATVEC", "default"))
 print("costs", " ".join(repr(r.cost) for r in s.iterations))
 print("pcg", [r.linear_solver_iterations for r in s.iterations])
 print("matvec: %.3f ms over %d executed launches = %.4f ms each ; device time %.2f ms" % (ms, n, ms / max(n, 1), 1e3 * s.minimizer_device_time_in_seconds))
+print("families", {k: (round(v[0], 2), v[1]) for k, v in kt.items() if v[1]})
