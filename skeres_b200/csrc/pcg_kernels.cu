@@ -122,36 +122,60 @@ __global__ void k_pcg_head(PcgDev* st, const double* part_rho, const double* par
   }
 }
 
-// Warp per camera: y = fixed-order sum of the camera's segment partials (or y_in when already reduced /
-// allreduced); p = z + beta p_old (iteration 1: p = z); q = y + D^2 p (stored in z, as Ceres does); p.q.
-__global__ void k_pcg_reduce(BaDev L, const double* __restrict__ seg_y, const double* __restrict__ y_in, const double* __restrict__ D,
-                             double* __restrict__ z, double* __restrict__ p, double* __restrict__ part_pq, const PcgDev* st) {
+// WPC warps per camera: y = fixed-order sum of the camera's segment partials (or y_in when already reduced / allreduced);
+// p = z + beta p_old (iteration 1: p = z); q = y + D^2 p (stored in z, as Ceres does); p.q.
+// A camera owns ~190 (tile, camera) partials on the Venice shape; with one warp (three segment lanes) the walk over them is
+// a 60-step chain of dependent L2 loads and was the longest of the small PCG kernels.  Each of the camera's WPC warps takes
+// every WPC-th group of three segments, the warp sums are added in warp order.
+constexpr int WPC = 4;
+
+__global__ void __launch_bounds__(WPB * WPC * 32) k_pcg_reduce(BaDev L, const double* __restrict__ seg_y, const double* __restrict__ y_in,
+                                                                const double* __restrict__ D, double* __restrict__ z, double* __restrict__ p,
+                                                                double* __restrict__ part_pq, const PcgDev* st) {
   if (st->active == 0) return;
-  __shared__ double red[8];
+  __shared__ double part[WPB][WPC][9];
+  __shared__ double red[WPB];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c = blockIdx.x * WPB + warp;
-  double pq = 0.0;
-  if (c < L.n_cams) {
-    const int k = lane % 9, j = lane / 9;             // 3 segment lanes x 9 components; lanes 27..31 idle
+  const int cl = warp / WPC, sub = warp % WPC;        // camera within the CTA, warp within the camera
+  const int c = blockIdx.x * WPB + cl;
+  const int k = lane % 9, j = lane / 9;               // 3 segment lanes x 9 components; lanes 27..31 idle
+  if (c < L.n_cams && y_in == nullptr) {
     double acc = 0.0;
-    if (y_in == nullptr) {
-      if (lane < 27)
-        for (int t = L.cam_seg_ptr[c] + j; t < L.cam_seg_ptr[c + 1]; t += 3) acc += seg_y[(size_t)L.cam_seg[t] * 9 + k];
-      const double a1 = __shfl_down_sync(0xffffffffu, acc, 9), a2 = __shfl_down_sync(0xffffffffu, acc, 18);
-      acc = (acc + a1) + a2;
-    } else if (lane < 9) acc = y_in[(size_t)c * 9 + lane];
-    if (lane < 9) {
-      const size_t e = (size_t)c * 9 + lane;
-      const double zk = z[e];
-      const double pk = (st->iter == 1) ? zk : (zk + st->beta * p[e]);
-      const double d = D[e];
-      const double qk = (d * d) * pk + acc;
-      p[e] = pk; z[e] = qk;
-      pq = pk * qk;
-    }
+    if (lane < 27)
+      for (int t = L.cam_seg_ptr[c] + sub * 3 + j; t < L.cam_seg_ptr[c + 1]; t += 3 * WPC) acc += seg_y[(size_t)L.cam_seg[t] * 9 + k];
+    const double a1 = __shfl_down_sync(0xffffffffu, acc, 9), a2 = __shfl_down_sync(0xffffffffu, acc, 18);
+    acc = (acc + a1) + a2;
+    if (lane < 9) part[cl][sub][lane] = acc;
   }
-  const double s = block_sum_fixed(pq, red);
-  if (threadIdx.x == 0) part_pq[blockIdx.x] = s;
+  __syncthreads();
+  double pq = 0.0;
+  if (c < L.n_cams && sub == 0 && lane < 9) {
+    double acc;
+    if (y_in == nullptr) {
+      acc = part[cl][0][lane];
+#pragma unroll
+      for (int w = 1; w < WPC; ++w) acc += part[cl][w][lane];
+    } else acc = y_in[(size_t)c * 9 + lane];
+    const size_t e = (size_t)c * 9 + lane;
+    const double zk = z[e];
+    const double pk = (st->iter == 1) ? zk : (zk + st->beta * p[e]);
+    const double d = D[e];
+    const double qk = (d * d) * pk + acc;
+    p[e] = pk; z[e] = qk;
+    pq = pk * qk;
+  }
+  if (sub == 0) {                                      // camera leaders: p.q of the camera into red[], then the CTA's 8 in order
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) pq += __shfl_down_sync(0xffffffffu, pq, o);   // lanes 0..8 hold data: 16-wide tree covers them
+    if (lane == 0) red[cl] = pq;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < WPB; ++w) s += red[w];
+    part_pq[blockIdx.x] = s;
+  }
 }
 
 // Warp per camera: x += alpha p; then either r -= alpha q (q lives in z) or, when `recompute`, nothing more
@@ -241,20 +265,31 @@ __global__ void k_pcg_resid2(BaDev L, const double* __restrict__ seg_y, const do
   if (threadIdx.x == 0) { part_Q[blockIdx.x] = s1; part_rho[blockIdx.x] = s2; }
 }
 
-// Warp per camera: y[c] = fixed-order sum of the camera's segment partials, in exactly the order k_pcg_reduce uses
-// (three interleaved segment lanes, combined (a0 + a1) + a2).  Used before the allreduce of the multi-GPU path.
-__global__ void k_cam_reduce9_warp(BaDev L, const double* __restrict__ seg_y, double* __restrict__ y, const int* guard) {
+// y[c] = fixed-order sum of the camera's segment partials, in exactly the order k_pcg_reduce uses (WPC warps per camera,
+// three interleaved segment lanes each, warp sums added in warp order).  Used before the allreduce of the multi-GPU path.
+__global__ void __launch_bounds__(WPB * WPC * 32) k_cam_reduce9_warp(BaDev L, const double* __restrict__ seg_y, double* __restrict__ y,
+                                                                      const int* guard) {
   if (guard != nullptr && *guard == 0) return;
+  __shared__ double part[WPB][WPC][9];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c = blockIdx.x * WPB + warp;
-  if (c >= L.n_cams) return;                       // warp-uniform
+  const int cl = warp / WPC, sub = warp % WPC;
+  const int c = blockIdx.x * WPB + cl;
   const int k = lane % 9, j = lane / 9;
-  double acc = 0.0;
-  if (lane < 27)
-    for (int t = L.cam_seg_ptr[c] + j; t < L.cam_seg_ptr[c + 1]; t += 3) acc += seg_y[(size_t)L.cam_seg[t] * 9 + k];
-  const double a1 = __shfl_down_sync(0xffffffffu, acc, 9), a2 = __shfl_down_sync(0xffffffffu, acc, 18);
-  acc = (acc + a1) + a2;
-  if (lane < 9) y[(size_t)c * 9 + lane] = acc;
+  if (c < L.n_cams) {
+    double acc = 0.0;
+    if (lane < 27)
+      for (int t = L.cam_seg_ptr[c] + sub * 3 + j; t < L.cam_seg_ptr[c + 1]; t += 3 * WPC) acc += seg_y[(size_t)L.cam_seg[t] * 9 + k];
+    const double a1 = __shfl_down_sync(0xffffffffu, acc, 9), a2 = __shfl_down_sync(0xffffffffu, acc, 18);
+    acc = (acc + a1) + a2;
+    if (lane < 9) part[cl][sub][lane] = acc;
+  }
+  __syncthreads();
+  if (c < L.n_cams && sub == 0 && lane < 9) {
+    double acc = part[cl][0][lane];
+#pragma unroll
+    for (int w = 1; w < WPC; ++w) acc += part[cl][w][lane];
+    y[(size_t)c * 9 + lane] = acc;
+  }
 }
 
 }  // namespace
@@ -262,7 +297,7 @@ __global__ void k_cam_reduce9_warp(BaDev L, const double* __restrict__ seg_y, do
 int pcg_blocks(int n_cams) { return cdiv(n_cams, WPB); }
 
 void launch_cam_reduce9_warp(const BaDev& L, const double* seg_y, double* y, const int* guard, cudaStream_t s) {
-  k_cam_reduce9_warp<<<pcg_blocks(L.n_cams), WPB * 32, 0, s>>>(L, seg_y, y, guard);
+  k_cam_reduce9_warp<<<pcg_blocks(L.n_cams), WPB * WPC * 32, 0, s>>>(L, seg_y, y, guard);
   check_launch("k_cam_reduce9_warp");
 }
 
@@ -280,7 +315,7 @@ void launch_pcg_head(PcgDev* st, const double* part_rho, const double* part_pq, 
 }
 void launch_pcg_reduce(const BaDev& L, const double* seg_y, const double* y_in, const double* D, double* z, double* p, double* part_pq,
                        const PcgDev* st, cudaStream_t s) {
-  k_pcg_reduce<<<pcg_blocks(L.n_cams), WPB * 32, 0, s>>>(L, seg_y, y_in, D, z, p, part_pq, st);
+  k_pcg_reduce<<<pcg_blocks(L.n_cams), WPB * WPC * 32, 0, s>>>(L, seg_y, y_in, D, z, p, part_pq, st);
   check_launch("k_pcg_reduce");
 }
 void launch_pcg_update(int n_cams, const double* Minv, const double* b, double* x, const double* p, double* r, double* z,
