@@ -270,21 +270,21 @@ void BaSolver::pcg_solve(const double* Minv) {
   while (!done && it < pp.max_iterations) {
     for (int b = 0; b < kBatch && it < pp.max_iterations; ++b) {
       ++it;
-      { KScope k(prof_, SK_KF_PCG_VECTOR); launch_pcg_head(pcg_.p, part_rho, part_pq, part_Q, nb, pp, 0, stream_); }
+      // the head step of iterations 2.. runs at the tail of the previous iteration's update / resid2 kernel
+      if (it == 1) { KScope k(prof_, SK_KF_PCG_VECTOR); launch_pcg_head(pcg_.p, part_rho, part_pq, part_Q, nb, pp, 0, stream_); }
       const double* y = matvec(pp_.p, true, active);
       const int recompute = (it % kResetPeriod == 0) ? 1 : 0;
       {
         KScope k(prof_, SK_KF_PCG_VECTOR, 2);
         launch_pcg_reduce(L_, seg_a_.p, y, D_.p, pz_.p, pp_.p, part_pq, pcg_.p, stream_);
-        launch_pcg_update(L_.n_cams, Minv, rhs_.p, px_.p, pp_.p, pr_.p, pz_.p, part_pq, recompute, part_Q, part_rho, pcg_.p, stream_);
+        launch_pcg_update(L_.n_cams, Minv, rhs_.p, px_.p, pp_.p, pr_.p, pz_.p, part_pq, recompute, part_Q, part_rho, pcg_.p, pp, stream_);
       }
       if (recompute) {
         const double* yx = matvec(px_.p, false, active);
         KScope k(prof_, SK_KF_PCG_VECTOR);
-        launch_pcg_resid2(L_, seg_a_.p, yx, D_.p, Minv, rhs_.p, px_.p, pr_.p, pz_.p, part_Q, part_rho, pcg_.p, stream_);
+        launch_pcg_resid2(L_, seg_a_.p, yx, D_.p, Minv, rhs_.p, px_.p, pr_.p, pz_.p, part_Q, part_rho, pcg_.p, part_pq, pp, stream_);
       }
     }
-    { KScope k(prof_, SK_KF_PCG_VECTOR); launch_pcg_head(pcg_.p, part_rho, part_pq, part_Q, nb, pp, 1, stream_); }
     SK_CUDA(cudaMemcpyAsync(pcg_h_.p, pcg_.p, sizeof(PcgDev), cudaMemcpyDeviceToHost, stream_));
     SK_CUDA(cudaStreamSynchronize(stream_));
     prof_.collect();

@@ -59,7 +59,9 @@ struct PcgDev {
   int iter;                   // ConjugateGradientsSolver summary.num_iterations
   int active;                 // guard: 1 while iterating
   int termination;            // LinTerm
-  int pad_;
+  int pad_;                   // last FINISHED iteration (k_pcg_head)
+  unsigned int done_count;    // CTAs of the current k_pcg_update / k_pcg_resid2 that have published their partials
+  int pad2_;
 };
 
 struct PcgParams { int min_iterations, max_iterations; double q_tolerance; };

@@ -1,9 +1,10 @@
 // pcg_kernels.cu — fused preconditioned conjugate gradients on the reduced camera system
 // (ConjugateGradientsSolver::Solve) with every scalar kept on the device.
 //
-// One PCG iteration is four launches:
-//   k_pcg_head    (1 CTA)  finishes the previous iteration (Q-based termination test, max iterations,
-//                          indefiniteness), then rho = r.z, beta, iteration counter
+// One PCG iteration is three launches (the first iteration of a solve has k_pcg_head in front):
+//   [head step]   (1 CTA)  finishes the previous iteration (Q-based termination test, max iterations,
+//                          indefiniteness), then rho = r.z, beta, iteration counter; executed at the tail of
+//                          k_pcg_update / k_pcg_resid2 by the CTA that publishes its partial sums last
 //   k_ba_matvec   (tiles)  implicit Schur product of p = z + beta p_old, formed on the fly (ba_kernels.cu)
 //   k_pcg_reduce  (warp per camera) p = z + beta p_old (stored), q = sum of the camera's segment partials
 //                          + D^2 p, and the p.q partials
@@ -37,7 +38,7 @@ __device__ __forceinline__ double block_sum_fixed(double x, double* red) {   // 
 
 __device__ double sum_fixed(const double* part, int n, double* red) {
   double a = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) a += part[i];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) a += __ldcg(part + i);   // L2: partials may come from other CTAs of this launch
   return block_sum_fixed(a, red);
 }
 
@@ -82,15 +83,17 @@ __global__ void k_pcg_start2(PcgDev* st, const double* part_bb, int nparts, cons
   st->rho = 1.0; st->last_rho = 1.0; st->pq = 0.0; st->alpha = 0.0; st->beta = 0.0;
   st->Q0 = 0.0; st->Q1 = 0.0;                                   // Q0 = -x.(b + r) with x = 0
   st->iter = 0; st->active = 1; st->termination = LIN_NO_CONVERGENCE; st->pad_ = 0;   // pad_ = last finished iteration
+  st->done_count = 0; st->pad2_ = 0;
   if (*lin_error) { st->active = 0; st->termination = LIN_FAILURE; }
   else if (st->norm_b == 0.0) { st->active = 0; st->termination = LIN_SUCCESS; }
 }
 
-// Finishes iteration st->iter (if not done yet) and, unless finish_only, opens the next one.
-__global__ void k_pcg_head(PcgDev* st, const double* part_rho, const double* part_pq, const double* part_Q, int nparts,
-                           PcgParams prm, int finish_only) {
+// Finishes iteration st->iter (if not done yet) and, unless finish_only, opens the next one.  Runs on one whole CTA of 256
+// threads: as its own kernel (first iteration of a solve) or at the tail of k_pcg_update / k_pcg_resid2, executed by the CTA
+// that publishes its partial sums last (pcg_last_block) -- same inputs, same fixed-order sums, one launch less per iteration.
+__device__ void pcg_head_step(PcgDev* st, const double* part_rho, const double* part_pq, const double* part_Q, int nparts,
+                              PcgParams prm, int finish_only, double* red) {
   if (st->active == 0) return;
-  __shared__ double red[8];
   const int it = st->iter;
   const bool need_finish = it >= 1 && st->pad_ != it;
   double pq = 0.0, xbr = 0.0;
@@ -120,6 +123,28 @@ __global__ void k_pcg_head(PcgDev* st, const double* part_rho, const double* par
     st->beta = rho / st->last_rho;
     if (zero_or_inf(st->beta)) { st->active = 0; st->termination = LIN_FAILURE; return; }
   }
+}
+
+__global__ void k_pcg_head(PcgDev* st, const double* part_rho, const double* part_pq, const double* part_Q, int nparts,
+                           PcgParams prm, int finish_only) {
+  __shared__ double red[8];
+  pcg_head_step(st, part_rho, part_pq, part_Q, nparts, prm, finish_only, red);
+}
+
+// True in every thread of exactly one CTA of the grid: the one whose thread 0 arrives last.  Callers publish their results
+// before the call; the fences make them visible to the last CTA.
+__device__ bool pcg_last_block(PcgDev* st) {
+  __shared__ int last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&st->done_count, 1u);
+    last = (t == gridDim.x - 1) ? 1 : 0;
+    if (last) st->done_count = 0;
+  }
+  __syncthreads();
+  if (last) __threadfence();
+  return last != 0;
 }
 
 // WPC warps per camera: y = fixed-order sum of the camera's segment partials (or y_in when already reduced / allreduced);
@@ -182,7 +207,8 @@ __global__ void __launch_bounds__(WPB * WPC * 32) k_pcg_reduce(BaDev L, const do
 // (r is rebuilt by k_pcg_resid after the extra matvec).  Without recompute also: Q partials, z = M^-1 r, r.z.
 __global__ void k_pcg_update(int n_cams, const double* __restrict__ Minv, const double* __restrict__ b, double* __restrict__ x,
                              const double* __restrict__ p, double* __restrict__ r, double* __restrict__ z, const double* __restrict__ part_pq,
-                             int nparts, int recompute, double* __restrict__ part_Q, double* __restrict__ part_rho, const PcgDev* st) {
+                             int nparts, int recompute, double* __restrict__ part_Q, double* __restrict__ part_rho, PcgDev* st,
+                             PcgParams prm) {
   if (st->active == 0) return;
   __shared__ double red[8];
   __shared__ double bc;
@@ -220,6 +246,8 @@ __global__ void k_pcg_update(int n_cams, const double* __restrict__ Minv, const 
   if (!recompute) {
     const double s1 = block_sum_fixed(qsum, red), s2 = block_sum_fixed(rz, red);
     if (threadIdx.x == 0) { part_Q[blockIdx.x] = s1; part_rho[blockIdx.x] = s2; }
+    // the CTA that publishes last finishes this iteration and opens the next one (what k_pcg_head would do next)
+    if (pcg_last_block(st)) pcg_head_step(st, part_rho, part_pq, part_Q, nparts, prm, 0, red);
   }
 }
 
@@ -228,7 +256,7 @@ __global__ void k_pcg_update(int n_cams, const double* __restrict__ Minv, const 
 __global__ void k_pcg_resid2(BaDev L, const double* __restrict__ seg_y, const double* __restrict__ y_in, const double* __restrict__ D,
                              const double* __restrict__ Minv, const double* __restrict__ b, const double* __restrict__ x,
                              double* __restrict__ r, double* __restrict__ z, double* __restrict__ part_Q, double* __restrict__ part_rho,
-                             const PcgDev* st) {
+                             PcgDev* st, const double* __restrict__ part_pq, PcgParams prm) {
   if (st->active == 0) return;
   __shared__ double red[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -263,6 +291,7 @@ __global__ void k_pcg_resid2(BaDev L, const double* __restrict__ seg_y, const do
   }
   const double s1 = block_sum_fixed(qsum, red), s2 = block_sum_fixed(rz, red);
   if (threadIdx.x == 0) { part_Q[blockIdx.x] = s1; part_rho[blockIdx.x] = s2; }
+  if (pcg_last_block(st)) pcg_head_step(st, part_rho, part_pq, part_Q, (int)gridDim.x, prm, 0, red);
 }
 
 // y[c] = fixed-order sum of the camera's segment partials, in exactly the order k_pcg_reduce uses (WPC warps per camera,
@@ -319,14 +348,15 @@ void launch_pcg_reduce(const BaDev& L, const double* seg_y, const double* y_in, 
   check_launch("k_pcg_reduce");
 }
 void launch_pcg_update(int n_cams, const double* Minv, const double* b, double* x, const double* p, double* r, double* z,
-                       const double* part_pq, int recompute, double* part_Q, double* part_rho, const PcgDev* st, cudaStream_t s) {
+                       const double* part_pq, int recompute, double* part_Q, double* part_rho, PcgDev* st, PcgParams prm, cudaStream_t s) {
   const int nb = pcg_blocks(n_cams);
-  k_pcg_update<<<nb, WPB * 32, 0, s>>>(n_cams, Minv, b, x, p, r, z, part_pq, nb, recompute, part_Q, part_rho, st);
+  k_pcg_update<<<nb, WPB * 32, 0, s>>>(n_cams, Minv, b, x, p, r, z, part_pq, nb, recompute, part_Q, part_rho, st, prm);
   check_launch("k_pcg_update");
 }
 void launch_pcg_resid2(const BaDev& L, const double* seg_y, const double* y_in, const double* D, const double* Minv, const double* b,
-                       const double* x, double* r, double* z, double* part_Q, double* part_rho, const PcgDev* st, cudaStream_t s) {
-  k_pcg_resid2<<<pcg_blocks(L.n_cams), WPB * 32, 0, s>>>(L, seg_y, y_in, D, Minv, b, x, r, z, part_Q, part_rho, st);
+                       const double* x, double* r, double* z, double* part_Q, double* part_rho, PcgDev* st, const double* part_pq,
+                       PcgParams prm, cudaStream_t s) {
+  k_pcg_resid2<<<pcg_blocks(L.n_cams), WPB * 32, 0, s>>>(L, seg_y, y_in, D, Minv, b, x, r, z, part_Q, part_rho, st, part_pq, prm);
   check_launch("k_pcg_resid2");
 }
 

@@ -14,8 +14,10 @@ void launch_pcg_head(PcgDev* st, const double* part_rho, const double* part_pq, 
 void launch_pcg_reduce(const BaDev& L, const double* seg_y, const double* y_in, const double* D, double* z, double* p, double* part_pq,
                        const PcgDev* st, cudaStream_t s);
 void launch_pcg_update(int n_cams, const double* Minv, const double* b, double* x, const double* p, double* r, double* z,
-                       const double* part_pq, int recompute, double* part_Q, double* part_rho, const PcgDev* st, cudaStream_t s);
+                       const double* part_pq, int recompute, double* part_Q, double* part_rho, PcgDev* st, PcgParams prm, cudaStream_t s);
+// update (without recompute) and resid2 also do what launch_pcg_head would do next: finish the iteration, open the next one.
 void launch_pcg_resid2(const BaDev& L, const double* seg_y, const double* y_in, const double* D, const double* Minv, const double* b,
-                       const double* x, double* r, double* z, double* part_Q, double* part_rho, const PcgDev* st, cudaStream_t s);
+                       const double* x, double* r, double* z, double* part_Q, double* part_rho, PcgDev* st, const double* part_pq,
+                       PcgParams prm, cudaStream_t s);
 
 }  // namespace sk
