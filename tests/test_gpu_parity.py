@@ -337,7 +337,21 @@ def test_ba_long_tracks_dense_schur_matches_oracle_fixture(sk):
     assert rel_param_diff(bal.parameters.toArray(), np.array(g["params"])) <= PARAM_RTOL
 
 
-@pytest.mark.parametrize("case", [dict(shape="small", seed=2), LONG_TRACK_SMALL])
+MEDIUM_TRACK_CASE = dict(n_cam=300, n_pt=900, n_obs=6000, seed=4, long_tracks=(33, 64, 100, 200, 256))   # up to exactly one tile
+
+
+def test_ba_medium_tracks_iterative_schur(sk, oracle):
+    """Tracks longer than one warp but within one tile (33 .. 256 observations; 256 fills a tile alone): the per-point
+    sums of the tile kernels walk them with one thread.  Rows must follow the oracle as everywhere else."""
+    d = synth.make_bal(**MEDIUM_TRACK_CASE)
+    assert np.sort(np.bincount(d.point_index))[-5:].tolist() == sorted(MEDIUM_TRACK_CASE["long_tracks"])
+    p, so = oracle_ba(oracle, d, _abi.ITERATIVE_SCHUR, _abi.JACOBI, max_num_iterations=12)
+    bal, s = gpu_ba(sk, d, _abi.ITERATIVE_SCHUR, _abi.JACOBI, max_num_iterations=12)
+    assert_same_trajectory(s, so, row_rtol=1e-9)
+    assert rel_param_diff(bal.parameters.toArray(), p.params) <= PARAM_RTOL
+
+
+@pytest.mark.parametrize("case", [dict(shape="small", seed=2), LONG_TRACK_SMALL, MEDIUM_TRACK_CASE])
 def test_matvec_kernels_agree_bitwise(sk, monkeypatch, case):
     """The default implicit-Schur product (persistent TMA-prefetching k_ba_matvec_tma) and the classic one-CTA-per-tile
     kernel add in the same order: every LM row and every parameter must be identical, not merely close."""
