@@ -188,11 +188,13 @@ def main():
     data = make_problem_data(max(world, 1), args.scale)
     bal = api.BalProblem.fromArrays(data)
     x0 = api.DoubleArray.fromArray(data.parameters)
-    problem = bal.buildProblem()
+    # N > 1: every rank ingests only the residual blocks of its own points (residual_blocks_are_local), all cameras declared
+    problem = bal.buildLocalProblem(rank, world) if world > 1 else bal.buildProblem()
     opt = api.Solver.Options()
     opt.setLinearSolverType(_abi.ITERATIVE_SCHUR)
     opt.setPreconditionerType(_abi.SCHUR_JACOBI)
     opt.setMaxNumIterations(max(K, W, 1))
+    opt.residual_blocks_are_local = 1 if world > 1 else 0
     # Events around EVERY launch cost ~10 % of the step at N = 2 (profiles/r01_multigpu_first_run.md), so the timed region
     # records them only around the dominant kernel (what the roofline needs); the full breakdown comes from a separate pass.
     opt.profile_kernels = 0 if args.no_profile else 2
@@ -275,8 +277,9 @@ def main():
             barrier()                                                 # two full passes, both reported, the faster one is `value`
             t0 = time.time()
             bal2 = api.BalProblem.fromArrays(data)                    # H2D: parameters
-            problem2 = bal2.buildProblem()                            # residual-block ingestion (host)
+            problem2 = bal2.buildLocalProblem(rank, world) if world > 1 else bal2.buildProblem()   # residual-block ingestion (host)
             opt2 = api.Solver.Options()
+            opt2.residual_blocks_are_local = 1 if world > 1 else 0
             opt2.setLinearSolverType(_abi.ITERATIVE_SCHUR)
             opt2.setPreconditionerType(_abi.SCHUR_JACOBI)
             opt2.setMaxNumIterations(K)

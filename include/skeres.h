@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SKERES_ABI_VERSION 1
+#define SKERES_ABI_VERSION 2
 
 typedef enum sk_status {
   SK_OK = 0,
@@ -174,6 +174,14 @@ int sk_problem_add_residual_blocks(sk_problem* p, int functor_id, int64_t n, con
                                    const sk_loss_function* loss, sk_double_array* array,
                                    const int64_t* block_offsets, sk_residual_block_id* first_id);
 
+/* Problem::AddParameterBlock(values, size) in bulk (ceres/problem.h; the reference exposes ceres::Problem wholesale,
+ * ceres.i:73): declares n parameter blocks of `block_size` doubles at `offsets` inside `array` without attaching a
+ * residual block.  As in Ceres, a declared block that no residual block uses does not take part in a solve -- except in
+ * the rank-local multi-GPU mode (sk_solver_options.residual_blocks_are_local), where every rank declares ALL cameras
+ * so that the replicated camera table is the same on every rank whichever observations it holds. */
+int sk_problem_add_parameter_blocks(sk_problem* p, sk_double_array* array, int64_t n,
+                                    const int64_t* offsets, int32_t block_size);
+
 int64_t sk_problem_num_residual_blocks(const sk_problem* p);
 int64_t sk_problem_num_residuals(const sk_problem* p);
 int64_t sk_problem_num_parameter_blocks(const sk_problem* p);
@@ -243,6 +251,14 @@ typedef struct sk_solver_options {
   double eta;                           /* 1e-1 */
   double max_solver_time_in_seconds;    /* 1e9 */
   sk_comm* comm;                        /* NULL = single GPU; else the point-partitioned multi-GPU path */
+  int32_t residual_blocks_are_local;    /* multi-GPU bundle adjustment only.  0 (default): every rank passes the WHOLE
+                                           problem and the solver keeps this rank's point range (sk_partition_points);
+                                           the solution of every point is published to every rank.  1: every rank passes
+                                           only the residual blocks of ITS OWN points (no point on two ranks) and declares
+                                           all cameras with sk_problem_add_parameter_blocks; ingestion then costs
+                                           O(local observations) and a rank's array receives all cameras and its own
+                                           points. */
+  int32_t reserved_;
 } sk_solver_options;
 
 /* Writes the Ceres 1.x defaults listed above. */

@@ -5,7 +5,7 @@ test-side oracle binding (`tests/oracle_lib.py`) can share them.
 """
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # sk_status
 OK, ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_UNSUPPORTED, ERR_NCCL, ERR_IO, ERR_INTERNAL = range(7)
@@ -79,6 +79,8 @@ class SolverOptions(C.Structure):
         ("eta", C.c_double),
         ("max_solver_time_in_seconds", C.c_double),
         ("comm", C.c_void_p),
+        ("residual_blocks_are_local", C.c_int32),
+        ("reserved_", C.c_int32),
     ]
 
 

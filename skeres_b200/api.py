@@ -306,6 +306,12 @@ class Problem:
                                                  array._h, _vp(off), C.byref(rid)))
         return rid.value
 
+    def addParameterBlocks(self, array, offsets, size):
+        """Problem::AddParameterBlock(values, size) in bulk: declares blocks without attaching residual blocks."""
+        off = np.ascontiguousarray(offsets, dtype=np.int64).ravel()
+        self._keep.append(array)
+        check(lib.sk_problem_add_parameter_blocks(self._h, array._h, off.size, _vp(off), int(size)))
+
     def numResidualBlocks(self):
         return lib.sk_problem_num_residual_blocks(self._h)
 
@@ -524,6 +530,31 @@ class BalProblem:
         loss = loss if loss is not None else PredefinedLossFunctions.trivialLoss()
         problem.addResidualBlocks(_abi.FUNCTOR_SNAVELY_REPROJECTION_ERROR, self.observations.reshape(-1, 2), loss,
                                   self.parameters, self.blockOffsets())
+        return problem
+
+    def localRange(self, rank, world_size):
+        """Observation range [o0, o1) of this rank's points (sk_partition_points); observations must be sorted by point."""
+        if world_size == 1:
+            return 0, self.numObservations
+        ptr = np.zeros(self.numPoints + 1, dtype=np.int64)
+        np.cumsum(np.bincount(self.pointIndex, minlength=self.numPoints), out=ptr[1:])
+        begin = partition_points(ptr, world_size)
+        return int(ptr[begin[rank]]), int(ptr[begin[rank + 1]])
+
+    def buildLocalProblem(self, rank, world_size, loss=None):
+        """Multi-GPU ingestion in O(local observations): only the residual blocks of this rank's points, every camera
+        declared (Problem::AddParameterBlock).  Solve with Options.residual_blocks_are_local = 1 and a communicator."""
+        assert np.all(np.diff(self.pointIndex) >= 0), "rank-local ingestion needs observations sorted by point"
+        o0, o1 = self.localRange(rank, world_size)
+        problem = Problem()
+        loss = loss if loss is not None else PredefinedLossFunctions.trivialLoss()
+        problem.addParameterBlocks(self.parameters, 9 * np.arange(self.numCameras, dtype=np.int64), 9)
+        off = np.empty((o1 - o0, 2), dtype=np.int64)
+        np.multiply(self.cameraIndex[o0:o1], 9, out=off[:, 0], dtype=np.int64)
+        np.multiply(self.pointIndex[o0:o1], 3, out=off[:, 1], dtype=np.int64)
+        off[:, 1] += 9 * self.numCameras
+        problem.addResidualBlocks(_abi.FUNCTOR_SNAVELY_REPROJECTION_ERROR, self.observations[2 * o0:2 * o1].reshape(-1, 2), loss,
+                                  self.parameters, off)
         return problem
 
 

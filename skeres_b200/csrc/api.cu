@@ -30,7 +30,8 @@ struct ResidualGroup {              // n residual blocks of one functor / loss o
   std::vector<int64_t> offsets;           // n * nblk
   int64_t n = 0;
 };
-struct sk_problem { std::vector<ResidualGroup> groups; int64_t num_residual_blocks = 0, num_residuals = 0; };
+struct DeclaredBlocks { sk_double_array* array; int32_t size; std::vector<int64_t> offsets; };   // AddParameterBlock
+struct sk_problem { std::vector<ResidualGroup> groups; std::vector<DeclaredBlocks> declared; int64_t num_residual_blocks = 0, num_residuals = 0; };
 
 struct sk_bal_problem {
   int32_t n_cam = 0, n_pt = 0, n_obs = 0;
@@ -373,6 +374,18 @@ int sk_problem_add_residual_blocks(sk_problem* p, int functor_id, int64_t n, con
   SK_API_END
 }
 
+int sk_problem_add_parameter_blocks(sk_problem* p, sk_double_array* array, int64_t n, const int64_t* offsets, int32_t block_size) {
+  SK_API_BEGIN
+  SK_REQUIRE(p != nullptr && array != nullptr && (offsets != nullptr || n == 0) && n >= 0 && block_size > 0, SK_ERR_INVALID_ARGUMENT,
+             "sk_problem_add_parameter_blocks: invalid argument");
+  for (int64_t i = 0; i < n; ++i)
+    SK_REQUIRE(offsets[i] >= 0 && offsets[i] + block_size <= array->n, SK_ERR_INVALID_ARGUMENT,
+               "parameter block %lld at offset %lld (size %d) is outside the array of %lld doubles", (long long)i, (long long)offsets[i],
+               block_size, (long long)array->n);
+  p->declared.push_back({array, block_size, std::vector<int64_t>(offsets, offsets + n)});
+  SK_API_END
+}
+
 int64_t sk_problem_num_residual_blocks(const sk_problem* p) { return p ? p->num_residual_blocks : -1; }
 int64_t sk_problem_num_residuals(const sk_problem* p) { return p ? p->num_residuals : -1; }
 
@@ -385,6 +398,8 @@ static void count_blocks(const sk_problem* p, int64_t* nblocks, int64_t* nparams
   for (auto& g : p->groups)
     for (int64_t i = 0; i < g.n; ++i)
       for (int k = 0; k < g.info.nblk; ++k) seen[{group_array(g, i, k), g.offsets[(size_t)i * g.info.nblk + k]}] = g.info.sizes[k];
+  for (auto& d : p->declared)
+    for (int64_t off : d.offsets) seen[{d.array, off}] = d.size;
   *nblocks = (int64_t)seen.size(); *nparams = 0;
   for (auto& kv : seen) *nparams += kv.second;
 }
@@ -403,7 +418,7 @@ void sk_solver_options_init(sk_solver_options* o) {
   o->initial_trust_region_radius = 1e4; o->max_trust_region_radius = 1e16; o->min_trust_region_radius = 1e-32;
   o->min_relative_decrease = 1e-3; o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32;
   o->function_tolerance = 1e-6; o->gradient_tolerance = 1e-10; o->parameter_tolerance = 1e-8; o->eta = 1e-1;
-  o->max_solver_time_in_seconds = 1e9; o->comm = nullptr;
+  o->max_solver_time_in_seconds = 1e9; o->comm = nullptr; o->residual_blocks_are_local = 0;
 }
 int sk_solver_summary_create(sk_solver_summary** out) {
   SK_API_BEGIN
@@ -462,12 +477,20 @@ static std::unique_ptr<LmSolver> prepare_ba(const sk_solver_options& opt, sk_pro
   const bool trace = getenv("SKERES_TRACE_HOST") != nullptr;   // development: where the preprocessor's time goes
   const double tp0 = wall();
   BaLayoutHost H;
-  const int rank = opt.comm ? opt.comm->rank : 0, world = opt.comm ? opt.comm->world : 1;
+  // Rank-local mode: the problem holds this rank's share only, so the layout is built as on one GPU; the camera table is
+  // made the same on every rank by the declared (AddParameterBlock) camera blocks.
+  const bool local = opt.residual_blocks_are_local != 0;
+  const int rank = (opt.comm && !local) ? opt.comm->rank : 0, world = (opt.comm && !local) ? opt.comm->world : 1;
+  std::vector<int64_t> declared_cams;
+  if (local)
+    for (auto& d : p->declared)
+      if (d.size == 9 && d.array == array) declared_cams.insert(declared_cams.end(), d.offsets.begin(), d.offsets.end());
+  const std::vector<int64_t>* extra = declared_cams.empty() ? nullptr : &declared_cams;
   const ResidualGroup* single = nullptr;                    // one bulk group (the usual case): read its arrays in place
   for (auto& g : p->groups) if (g.n == n) single = &g;
   double tp1 = tp0;
   if (single != nullptr) {
-    build_ba_layout(n, single->offsets.data(), single->offsets.data() + 1, single->consts.data(), rank, world, &H, 2);
+    build_ba_layout(n, single->offsets.data(), single->offsets.data() + 1, single->consts.data(), rank, world, &H, 2, extra);
   } else {
     std::vector<int64_t> cam_off((size_t)n), pt_off((size_t)n);
     std::vector<double> obs((size_t)2 * n);
@@ -478,7 +501,7 @@ static std::unique_ptr<LmSolver> prepare_ba(const sk_solver_options& opt, sk_pro
         obs[2 * at] = g.consts[2 * i]; obs[2 * at + 1] = g.consts[2 * i + 1];
       }
     tp1 = wall();
-    build_ba_layout(n, cam_off.data(), pt_off.data(), obs.data(), rank, world, &H);
+    build_ba_layout(n, cam_off.data(), pt_off.data(), obs.data(), rank, world, &H, 1, extra);
   }
   const double tp2 = wall();
   std::vector<int64_t> all_pt;
@@ -490,6 +513,7 @@ static std::unique_ptr<LmSolver> prepare_ba(const sk_solver_options& opt, sk_pro
   const int64_t n_cams = H.n_cams;
   std::unique_ptr<BaSolver> solver(new BaSolver(opt, stream, std::move(H), array->d.p, array->n, loss));
   solver->fill_totals(n, n_cams + total_points, 9 * n_cams + 3 * total_points, std::move(all_pt));
+  if (local && opt.comm != nullptr && opt.comm->world > 1) solver->exchange_local_totals();
   if (trace) fprintf(stderr, "[skeres] preprocess: flatten %.3f s, layout %.3f s, device set-up %.3f s\n", tp1 - tp0, tp2 - tp1, wall() - tp2);
   return solver;
 }

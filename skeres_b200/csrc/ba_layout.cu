@@ -43,7 +43,7 @@ void partition_points(int64_t n_points, const int64_t* point_ptr, int world_size
 
 // Maps arbitrary block offsets to dense ids ordered by offset.
 static void dense_ids(int64_t n, const int64_t* off_base, int64_t stride, int block_size, std::vector<int64_t>* uniq,
-                      std::vector<int32_t>* ids) {
+                      std::vector<int32_t>* ids, const std::vector<int64_t>* extra = nullptr) {
   struct Strided { const int64_t* p; int64_t s; int64_t operator[](int64_t i) const { return p[i * s]; } } off{off_base, stride};
   int64_t lo = off[0], hi = off[0];
   {
@@ -55,12 +55,14 @@ static void dense_ids(int64_t n, const int64_t* off_base, int64_t stride, int bl
       lo = std::min(lo, l); hi = std::max(hi, h);
     });
   }
+  if (extra != nullptr) for (int64_t o : *extra) { lo = std::min(lo, o); hi = std::max(hi, o); }
   const int64_t range = hi - lo + 1;
   ids->resize(n);
   if (range <= std::max<int64_t>(64 * n, 1 << 20)) {           // direct table
     std::vector<int32_t> table((size_t)range, -1);
     // every thread stores the same value: relaxed atomic stores keep that defined
     parallel_for(n, [&](int64_t a, int64_t b) { for (int64_t i = a; i < b; ++i) __atomic_store_n(&table[off[i] - lo], 0, __ATOMIC_RELAXED); });
+    if (extra != nullptr) for (int64_t o : *extra) table[o - lo] = 0;
     int32_t next = 0;
     int64_t last = -(int64_t)block_size;
     uniq->clear();
@@ -73,6 +75,7 @@ static void dense_ids(int64_t n, const int64_t* off_base, int64_t stride, int bl
   } else {                                                       // sort + binary search
     std::vector<int64_t> u((size_t)n);
     for (int64_t i = 0; i < n; ++i) u[i] = off[i];
+    if (extra != nullptr) u.insert(u.end(), extra->begin(), extra->end());
     std::sort(u.begin(), u.end());
     u.erase(std::unique(u.begin(), u.end()), u.end());
     for (size_t k = 1; k < u.size(); ++k)
@@ -83,14 +86,14 @@ static void dense_ids(int64_t n, const int64_t* off_base, int64_t stride, int bl
 }
 
 void build_ba_layout(int64_t n, const int64_t* cam_off, const int64_t* pt_off, const double* obs_xy,
-                     int rank, int world_size, BaLayoutHost* out, int64_t offset_stride) {
+                     int rank, int world_size, BaLayoutHost* out, int64_t offset_stride, const std::vector<int64_t>* extra_cam_off) {
   BaLayoutHost& L = *out;
   SK_REQUIRE(n > 0, SK_ERR_INVALID_ARGUMENT, "bundle adjustment problem without observations");
   SK_REQUIRE(n < (int64_t)2000000000, SK_ERR_UNSUPPORTED, "more than 2e9 observations");
   std::vector<int32_t> cam_id, pt_id;
   std::vector<int64_t> pt_offsets_all;
   Lap lap;
-  dense_ids(n, cam_off, offset_stride, 9, &L.cam_offset, &cam_id);
+  dense_ids(n, cam_off, offset_stride, 9, &L.cam_offset, &cam_id, extra_cam_off);
   dense_ids(n, pt_off, offset_stride, 3, &pt_offsets_all, &pt_id);
   lap("dense ids");
   L.n_cams = (int32_t)L.cam_offset.size();

@@ -58,9 +58,12 @@ struct BaLayoutHost {
 // Throws sk::Error on unsupported structure (duplicate (camera, point) pairs, tracks longer than
 // overlapping blocks).
 void build_ba_layout(int64_t n, const int64_t* cam_off, const int64_t* pt_off, const double* obs_xy,
-                     int rank, int world_size, BaLayoutHost* out, int64_t offset_stride = 1);
+                     int rank, int world_size, BaLayoutHost* out, int64_t offset_stride = 1,
+                     const std::vector<int64_t>* extra_cam_off = nullptr);
 // offset_stride: cam_off[i * stride] / pt_off[i * stride] -- 2 lets the builder read a problem's interleaved
 // (camera, point) offset pairs in place.
+// extra_cam_off: camera blocks that exist although no observation of this call uses them (declared with
+// Problem::AddParameterBlock): they get ids like any camera, so ranks holding different observations agree on the table.
 
 // Contiguous point ranges balanced by observation count (out_begin has world_size + 1 entries).
 void partition_points(int64_t n_points, const int64_t* point_ptr, int world_size, int64_t* out_begin);

@@ -126,7 +126,7 @@ void BaSolver::load_state() {
 }
 
 void BaSolver::store_state() {
-  if (comm_ && comm_->world > 1) {
+  if (comm_ && comm_->world > 1 && !local_blocks_) {
     // every rank owns a slice of the points; publish them all through a zero-padded sum
     DBuf<double> tmp((size_t)user_n_);
     tmp.zero(stream_);
@@ -292,6 +292,27 @@ void BaSolver::pcg_solve(const double* Minv) {
   }
   const int its = pcg_h_.p->iter;
   n_real_matvecs_ += (its + its / kResetPeriod) * (L_.n_giant ? 2 : 1);
+}
+
+void BaSolver::exchange_local_totals() {
+  local_blocks_ = true;
+  const int world = comm_ ? comm_->world : 1;
+  if (world == 1) return;
+  double check = 0.0;                                        // exact in a double: < 2^24 cameras x offsets mod 2^20
+  for (int64_t o : H_.cam_offset) check += (double)(o & 0xfffff);
+  std::vector<double> h = {(double)L_.n_obs, (double)L_.n_pts, (double)L_.n_cams, check};
+  DBuf<double> d(h.size());
+  d.upload(h, stream_);
+  comm_allreduce_sum(comm_, d.p, h.size(), stream_);
+  std::vector<double> g(h.size());
+  d.download(g.data(), g.size(), stream_);
+  SK_CUDA(cudaStreamSynchronize(stream_));
+  SK_REQUIRE(g[2] == h[2] * world && g[3] == h[3] * world, SK_ERR_INVALID_ARGUMENT,
+             "rank-local residual blocks: the ranks do not agree on the camera blocks (this rank has %d; declare every camera on "
+             "every rank with sk_problem_add_parameter_blocks)", L_.n_cams);
+  total_obs_ = (int64_t)g[0];
+  total_param_blocks_ = (int64_t)L_.n_cams + (int64_t)g[1];
+  total_params_ = 9 * (int64_t)L_.n_cams + 3 * (int64_t)g[1];
 }
 
 void BaSolver::fill_totals(int64_t total_obs, int64_t total_blocks, int64_t total_params, std::vector<int64_t>&& all_pt_off) {

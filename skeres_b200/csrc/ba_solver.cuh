@@ -11,6 +11,9 @@ class BaSolver : public LmSolver {
   BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHost&& layout, double* user_params,
            int64_t user_n, LossSpec loss);
   void fill_totals(int64_t total_obs, int64_t total_blocks, int64_t total_params, std::vector<int64_t>&& all_pt_off);
+  // Rank-local ingestion (sk_solver_options.residual_blocks_are_local): sums the per-rank observation / point counts for
+  // the summary and checks that every rank built the same camera table.  Collective: every rank must call it.
+  void exchange_local_totals();
 
   // ---- test / debug access (sk_debug_* entry points) ---------------------------------------------
   const BaDev& layout() const { return L_; }
@@ -37,6 +40,7 @@ class BaSolver : public LmSolver {
   double* user_; int64_t user_n_;
   LossSpec loss_;
   bool explicit_schur_ = false;
+  bool local_blocks_ = false;          // this rank was given only its own residual blocks (no publication of foreign points)
   int64_t total_obs_ = 0, total_param_blocks_ = 0, total_params_ = 0;
   std::vector<int64_t> all_pt_off_;
   DBuf<int> d_tile_obs_, d_tile_pt_, d_tile_seg_, d_pt_ptr_, d_seg_ptr_, d_seg_cam_, d_cam_seg_ptr_, d_cam_seg_;

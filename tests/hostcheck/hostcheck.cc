@@ -39,6 +39,16 @@ HcLayout* hc_layout_build(int64_t n, const int64_t* cam_off, const int64_t* pt_o
   catch (const sk::Error& e) { *status = e.status; std::strncpy(err, e.what(), 255); err[255] = 0; delete h; return nullptr; }
   return h;
 }
+// The rank-local ingestion of the multi-GPU path: one-GPU layout of a rank's own observations, with camera blocks that
+// exist without a local observation (extra).
+HcLayout* hc_layout_build_extra(int64_t n, const int64_t* cam_off, const int64_t* pt_off, const double* obs, int64_t n_extra,
+                                const int64_t* extra, int* status, char* err) {
+  HcLayout* h = new HcLayout;
+  std::vector<int64_t> ex(extra, extra + n_extra);
+  try { sk::build_ba_layout(n, cam_off, pt_off, obs, 0, 1, &h->L, 1, &ex); *status = 0; }
+  catch (const sk::Error& e) { *status = e.status; std::strncpy(err, e.what(), 255); err[255] = 0; delete h; return nullptr; }
+  return h;
+}
 void hc_layout_free(HcLayout* h) { delete h; }
 void hc_layout_dims(const HcLayout* h, int32_t* out /*8*/) {
   const auto& L = h->L;

@@ -459,6 +459,31 @@ def test_ba_per_block_api_equals_bulk_api(sk):
     assert "DENSE_SCHUR" in s1.fullReport()
 
 
+def test_rank_local_blocks_and_declared_cameras(sk):
+    """sk_solver_options.residual_blocks_are_local on one GPU: declared cameras (Problem::AddParameterBlock) enter the
+    camera table even without an observation.  An unobserved all-zero camera has zero gradient and takes no step, so the
+    solve must be the one of the plain problem, bit for bit; without the flag a declared block is ignored, as in Ceres."""
+    d = synth.make_bal("small", seed=2)
+    bal0, s0 = gpu_ba(sk, d, _abi.ITERATIVE_SCHUR, _abi.SCHUR_JACOBI)
+    n = d.parameters.size
+    for local in (1, 0):
+        arr = sk.DoubleArray.fromArray(np.concatenate([d.parameters, np.zeros(9)]))      # the extra camera lives behind the points
+        bal = sk.BalProblem(d.num_cameras, d.num_points, d.camera_index, d.point_index, d.observations, arr)
+        problem = bal.buildLocalProblem(0, 1)
+        problem.addParameterBlocks(arr, [n], 9)
+        assert problem.numParameterBlocks() == d.num_cameras + d.num_points + 1
+        o = sk.Solver.Options()
+        o.setLinearSolverType(_abi.ITERATIVE_SCHUR); o.setPreconditionerType(_abi.SCHUR_JACOBI)
+        o.residual_blocks_are_local = local
+        s = sk.Solver.Summary()
+        sk.ceres.solve(o, problem, s)
+        assert [r.cost for r in s.iterations] == [r.cost for r in s0.iterations]
+        assert [r.linear_solver_iterations for r in s.iterations] == [r.linear_solver_iterations for r in s0.iterations]
+        x = arr.toArray()
+        assert np.array_equal(x[:n], bal0.parameters.toArray()) and np.all(x[n:] == 0.0)
+        assert s.num_parameter_blocks == d.num_cameras + d.num_points + local
+
+
 def test_bal_file_round_trip(sk, tmp_path):
     """BalProblem.fromFile (SimpleBundleAdjuster.scala:37-77) on a file in the BAL text layout."""
     d = synth.make_bal("tiny", seed=10)

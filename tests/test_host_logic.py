@@ -113,11 +113,17 @@ class Layout:
               "seg_cam": np.int32, "cam_seg_ptr": np.int32, "cam_seg": np.int32, "cam_offset": np.int64, "pt_offset": np.int64, "obs": np.float64,
               "tile_np": np.int32, "tile_chunk": np.int32, "gp_tile_begin": np.int32, "gp_tile_count": np.int32, "gp_point": np.int32}
 
-    def __init__(self, L, cam_off, pt_off, obs, rank=0, world=1):
+    def __init__(self, L, cam_off, pt_off, obs, rank=0, world=1, extra_cams=None):
         cam_off = np.ascontiguousarray(cam_off, dtype=np.int64); pt_off = np.ascontiguousarray(pt_off, dtype=np.int64)
         obs = np.ascontiguousarray(obs, dtype=np.float64)
         st = C.c_int(); err = C.create_string_buffer(256)
-        h = L.hc_layout_build(cam_off.size, p(cam_off), p(pt_off), p(obs), rank, world, C.byref(st), err)
+        if extra_cams is None:
+            h = L.hc_layout_build(cam_off.size, p(cam_off), p(pt_off), p(obs), rank, world, C.byref(st), err)
+        else:
+            ex = np.ascontiguousarray(extra_cams, dtype=np.int64)
+            L.hc_layout_build_extra.restype = C.c_void_p
+            L.hc_layout_build_extra.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int), C.c_char_p]
+            h = L.hc_layout_build_extra(cam_off.size, p(cam_off), p(pt_off), p(obs), ex.size, p(ex), C.byref(st), err)
         self.status, self.error = st.value, err.value.decode()
         if not h:
             return
@@ -266,6 +272,41 @@ def test_ragged_tracks_fill_tiles(hc):
     lay = Layout(hc, cam_off, pt_off, obs)
     assert lay.status == 0
     check_layout(lay, cam_off, pt_off, obs)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("sparse_offsets", [False, True])
+def test_rank_local_ingestion_builds_the_same_layout(hc, world, sparse_offsets):
+    """sk_solver_options.residual_blocks_are_local: a rank that is handed only the residual blocks of its own points, with
+    every camera declared (Problem::AddParameterBlock), must end up with exactly the layout the replicated ingestion
+    cuts out of the whole problem -- same camera table, same tiles, same segments -- so both modes give the same bits."""
+    from skeres_b200 import api
+    d = synth.make_bal("ladybug-49", seed=1)
+    off = d.block_offsets()
+    cam_off, pt_off = off[:, 0].copy(), off[:, 1].copy()
+    all_cams = 9 * np.arange(d.num_cameras, dtype=np.int64)
+    if sparse_offsets:                                   # the sort + binary-search id path of the builder
+        cam_off = cam_off * 1000003; pt_off = pt_off * 1000003 + 5; all_cams = all_cams * 1000003
+    ptr = np.concatenate([[0], np.cumsum(np.bincount(d.point_index, minlength=d.num_points))]).astype(np.int64)
+    begin = api.partition_points(ptr, world)
+    for r in range(world):
+        o0, o1 = ptr[begin[r]], ptr[begin[r + 1]]
+        # drop one camera's observations from this rank so that the declared list matters
+        whole = Layout(hc, cam_off, pt_off, d.observations, rank=r, world=world)
+        mine = Layout(hc, cam_off[o0:o1], pt_off[o0:o1], d.observations[2 * o0:2 * o1], extra_cams=all_cams)
+        assert whole.status == 0 and mine.status == 0
+        for name in Layout.FIELDS:
+            a, b = getattr(whole, name), getattr(mine, name)
+            if name == "perm":
+                a = a - o0                               # the replicated builder indexes the whole input
+            assert np.array_equal(a, b), name
+    # a camera without any local observation still gets its id
+    keep = cam_off != cam_off.min()
+    part = Layout(hc, cam_off[keep], pt_off[keep], d.observations.reshape(-1, 2)[keep].ravel(), extra_cams=all_cams)
+    assert part.status == 0 and part.n_cams == d.num_cameras and np.array_equal(part.cam_offset, all_cams)
+    assert part.cam_seg_ptr[1] == 0                      # ... and owns no segment
+    bare = Layout(hc, cam_off[keep], pt_off[keep], d.observations.reshape(-1, 2)[keep].ravel())
+    assert bare.n_cams == d.num_cameras - 1
 
 
 @pytest.mark.parametrize("world", [2, 3, 8])

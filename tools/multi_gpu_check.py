@@ -19,11 +19,12 @@ comm = api.Communicator(ids[0], rank, world)
 shape = sys.argv[1] if len(sys.argv) > 1 else "ladybug-49"
 d = synth.make_bal(shape, seed=1)
 
-def solve(use_comm):
+def solve(use_comm, local=False):
     bal = api.BalProblem.fromArrays(d)
-    prob = bal.buildProblem()
+    prob = bal.buildLocalProblem(rank, world) if local else bal.buildProblem()
     o = api.Solver.Options(); o.setLinearSolverType(_abi.ITERATIVE_SCHUR); o.setPreconditionerType(_abi.SCHUR_JACOBI)
     if use_comm: o.comm = comm
+    o.residual_blocks_are_local = 1 if local else 0
     s = api.Solver.Summary()
     t = time.time(); api.ceres.solve(o, prob, s); dt = time.time() - t
     return bal.parameters.toArray(), s, dt
@@ -33,6 +34,21 @@ rows = [(r.iteration, r.cost, r.linear_solver_iterations) for r in s.iterations]
 print(f"rank {rank}: {s.message} final {s.final_cost:.9e} its {len(rows)} pcg {[r[2] for r in rows]} {dt:.3f}s gpus {s.num_gpus}", flush=True)
 gathered = [None] * world
 dist.all_gather_object(gathered, (x.tobytes(), rows))
+# rank-local ingestion (each rank is handed only its own residual blocks): same bits for the trajectory, the cameras and
+# this rank's points; foreign points are left as they were
+xl, sl, dtl = solve(True, local=True)
+rows_l = [(r.iteration, r.cost, r.linear_solver_iterations) for r in sl.iterations]
+assert rows_l == rows, "rank-local ingestion changed the trajectory"
+balr = api.BalProblem.fromArrays(d)
+o0, o1 = balr.localRange(rank, world)
+mine = np.unique(d.point_index[o0:o1])
+nc9 = 9 * d.num_cameras
+own = np.concatenate([np.arange(nc9), (nc9 + 3 * mine[:, None] + np.arange(3)).ravel()])
+assert np.array_equal(xl[own], x[own]), "rank-local ingestion changed the solution"
+other = np.setdiff1d(np.arange(x.size), own)
+assert np.array_equal(xl[other], d.parameters[other]), "foreign points must stay untouched"
+assert (sl.num_residual_blocks, sl.num_parameter_blocks) == (s.num_residual_blocks, s.num_parameter_blocks)
+print(f"rank {rank}: rank-local ingestion OK ({o1 - o0} of {d.num_observations} observations ingested, {dtl:.3f}s vs {dt:.3f}s)", flush=True)
 if rank == 0:
     for g in gathered[1:]:
         assert g[0] == gathered[0][0], "ranks disagree on the solution"
