@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <utility>
 
 #include "lm_kernels.cuh"
 
@@ -94,6 +95,40 @@ __device__ __forceinline__ double block_sum(double x, double* red) {
 
 __device__ __forceinline__ double2 ldcs2(const double2* p) { return __ldcs(p); }
 
+// Tile metadata needed by the later phases, fetched at the top of the kernel so that its latency
+// overlaps the streaming Jacobian loads: tile-local segment permutation / segment starts / point starts.
+struct TileMetaSmem { unsigned short* sperm; int* sptr; int* pptr; };
+
+__device__ __forceinline__ void stage_tile_meta(const BaDev& L, const Tile& q, const TileMetaSmem& m) {
+  const int tid = threadIdx.x;
+  if (tid < q.no) m.sperm[tid] = L.seg_perm[q.ob + tid];
+  for (int idx = tid; idx <= q.ns; idx += T) m.sptr[idx] = L.seg_ptr[q.sb + idx] - q.ob;
+  for (int idx = tid; idx <= q.np; idx += T) m.pptr[idx] = L.pt_ptr[q.pb + idx] - q.ob;
+}
+
+// Segment sums of NP staged planes with the tile's segment structure in shared memory: item (s, k) adds plane k over
+// segment s in the fixed (point) order, four staged values in flight at a time.  k < split goes to out0 (row stride
+// s0), the rest to out1 (row stride s1, offset o1).
+template <int NP>
+__device__ __forceinline__ void seg_reduce_planes(const Tile& q, const TileMetaSmem& m, const double* v, int split,
+                                                  double* out0, int s0, double* out1, int s1, int o1) {
+  for (int idx = threadIdx.x; idx < q.ns * NP; idx += T) {
+    const int s = idx / NP, k = idx - s * NP;
+    const int b = m.sptr[s], e = m.sptr[s + 1];
+    const double* vk = v + k * VLD;
+    double sum = 0.0;
+    int pos = b;
+    for (; pos + 4 <= e; pos += 4) {
+      const int i0 = m.sperm[pos], i1 = m.sperm[pos + 1], i2 = m.sperm[pos + 2], i3 = m.sperm[pos + 3];
+      const double x0 = vk[i0], x1 = vk[i1], x2 = vk[i2], x3 = vk[i3];
+      sum += x0; sum += x1; sum += x2; sum += x3;
+    }
+    for (; pos < e; ++pos) sum += vk[m.sperm[pos]];
+    if (k < split) out0[(size_t)(q.sb + s) * s0 + k] = sum;
+    else out1[(size_t)(q.sb + s) * s1 + o1 + (k - split)] = sum;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 template <bool JAC>
 __global__ void __launch_bounds__(T) k_ba_evaluate(BaDev L, const double* __restrict__ x, const double* __restrict__ scale,
@@ -110,8 +145,13 @@ __global__ void __launch_bounds__(T) k_ba_evaluate(BaDev L, const double* __rest
   double* pt_s = cam_s + L.max_seg_tile * 9;        // [max_pt][3]
   double* csc_s = pt_s + L.max_pt_tile * 3;         // [max_seg][9]  column scales (JAC)
   double* psc_s = csc_s + L.max_seg_tile * 9;       // [max_pt][3]
-  double* v = psc_s + L.max_pt_tile * 3;            // [9][VLD]      (JAC)
-  double* red = JAC ? (v + 9 * VLD) : csc_s;        // [8]
+  double* v = psc_s + L.max_pt_tile * 3;            // [18][VLD]     (JAC)
+  double* red = JAC ? (v + 18 * VLD) : csc_s;       // [8]
+  TileMetaSmem meta;                                // the tile's segment structure (JAC), fetched behind the functor's arithmetic
+  meta.sptr = reinterpret_cast<int*>(red + 8);                       // [max_seg + 1]
+  meta.pptr = meta.sptr + L.max_seg_tile + 1;                        // [max_pt + 1]
+  meta.sperm = reinterpret_cast<unsigned short*>(meta.pptr + L.max_pt_tile + 1);   // [T]
+  if (JAC) stage_tile_meta(L, q, meta);
   const size_t pbase = (size_t)9 * L.n_cams;
   for (int idx = tid; idx < q.ns * 9; idx += T) {
     const int s = idx / 9, k = idx - s * 9;
@@ -172,7 +212,7 @@ __global__ void __launch_bounds__(T) k_ba_evaluate(BaDev L, const double* __rest
     }
   } else if (tid < q.np) {
     const int p = q.pb + tid;
-    const int b = L.pt_ptr[p] - q.ob, e = L.pt_ptr[p + 1] - q.ob;
+    const int b = meta.pptr[tid], e = meta.pptr[tid + 1];
     double s6[6] = {0, 0, 0, 0, 0, 0};
     for (int j = b; j < e; ++j) {
 #pragma unroll
@@ -182,36 +222,53 @@ __global__ void __launch_bounds__(T) k_ba_evaluate(BaDev L, const double* __rest
     for (int k = 0; k < 3; ++k) { grad[pbase + (size_t)p * 3 + k] = s6[k]; cnorm2[pbase + (size_t)p * 3 + k] = s6[3 + k]; }
   }
   __syncthreads();
-  double fs[18];
+  // camera part: planes 0..8 = gradient terms, planes 9..17 = squared column norms of the scaled Jacobian; one pass of
+  // segment sums over the 18 planes
   if (active) {
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
       const double sc = csc_s[slot * 9 + k];
-      fs[k] = F[k] * sc; fs[9 + k] = F[9 + k] * sc;
+      const double f0 = F[k] * sc, f1 = F[9 + k] * sc;
       v[k * VLD + tid] = F[k] * res[0] + F[9 + k] * res[1];
-      if (write_j) J2[(size_t)k * L.n_obs + i] = make_double2(fs[k], fs[9 + k]);
+      v[(9 + k) * VLD + tid] = f0 * f0 + f1 * f1;
+      if (write_j) J2[(size_t)k * L.n_obs + i] = make_double2(f0, f1);
     }
   }
   __syncthreads();
-  seg_reduce9(L, q, v, seg_g, 9, 0);
-  __syncthreads();
-  if (active) {
-#pragma unroll
-    for (int k = 0; k < 9; ++k) v[k * VLD + tid] = fs[k] * fs[k] + fs[9 + k] * fs[9 + k];
-  }
-  __syncthreads();
-  seg_reduce9(L, q, v, seg_n, 9, 0);
+  seg_reduce_planes<18>(q, meta, v, 9, seg_g, 9, seg_n, 9, 0);
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void k_cam_reduce(BaDev L, int K, const double* __restrict__ seg, double* __restrict__ out, const int* guard) {
+// Second level of the per-camera sums: out[c][k] = sum over the camera's (tile, camera) partials seg[s][k], tile order.
+// One CTA per camera.  The partial list (~190 entries on the Venice shape) is dealt round-robin to R = 288 / K sub-ranges
+// (32 for K = 9, 6 for K = 45), each summed by K threads with four loads in flight; the R sub-sums are then added in
+// sub-range order.  Fixed order, no atomics.  (One thread per (camera, k) walking the whole list cost 37-41 us per launch.)
+constexpr int kCamReduceThreads = 288;
+__global__ void __launch_bounds__(kCamReduceThreads) k_cam_reduce(BaDev L, int K, const double* __restrict__ seg, double* __restrict__ out,
+                                                                 const int* guard) {
   if (guard != nullptr && *guard == 0) return;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= L.n_cams * K) return;
-  const int c = idx / K, k = idx - c * K;
-  double sum = 0.0;
-  for (int t = L.cam_seg_ptr[c]; t < L.cam_seg_ptr[c + 1]; ++t) sum += seg[(size_t)L.cam_seg[t] * K + k];
-  out[idx] = sum;
+  __shared__ double part[kCamReduceThreads];
+  const int c = blockIdx.x;
+  const int R = kCamReduceThreads / K;
+  const int r = threadIdx.x / K, k = threadIdx.x - r * K;
+  const int e = L.cam_seg_ptr[c + 1];
+  if (r < R) {
+    double sum = 0.0;
+    int t = L.cam_seg_ptr[c] + r;
+    for (; t + 3 * R < e; t += 4 * R) {
+      const int s0 = L.cam_seg[t], s1 = L.cam_seg[t + R], s2 = L.cam_seg[t + 2 * R], s3 = L.cam_seg[t + 3 * R];
+      const double x0 = seg[(size_t)s0 * K + k], x1 = seg[(size_t)s1 * K + k], x2 = seg[(size_t)s2 * K + k], x3 = seg[(size_t)s3 * K + k];
+      sum += x0; sum += x1; sum += x2; sum += x3;
+    }
+    for (; t < e; t += R) sum += seg[(size_t)L.cam_seg[t] * K + k];
+    part[threadIdx.x] = sum;                       // == part[r * K + k]
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < K) {
+    double a = part[threadIdx.x];
+    for (int q = 1; q < R; ++q) a += part[q * K + threadIdx.x];
+    out[(size_t)c * K + threadIdx.x] = a;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -226,18 +283,42 @@ __host__ __device__ constexpr int upper_col(int idx) {
   return k + (idx - start);
 }
 
+// Entry IDX (0..44) of the packed upper 9x9 block one observation contributes: F^T F - G^T (E^T E)^-1 G, indices folded at
+// compile time so that F, G, H stay in registers.
+template <int IDX>
+__device__ __forceinline__ double block_entry(const double2 (&Fv)[9], const double (&G)[3][9], const double (&H)[3][9], int ftf_only) {
+  constexpr int k = upper_row(IDX), l = upper_col(IDX);
+  const double ftf = Fv[k].x * Fv[l].x + Fv[k].y * Fv[l].y;
+  return ftf_only ? ftf : (ftf - (G[0][k] * H[0][l] + G[1][k] * H[1][l] + G[2][k] * H[2][l]));
+}
+// Stages entries FIRST + 0, 1, ... into consecutive planes starting at vt (= plane base + thread's column).
+template <int FIRST, int... Is>
+__device__ __forceinline__ void stage_block_entries(double* vt, const double2 (&Fv)[9], const double (&G)[3][9], const double (&H)[3][9],
+                                                    int ftf_only, std::integer_sequence<int, Is...>) {
+  ((vt[Is * VLD] = block_entry<FIRST + Is>(Fv, G, H, ftf_only)), ...);
+}
+
+constexpr int kSetupPlanes = 18;     // staged planes per round of k_ba_schur_setup: 9 rhs + 45 block entries = 3 rounds of 18
+
 __global__ void __launch_bounds__(T, 2) k_ba_schur_setup(BaDev L, const double2* __restrict__ J2, const double2* __restrict__ r2,
                                                       const double* __restrict__ D, double* __restrict__ einv,
                                                       double* __restrict__ seg_rhs, double* __restrict__ seg_M,
                                                       int* error_flag, int ftf_only) {
   // ftf_only: the diagonal blocks keep only F^T F (JACOBI preconditioner = block_diagonal_FtF_inverse of the implicit
   // Schur complement) instead of F^T F - G^T (E^T E)^-1 G (SCHUR_JACOBI / the explicit reduced matrix).
+  // The 54 per-observation values that go to a camera (9 of the reduced right-hand side, 45 of the packed upper block)
+  // are staged 18 planes at a time, so that every thread of the CTA has a segment sum to form; the tile's segment
+  // structure is fetched into shared memory once, behind the Jacobian loads.
   extern __shared__ double sm[];
   const Tile q = load_tile(L, blockIdx.x);
   if (q.chunk >= 0) return;            // long tracks: k_ba_schur_setup_giant
   const int tid = threadIdx.x;
-  double* v = sm;                      // [9][VLD]
-  double* pinv = v + 9 * VLD;          // [max_pt][9]: inverse (6, upper) + inverse * g (3)
+  double* v = sm;                      // [18][VLD]
+  double* pinv = v + kSetupPlanes * VLD;   // [max_pt][9]: inverse (6, upper) + inverse * g (3)
+  TileMetaSmem meta;
+  meta.sptr = reinterpret_cast<int*>(pinv + L.max_pt_tile * 9);      // [max_seg + 1]
+  meta.pptr = meta.sptr + L.max_seg_tile + 1;                        // [max_pt + 1]
+  meta.sperm = reinterpret_cast<unsigned short*>(meta.pptr + L.max_pt_tile + 1);   // [T]
   const bool active = tid < q.no;
   const int i = q.ob + tid;
   const size_t O = (size_t)L.n_obs;
@@ -250,6 +331,9 @@ __global__ void __launch_bounds__(T, 2) k_ba_schur_setup(BaDev L, const double2*
     for (int k = 0; k < 3; ++k) Ev[k] = ldcs2(J2 + (9 + k) * O + i);
     r = r2[i];
     ptl = L.obs_ptl[i];
+  }
+  stage_tile_meta(L, q, meta);
+  if (active) {
     // E^T E (upper: 00 01 02 11 12 22) and E^T r
     v[0 * VLD + tid] = Ev[0].x * Ev[0].x + Ev[0].y * Ev[0].y;
     v[1 * VLD + tid] = Ev[0].x * Ev[1].x + Ev[0].y * Ev[1].y;
@@ -263,7 +347,7 @@ __global__ void __launch_bounds__(T, 2) k_ba_schur_setup(BaDev L, const double2*
   __syncthreads();
   if (tid < q.np) {
     const int p = q.pb + tid;
-    const int b = L.pt_ptr[p] - q.ob, e = L.pt_ptr[p + 1] - q.ob;
+    const int b = meta.pptr[tid], e = meta.pptr[tid + 1];
     const double* Dp = D + (size_t)9 * L.n_cams + (size_t)p * 3;
     double m[6] = {Dp[0] * Dp[0], 0.0, 0.0, Dp[1] * Dp[1], 0.0, Dp[2] * Dp[2]};
     double g[3] = {0.0, 0.0, 0.0};
@@ -303,24 +387,20 @@ __global__ void __launch_bounds__(T, 2) k_ba_schur_setup(BaDev L, const double2*
       H[1][k] = pi[1] * G[0][k] + pi[3] * G[1][k] + pi[4] * G[2][k];
       H[2][k] = pi[2] * G[0][k] + pi[4] * G[1][k] + pi[5] * G[2][k];
     }
+    // round 0: planes 0..8 = reduced rhs (above), planes 9..17 = block entries 0..8
+    stage_block_entries<0>(v + 9 * VLD + tid, Fv, G, H, ftf_only, std::make_integer_sequence<int, 9>());
   }
   __syncthreads();
-  seg_reduce9(L, q, v, seg_rhs, 9, 0);
-  // diagonal block contribution F^T F - G^T (E^T E)^-1 G, packed upper triangle, 5 rounds of 9
-#pragma unroll
-  for (int round = 0; round < 5; ++round) {
-    __syncthreads();
-    if (active) {
-#pragma unroll
-      for (int j = 0; j < 9; ++j) {
-        const int k = upper_row(round * 9 + j), l = upper_col(round * 9 + j);
-        const double ftf = Fv[k].x * Fv[l].x + Fv[k].y * Fv[l].y;
-        v[j * VLD + tid] = ftf_only ? ftf : (ftf - (G[0][k] * H[0][l] + G[1][k] * H[1][l] + G[2][k] * H[2][l]));
-      }
-    }
-    __syncthreads();
-    seg_reduce9(L, q, v, seg_M, 45, round * 9);
-  }
+  seg_reduce_planes<kSetupPlanes>(q, meta, v, 9, seg_rhs, 9, seg_M, 45, 0);
+  // rounds 1, 2: block entries 9..26 and 27..44
+  __syncthreads();
+  if (active) stage_block_entries<9>(v + tid, Fv, G, H, ftf_only, std::make_integer_sequence<int, kSetupPlanes>());
+  __syncthreads();
+  seg_reduce_planes<kSetupPlanes>(q, meta, v, 0, seg_M, 45, seg_M, 45, 9);
+  __syncthreads();
+  if (active) stage_block_entries<9 + kSetupPlanes>(v + tid, Fv, G, H, ftf_only, std::make_integer_sequence<int, kSetupPlanes>());
+  __syncthreads();
+  seg_reduce_planes<kSetupPlanes>(q, meta, v, 0, seg_M, 45, seg_M, 45, 9 + kSetupPlanes);
 }
 
 __global__ void k_ba_precond_invert(BaDev L, const double* __restrict__ M45, const double* __restrict__ D,
@@ -340,17 +420,6 @@ __global__ void k_ba_precond_invert(BaDev L, const double* __restrict__ M45, con
 }
 
 // ------------------------------------------------------------------------------------------------
-// Tile metadata needed by the later phases, fetched at the top of the kernel so that its latency
-// overlaps the streaming Jacobian loads: tile-local segment permutation / segment starts / point starts.
-struct TileMetaSmem { unsigned short* sperm; int* sptr; int* pptr; };
-
-__device__ __forceinline__ void stage_tile_meta(const BaDev& L, const Tile& q, const TileMetaSmem& m) {
-  const int tid = threadIdx.x;
-  if (tid < q.no) m.sperm[tid] = L.seg_perm[q.ob + tid];
-  for (int idx = tid; idx <= q.ns; idx += T) m.sptr[idx] = L.seg_ptr[q.sb + idx] - q.ob;
-  for (int idx = tid; idx <= q.np; idx += T) m.pptr[idx] = L.pt_ptr[q.pb + idx] - q.ob;
-}
-
 // seg_reduce9 with the metadata already in shared memory.
 __device__ __forceinline__ void seg_reduce9_s(const Tile& q, const TileMetaSmem& m, const double* v, double* out, int ostride, int ooff) {
   for (int idx = threadIdx.x; idx < q.ns * 9; idx += T) {
@@ -968,7 +1037,8 @@ void launch_ba_evaluate(const BaDev& L, const double* x, const double* scale, Lo
                         double* seg_n, double* tile_cost, double* chunk_pt, int* fail_flag, const int* guard, cudaStream_t s) {
   if (L.n_tiles == 0) return;
   if (with_jacobian) {
-    const size_t smem = sizeof(double) * ((size_t)2 * (L.max_seg_tile * 9 + L.max_pt_tile * 3) + 9 * VLD + 8);
+    const size_t smem = sizeof(double) * ((size_t)2 * (L.max_seg_tile * 9 + L.max_pt_tile * 3) + 18 * VLD + 8) +
+                        sizeof(int) * ((size_t)L.max_seg_tile + L.max_pt_tile + 2) + sizeof(unsigned short) * T;
     set_smem(k_ba_evaluate<true>, smem);
     k_ba_evaluate<true><<<L.n_tiles, T, smem, s>>>(L, x, scale, loss, write_jacobian ? 1 : 0, J2, r2, grad, cnorm2, seg_g,
                                                    seg_n, tile_cost, chunk_pt, fail_flag, guard);
@@ -983,15 +1053,17 @@ void launch_ba_evaluate(const BaDev& L, const double* x, const double* scale, Lo
 }
 
 void launch_cam_reduce(const BaDev& L, int K, const double* seg, double* out, const int* guard, cudaStream_t s) {
-  const int n = L.n_cams * K;
-  k_cam_reduce<<<cdiv(n, 256), 256, 0, s>>>(L, K, seg, out, guard);
+  SK_REQUIRE(K >= 1 && K <= kCamReduceThreads, SK_ERR_INTERNAL, "k_cam_reduce: bad K");
+  if (L.n_cams == 0) return;
+  k_cam_reduce<<<L.n_cams, kCamReduceThreads, 0, s>>>(L, K, seg, out, guard);
   check_launch("k_cam_reduce");
 }
 
 void launch_ba_schur_setup(const BaDev& L, const double2* J2, const double2* r2, const double* D, double* einv,
                            double* seg_rhs, double* seg_M, int* error_flag, bool ftf_only, cudaStream_t s) {
   if (L.n_tiles == 0) return;
-  const size_t smem = sizeof(double) * ((size_t)9 * VLD + (size_t)L.max_pt_tile * 9);
+  const size_t smem = sizeof(double) * ((size_t)kSetupPlanes * VLD + (size_t)L.max_pt_tile * 9) +
+                      sizeof(int) * ((size_t)L.max_seg_tile + L.max_pt_tile + 2) + sizeof(unsigned short) * T;
   set_smem(k_ba_schur_setup, smem);
   k_ba_schur_setup<<<L.n_tiles, T, smem, s>>>(L, J2, r2, D, einv, seg_rhs, seg_M, error_flag, ftf_only ? 1 : 0);
   if (L.n_giant) {

@@ -44,9 +44,20 @@ __device__ __forceinline__ double block_max256(double x, double* red) {
 }
 
 // Fixed-order sum of a partial array by one block.
+// Thread t adds part[t], part[t + 256], ... in that order; eight loads are in flight at a time (a tile-sized partial array
+// is ~80 elements per thread, and one L2 round trip per element made this kernel cost 38 us).
 __device__ double sum_partials(const double* part, int n, double* red) {
   double a = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) a += part[i];
+  const int step = blockDim.x;
+  int i = threadIdx.x;
+  for (; i + 7 * step < n; i += 8 * step) {
+    double x[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) x[u] = __ldcg(part + i + u * step);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) a += x[u];
+  }
+  for (; i < n; i += step) a += __ldcg(part + i);
   return block_sum256(a, red);
 }
 
@@ -127,7 +138,19 @@ __global__ void k_reduce_jobs(ReduceJobs jobs, double* sbuf, const int* guard) {
   __shared__ double red[8];
   const ReduceJob jb = jobs.j[blockIdx.x];
   double a = 0.0;
-  if (jb.is_max) { for (int i = threadIdx.x; i < jb.n; i += blockDim.x) a = fmax(a, jb.part[i]); a = block_max256(a, red); }
+  if (jb.is_max) {
+    const int step = blockDim.x;
+    int i = threadIdx.x;
+    for (; i + 7 * step < jb.n; i += 8 * step) {
+      double x[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) x[u] = __ldcg(jb.part + i + u * step);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a = fmax(a, x[u]);
+    }
+    for (; i < jb.n; i += step) a = fmax(a, __ldcg(jb.part + i));
+    a = block_max256(a, red);
+  }
   else a = sum_partials(jb.part, jb.n, red);
   if (threadIdx.x == 0) sbuf[jb.slot] = a;
 }

@@ -604,3 +604,29 @@ def test_full_size_properties(sk, shape):
     bal3, s3 = gpu_ba(sk, d, _abi.ITERATIVE_SCHUR, _abi.SCHUR_JACOBI, order=order, max_num_iterations=4)
     assert [r.linear_solver_iterations for r in s3.iterations] == [r.linear_solver_iterations for r in rows]
     assert np.array_equal(x1, bal3.parameters.toArray())               # the internal order is canonical
+
+
+def test_batched_curve_fits_full_size_properties(sk):
+    """BASELINE.json configs[3] at its full size: 1M independent CurveFitting-sized problems, one launch per LM iteration.
+    Size-independent properties: every problem terminates with CONVERGENCE, no cost rises, the fitted (m, c) scatter
+    around the truth as the noise level predicts, and the run is bit-reproducible."""
+    n = 1_000_000
+    x, y, truth = synth.make_curve_fit_batch(n, seed=1)
+    xa, ya = sk.DoubleArray.fromArray(x), sk.DoubleArray.fromArray(y)
+    o = sk.Solver.Options()
+    o.setLinearSolverType(_abi.DENSE_QR)
+    o.setMaxNumIterations(25)
+    runs = []
+    for _ in range(2):
+        mc = sk.DoubleArray(2 * n)
+        summary, ic, fc, it, tt = sk.curve_fit_batch_solve(o, xa, ya, mc)
+        runs.append((mc.toArray(), fc.copy(), it.copy()))
+        assert np.all(tt == _abi.CONVERGENCE)
+        assert np.all(fc <= ic)
+    sol = runs[0][0].reshape(2, n)
+    err = sol - truth
+    assert abs(err[0].mean()) < 1e-3 and abs(err[1].mean()) < 3e-3           # unbiased up to the nonlinearity
+    assert 0.005 < err[0].std() < 0.08 and 0.01 < err[1].std() < 0.25
+    assert np.median(runs[0][1]) == pytest.approx(0.5 * 67 * 0.2 ** 2, rel=0.1)   # residual cost ~ (n_obs - 2) sigma^2 / 2
+    assert 1 <= runs[0][2].min() and runs[0][2].max() <= 25
+    assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][2], runs[1][2])
