@@ -62,8 +62,8 @@ def matvec_algorithmic_bytes(n_obs, n_pts, n_cams):
 # DRAM traffic of the dominant kernel per launch, from the committed `ncu --set full` capture of the SAME workload
 # (Venice-1778 shape x 1 GPU): dram__bytes_read.sum + dram__bytes_write.sum of k_ba_matvec_tma, launch 0.
 # bench.py cannot run ncu itself; the figure is only attached when the workload is the captured one.
-MATVEC_NCU_TRAFFIC = {"bytes_per_launch": 1.058238e9 + 25.296896e6, "n_obs": 5001946,
-                      "source": "profiles/r01_v6_matvec_tma_summary.md (gpurun_out/prof_matvec_v6.ncu-rep)"}
+MATVEC_NCU_TRAFFIC = {"bytes_per_launch": 1.058313e9 + 25.707008e6, "n_obs": 5001946,
+                      "source": "profiles/r01_v9_matvec_tma_summary.md (ncu --set full, launch 0 of gpurun_out/prof_matvec_v9.ncu-rep)"}
 
 
 class ClockSampler:
@@ -301,7 +301,8 @@ def main():
         e2e = {"value": n_obs * its / t1, "unit": UNIT, "h2d_bytes_per_step": int(h2d / max(its, 1)), "d2h_bytes_per_step": int(d2h / max(its, 1)),
                "lm_iterations": its, "wall_s": t1, "wall_s_runs": [r[0] for r in runs], "preprocessor_s": pre_s, "final_cost": final_cost,
                "what": "DoubleArray upload + addResidualBlocks + ceres.solve (preprocess, layout upload, K LM iterations) + parameter download; "
-                       "two full passes, the faster one reported"}
+                       "two full passes, the faster one reported" + ("; every rank ingests only the residual blocks of its own points "
+                                                                    "(residual_blocks_are_local), all cameras declared" if world > 1 else "")}
 
     # ------------------------------------------------------------------ CPU baseline beside it (rank 0, N = 1 only)
     cpu = None
@@ -325,7 +326,7 @@ def main():
                 "pcg_iteration_ms": None if fam_ms is None or fam_launches[3] == 0 else
                     float((fam_ms[3] + fam_ms[4] + fam_ms[8]) / fam_launches[3]),
                 "pcg_iteration_ms_note": "(k_ba_matvec + PCG vector kernels + allreduce) device time / executed matvecs, from the "
-                                         "instrumented pass; N=1 reference 0.324 ms",
+                                         "instrumented pass (N=1: 0.262 ms, profiles/r01_v10_bench_venice_n1.json)",
                 "wall_s_timed_region": t_wall, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "clocks": clocks, "final_cost_last_solve": last.final_cost if last is not None else None,
                 "pcg_iterations_last_solve": [r.linear_solver_iterations for r in last.iterations] if last is not None else None}

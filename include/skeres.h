@@ -387,6 +387,12 @@ const int32_t* sk_bal_problem_point_index(const sk_bal_problem* b);  /* :23  hos
 const double* sk_bal_problem_observations(const sk_bal_problem* b);  /* :25  host memory, 2*nobs */
 /* The loop of SimpleBundleAdjuster.scala:139-145 as one call. */
 int sk_bal_problem_build(sk_bal_problem* b, const sk_loss_function* loss, sk_problem* problem);
+/* mutableCameraForObservation(i) / mutablePointForObservation(i) (SimpleBundleAdjuster.scala:31-33) for observations
+ * [0, n_obs) at once, as offsets into the BalProblem parameter array (cameras first, :28-29): out[2i] = 9 * camera_index[i],
+ * out[2i + 1] = 9 * num_cameras + 3 * point_index[i].  Host-only helper: the interleaved array is what
+ * sk_problem_add_residual_blocks takes.  Fails on an index outside [0, num_cameras) / [0, num_points). */
+int sk_bal_block_offsets(int64_t n_obs, const int32_t* camera_index, const int32_t* point_index,
+                         int32_t num_cameras, int32_t num_points, int64_t* out_offsets);
 
 /* ------------------------------------------------------------------------------------------
  * Multi-GPU (no counterpart in the reference, which is single-threaded): one process per GPU,

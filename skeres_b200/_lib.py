@@ -61,6 +61,7 @@ def _load():
         "sk_problem_add_residual_block": (i32, [vp, vp, vp, vp, i32, P(i64)]),
         "sk_problem_add_residual_blocks": (i32, [vp, i32, i64, vp, vp, vp, vp, P(i64)]),
         "sk_problem_add_parameter_blocks": (i32, [vp, vp, i64, vp, i32]),
+        "sk_bal_block_offsets": (i32, [i64, vp, vp, i32, i32, vp]),
         "sk_problem_num_residual_blocks": (i64, [vp]),
         "sk_problem_num_residuals": (i64, [vp]),
         "sk_problem_num_parameter_blocks": (i64, [vp]),

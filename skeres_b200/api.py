@@ -516,12 +516,12 @@ class BalProblem:
     def mutablePointForObservation(self, i):
         return self.mutablePoints().slice(int(self.pointIndex[i]) * 3)
 
-    def blockOffsets(self):
-        off = np.empty((self.numObservations, 2), dtype=np.int64)
-        # written straight into the interleaved array, in int64, without temporaries (this is on the e2e path)
-        np.multiply(self.cameraIndex, 9, out=off[:, 0], dtype=np.int64)
-        np.multiply(self.pointIndex, 3, out=off[:, 1], dtype=np.int64)
-        off[:, 1] += 9 * self.numCameras
+    def blockOffsets(self, o0=0, o1=None):
+        """Offsets of mutableCameraForObservation(i) / mutablePointForObservation(i) for observations [o0, o1), interleaved."""
+        o1 = self.numObservations if o1 is None else o1
+        off = np.empty((o1 - o0, 2), dtype=np.int64)
+        check(lib.sk_bal_block_offsets(o1 - o0, _vp(self.cameraIndex[o0:o1]), _vp(self.pointIndex[o0:o1]), self.numCameras, self.numPoints,
+                                       _vp(off)))
         return off
 
     def buildProblem(self, loss=None):
@@ -549,10 +549,7 @@ class BalProblem:
         problem = Problem()
         loss = loss if loss is not None else PredefinedLossFunctions.trivialLoss()
         problem.addParameterBlocks(self.parameters, 9 * np.arange(self.numCameras, dtype=np.int64), 9)
-        off = np.empty((o1 - o0, 2), dtype=np.int64)
-        np.multiply(self.cameraIndex[o0:o1], 9, out=off[:, 0], dtype=np.int64)
-        np.multiply(self.pointIndex[o0:o1], 3, out=off[:, 1], dtype=np.int64)
-        off[:, 1] += 9 * self.numCameras
+        off = self.blockOffsets(o0, o1)
         problem.addResidualBlocks(_abi.FUNCTOR_SNAVELY_REPROJECTION_ERROR, self.observations[2 * o0:2 * o1].reshape(-1, 2), loss,
                                   self.parameters, off)
         return problem

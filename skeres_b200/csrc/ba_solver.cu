@@ -3,7 +3,10 @@
 // explicit reduced camera system (DENSE_SCHUR / SPARSE_SCHUR, dense Cholesky).
 #include "ba_solver.cuh"
 
+#include "host_parallel.h"
+
 #include <chrono>
+#include <thread>
 #include <cstdlib>
 
 #include "dense_kernels.cuh"
@@ -101,7 +104,8 @@ void BaSolver::build_tile_records() {
   const int sp = (std::max(H.max_seg_tile, 1) + 1 + 3) & ~3, pp = (std::max(H.max_pt_tile, 1) + 1 + 3) & ~3;
   const size_t stride = (size_t)8 * T + 4 * ((size_t)2 * sp + pp);
   std::vector<unsigned char> rec((size_t)std::max(H.n_tiles, 1) * stride, 0);
-  for (int t = 0; t < H.n_tiles; ++t) {
+  parallel_for(H.n_tiles, [&](int64_t t_begin, int64_t t_end) {
+  for (int64_t t = t_begin; t < t_end; ++t) {
     unsigned char* base = rec.data() + (size_t)t * stride;
     uint16_t* slot = reinterpret_cast<uint16_t*>(base); uint16_t* ptl = slot + T; uint16_t* sperm = ptl + T;
     int32_t* sptr = reinterpret_cast<int32_t*>(base + 8 * T); int32_t* pptr = sptr + sp; int32_t* scam = pptr + pp;
@@ -112,6 +116,7 @@ void BaSolver::build_tile_records() {
     for (int s = 0; s < ns; ++s) scam[s] = H.seg_cam[sb + s];
     if (H.tile_chunk[t] < 0) for (int q = 0; q <= np; ++q) pptr[q] = H.pt_ptr[pb + q] - ob;
   }
+  });
   d_tile_rec_.upload(rec, stream_);
   SK_CUDA(cudaStreamSynchronize(stream_));
   L_.tile_rec = d_tile_rec_.p; L_.rec_stride = (int)stride; L_.rec_sp = sp; L_.rec_pp = pp;
@@ -292,6 +297,14 @@ void BaSolver::pcg_solve(const double* Minv) {
   }
   const int its = pcg_h_.p->iter;
   n_real_matvecs_ += (its + its / kResetPeriod) * (L_.n_giant ? 2 : 1);
+}
+
+BaSolver::~BaSolver() {
+  if ((size_t)H_.n_obs < (size_t)1 << 20) return;            // small: freed in place with the other members
+  try {
+    auto* drop = new BaLayoutHost(std::move(H_));
+    std::thread([drop] { delete drop; }).detach();
+  } catch (...) {}                                          // no thread: H_ (or *drop, leaked at worst) is freed the usual way
 }
 
 void BaSolver::exchange_local_totals() {

@@ -10,6 +10,9 @@ class BaSolver : public LmSolver {
   // user_params: device pointer of the user's parameter DoubleArray (all blocks live in it).
   BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHost&& layout, double* user_params,
            int64_t user_n, LossSpec loss);
+  // The host copy of the layout is hundreds of MB at Venice scale; unmapping it took up to 80 ms of sk_solver_destroy, so it
+  // is handed to a detached thread (plain host memory, no CUDA calls).
+  ~BaSolver() override;
   void fill_totals(int64_t total_obs, int64_t total_blocks, int64_t total_params, std::vector<int64_t>&& all_pt_off);
   // Rank-local ingestion (sk_solver_options.residual_blocks_are_local): sums the per-rank observation / point counts for
   // the summary and checks that every rank built the same camera table.  Collective: every rank must call it.

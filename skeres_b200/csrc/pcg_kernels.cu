@@ -36,6 +36,33 @@ __device__ __forceinline__ double block_sum_fixed(double x, double* red) {   // 
   return r;                               // valid in thread 0
 }
 
+// N block sums at once: the same per-thread order and the same trees as N calls of block_sum_fixed, one barrier pair.
+// red: [N][8].  Valid in thread 0.
+template <int N>
+__device__ __forceinline__ void block_sum_fixed_n(double (&x)[N], double* red) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x[n] += __shfl_down_sync(0xffffffffu, x[n], o);
+  }
+  __syncthreads();
+  if (l == 0) {
+#pragma unroll
+    for (int n = 0; n < N; ++n) red[n * 8 + w] = x[n];
+  }
+  __syncthreads();
+  if (w == 0) {
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      double r = (l < (int)(blockDim.x >> 5)) ? red[n * 8 + l] : 0.0;
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
+      x[n] = r;
+    }
+  }
+}
+
 __device__ double sum_fixed(const double* part, int n, double* red) {
   double a = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) a += __ldcg(part + i);   // L2: partials may come from other CTAs of this launch
@@ -96,10 +123,16 @@ __device__ void pcg_head_step(PcgDev* st, const double* part_rho, const double* 
   if (st->active == 0) return;
   const int it = st->iter;
   const bool need_finish = it >= 1 && st->pad_ != it;
-  double pq = 0.0, xbr = 0.0;
-  if (need_finish) { pq = sum_fixed(part_pq, nparts, red); xbr = sum_fixed(part_Q, nparts, red); }
-  double rho = 0.0;
-  if (!finish_only) rho = sum_fixed(part_rho, nparts, red);
+  // p.q and x.(b + r) of the iteration being finished, r.z of the one being opened: one pass, one barrier pair (each sum
+  // keeps the order sum_fixed gives it)
+  __shared__ double red3[3 * 8];
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) {
+    if (need_finish) { acc[0] += __ldcg(part_pq + i); acc[1] += __ldcg(part_Q + i); }
+    if (!finish_only) acc[2] += __ldcg(part_rho + i);
+  }
+  block_sum_fixed_n<3>(acc, red3);
+  const double pq = acc[0], xbr = acc[1], rho = acc[2];
   if (threadIdx.x != 0) return;
   if (need_finish) {
     st->pad_ = it;
@@ -154,6 +187,20 @@ __device__ bool pcg_last_block(PcgDev* st) {
 // every WPC-th group of three segments, the warp sums are added in warp order.
 constexpr int WPC = 4;
 
+// acc = seg_y[cam_seg[t]][k] + seg_y[cam_seg[t + 3 WPC]][k] + ... in that order, four partials in flight (the walk is a
+// chain of dependent index -> value loads out of L2 otherwise).
+__device__ __forceinline__ double walk_segments(const BaDev& L, const double* __restrict__ seg_y, int t, int e, int k) {
+  constexpr int S = 3 * WPC;
+  double acc = 0.0;
+  for (; t + 3 * S < e; t += 4 * S) {
+    const int s0 = L.cam_seg[t], s1 = L.cam_seg[t + S], s2 = L.cam_seg[t + 2 * S], s3 = L.cam_seg[t + 3 * S];
+    const double x0 = seg_y[(size_t)s0 * 9 + k], x1 = seg_y[(size_t)s1 * 9 + k], x2 = seg_y[(size_t)s2 * 9 + k], x3 = seg_y[(size_t)s3 * 9 + k];
+    acc += x0; acc += x1; acc += x2; acc += x3;
+  }
+  for (; t < e; t += S) acc += seg_y[(size_t)L.cam_seg[t] * 9 + k];
+  return acc;
+}
+
 __global__ void __launch_bounds__(WPB * WPC * 32) k_pcg_reduce(BaDev L, const double* __restrict__ seg_y, const double* __restrict__ y_in,
                                                                 const double* __restrict__ D, double* __restrict__ z, double* __restrict__ p,
                                                                 double* __restrict__ part_pq, const PcgDev* st) {
@@ -167,7 +214,7 @@ __global__ void __launch_bounds__(WPB * WPC * 32) k_pcg_reduce(BaDev L, const do
   if (c < L.n_cams && y_in == nullptr) {
     double acc = 0.0;
     if (lane < 27)
-      for (int t = L.cam_seg_ptr[c] + sub * 3 + j; t < L.cam_seg_ptr[c + 1]; t += 3 * WPC) acc += seg_y[(size_t)L.cam_seg[t] * 9 + k];
+      acc = walk_segments(L, seg_y, L.cam_seg_ptr[c] + sub * 3 + j, L.cam_seg_ptr[c + 1], k);
     const double a1 = __shfl_down_sync(0xffffffffu, acc, 9), a2 = __shfl_down_sync(0xffffffffu, acc, 18);
     acc = (acc + a1) + a2;
     if (lane < 9) part[cl][sub][lane] = acc;
@@ -244,8 +291,10 @@ __global__ void k_pcg_update(int n_cams, const double* __restrict__ Minv, const 
     }
   }
   if (!recompute) {
-    const double s1 = block_sum_fixed(qsum, red), s2 = block_sum_fixed(rz, red);
-    if (threadIdx.x == 0) { part_Q[blockIdx.x] = s1; part_rho[blockIdx.x] = s2; }
+    __shared__ double red2[2 * 8];
+    double s12[2] = {qsum, rz};
+    block_sum_fixed_n<2>(s12, red2);
+    if (threadIdx.x == 0) { part_Q[blockIdx.x] = s12[0]; part_rho[blockIdx.x] = s12[1]; }
     // the CTA that publishes last finishes this iteration and opens the next one (what k_pcg_head would do next)
     if (pcg_last_block(st)) pcg_head_step(st, part_rho, part_pq, part_Q, nparts, prm, 0, red);
   }
@@ -307,7 +356,7 @@ __global__ void __launch_bounds__(WPB * WPC * 32) k_cam_reduce9_warp(BaDev L, co
   if (c < L.n_cams) {
     double acc = 0.0;
     if (lane < 27)
-      for (int t = L.cam_seg_ptr[c] + sub * 3 + j; t < L.cam_seg_ptr[c + 1]; t += 3 * WPC) acc += seg_y[(size_t)L.cam_seg[t] * 9 + k];
+      acc = walk_segments(L, seg_y, L.cam_seg_ptr[c] + sub * 3 + j, L.cam_seg_ptr[c + 1], k);
     const double a1 = __shfl_down_sync(0xffffffffu, acc, 9), a2 = __shfl_down_sync(0xffffffffu, acc, 18);
     acc = (acc + a1) + a2;
     if (lane < 9) part[cl][sub][lane] = acc;

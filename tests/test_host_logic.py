@@ -398,3 +398,22 @@ def test_small_spd_inverses(hc):
         assert hc.hc_invert_spd9(p(S), 9) == 1 and np.allclose(S, want, rtol=1e-9, atol=1e-12)
     bad = np.array([1.0, 2.0, 0.0, 1.0, 0.0, 1.0]); out = np.zeros(6)
     assert hc.hc_invert_spd3(p(bad), p(out)) == 0            # not positive definite -> reported, not NaN-propagated
+
+
+def test_bal_block_offsets_helper():
+    """sk_bal_block_offsets == BalProblem.mutableCameraForObservation / mutablePointForObservation for every observation
+    (SimpleBundleAdjuster.scala:28-33); host-only, index errors are reported with the lowest offending observation."""
+    from skeres_b200 import api
+    d = synth.make_bal("ladybug-49", seed=3)
+    bal = api.BalProblem(d.num_cameras, d.num_points, d.camera_index, d.point_index, d.observations, None)
+    off = bal.blockOffsets()
+    assert np.array_equal(off, d.block_offsets())
+    assert np.array_equal(off[:, 0], 9 * d.camera_index.astype(np.int64))
+    assert np.array_equal(off[:, 1], 9 * d.num_cameras + 3 * d.point_index.astype(np.int64))
+    assert np.array_equal(bal.blockOffsets(100, 250), off[100:250])
+    assert bal.blockOffsets(5, 5).shape == (0, 2)
+    bal.cameraIndex = bal.cameraIndex.copy()
+    bal.cameraIndex[[11, 300]] = [-1, d.num_cameras]
+    with pytest.raises(api.SkeresError) as e:
+        bal.blockOffsets()
+    assert e.value.status == _abi.ERR_INVALID_ARGUMENT and "observation 11" in str(e.value)
