@@ -417,3 +417,14 @@ def test_bal_block_offsets_helper():
     with pytest.raises(api.SkeresError) as e:
         bal.blockOffsets()
     assert e.value.status == _abi.ERR_INVALID_ARGUMENT and "observation 11" in str(e.value)
+
+
+def test_graft_entry_build_runs():
+    """__graft_entry__.build() is the driver's "does it build" check: incremental make + import + ABI version."""
+    sys_path = list(__import__("sys").path)
+    __import__("sys").path.insert(0, ROOT)
+    try:
+        import __graft_entry__ as g
+        g.build()
+    finally:
+        __import__("sys").path[:] = sys_path
