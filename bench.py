@@ -26,6 +26,9 @@ import time
 
 import numpy as np
 
+# stdout carries exactly ONE JSON line: NCCL's version banner (printed when the box sets NCCL_DEBUG) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 

@@ -14,6 +14,8 @@
 
 namespace sk {
 
+static bool lst_is_explicit(int lst) { return lst == SK_DENSE_SCHUR || lst == SK_SPARSE_SCHUR; }
+
 namespace {
 __global__ void k_gather_blocks(int nblocks, int bsize, const long long* __restrict__ offsets, const double* __restrict__ user,
                                 double* __restrict__ x) {
@@ -70,6 +72,7 @@ BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHo
   rhs_.alloc(nc); px_.alloc(nc); pr_.alloc(nc); pp_.alloc(nc); pz_.alloc(nc); ybuf_.alloc(nc);
   pcg_.alloc(1); pcg_h_.alloc(1);
   pcg_part_.alloc(4 * kMaxPartials);
+  if (comm_ && comm_->world > 1 && !(lst_is_explicit(opt.linear_solver_type))) peer_allreduce_create(comm_, (size_t)nc, s, &peer_);   // collective
   SK_REQUIRE(cdiv(H.n_cams, 8) <= kMaxPartials, SK_ERR_UNSUPPORTED, "more than %d cameras", kMaxPartials * 256 / 9);
   const int lst = opt.linear_solver_type;
   explicit_schur_ = (lst == SK_DENSE_SCHUR || lst == SK_SPARSE_SCHUR);
@@ -208,6 +211,14 @@ const double* BaSolver::matvec(const double* in, bool pcg_dir, const int* guard)
                      seg_a_.p, guard, stream_, have_tmapJ_ ? &tmapJ_ : nullptr);
   }
   if (comm_ && comm_->world > 1) {
+    if (peer_.ok) {
+      // the exchange is fused into the kernels on either side: this rank's reduced vector goes into its peer window and is
+      // published; the consumer (k_pcg_reduce / k_pcg_resid2, same sequence number) adds all ranks' windows in rank order
+      ++peer_.seq;
+      KScope k(prof_, SK_KF_PCG_VECTOR);
+      launch_cam_reduce9_warp(L_, seg_a_.p, nullptr, guard, stream_, &peer_.win, peer_.seq);
+      return nullptr;
+    }
     { KScope k(prof_, SK_KF_PCG_VECTOR); launch_cam_reduce9_warp(L_, seg_a_.p, ybuf_.p, guard, stream_); }
     KScope k(prof_, SK_KF_COMM);
     comm_allreduce_sum(comm_, ybuf_.p, (size_t)nc_, stream_);
@@ -281,13 +292,14 @@ void BaSolver::pcg_solve(const double* Minv) {
       const int recompute = (it % kResetPeriod == 0) ? 1 : 0;
       {
         KScope k(prof_, SK_KF_PCG_VECTOR, 2);
-        launch_pcg_reduce(L_, seg_a_.p, y, D_.p, pz_.p, pp_.p, part_pq, pcg_.p, stream_);
+        launch_pcg_reduce(L_, seg_a_.p, y, D_.p, pz_.p, pp_.p, part_pq, pcg_.p, stream_, peer_.ok ? &peer_.win : nullptr, peer_.seq);
         launch_pcg_update(L_.n_cams, Minv, rhs_.p, px_.p, pp_.p, pr_.p, pz_.p, part_pq, recompute, part_Q, part_rho, pcg_.p, pp, stream_);
       }
       if (recompute) {
         const double* yx = matvec(px_.p, false, active);
         KScope k(prof_, SK_KF_PCG_VECTOR);
-        launch_pcg_resid2(L_, seg_a_.p, yx, D_.p, Minv, rhs_.p, px_.p, pr_.p, pz_.p, part_Q, part_rho, pcg_.p, part_pq, pp, stream_);
+        launch_pcg_resid2(L_, seg_a_.p, yx, D_.p, Minv, rhs_.p, px_.p, pr_.p, pz_.p, part_Q, part_rho, pcg_.p, part_pq, pp, stream_,
+                          peer_.ok ? &peer_.win : nullptr, peer_.seq);
       }
     }
     SK_CUDA(cudaMemcpyAsync(pcg_h_.p, pcg_.p, sizeof(PcgDev), cudaMemcpyDeviceToHost, stream_));
@@ -295,11 +307,18 @@ void BaSolver::pcg_solve(const double* Minv) {
     prof_.collect();
     done = pcg_h_.p->active == 0;
   }
+  if (peer_.ok) {
+    int perr = 0;
+    SK_CUDA(cudaMemcpyAsync(&perr, peer_.win.error, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    SK_CUDA(cudaStreamSynchronize(stream_));
+    SK_REQUIRE(perr == 0, SK_ERR_NCCL, "multi-GPU exchange timed out: a rank stopped or the ranks lost lockstep (rank %d)", comm_->rank);
+  }
   const int its = pcg_h_.p->iter;
   n_real_matvecs_ += (its + its / kResetPeriod) * (L_.n_giant ? 2 : 1);
 }
 
 BaSolver::~BaSolver() {
+  peer_allreduce_destroy(&peer_);
   if ((size_t)H_.n_obs < (size_t)1 << 20) return;            // small: freed in place with the other members
   try {
     auto* drop = new BaLayoutHost(std::move(H_));

@@ -43,6 +43,7 @@ class BaSolver : public LmSolver {
   double* user_; int64_t user_n_;
   LossSpec loss_;
   bool explicit_schur_ = false;
+  PeerAllreduce peer_;                 // multi-GPU: NVLink peer window for the per-PCG-iteration exchange (comm.cuh)
   bool local_blocks_ = false;          // this rank was given only its own residual blocks (no publication of foreign points)
   int64_t total_obs_ = 0, total_param_blocks_ = 0, total_params_ = 0;
   std::vector<int64_t> all_pt_off_;

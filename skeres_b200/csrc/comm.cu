@@ -5,7 +5,10 @@
 #include <dlfcn.h>
 
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
+#include <vector>
 
 namespace sk {
 
@@ -98,5 +101,64 @@ void comm_allreduce_max(sk_comm* c, double* buf, size_t count, cudaStream_t stre
 }
 void comm_group_start(sk_comm* c) { if (c && c->world > 1) check(api().GroupStart(), "ncclGroupStart"); }
 void comm_group_end(sk_comm* c) { if (c && c->world > 1) check(api().GroupEnd(), "ncclGroupEnd"); }
+
+// ---- peer window ---------------------------------------------------------------------------------------------------------
+void peer_allreduce_create(sk_comm* c, size_t count, cudaStream_t stream, PeerAllreduce* pa) {
+  pa->ok = false; pa->win = PeerWindow{}; pa->seq = 0;
+  if (!c || c->world <= 1 || c->world > kMaxPeers) return;
+  { const char* e = getenv("SKERES_PEER_ALLREDUCE"); if (e && e[0] == '0') return; }
+  const int world = c->world, rank = c->rank;
+  const size_t stride = (count + 15) & ~(size_t)15;
+  const size_t flag_doubles = (size_t)kMaxPeers * 2, tail_doubles = 2;            // flags, then error + done_count
+  pa->mem.alloc(2 * stride + flag_doubles + tail_doubles);
+  pa->mem.zero(stream);                                                            // flags = 0 before anybody can publish
+  // exchange the IPC handles: rank r's 64 bytes travel as 64 doubles (one byte each: exact under a sum of zeros) plus a
+  // "can export" marker, in one NCCL allreduce -- which also orders every rank's zeroing before the first exchange
+  cudaIpcMemHandle_t mine;
+  const bool exported = cudaIpcGetMemHandle(&mine, pa->mem.p) == cudaSuccess;
+  if (!exported) cudaGetLastError();
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  const size_t per = 65;
+  std::vector<double> h((size_t)world * per, 0.0);
+  for (size_t b = 0; b < 64; ++b) h[rank * per + b] = (double)reinterpret_cast<const unsigned char*>(&mine)[b];
+  h[rank * per + 64] = exported ? 1.0 : 0.0;
+  DBuf<double> d(h.size());
+  d.upload(h, stream);
+  comm_allreduce_sum(c, d.p, h.size(), stream);
+  d.download(h.data(), h.size(), stream);
+  SK_CUDA(cudaStreamSynchronize(stream));
+  bool all = true;
+  for (int r = 0; r < world; ++r) all = all && h[r * per + 64] == 1.0;
+  // every rank takes the same decision from the same data; a mapping failure below is reported to the others as well
+  double mapped = all ? 1.0 : 0.0;
+  if (all) {
+    for (int r = 0; r < world && mapped == 1.0; ++r) {
+      if (r == rank) { pa->opened[r] = nullptr; pa->win.data[r] = pa->mem.p; continue; }
+      cudaIpcMemHandle_t hr;
+      for (size_t b = 0; b < 64; ++b) reinterpret_cast<unsigned char*>(&hr)[b] = (unsigned char)h[r * per + b];
+      void* ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, hr, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); mapped = 0.0; break; }
+      pa->opened[r] = ptr; pa->win.data[r] = static_cast<double*>(ptr);
+    }
+  }
+  std::vector<double> m = {mapped};
+  d.upload(m.data(), 1, stream);
+  comm_allreduce_sum(c, d.p, 1, stream);
+  d.download(m.data(), 1, stream);
+  SK_CUDA(cudaStreamSynchronize(stream));
+  if (m[0] != (double)world) { peer_allreduce_destroy(pa); return; }
+  for (int r = 0; r < world; ++r) pa->win.flags[r] = reinterpret_cast<unsigned long long*>(pa->win.data[r] + 2 * stride);
+  pa->win.error = reinterpret_cast<int*>(pa->mem.p + 2 * stride + flag_doubles);
+  pa->win.done_count = reinterpret_cast<unsigned int*>(pa->win.error + 1);
+  pa->win.stride = (long long)stride; pa->win.rank = rank; pa->win.world = world;
+  pa->ok = true;
+  if (getenv("SKERES_TRACE_HOST")) fprintf(stderr, "[skeres] rank %d: peer window of %zu doubles mapped on %d ranks\n", rank, count, world);
+}
+
+void peer_allreduce_destroy(PeerAllreduce* pa) {
+  for (int r = 0; r < kMaxPeers; ++r)
+    if (pa->opened[r]) { cudaIpcCloseMemHandle(pa->opened[r]); pa->opened[r] = nullptr; }
+  pa->ok = false; pa->win = PeerWindow{};
+}
 
 }  // namespace sk

@@ -20,6 +20,35 @@ void comm_allreduce_max(sk_comm* c, double* buf, size_t count, cudaStream_t stre
 extern double g_comm_host_seconds;   // development trace (SKERES_TRACE_HOST)
 extern long g_comm_calls;
 void comm_group_start(sk_comm* c);
+
+// ---- peer window: allreduce of a camera-sized vector through NVLink peer memory, fused into the kernels on either side ----
+// Every rank owns one device allocation, mapped into every other rank with CUDA IPC:
+//   double data[2][stride]            the rank's contribution, double-buffered by the parity of the sequence number
+//   u64    flags[kMaxPeers][2]        flags[r][parity] = sequence number of the last contribution rank r has published
+//   int    error                      set when a wait timed out (a rank died or the ranks lost lockstep)
+// Producer kernel (k_cam_reduce9_warp): writes its data, then its last CTA stores the sequence number into flags[me][parity] of
+// EVERY rank (release, system scope).  Consumer kernels (k_pcg_reduce, k_pcg_resid2): wait until their own flags[r][parity]
+// reach the sequence number for every r, then add the ranks' contributions in rank order -- the same bits on every rank.
+constexpr int kMaxPeers = 8;
+struct PeerWindow {
+  double* data[kMaxPeers];                  // base of rank r's window (own: the local pointer)
+  unsigned long long* flags[kMaxPeers];     // flags array inside rank r's window
+  int* error;                               // own error word
+  unsigned int* done_count;                 // own: CTAs of the running producer kernel that have written their part
+  long long stride;                         // doubles per parity slot
+  int rank, world;                          // world == 0: no peer window (single GPU or NCCL path)
+};
+struct PeerAllreduce {
+  PeerWindow win{};
+  void* opened[kMaxPeers] = {};
+  DBuf<double> mem;
+  unsigned long long seq = 0;               // sequence number of the last exchange
+  bool ok = false;
+};
+// Collective over `c`: allocates the window for `count` doubles and exchanges the IPC handles (through one NCCL allreduce).
+// Leaves pa->ok == false (NCCL allreduce stays in use) when peer mapping is unavailable or SKERES_PEER_ALLREDUCE=0.
+void peer_allreduce_create(sk_comm* c, size_t count, cudaStream_t stream, PeerAllreduce* pa);
+void peer_allreduce_destroy(PeerAllreduce* pa);
 void comm_group_end(sk_comm* c);
 
 }  // namespace sk

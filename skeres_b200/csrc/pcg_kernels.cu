@@ -79,6 +79,62 @@ __device__ double sum_fixed_all(const double* part, int n, double* red, double* 
 
 __device__ __forceinline__ bool zero_or_inf(double x) { return x == 0.0 || isinf(x); }
 
+// ---- peer window (comm.cuh): system-scope flag / data accesses over NVLink peer memory ----------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];\n" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+// Consumer side: every CTA waits until all ranks have published exchange `seq` (one polling thread per rank, bounded: a rank
+// that died or lost lockstep must not hang the GPU -- the error word is checked by the host after the solve).
+__device__ __forceinline__ void peer_wait(const PeerWindow& win, int parity, unsigned long long seq) {
+  if ((int)threadIdx.x < win.world) {
+    const unsigned long long* f = win.flags[win.rank] + threadIdx.x * 2 + parity;
+    long long spins = 0;
+    while (ld_acquire_sys(f) < seq) {
+      __nanosleep(40);
+      if (++spins > (1ll << 25)) { atomicExch(win.error, 1); break; }
+    }
+  }
+  __syncthreads();
+}
+// y[e] summed over the ranks' contributions in rank order (the same bits on every rank).
+__device__ __forceinline__ double peer_gather(const PeerWindow& win, int parity, size_t e) {
+  double x[kMaxPeers];
+#pragma unroll
+  for (int r = 0; r < kMaxPeers; ++r)                     // all loads in flight before the first add (remote latency once, not world times)
+    x[r] = (r < win.world) ? ld_relaxed_sys(win.data[r] + (size_t)parity * win.stride + e) : 0.0;
+  double acc = 0.0;
+#pragma unroll
+  for (int r = 0; r < kMaxPeers; ++r) if (r < win.world) acc += x[r];
+  return acc;
+}
+// Producer side, at the end of the kernel that wrote this rank's contribution: the CTA that finishes last publishes `seq` to
+// every rank.  Executed unconditionally (also by a kernel whose guard says "skip") so that the ranks' exchanges stay paired.
+__device__ __forceinline__ void peer_publish(const PeerWindow& win, int parity, unsigned long long seq) {
+  __shared__ int last;
+  __syncthreads();                                          // the CTA's writes happen before thread 0's fence (cumulativity)
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(win.done_count, 1u);
+    last = (t == gridDim.x - 1) ? 1 : 0;
+    if (last) *win.done_count = 0;
+  }
+  __syncthreads();
+  if (last && (int)threadIdx.x < win.world) {
+    __threadfence_system();
+    st_release_sys(win.flags[threadIdx.x] + win.rank * 2 + parity, seq);
+  }
+}
+
 __global__ void k_pcg_begin(int n_cams, const double* __restrict__ rhs, const double* __restrict__ Minv, double* __restrict__ x,
                             double* __restrict__ r, double* __restrict__ z, double* __restrict__ part_bb, double* __restrict__ part_rho) {
   // x0 = 0 => r = b - S*0 = b;  z = M^-1 r;  partials of |b|^2 and r.z
@@ -203,15 +259,18 @@ __device__ __forceinline__ double walk_segments(const BaDev& L, const double* __
 
 __global__ void __launch_bounds__(WPB * WPC * 32) k_pcg_reduce(BaDev L, const double* __restrict__ seg_y, const double* __restrict__ y_in,
                                                                 const double* __restrict__ D, double* __restrict__ z, double* __restrict__ p,
-                                                                double* __restrict__ part_pq, const PcgDev* st) {
+                                                                double* __restrict__ part_pq, const PcgDev* st, PeerWindow win, int parity,
+                                                                unsigned long long seq) {
   if (st->active == 0) return;
+  const bool peer = win.world > 1;                     // y = sum over the ranks' windows (k_cam_reduce9_warp published them)
+  if (peer) peer_wait(win, parity, seq);
   __shared__ double part[WPB][WPC][9];
   __shared__ double red[WPB];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cl = warp / WPC, sub = warp % WPC;        // camera within the CTA, warp within the camera
   const int c = blockIdx.x * WPB + cl;
   const int k = lane % 9, j = lane / 9;               // 3 segment lanes x 9 components; lanes 27..31 idle
-  if (c < L.n_cams && y_in == nullptr) {
+  if (c < L.n_cams && y_in == nullptr && !peer) {
     double acc = 0.0;
     if (lane < 27)
       acc = walk_segments(L, seg_y, L.cam_seg_ptr[c] + sub * 3 + j, L.cam_seg_ptr[c + 1], k);
@@ -223,7 +282,8 @@ __global__ void __launch_bounds__(WPB * WPC * 32) k_pcg_reduce(BaDev L, const do
   double pq = 0.0;
   if (c < L.n_cams && sub == 0 && lane < 9) {
     double acc;
-    if (y_in == nullptr) {
+    if (peer) acc = peer_gather(win, parity, (size_t)c * 9 + lane);
+    else if (y_in == nullptr) {
       acc = part[cl][0][lane];
 #pragma unroll
       for (int w = 1; w < WPC; ++w) acc += part[cl][w][lane];
@@ -305,8 +365,11 @@ __global__ void k_pcg_update(int n_cams, const double* __restrict__ Minv, const 
 __global__ void k_pcg_resid2(BaDev L, const double* __restrict__ seg_y, const double* __restrict__ y_in, const double* __restrict__ D,
                              const double* __restrict__ Minv, const double* __restrict__ b, const double* __restrict__ x,
                              double* __restrict__ r, double* __restrict__ z, double* __restrict__ part_Q, double* __restrict__ part_rho,
-                             PcgDev* st, const double* __restrict__ part_pq, PcgParams prm) {
+                             PcgDev* st, const double* __restrict__ part_pq, PcgParams prm, PeerWindow win, int parity,
+                             unsigned long long seq) {
   if (st->active == 0) return;
+  const bool peer = win.world > 1;
+  if (peer) peer_wait(win, parity, seq);
   __shared__ double red[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x * WPB + warp;
@@ -314,7 +377,8 @@ __global__ void k_pcg_resid2(BaDev L, const double* __restrict__ seg_y, const do
   if (c < L.n_cams) {
     const int k = lane % 9, j = lane / 9;
     double acc = 0.0;
-    if (y_in == nullptr) {
+    if (peer) { if (lane < 9) acc = peer_gather(win, parity, (size_t)c * 9 + lane); }
+    else if (y_in == nullptr) {
       if (lane < 27)
         for (int t = L.cam_seg_ptr[c] + j; t < L.cam_seg_ptr[c + 1]; t += 3) acc += seg_y[(size_t)L.cam_seg[t] * 9 + k];
       const double a1 = __shfl_down_sync(0xffffffffu, acc, 9), a2 = __shfl_down_sync(0xffffffffu, acc, 18);
@@ -346,14 +410,14 @@ __global__ void k_pcg_resid2(BaDev L, const double* __restrict__ seg_y, const do
 // y[c] = fixed-order sum of the camera's segment partials, in exactly the order k_pcg_reduce uses (WPC warps per camera,
 // three interleaved segment lanes each, warp sums added in warp order).  Used before the allreduce of the multi-GPU path.
 __global__ void __launch_bounds__(WPB * WPC * 32) k_cam_reduce9_warp(BaDev L, const double* __restrict__ seg_y, double* __restrict__ y,
-                                                                      const int* guard) {
-  if (guard != nullptr && *guard == 0) return;
+                                                                      const int* guard, PeerWindow win, int parity, unsigned long long seq) {
+  const bool run = guard == nullptr || *guard != 0;
   __shared__ double part[WPB][WPC][9];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cl = warp / WPC, sub = warp % WPC;
   const int c = blockIdx.x * WPB + cl;
   const int k = lane % 9, j = lane / 9;
-  if (c < L.n_cams) {
+  if (run && c < L.n_cams) {
     double acc = 0.0;
     if (lane < 27)
       acc = walk_segments(L, seg_y, L.cam_seg_ptr[c] + sub * 3 + j, L.cam_seg_ptr[c + 1], k);
@@ -362,20 +426,26 @@ __global__ void __launch_bounds__(WPB * WPC * 32) k_cam_reduce9_warp(BaDev L, co
     if (lane < 9) part[cl][sub][lane] = acc;
   }
   __syncthreads();
-  if (c < L.n_cams && sub == 0 && lane < 9) {
+  if (run && c < L.n_cams && sub == 0 && lane < 9) {
     double acc = part[cl][0][lane];
 #pragma unroll
     for (int w = 1; w < WPC; ++w) acc += part[cl][w][lane];
     y[(size_t)c * 9 + lane] = acc;
   }
+  if (win.world > 1) peer_publish(win, parity, seq);       // y is this rank's window slot
 }
 
 }  // namespace
 
 int pcg_blocks(int n_cams) { return cdiv(n_cams, WPB); }
 
-void launch_cam_reduce9_warp(const BaDev& L, const double* seg_y, double* y, const int* guard, cudaStream_t s) {
-  k_cam_reduce9_warp<<<pcg_blocks(L.n_cams), WPB * WPC * 32, 0, s>>>(L, seg_y, y, guard);
+void launch_cam_reduce9_warp(const BaDev& L, const double* seg_y, double* y, const int* guard, cudaStream_t s, const PeerWindow* win,
+                             unsigned long long seq) {
+  PeerWindow w{};
+  if (win) w = *win;
+  const int parity = (int)(seq & 1);
+  if (w.world > 1) y = w.data[w.rank] + (size_t)parity * w.stride;
+  k_cam_reduce9_warp<<<pcg_blocks(L.n_cams), WPB * WPC * 32, 0, s>>>(L, seg_y, y, guard, w, parity, seq);
   check_launch("k_cam_reduce9_warp");
 }
 
@@ -392,8 +462,10 @@ void launch_pcg_head(PcgDev* st, const double* part_rho, const double* part_pq, 
   check_launch("k_pcg_head");
 }
 void launch_pcg_reduce(const BaDev& L, const double* seg_y, const double* y_in, const double* D, double* z, double* p, double* part_pq,
-                       const PcgDev* st, cudaStream_t s) {
-  k_pcg_reduce<<<pcg_blocks(L.n_cams), WPB * WPC * 32, 0, s>>>(L, seg_y, y_in, D, z, p, part_pq, st);
+                       const PcgDev* st, cudaStream_t s, const PeerWindow* win, unsigned long long seq) {
+  PeerWindow w{};
+  if (win) w = *win;
+  k_pcg_reduce<<<pcg_blocks(L.n_cams), WPB * WPC * 32, 0, s>>>(L, seg_y, y_in, D, z, p, part_pq, st, w, (int)(seq & 1), seq);
   check_launch("k_pcg_reduce");
 }
 void launch_pcg_update(int n_cams, const double* Minv, const double* b, double* x, const double* p, double* r, double* z,
@@ -404,8 +476,11 @@ void launch_pcg_update(int n_cams, const double* Minv, const double* b, double* 
 }
 void launch_pcg_resid2(const BaDev& L, const double* seg_y, const double* y_in, const double* D, const double* Minv, const double* b,
                        const double* x, double* r, double* z, double* part_Q, double* part_rho, PcgDev* st, const double* part_pq,
-                       PcgParams prm, cudaStream_t s) {
-  k_pcg_resid2<<<pcg_blocks(L.n_cams), WPB * 32, 0, s>>>(L, seg_y, y_in, D, Minv, b, x, r, z, part_Q, part_rho, st, part_pq, prm);
+                       PcgParams prm, cudaStream_t s, const PeerWindow* win, unsigned long long seq) {
+  PeerWindow w{};
+  if (win) w = *win;
+  k_pcg_resid2<<<pcg_blocks(L.n_cams), WPB * 32, 0, s>>>(L, seg_y, y_in, D, Minv, b, x, r, z, part_Q, part_rho, st, part_pq, prm, w,
+                                                          (int)(seq & 1), seq);
   check_launch("k_pcg_resid2");
 }
 
