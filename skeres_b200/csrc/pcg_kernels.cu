@@ -14,6 +14,8 @@
 // All sums are fixed-order (per-warp partials reduced by one CTA), hence bit-reproducible.
 #include "pcg_kernels.cuh"
 
+#include <cstdlib>
+
 namespace sk {
 
 namespace {
@@ -241,10 +243,13 @@ __device__ bool pcg_last_block(PcgDev* st) {
 // A camera owns ~190 (tile, camera) partials on the Venice shape; with one warp (three segment lanes) the walk over them is
 // a 60-step chain of dependent L2 loads and was the longest of the small PCG kernels.  Each of the camera's WPC warps takes
 // every WPC-th group of three segments, the warp sums are added in warp order.
-constexpr int WPC = 4;
+// WPC is chosen per problem from the average number of partials per camera (pcg_wpc): 4 at ~190 (one Venice-sized share on
+// one GPU), 2 or 1 when the cameras of a larger problem are spread over more ranks and each rank holds few partials per camera
+// -- four warps walking two partials each made these kernels six waves of near-empty CTAs at 14,224 cameras.
 
 // acc = seg_y[cam_seg[t]][k] + seg_y[cam_seg[t + 3 WPC]][k] + ... in that order, four partials in flight (the walk is a
 // chain of dependent index -> value loads out of L2 otherwise).
+template <int WPC>
 __device__ __forceinline__ double walk_segments(const BaDev& L, const double* __restrict__ seg_y, int t, int e, int k) {
   constexpr int S = 3 * WPC;
   double acc = 0.0;
@@ -257,6 +262,7 @@ __device__ __forceinline__ double walk_segments(const BaDev& L, const double* __
   return acc;
 }
 
+template <int WPC>
 __global__ void __launch_bounds__(WPB * WPC * 32) k_pcg_reduce(BaDev L, const double* __restrict__ seg_y, const double* __restrict__ y_in,
                                                                 const double* __restrict__ D, double* __restrict__ z, double* __restrict__ p,
                                                                 double* __restrict__ part_pq, const PcgDev* st, PeerWindow win, int parity,
@@ -273,7 +279,7 @@ __global__ void __launch_bounds__(WPB * WPC * 32) k_pcg_reduce(BaDev L, const do
   if (c < L.n_cams && y_in == nullptr && !peer) {
     double acc = 0.0;
     if (lane < 27)
-      acc = walk_segments(L, seg_y, L.cam_seg_ptr[c] + sub * 3 + j, L.cam_seg_ptr[c + 1], k);
+      acc = walk_segments<WPC>(L, seg_y, L.cam_seg_ptr[c] + sub * 3 + j, L.cam_seg_ptr[c + 1], k);
     const double a1 = __shfl_down_sync(0xffffffffu, acc, 9), a2 = __shfl_down_sync(0xffffffffu, acc, 18);
     acc = (acc + a1) + a2;
     if (lane < 9) part[cl][sub][lane] = acc;
@@ -409,6 +415,7 @@ __global__ void k_pcg_resid2(BaDev L, const double* __restrict__ seg_y, const do
 
 // y[c] = fixed-order sum of the camera's segment partials, in exactly the order k_pcg_reduce uses (WPC warps per camera,
 // three interleaved segment lanes each, warp sums added in warp order).  Used before the allreduce of the multi-GPU path.
+template <int WPC>
 __global__ void __launch_bounds__(WPB * WPC * 32) k_cam_reduce9_warp(BaDev L, const double* __restrict__ seg_y, double* __restrict__ y,
                                                                       const int* guard, PeerWindow win, int parity, unsigned long long seq) {
   const bool run = guard == nullptr || *guard != 0;
@@ -420,7 +427,7 @@ __global__ void __launch_bounds__(WPB * WPC * 32) k_cam_reduce9_warp(BaDev L, co
   if (run && c < L.n_cams) {
     double acc = 0.0;
     if (lane < 27)
-      acc = walk_segments(L, seg_y, L.cam_seg_ptr[c] + sub * 3 + j, L.cam_seg_ptr[c + 1], k);
+      acc = walk_segments<WPC>(L, seg_y, L.cam_seg_ptr[c] + sub * 3 + j, L.cam_seg_ptr[c + 1], k);
     const double a1 = __shfl_down_sync(0xffffffffu, acc, 9), a2 = __shfl_down_sync(0xffffffffu, acc, 18);
     acc = (acc + a1) + a2;
     if (lane < 9) part[cl][sub][lane] = acc;
@@ -439,13 +446,26 @@ __global__ void __launch_bounds__(WPB * WPC * 32) k_cam_reduce9_warp(BaDev L, co
 
 int pcg_blocks(int n_cams) { return cdiv(n_cams, WPB); }
 
+// Warps per camera of the segment walks (k_pcg_reduce, k_cam_reduce9_warp): each warp holds three partials per step.
+static int pcg_wpc(const BaDev& L) {
+  static const int forced = [] { const char* e = getenv("SKERES_PCG_WPC"); return e ? atoi(e) : 0; }();   // development / tests
+  if (forced == 1 || forced == 2 || forced == 4) return forced;
+  if (pcg_blocks(L.n_cams) <= 296) return 4;               // one wave of 1024-thread CTAs (2 per SM x 148 SMs): nothing to gain
+  const double per_cam = (double)L.n_segs / (double)(L.n_cams > 0 ? L.n_cams : 1);
+  return per_cam >= 96.0 ? 4 : (per_cam >= 36.0 ? 2 : 1);
+}
+
 void launch_cam_reduce9_warp(const BaDev& L, const double* seg_y, double* y, const int* guard, cudaStream_t s, const PeerWindow* win,
                              unsigned long long seq) {
   PeerWindow w{};
   if (win) w = *win;
   const int parity = (int)(seq & 1);
   if (w.world > 1) y = w.data[w.rank] + (size_t)parity * w.stride;
-  k_cam_reduce9_warp<<<pcg_blocks(L.n_cams), WPB * WPC * 32, 0, s>>>(L, seg_y, y, guard, w, parity, seq);
+  switch (pcg_wpc(L)) {
+    case 4: k_cam_reduce9_warp<4><<<pcg_blocks(L.n_cams), WPB * 4 * 32, 0, s>>>(L, seg_y, y, guard, w, parity, seq); break;
+    case 2: k_cam_reduce9_warp<2><<<pcg_blocks(L.n_cams), WPB * 2 * 32, 0, s>>>(L, seg_y, y, guard, w, parity, seq); break;
+    default: k_cam_reduce9_warp<1><<<pcg_blocks(L.n_cams), WPB * 32, 0, s>>>(L, seg_y, y, guard, w, parity, seq); break;
+  }
   check_launch("k_cam_reduce9_warp");
 }
 
@@ -465,7 +485,12 @@ void launch_pcg_reduce(const BaDev& L, const double* seg_y, const double* y_in, 
                        const PcgDev* st, cudaStream_t s, const PeerWindow* win, unsigned long long seq) {
   PeerWindow w{};
   if (win) w = *win;
-  k_pcg_reduce<<<pcg_blocks(L.n_cams), WPB * WPC * 32, 0, s>>>(L, seg_y, y_in, D, z, p, part_pq, st, w, (int)(seq & 1), seq);
+  const int parity = (int)(seq & 1);
+  switch (pcg_wpc(L)) {
+    case 4: k_pcg_reduce<4><<<pcg_blocks(L.n_cams), WPB * 4 * 32, 0, s>>>(L, seg_y, y_in, D, z, p, part_pq, st, w, parity, seq); break;
+    case 2: k_pcg_reduce<2><<<pcg_blocks(L.n_cams), WPB * 2 * 32, 0, s>>>(L, seg_y, y_in, D, z, p, part_pq, st, w, parity, seq); break;
+    default: k_pcg_reduce<1><<<pcg_blocks(L.n_cams), WPB * 32, 0, s>>>(L, seg_y, y_in, D, z, p, part_pq, st, w, parity, seq); break;
+  }
   check_launch("k_pcg_reduce");
 }
 void launch_pcg_update(int n_cams, const double* Minv, const double* b, double* x, const double* p, double* r, double* z,
