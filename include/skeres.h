@@ -112,6 +112,18 @@ typedef enum sk_functor_id {
   SK_FUNCTOR_SNAVELY_REPROJECTION_ERROR = 1,
   /* CurveFitting.scala:92-98  ExponentialResidual(1; 1, 1); consts = (x, y) */
   SK_FUNCTOR_EXPONENTIAL_RESIDUAL = 2,
+  /* HelloWorld.scala:11-14  HelloCostFunctor(1; 1): 10 - x; consts = () */
+  SK_FUNCTOR_HELLO_WORLD = 3,
+  /* Powell.scala:13-51  F1..F4 (1; 1, 1), consts = (): x1 + 10 x2 | sqrt(5) x3 - x4 (as the code computes it, :28 -- its
+   * comment and PowellAnalytic.scala:37 say sqrt(5) (x3 - x4)) | (x2 - 2 x3)^2 | sqrt(10) (x1 - x4)^2 */
+  SK_FUNCTOR_POWELL_F1 = 4,
+  SK_FUNCTOR_POWELL_F2 = 5,
+  SK_FUNCTOR_POWELL_F3 = 6,
+  SK_FUNCTOR_POWELL_F4 = 7,
+  /* PowellAnalytic.scala:25-43  F2a (1; 1, 1): sqrt(5) (x3 - x4), the residual of the analytic-derivative example (a
+   * SizedCostFunction there; here its formula on device duals, whose derivatives are the analytic ones).  With F1, F3, F4
+   * it is the problem of the Ceres tutorial, whose published log pins the solver (tests/golden). */
+  SK_FUNCTOR_POWELL_ANALYTIC_F2 = 8,
   /* The three functors of AutodiffCostFuntionSpec.scala, registered so the reference's own
    * golden vectors can be replayed against the device Jet machinery. */
   SK_FUNCTOR_TEST_BILINEAR_SCALAR = 100,  /* :14-26   (1; 2, 2)   consts = (a)  */

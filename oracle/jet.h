@@ -171,6 +171,21 @@ inline bool testBilinearVector3(const double* consts, T const* const* p, T* z) {
   z[2] = x[0] * x[1] + y[0] * y[1] + 10 * a;
   return true;
 }
+// HelloWorld.scala:11-14
+template <class T>
+inline bool helloWorld(const double*, T const* const* x, T* res) { res[0] = 10.0 - x[0][0]; return true; }
+// Powell.scala:13-51 (F2 as the code computes it, :28: sqrt(5) * x3 - x4)
+template <class T>
+inline bool powellF1(const double*, T const* const* x, T* res) { res[0] = x[0][0] + 10.0 * x[1][0]; return true; }
+template <class T>
+inline bool powellF2(const double*, T const* const* x, T* res) { res[0] = std::sqrt(5.0) * x[0][0] - x[1][0]; return true; }
+template <class T>   // PowellAnalytic.scala:36
+inline bool powellF2a(const double*, T const* const* x, T* res) { res[0] = std::sqrt(5.0) * (x[0][0] - x[1][0]); return true; }
+template <class T>
+inline bool powellF3(const double*, T const* const* x, T* res) { const T d = x[0][0] - 2.0 * x[1][0]; res[0] = d * d; return true; }
+template <class T>
+inline bool powellF4(const double*, T const* const* x, T* res) { const T d = x[0][0] - x[1][0]; res[0] = (std::sqrt(10.0) * d) * d; return true; }
+
 // AutodiffCostFuntionSpec.scala:110-119
 template <class T>
 inline bool testSum10(const double*, T const* const* p, T* z) {

@@ -51,6 +51,12 @@ struct FunctorInfo { int id, nres, nblk, sizes[kMaxBlocks], nconsts; };
 static const FunctorInfo kFunctors[] = {
     {SK_FUNCTOR_SNAVELY_REPROJECTION_ERROR, 2, 2, {9, 3}, 2},
     {SK_FUNCTOR_EXPONENTIAL_RESIDUAL, 1, 2, {1, 1}, 2},
+    {SK_FUNCTOR_HELLO_WORLD, 1, 1, {1}, 0},
+    {SK_FUNCTOR_POWELL_F1, 1, 2, {1, 1}, 0},
+    {SK_FUNCTOR_POWELL_F2, 1, 2, {1, 1}, 0},
+    {SK_FUNCTOR_POWELL_F3, 1, 2, {1, 1}, 0},
+    {SK_FUNCTOR_POWELL_F4, 1, 2, {1, 1}, 0},
+    {SK_FUNCTOR_POWELL_ANALYTIC_F2, 1, 2, {1, 1}, 0},
     {SK_FUNCTOR_TEST_BILINEAR_SCALAR, 1, 2, {2, 2}, 1},
     {SK_FUNCTOR_TEST_BILINEAR_VECTOR3, 3, 2, {2, 2}, 1},
     {SK_FUNCTOR_TEST_SUM10, 1, 10, {1, 1, 1, 1, 1, 1, 1, 1, 1, 1}, 0},
@@ -102,6 +108,24 @@ static bool evaluate_functor(const FunctorInfo& fi, const double* consts, double
     case SK_FUNCTOR_EXPONENTIAL_RESIDUAL:
       return autodiff_evaluate<1, 2, 2>([](const double* c, auto const* const* p, auto* r) {
         return exponentialResidual(c, p, r); }, fi.sizes, consts, params, residuals, jacobians);
+    case SK_FUNCTOR_HELLO_WORLD:
+      return autodiff_evaluate<1, 1, 1>([](const double* c, auto const* const* p, auto* r) {
+        return helloWorld(c, p, r); }, fi.sizes, consts, params, residuals, jacobians);
+    case SK_FUNCTOR_POWELL_F1:
+      return autodiff_evaluate<1, 2, 2>([](const double* c, auto const* const* p, auto* r) {
+        return powellF1(c, p, r); }, fi.sizes, consts, params, residuals, jacobians);
+    case SK_FUNCTOR_POWELL_F2:
+      return autodiff_evaluate<1, 2, 2>([](const double* c, auto const* const* p, auto* r) {
+        return powellF2(c, p, r); }, fi.sizes, consts, params, residuals, jacobians);
+    case SK_FUNCTOR_POWELL_ANALYTIC_F2:
+      return autodiff_evaluate<1, 2, 2>([](const double* c, auto const* const* p, auto* r) {
+        return powellF2a(c, p, r); }, fi.sizes, consts, params, residuals, jacobians);
+    case SK_FUNCTOR_POWELL_F3:
+      return autodiff_evaluate<1, 2, 2>([](const double* c, auto const* const* p, auto* r) {
+        return powellF3(c, p, r); }, fi.sizes, consts, params, residuals, jacobians);
+    case SK_FUNCTOR_POWELL_F4:
+      return autodiff_evaluate<1, 2, 2>([](const double* c, auto const* const* p, auto* r) {
+        return powellF4(c, p, r); }, fi.sizes, consts, params, residuals, jacobians);
     case SK_FUNCTOR_TEST_BILINEAR_SCALAR:
       return autodiff_evaluate<1, 2, 4>([](const double* c, auto const* const* p, auto* r) {
         return testBilinearScalar(c, p, r); }, fi.sizes, consts, params, residuals, jacobians);

@@ -13,6 +13,9 @@ OK, ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_UNSUPPORTED, ERR_NCCL, ERR_IO, ERR_INTER
 # sk_functor_id
 FUNCTOR_SNAVELY_REPROJECTION_ERROR = 1
 FUNCTOR_EXPONENTIAL_RESIDUAL = 2
+FUNCTOR_HELLO_WORLD = 3
+FUNCTOR_POWELL_F1, FUNCTOR_POWELL_F2, FUNCTOR_POWELL_F3, FUNCTOR_POWELL_F4 = 4, 5, 6, 7
+FUNCTOR_POWELL_ANALYTIC_F2 = 8
 FUNCTOR_TEST_BILINEAR_SCALAR = 100
 FUNCTOR_TEST_BILINEAR_VECTOR3 = 101
 FUNCTOR_TEST_SUM10 = 102

@@ -273,6 +273,34 @@ class ExponentialResidual(AutoDiffCostFunctor):
         return [self.x, self.y]
 
 
+class HelloCostFunctor(AutoDiffCostFunctor):
+    """HelloWorld.scala:11-14: 10 - x."""
+    functor_id = _abi.FUNCTOR_HELLO_WORLD
+
+    def __init__(self):
+        super().__init__(1, 1)
+
+    def consts(self):
+        return []
+
+
+class _PowellFunctor(AutoDiffCostFunctor):
+    def __init__(self):
+        super().__init__(1, 1, 1)
+
+    def consts(self):
+        return []
+
+
+class Powell:
+    """Powell.scala:13-51: the four autodiff functors (F2 as the code computes it, sqrt(5) x3 - x4)."""
+    class F1(_PowellFunctor): functor_id = _abi.FUNCTOR_POWELL_F1
+    class F2(_PowellFunctor): functor_id = _abi.FUNCTOR_POWELL_F2
+    class F3(_PowellFunctor): functor_id = _abi.FUNCTOR_POWELL_F3
+    class F4(_PowellFunctor): functor_id = _abi.FUNCTOR_POWELL_F4
+    class F2a(_PowellFunctor): functor_id = _abi.FUNCTOR_POWELL_ANALYTIC_F2   # PowellAnalytic.scala:25-43: sqrt(5) (x3 - x4)
+
+
 class Problem:
     """Problem.scala:16-33."""
 

@@ -178,6 +178,16 @@ template <class T> SK_HD bool functor_exponential(const double* c, const T* m, c
   res[0] = c[1] - jexp(m[0] * c[0] + cc[0]);      // CurveFitting.scala:96
   return true;
 }
+template <class T> SK_HD bool functor_hello_world(const T* x, T* res) {
+  res[0] = 10.0 - x[0];                            // HelloWorld.scala:13
+  return true;
+}
+// Powell.scala:13-51; block 0 / block 1 of each functor are a[0] / b[0]
+template <class T> SK_HD bool functor_powell_f1(const T* a, const T* b, T* res) { res[0] = a[0] + 10.0 * b[0]; return true; }          // :18
+template <class T> SK_HD bool functor_powell_f2(const T* a, const T* b, T* res) { res[0] = sqrt(5.0) * a[0] - b[0]; return true; }    // :28 (sic)
+template <class T> SK_HD bool functor_powell_f2a(const T* a, const T* b, T* res) { res[0] = sqrt(5.0) * (a[0] - b[0]); return true; }   // PowellAnalytic.scala:36
+template <class T> SK_HD bool functor_powell_f3(const T* a, const T* b, T* res) { const T d = a[0] - 2.0 * b[0]; res[0] = d * d; return true; }   // :38-39
+template <class T> SK_HD bool functor_powell_f4(const T* a, const T* b, T* res) { const T d = a[0] - b[0]; res[0] = (sqrt(10.0) * d) * d; return true; }   // :48-49
 template <class T> SK_HD bool functor_bilinear_scalar(const double* c, const T* x, const T* y, T* z) {
   z[0] = x[0] * y[0] + x[1] * y[1] - c[0];        // AutodiffCostFuntionSpec.scala:23
   return true;
@@ -205,6 +215,10 @@ SK_HD bool functor_info(int id, FunctorInfo* f) {
   switch (id) {
     case SK_FUNCTOR_SNAVELY_REPROJECTION_ERROR: f->nres = 2; f->nblk = 2; f->sizes[0] = 9; f->sizes[1] = 3; f->nconsts = 2; f->ntot = 12; return true;
     case SK_FUNCTOR_EXPONENTIAL_RESIDUAL: f->nres = 1; f->nblk = 2; f->sizes[0] = 1; f->sizes[1] = 1; f->nconsts = 2; f->ntot = 2; return true;
+    case SK_FUNCTOR_HELLO_WORLD: f->nres = 1; f->nblk = 1; f->sizes[0] = 1; f->nconsts = 0; f->ntot = 1; return true;
+    case SK_FUNCTOR_POWELL_F1: case SK_FUNCTOR_POWELL_F2: case SK_FUNCTOR_POWELL_F3: case SK_FUNCTOR_POWELL_F4:
+    case SK_FUNCTOR_POWELL_ANALYTIC_F2:
+      f->nres = 1; f->nblk = 2; f->sizes[0] = 1; f->sizes[1] = 1; f->nconsts = 0; f->ntot = 2; return true;
     case SK_FUNCTOR_TEST_BILINEAR_SCALAR: f->nres = 1; f->nblk = 2; f->sizes[0] = 2; f->sizes[1] = 2; f->nconsts = 1; f->ntot = 4; return true;
     case SK_FUNCTOR_TEST_BILINEAR_VECTOR3: f->nres = 3; f->nblk = 2; f->sizes[0] = 2; f->sizes[1] = 2; f->nconsts = 1; f->ntot = 4; return true;
     case SK_FUNCTOR_TEST_SUM10: f->nres = 1; f->nblk = 10; for (int i = 0; i < 10; ++i) f->sizes[i] = 1; f->nconsts = 0; f->ntot = 10; return true;
@@ -232,6 +246,37 @@ SK_HD bool evaluate_functor(int id, const double* c, const double* x, double* re
       if (!jac) return functor_exponential(c, x, x + 1, res);
       Jet<2> jx[2] = {Jet<2>(x[0], 0), Jet<2>(x[1], 1)}, jr[1];
       if (!functor_exponential(c, jx, jx + 1, jr)) return false;
+      res[0] = jr[0].a; jac[0] = jr[0].v[0]; jac[1] = jr[0].v[1];
+      return true;
+    }
+    case SK_FUNCTOR_HELLO_WORLD: {
+      if (!jac) return functor_hello_world(x, res);
+      Jet<1> jx[1] = {Jet<1>(x[0], 0)}, jr[1];
+      if (!functor_hello_world(jx, jr)) return false;
+      res[0] = jr[0].a; jac[0] = jr[0].v[0];
+      return true;
+    }
+    case SK_FUNCTOR_POWELL_F1: case SK_FUNCTOR_POWELL_F2: case SK_FUNCTOR_POWELL_F3: case SK_FUNCTOR_POWELL_F4:
+    case SK_FUNCTOR_POWELL_ANALYTIC_F2: {
+      if (!jac) {
+        switch (id) {
+          case SK_FUNCTOR_POWELL_F1: return functor_powell_f1(x, x + 1, res);
+          case SK_FUNCTOR_POWELL_F2: return functor_powell_f2(x, x + 1, res);
+          case SK_FUNCTOR_POWELL_F3: return functor_powell_f3(x, x + 1, res);
+          case SK_FUNCTOR_POWELL_ANALYTIC_F2: return functor_powell_f2a(x, x + 1, res);
+          default: return functor_powell_f4(x, x + 1, res);
+        }
+      }
+      Jet<2> jx[2] = {Jet<2>(x[0], 0), Jet<2>(x[1], 1)}, jr[1];
+      bool ok;
+      switch (id) {
+        case SK_FUNCTOR_POWELL_F1: ok = functor_powell_f1(jx, jx + 1, jr); break;
+        case SK_FUNCTOR_POWELL_F2: ok = functor_powell_f2(jx, jx + 1, jr); break;
+        case SK_FUNCTOR_POWELL_F3: ok = functor_powell_f3(jx, jx + 1, jr); break;
+        case SK_FUNCTOR_POWELL_ANALYTIC_F2: ok = functor_powell_f2a(jx, jx + 1, jr); break;
+        default: ok = functor_powell_f4(jx, jx + 1, jr); break;
+      }
+      if (!ok) return false;
       res[0] = jr[0].a; jac[0] = jr[0].v[0]; jac[1] = jr[0].v[1];
       return true;
     }

@@ -177,6 +177,84 @@ def test_curve_fitting_matches_oracle_and_ceres_tutorial(sk, oracle):
     assert s.briefReport().startswith("Ceres Solver Report: Iterations: 14, Initial cost: 1.211734e+02, Final cost: 1.056751e+00")
 
 
+def test_hello_world_example(sk, oracle):
+    """HelloWorld.scala:11-35 through the mirrored API: x 0.5 -> 10, rows equal the oracle's and the Ceres tutorial's log."""
+    x = sk.DoubleArray(1)
+    x.set(0, 0.5)
+    problem = sk.Problem()
+    problem.addResidualBlock(sk.HelloCostFunctor().toAutoDiffCostFunction(), sk.PredefinedLossFunctions.trivialLoss(), x.toPointer())
+    options = sk.Solver.Options()
+    with pytest.raises(sk.SkeresError):                      # the example keeps Ceres' default SPARSE_NORMAL_CHOLESKY: no device path
+        sk.ceres.solve(options, problem, sk.Solver.Summary())
+    options.setLinearSolverType(_abi.DENSE_QR)
+    s = sk.Solver.Summary()
+    sk.ceres.solve(options, problem, s)
+    p = oracle.OracleProblem(np.array([0.5]))
+    p.add_residual_blocks(_abi.FUNCTOR_HELLO_WORLD, np.zeros((1, 0)), np.array([[0]]))
+    o = _abi.default_options()
+    o.linear_solver_type = _abi.DENSE_QR
+    assert_same_trajectory(s, p.solve(o))
+    gold = load("ceres_tutorial_helloworld_log.json")
+    assert len(s.iterations) == len(gold["rows"])
+    for r, g in zip(s.iterations, gold["rows"]):            # the last cost is rounding-dominated (x = 10 - 3e-8): 1e-5, not 6 digits
+        assert np.isclose(r.cost, g[1], rtol=1e-5) and float(f"{r.trust_region_radius:.2e}") == g[6]
+        assert np.isclose(r.gradient_max_norm, g[3], rtol=1e-2) and np.isclose(r.step_norm, g[4], rtol=1e-2)
+    assert abs(x.get(0) - 10.0) < 1e-7
+    assert s.briefReport().startswith("Ceres Solver Report: Iterations: 3, Initial cost: 4.512500e+01, Final cost: 5.0125")
+
+
+@pytest.mark.parametrize("f2", ["F2", "F2a"])
+def test_powell_example(sk, oracle, f2):
+    """Powell.scala:54-95 (four scalar blocks in four DoubleArrays, DENSE_QR, 100 iterations) with F2 as Powell.scala computes
+    it, and with PowellAnalytic.scala's f2 -- the Ceres tutorial's problem, whose published log the rows must reproduce."""
+    xs = [sk.DoubleArray(1) for _ in range(4)]
+    for a, v in zip(xs, [3.0, -1.0, 0.0, 1.0]):
+        a.set(0, v)
+    loss = sk.PredefinedLossFunctions.trivialLoss()
+    problem = sk.Problem()
+    F2 = getattr(sk.Powell, f2)
+    for functor, (i, j) in zip([sk.Powell.F1, F2, sk.Powell.F3, sk.Powell.F4], [(0, 1), (2, 3), (1, 2), (0, 3)]):
+        problem.addResidualBlock(functor().toAutoDiffCostFunction(), loss, xs[i].toPointer(), xs[j].toPointer())
+    options = sk.Solver.Options()
+    options.setMaxNumIterations(100)
+    options.setLinearSolverType(_abi.DENSE_QR)
+    s = sk.Solver.Summary()
+    sk.ceres.solve(options, problem, s)
+    xout = np.array([a.get(0) for a in xs])
+    p = oracle.OracleProblem(np.array([3.0, -1.0, 0.0, 1.0]))
+    for fid, blocks in zip([_abi.FUNCTOR_POWELL_F1, F2.functor_id, _abi.FUNCTOR_POWELL_F3, _abi.FUNCTOR_POWELL_F4], [(0, 1), (2, 3), (1, 2), (0, 3)]):
+        p.add_residual_blocks(fid, np.zeros((1, 0)), np.array([blocks]))
+    o = _abi.default_options()
+    o.linear_solver_type, o.max_num_iterations = _abi.DENSE_QR, 100
+    so = p.solve(o)
+    assert_same_trajectory(s, so)
+    assert np.allclose(xout, p.params, rtol=1e-6, atol=1e-12) and np.all(np.abs(xout) < 1e-3) and s.final_cost < 1e-14
+    if f2 == "F2a":
+        gold = load("ceres_tutorial_powell_log.json")
+        assert len(s.iterations) == len(gold["rows"])
+        for r, g in zip(s.iterations, gold["rows"]):
+            assert np.isclose(r.cost, g[1], rtol=2e-6) and float(f"{r.trust_region_radius:.2e}") == g[6]
+            assert np.isclose(r.step_norm, g[4], rtol=1e-2) and np.isclose(r.gradient_max_norm, g[3], rtol=1e-2)
+        assert [float(f"{v:.5e}") for v in xout] == [float(f"{v:.5e}") for v in gold["final"]["x"]]
+
+
+def test_example_functors_at_the_evaluate_boundary(sk, oracle):
+    """HelloWorld / Powell functors through AutoDiffCostFunction.evaluate: residuals and row-major Jacobian blocks equal the
+    oracle's Jet evaluation, and the hand derivatives."""
+    cases = [(_abi.FUNCTOR_HELLO_WORLD, [[0.5]]), (_abi.FUNCTOR_POWELL_F1, [[3.0], [-1.0]]), (_abi.FUNCTOR_POWELL_F2, [[0.25], [1.0]]),
+             (_abi.FUNCTOR_POWELL_ANALYTIC_F2, [[0.25], [1.0]]), (_abi.FUNCTOR_POWELL_F3, [[-1.0], [0.5]]), (_abi.FUNCTOR_POWELL_F4, [[3.0], [1.0]])]
+    hand = {_abi.FUNCTOR_HELLO_WORLD: ([9.5], [[-1.0]]), _abi.FUNCTOR_POWELL_F1: ([-7.0], [[1.0], [10.0]]),
+            _abi.FUNCTOR_POWELL_F2: ([np.sqrt(5.0) * 0.25 - 1.0], [[np.sqrt(5.0)], [-1.0]]),
+            _abi.FUNCTOR_POWELL_ANALYTIC_F2: ([np.sqrt(5.0) * (0.25 - 1.0)], [[np.sqrt(5.0)], [-np.sqrt(5.0)]]),
+            _abi.FUNCTOR_POWELL_F3: ([4.0], [[-4.0], [8.0]]), _abi.FUNCTOR_POWELL_F4: ([np.sqrt(10.0) * 4.0], [[4.0 * np.sqrt(10.0)], [-4.0 * np.sqrt(10.0)]])}
+    for fid, params in cases:
+        ok, res, jac = sk.CostFunction(fid, []).evaluate_host(params)
+        oko, ro, jo = oracle.evaluate(fid, [], params)
+        assert ok and oko
+        assert np.allclose(res, ro, rtol=4e-15, atol=0) and all(np.allclose(a, b, rtol=4e-15, atol=0) for a, b in zip(jac, jo))
+        assert np.allclose(res, hand[fid][0], rtol=1e-14) and all(np.allclose(np.ravel(a), b, rtol=1e-14) for a, b in zip(jac, hand[fid][1]))
+
+
 def test_robust_curve_fitting(sk, oracle):
     """RobustCurveFitting.scala: outliers (:41-42) + CauchyLoss(0.5) (:107) — Corrector on the device."""
     def spoil(y):

@@ -362,6 +362,25 @@ def test_device_functors_match_the_oracle(hc, oracle):
             col += len(blk)
 
 
+def test_example_functors_device_code_matches_the_oracle(hc, oracle):
+    """HelloWorld.scala / Powell.scala / PowellAnalytic.scala functors: the device Jet code (host build) equals the oracle's
+    restatement bit for bit, at the examples' start points and at random points."""
+    rng = np.random.default_rng(4)
+    fids = [_abi.FUNCTOR_HELLO_WORLD, _abi.FUNCTOR_POWELL_F1, _abi.FUNCTOR_POWELL_F2, _abi.FUNCTOR_POWELL_ANALYTIC_F2, _abi.FUNCTOR_POWELL_F3,
+            _abi.FUNCTOR_POWELL_F4]
+    for fid in fids:
+        nres, sizes, nconst = oracle.functor_info(fid)
+        assert (nres, nconst) == (1, 0) and sizes == ([1] if fid == _abi.FUNCTOR_HELLO_WORLD else [1, 1])
+        for trial in range(20):
+            params = [[0.5]] if (fid == _abi.FUNCTOR_HELLO_WORLD and trial == 0) else [list(rng.normal(0, 3, n)) for n in sizes]
+            ok, ro, jo = oracle.evaluate(fid, [], params)
+            x = np.ascontiguousarray(np.concatenate(params)); res = np.zeros(3); jac = np.zeros(36); c = np.zeros(4)
+            assert ok and hc.hc_evaluate(fid, p(c), p(x), p(res), p(jac)) == 1
+            assert res[0] == ro[0] and np.array_equal(jac[:x.size], np.concatenate([np.ravel(j) for j in jo]))
+            res2 = np.zeros(3)
+            assert hc.hc_evaluate(fid, p(c), p(x), p(res2), None) == 1 and res2[0] == ro[0]          # residual-only branch
+
+
 def test_device_loss_and_corrector_match_the_oracle(hc, oracle):
     rng = np.random.default_rng(1)
     for kind, a in [(_abi.LOSS_TRIVIAL, 0.0), (_abi.LOSS_HUBER, 0.7), (_abi.LOSS_CAUCHY, 0.5)]:

@@ -21,6 +21,64 @@ def load(name):
     return json.load(open(os.path.join(HERE, "golden", name)))
 
 
+def powell_problem(oracle, f2):
+    """Powell.scala:56-76 / PowellAnalytic.scala: four residual blocks over the scalar blocks x1..x4 from (3, -1, 0, 1)."""
+    p = oracle.OracleProblem(np.array([3.0, -1.0, 0.0, 1.0]))
+    for fid, blocks in zip([_abi.FUNCTOR_POWELL_F1, f2, _abi.FUNCTOR_POWELL_F3, _abi.FUNCTOR_POWELL_F4], [(0, 1), (2, 3), (1, 2), (0, 3)]):
+        p.add_residual_blocks(fid, np.zeros((1, 0)), np.array([blocks]))
+    o = _abi.default_options()
+    o.linear_solver_type, o.max_num_iterations = _abi.DENSE_QR, 100          # Powell.scala:80-81
+    return p, o
+
+
+def check_rows_against_log(rows, gold, only=None):
+    sig = lambda v, digits: float(f"{v:.{digits}e}")
+    assert len(rows) == len(gold["rows"])
+    for row, g in zip(rows, gold["rows"]):
+        if only is not None and g[0] not in only:
+            continue
+        assert row.iteration == g[0] and row.step_is_successful
+        assert sig(row.cost, 6) == g[1] and sig(row.cost_change, 2) == g[2] and sig(row.gradient_max_norm, 2) == g[3]
+        assert sig(row.step_norm, 2) == g[4] and sig(row.relative_decrease, 2) == g[5] and sig(row.trust_region_radius, 2) == g[6]
+
+
+def test_hello_world_reproduces_ceres_tutorial_log(oracle):
+    """HelloWorld.scala:11-35 (x: 0.5 -> 10): every figure of the published three-row log, recalled before the oracle was run."""
+    gold = load("ceres_tutorial_helloworld_log.json")
+    p = oracle.OracleProblem(np.array([0.5]))
+    p.add_residual_blocks(_abi.FUNCTOR_HELLO_WORLD, np.zeros((1, 0)), np.array([[0]]))
+    o = _abi.default_options()
+    o.linear_solver_type = _abi.DENSE_QR        # the example keeps Ceres' default solver; one scalar block: any exact solver is the same
+    s = p.solve(o)
+    check_rows_against_log(s.iterations, gold)
+    assert _abi.TERMINATION_NAMES[s.termination_type] == gold["final"]["termination"]
+    assert abs(p.params[0] - gold["final"]["x"]) < 1e-7 and float(f"{s.final_cost:.6e}") == gold["final"]["final_cost"]
+
+
+def test_powell_reproduces_ceres_tutorial_log(oracle):
+    """PowellAnalytic.scala's problem (f2 = sqrt(5) (x3 - x4)) is the Ceres tutorial's: rows 0-4 and 14 and the final point of
+    the published log were recalled before the oracle was run; all 15 rows are kept as a regression vector."""
+    gold = load("ceres_tutorial_powell_log.json")
+    p, o = powell_problem(oracle, _abi.FUNCTOR_POWELL_ANALYTIC_F2)
+    s = p.solve(o)
+    check_rows_against_log(s.iterations, gold, only=gold["recalled_rows"])
+    check_rows_against_log(s.iterations, gold)
+    assert _abi.TERMINATION_NAMES[s.termination_type] == gold["final"]["termination"] and "Gradient tolerance reached" in s.message
+    assert [float(f"{v:.5e}") for v in p.params] == [float(f"{v:.5e}") for v in gold["final"]["x"]]
+    assert float(f"{s.initial_cost:.6e}") == gold["final"]["initial_cost"] and float(f"{s.final_cost:.6e}") == gold["final"]["final_cost"]
+
+
+def test_powell_as_the_reference_computes_it(oracle):
+    """Powell.scala:28 evaluates sqrt(5) x3 - x4 (its comment says sqrt(5) (x3 - x4)): a different problem with the same
+    minimiser 0.  Known answers: initial cost 105.5 (by hand: (49 + 1 + 1 + 160) / 2), all four parameters -> 0."""
+    p, o = powell_problem(oracle, _abi.FUNCTOR_POWELL_F2)
+    cost, r, g, J = p.evaluate()
+    assert np.allclose(r, [3.0 - 10.0, np.sqrt(5.0) * 0.0 - 1.0, (-1.0 - 0.0) ** 2, np.sqrt(10.0) * (3.0 - 1.0) ** 2], rtol=1e-15)
+    assert abs(cost - 0.5 * (49.0 + 1.0 + 1.0 + 160.0)) < 1e-12
+    s = p.solve(o)
+    assert s.termination_type == _abi.CONVERGENCE and s.final_cost < 1e-14 and np.all(np.abs(p.params) < 1e-3)
+
+
 # ---------------------------------------------------------------------------------------------------
 def test_autodiff_spec_vectors(oracle):
     for case in load("autodiff_spec_vectors.json")["cases"]:
