@@ -69,6 +69,16 @@ MATVEC_NCU_TRAFFIC = {"bytes_per_launch": 1.058313e9 + 25.707008e6, "n_obs": 500
                       "source": "profiles/r01_v9_matvec_tma_summary.md (ncu --set full, launch 0 of gpurun_out/prof_matvec_v9.ncu-rep)"}
 
 
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -165,7 +175,7 @@ def main():
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
                 "ms_per_step": 1e3 * t_steps / max(its, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": cfg, "lm_iterations_per_s": its / t_steps if t_steps > 0 else 0.0,
-                "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "cpu_model": cpu_model(),
                                  "sample": f"first {its} of {K} LM iterations of the same full-size problem (150 s budget), "
                                            "CPU oracle = Ceres-algorithm restatement (libceres is not buildable here)"},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -312,7 +322,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         its, t_steps, wall, s = run_oracle(data, 1, 0, threads, time_budget_s=25.0)
-        cpu = {"value": n_obs * its / t_steps if t_steps > 0 else 0.0, "unit": UNIT, "cores": threads, "kind": "port",
+        cpu = {"value": n_obs * its / t_steps if t_steps > 0 else 0.0, "unit": UNIT, "cores": threads, "kind": "port", "cpu_model": cpu_model(),
                "sample": "first LM iteration (evaluate + SchurJacobi + PCG + candidate cost + re-evaluation) of the same full-size problem",
                "lm_iterations_per_s": its / t_steps if t_steps > 0 else 0.0}
 
