@@ -447,3 +447,18 @@ def test_graft_entry_build_runs():
         g.build()
     finally:
         __import__("sys").path[:] = sys_path
+
+
+def test_jni_shim_type_checks():
+    """bindings/jni/skeres_jni.c (the reference-side binding) cannot run here -- no JDK -- but its calls into
+    include/skeres.h are type-checked against a mock jni.h; every native method the Scala facade declares has its C export."""
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I" + os.path.join(ROOT, "tests", "mock_jni"),
+                        "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "bindings", "jni", "skeres_jni.c")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    shim = open(os.path.join(ROOT, "bindings", "jni", "skeres_jni.c")).read()
+    natives = re.findall(r"@native def (\w+)\(", open(os.path.join(ROOT, "bindings", "scala", "Native.scala")).read())
+    exported = set(re.findall(r"FN\((\w+)\)\(JNIEnv", shim))
+    assert len(natives) > 40 and set(natives) == exported, set(natives) ^ exported
+    used = set(re.findall(r"\b(sk_[a-z0-9_]+)\s*\(", shim))
+    assert used <= set(declared_functions())            # the shim calls only what the header declares
