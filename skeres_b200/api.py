@@ -561,19 +561,34 @@ class BalProblem:
         return problem
 
     def localRange(self, rank, world_size):
-        """Observation range [o0, o1) of this rank's points (sk_partition_points); observations must be sorted by point."""
-        if world_size == 1:
-            return 0, self.numObservations
-        ptr = np.zeros(self.numPoints + 1, dtype=np.int64)
-        np.cumsum(np.bincount(self.pointIndex, minlength=self.numPoints), out=ptr[1:])
-        begin = partition_points(ptr, world_size)
-        return int(ptr[begin[rank]]), int(ptr[begin[rank + 1]])
+        """Observation range [o0, o1) of this rank's points -- the partition of sk_partition_points (first point whose
+        observation prefix reaches rank / world of the total), found without building the point CSR: observations are
+        sorted by point, so a boundary is the first point start at or behind the target observation."""
+        n = self.numObservations
+        pt = self.pointIndex
+
+        def boundary(r):
+            if r <= 0:
+                return 0
+            if r >= world_size:
+                return n
+            j = (n * r) // world_size
+            while 0 < j < n and pt[j] == pt[j - 1]:
+                j += 1
+            return j
+
+        return boundary(rank), boundary(rank + 1)
 
     def buildLocalProblem(self, rank, world_size, loss=None):
         """Multi-GPU ingestion in O(local observations): only the residual blocks of this rank's points, every camera
         declared (Problem::AddParameterBlock).  Solve with Options.residual_blocks_are_local = 1 and a communicator."""
-        assert np.all(np.diff(self.pointIndex) >= 0), "rank-local ingestion needs observations sorted by point"
         o0, o1 = self.localRange(rank, world_size)
+        # only this rank's share is touched (the whole list is N times longer): sorted by point inside, true point boundaries outside
+        loc = self.pointIndex[o0:o1]
+        assert np.all(loc[1:] >= loc[:-1]), "rank-local ingestion needs observations sorted by point"
+        assert (o0 == 0 or self.pointIndex[o0 - 1] < self.pointIndex[o0]) and \
+               (o1 == self.numObservations or o1 == o0 or self.pointIndex[o1 - 1] < self.pointIndex[o1]), "observations are not sorted by point"
+
         problem = Problem()
         loss = loss if loss is not None else PredefinedLossFunctions.trivialLoss()
         problem.addParameterBlocks(self.parameters, 9 * np.arange(self.numCameras, dtype=np.int64), 9)

@@ -462,3 +462,19 @@ def test_jni_shim_type_checks():
     assert len(natives) > 40 and set(natives) == exported, set(natives) ^ exported
     used = set(re.findall(r"\b(sk_[a-z0-9_]+)\s*\(", shim))
     assert used <= set(declared_functions())            # the shim calls only what the header declares
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 5, 8])
+def test_local_range_equals_partition_points(world):
+    """BalProblem.localRange (boundary scan, O(track length)) gives exactly the ranges of sk_partition_points over the point
+    CSR -- including tracks that straddle a target and ranks that end up empty."""
+    from skeres_b200 import api
+    rng = np.random.default_rng(world)
+    cases = [synth.make_bal("ladybug-49", seed=2), synth.make_bal(n_cam=40, n_pt=7, n_obs=120, seed=1, long_tracks=(40, 35))]
+    for d in cases:
+        bal = api.BalProblem(d.num_cameras, d.num_points, d.camera_index, d.point_index, d.observations, None)
+        ptr = np.concatenate([[0], np.cumsum(np.bincount(d.point_index, minlength=d.num_points))]).astype(np.int64)
+        begin = api.partition_points(ptr, world)
+        for r in range(world):
+            assert bal.localRange(r, world) == (int(ptr[begin[r]]), int(ptr[begin[r + 1]])), (r, world)
+        assert bal.localRange(0, world)[0] == 0 and bal.localRange(world - 1, world)[1] == d.num_observations
