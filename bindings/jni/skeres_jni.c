@@ -87,6 +87,11 @@ JNIEXPORT jlong JNICALL FN(lossCauchy)(JNIEnv* env, jclass cls, jdouble a) {
   (void)cls;
   return ok(env, sk_loss_cauchy(a, &l)) ? J(l) : 0;
 }
+JNIEXPORT jlong JNICALL FN(lossTolerant)(JNIEnv* env, jclass cls, jdouble a, jdouble b) {
+  sk_loss_function* l = NULL;
+  (void)cls;
+  return ok(env, sk_loss_tolerant(a, b, &l)) ? J(l) : 0;
+}
 JNIEXPORT void JNICALL FN(lossDestroy)(JNIEnv* env, jclass cls, jlong h) { (void)cls; ok(env, sk_loss_destroy(H(sk_loss_function, h))); }
 
 /* ---- CostFunction (CostFunctor.scala:31-51, AutodiffCostFunction.scala:68-134) ------------------------------------ */

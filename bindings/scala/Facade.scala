@@ -26,6 +26,7 @@ object PredefinedLossFunctions {                                               /
   def trivialLoss: LossFunction = new LossFunction(Native.lossTrivial())
   def huberLoss(a: Double): LossFunction = new LossFunction(Native.lossHuber(a))
   def cauchyLoss(a: Double): LossFunction = new LossFunction(Native.lossCauchy(a))
+  def tolerantLoss(a: Double, b: Double): LossFunction = new LossFunction(Native.lossTolerant(a, b))
 }
 
 /** AutoDiffCostFunction of a registered device functor (AutodiffCostFunction.scala:68). */

@@ -18,6 +18,7 @@ object Native {
   @native def lossTrivial(): Long
   @native def lossHuber(a: Double): Long
   @native def lossCauchy(a: Double): Long
+  @native def lossTolerant(a: Double, b: Double): Long
   @native def lossDestroy(h: Long): Unit
 
   @native def costFunctionCreate(functorId: Int, consts: Array[Double]): Long

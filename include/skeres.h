@@ -80,14 +80,16 @@ typedef struct sk_double_pointer {
 
 /* ------------------------------------------------------------------------------------------
  * LossFunction — ceres.i:160-184 PredefinedLossFunctions
- * trivial / huber / cauchy have device implementations (Corrector applied inside the
- * evaluator kernel).  The other five factories report SK_ERR_UNSUPPORTED.
+ * trivial / huber / cauchy / tolerant have device implementations (Corrector applied inside the
+ * evaluator kernel).  The other factories report SK_ERR_UNSUPPORTED.
  * ---------------------------------------------------------------------------------------- */
 typedef struct sk_loss_function sk_loss_function;
 typedef enum sk_loss_type {
   SK_LOSS_TRIVIAL = 0, /* ceres.i:170 */
   SK_LOSS_HUBER = 1,   /* ceres.i:171 */
-  SK_LOSS_CAUCHY = 2   /* ceres.i:173 */
+  SK_LOSS_CAUCHY = 2,  /* ceres.i:173 */
+  SK_LOSS_TOLERANT = 3 /* ceres.i:175: rho(s) = b log(1 + e^((s - a) / b)) - b log(1 + e^(-a / b)); rho'' > 0, so it is the
+                          one registered loss that drives the Corrector through its alpha != 0 branch */
 } sk_loss_type;
 
 int sk_loss_trivial(sk_loss_function** out);
@@ -95,7 +97,7 @@ int sk_loss_huber(double a, sk_loss_function** out);
 int sk_loss_cauchy(double a, sk_loss_function** out);
 int sk_loss_soft_l_one(double a, sk_loss_function** out);                 /* ceres.i:172 unsupported */
 int sk_loss_tukey(double a, sk_loss_function** out);                      /* ceres.i:174 unsupported */
-int sk_loss_tolerant(double a, double b, sk_loss_function** out);         /* ceres.i:175 unsupported */
+int sk_loss_tolerant(double a, double b, sk_loss_function** out);         /* ceres.i:175: a >= 0, b > 0 */
 int sk_loss_destroy(sk_loss_function* loss);
 /* rho[0..2] = rho(s), rho'(s), rho''(s) evaluated on the device (LossFunction::Evaluate). */
 int sk_loss_evaluate(const sk_loss_function* loss, double s, double rho[3]);

@@ -142,7 +142,7 @@ static bool evaluate_functor(const FunctorInfo& fi, const double* consts, double
 // ------------------------------------------------------------------------------------------------
 // Loss functions (ceres/loss_function.cc) and Corrector (internal/ceres/corrector.cc) — A.2
 // ------------------------------------------------------------------------------------------------
-static void loss_evaluate(int type, double a, double s, double rho[3]) {
+static void loss_evaluate(int type, double a, double b2, double s, double rho[3]) {
   const double kMin = std::numeric_limits<double>::min();
   switch (type) {
     case SK_LOSS_HUBER: {
@@ -161,6 +161,17 @@ static void loss_evaluate(int type, double a, double s, double rho[3]) {
       rho[0] = b * std::log(sum);
       rho[1] = std::max(kMin, inv);
       rho[2] = -c * (inv * inv);
+      return;
+    }
+    case SK_LOSS_TOLERANT: {                                  // loss_function.cc TolerantLoss (a = a_, b2 = b_)
+      const double c = b2 * std::log(1.0 + std::exp(-a / b2));
+      const double x = (s - a) / b2;
+      const double kLog2Pow53 = 36.7;                         // ln(2^53): beyond it e^x swamps the 1
+      if (x > kLog2Pow53) { rho[0] = s - a - c; rho[1] = 1.0; rho[2] = 0.0; return; }
+      const double e_x = std::exp(x);
+      rho[0] = b2 * std::log(1.0 + e_x) - c;
+      rho[1] = std::max(kMin, e_x / (1.0 + e_x));
+      rho[2] = 0.5 / (b2 * (1.0 + std::cosh(x)));
       return;
     }
     default: rho[0] = s; rho[1] = 1.0; rho[2] = 0.0; return;
@@ -193,7 +204,7 @@ struct Corrector {
 // ------------------------------------------------------------------------------------------------
 struct RB {
   const FunctorInfo* fi;
-  int loss; double loss_a;
+  int loss; double loss_a, loss_b;
   double consts[kMaxConsts];
   int64_t off[kMaxBlocks];
 };
@@ -367,7 +378,7 @@ static bool evaluate(const Problem& prob, const Program& P, const double* x, dou
     double sq = 0.0;
     for (int q = 0; q < fi.nres; ++q) sq += res[q] * res[q];
     double rho[3];
-    loss_evaluate(rb.loss, rb.loss_a, sq, rho);
+    loss_evaluate(rb.loss, rb.loss_a, rb.loss_b, sq, rho);
     block_cost[r] = 0.5 * rho[0];
     if (jvals || residuals) {
       Corrector corr(sq, rho);
@@ -1259,20 +1270,28 @@ int oracle_evaluate(int functor_id, const double* consts, double const* const* p
 
 void oracle_angle_axis_rotate_point(const double* aa, const double* pt, double* out) { angleAxisRotatePoint(aa, pt, out); }
 void oracle_angle_axis_to_rotation_matrix(const double* aa, double* R) { angleAxisToRotationMatrix(aa, R); }
-void oracle_loss_evaluate(int type, double a, double s, double* rho) { loss_evaluate(type, a, s, rho); }
+void oracle_loss_evaluate(int type, double a, double s, double* rho) { loss_evaluate(type, a, 0.0, s, rho); }
+void oracle_loss_evaluate2(int type, double a, double b, double s, double* rho) { loss_evaluate(type, a, b, s, rho); }
 
 oracle_problem* oracle_problem_create(double* params, int64_t n) {
   auto* o = new oracle_problem; o->p.params = params; o->p.n = n; return o;
 }
 void oracle_problem_destroy(oracle_problem* o) { delete o; }
 
+int oracle_problem_add_residual_blocks2(oracle_problem* o, int functor_id, int64_t n, const double* consts,
+                                        int loss_type, double loss_a, double loss_b, const int64_t* block_offsets);
 int oracle_problem_add_residual_blocks(oracle_problem* o, int functor_id, int64_t n, const double* consts,
                                        int loss_type, double loss_a, const int64_t* block_offsets) {
+  return oracle_problem_add_residual_blocks2(o, functor_id, n, consts, loss_type, loss_a, 0.0, block_offsets);
+}
+// loss_b: second loss parameter (TolerantLoss)
+int oracle_problem_add_residual_blocks2(oracle_problem* o, int functor_id, int64_t n, const double* consts,
+                                        int loss_type, double loss_a, double loss_b, const int64_t* block_offsets) {
   const FunctorInfo* f = find_functor(functor_id);
   if (!f) return 0;
   o->p.rbs.reserve(o->p.rbs.size() + (size_t)n);
   for (int64_t i = 0; i < n; ++i) {
-    RB rb{}; rb.fi = f; rb.loss = loss_type; rb.loss_a = loss_a;
+    RB rb{}; rb.fi = f; rb.loss = loss_type; rb.loss_a = loss_a; rb.loss_b = loss_b;
     for (int k = 0; k < f->nconsts; ++k) rb.consts[k] = consts[i * f->nconsts + k];
     for (int k = 0; k < f->nblk; ++k) {
       rb.off[k] = block_offsets[i * f->nblk + k];

@@ -24,7 +24,7 @@ MAX_PARAMETER_BLOCKS = 10
 MAX_CONSTS = 4
 
 # sk_loss_type
-LOSS_TRIVIAL, LOSS_HUBER, LOSS_CAUCHY = 0, 1, 2
+LOSS_TRIVIAL, LOSS_HUBER, LOSS_CAUCHY, LOSS_TOLERANT = 0, 1, 2, 3
 
 # ceres/types.h enumerators (ceres.i:137)
 DENSE_NORMAL_CHOLESKY, DENSE_QR, SPARSE_NORMAL_CHOLESKY, DENSE_SCHUR, SPARSE_SCHUR, ITERATIVE_SCHUR, CGNR = range(7)

@@ -129,8 +129,8 @@ class DoubleArray:
 
 
 class LossFunction:
-    def __init__(self, handle, kind, a=0.0):
-        self._h, self.kind, self.a = handle, kind, a
+    def __init__(self, handle, kind, a=0.0, b=0.0):
+        self._h, self.kind, self.a, self.b = handle, kind, a, b
 
     def __del__(self, _destroy=_destroy):
         if getattr(self, "_h", None):
@@ -145,13 +145,13 @@ class LossFunction:
 
 
 class PredefinedLossFunctions:
-    """ceres.i:160-184. trivial / huber / cauchy run on the device; the others are rejected."""
+    """ceres.i:160-184. trivial / huber / cauchy / tolerant run on the device; the others are rejected."""
 
     @staticmethod
     def _make(fn, kind, *args):
         h = C.c_void_p()
         check(fn(*[float(a) for a in args], C.byref(h)))
-        return LossFunction(h, kind, args[0] if args else 0.0)
+        return LossFunction(h, kind, args[0] if args else 0.0, args[1] if len(args) > 1 else 0.0)
 
     @staticmethod
     def trivialLoss():
@@ -175,7 +175,7 @@ class PredefinedLossFunctions:
 
     @staticmethod
     def tolerantLoss(a, b):
-        return PredefinedLossFunctions._make(lib.sk_loss_tolerant, -1, a, b)
+        return PredefinedLossFunctions._make(lib.sk_loss_tolerant, _abi.LOSS_TOLERANT, a, b)
 
 
 def functor_info(functor_id):

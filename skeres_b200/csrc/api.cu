@@ -174,19 +174,20 @@ int sk_double_array_copy(sk_double_array* dst, int64_t dst_offset, const sk_doub
 }
 
 // ---- LossFunction ------------------------------------------------------------------------------------
-static int make_loss(int type, double a, sk_loss_function** out) {
+static int make_loss(int type, double a, sk_loss_function** out, double b = 0.0) {
   SK_API_BEGIN
   SK_REQUIRE(out != nullptr, SK_ERR_INVALID_ARGUMENT, "loss factory: null output");
-  SK_REQUIRE(type == SK_LOSS_TRIVIAL || a > 0.0, SK_ERR_INVALID_ARGUMENT, "loss scale must be positive");
-  *out = new sk_loss_function{LossSpec{type, a}};
+  if (type == SK_LOSS_TOLERANT) SK_REQUIRE(a >= 0.0 && b > 0.0, SK_ERR_INVALID_ARGUMENT, "TolerantLoss needs a >= 0 and b > 0");   // Ceres CHECKs
+  else SK_REQUIRE(type == SK_LOSS_TRIVIAL || a > 0.0, SK_ERR_INVALID_ARGUMENT, "loss scale must be positive");
+  *out = new sk_loss_function{LossSpec{type, a, b}};
   SK_API_END
 }
 int sk_loss_trivial(sk_loss_function** out) { return make_loss(SK_LOSS_TRIVIAL, 0.0, out); }
 int sk_loss_huber(double a, sk_loss_function** out) { return make_loss(SK_LOSS_HUBER, a, out); }
 int sk_loss_cauchy(double a, sk_loss_function** out) { return make_loss(SK_LOSS_CAUCHY, a, out); }
-int sk_loss_soft_l_one(double, sk_loss_function**) { return fail(SK_ERR_UNSUPPORTED, "SoftLOneLoss has no device implementation (ceres.i:172); registered losses: trivial, huber, cauchy"); }
-int sk_loss_tukey(double, sk_loss_function**) { return fail(SK_ERR_UNSUPPORTED, "TukeyLoss has no device implementation (ceres.i:174); registered losses: trivial, huber, cauchy"); }
-int sk_loss_tolerant(double, double, sk_loss_function**) { return fail(SK_ERR_UNSUPPORTED, "TolerantLoss has no device implementation (ceres.i:175); registered losses: trivial, huber, cauchy"); }
+int sk_loss_soft_l_one(double, sk_loss_function**) { return fail(SK_ERR_UNSUPPORTED, "SoftLOneLoss has no device implementation (ceres.i:172); registered losses: trivial, huber, cauchy, tolerant"); }
+int sk_loss_tukey(double, sk_loss_function**) { return fail(SK_ERR_UNSUPPORTED, "TukeyLoss has no device implementation (ceres.i:174); registered losses: trivial, huber, cauchy, tolerant"); }
+int sk_loss_tolerant(double a, double b, sk_loss_function** out) { return make_loss(SK_LOSS_TOLERANT, a, out, b); }
 int sk_loss_destroy(sk_loss_function* l) { SK_API_BEGIN delete l; SK_API_END }
 int sk_loss_evaluate(const sk_loss_function* loss, double s, double rho[3]) {
   SK_API_BEGIN
@@ -306,7 +307,7 @@ int sk_problem_destroy(sk_problem* p) { SK_API_BEGIN delete p; SK_API_END }
 static ResidualGroup& group_for(sk_problem* p, int functor_id, const FunctorInfo& fi, LossSpec loss) {
   if (!p->groups.empty()) {
     ResidualGroup& g = p->groups.back();
-    if (g.functor_id == functor_id && g.loss.type == loss.type && g.loss.a == loss.a) return g;
+    if (g.functor_id == functor_id && g.loss.type == loss.type && g.loss.a == loss.a && g.loss.b == loss.b) return g;
   }
   p->groups.emplace_back();
   ResidualGroup& g = p->groups.back();
@@ -477,7 +478,7 @@ static std::unique_ptr<LmSolver> prepare_ba(const sk_solver_options& opt, sk_pro
       SK_REQUIRE(g.arrays[a] == array, SK_ERR_UNSUPPORTED, "bundle adjustment parameter blocks must live in one DoubleArray");
     }
     if (first) { loss = g.loss; first = false; }
-    SK_REQUIRE(g.loss.type == loss.type && g.loss.a == loss.a, SK_ERR_UNSUPPORTED, "one loss function per bundle adjustment problem");
+    SK_REQUIRE(g.loss.type == loss.type && g.loss.a == loss.a && g.loss.b == loss.b, SK_ERR_UNSUPPORTED, "one loss function per bundle adjustment problem");
     n += g.n;
   }
   SK_REQUIRE(n > 0, SK_ERR_INVALID_ARGUMENT, "problem has no residual blocks");
@@ -533,7 +534,7 @@ static std::unique_ptr<LmSolver> prepare_dense(const sk_solver_options& opt, sk_
   for (auto& g : p->groups)
     for (int64_t i = 0; i < g.n; ++i) {
       DenseRb rb{};
-      rb.functor = g.functor_id; rb.row = row; rb.loss_type = g.loss.type; rb.loss_a = g.loss.a;
+      rb.functor = g.functor_id; rb.row = row; rb.loss_type = g.loss.type; rb.loss_a = g.loss.a; rb.loss_b = g.loss.b;
       for (int c = 0; c < g.info.nconsts; ++c) rb.consts[c] = g.consts[(size_t)i * g.info.nconsts + c];
       for (int k = 0; k < g.info.nblk; ++k) {
         auto key = std::make_pair(group_array(g, i, k), g.offsets[(size_t)i * g.info.nblk + k]);

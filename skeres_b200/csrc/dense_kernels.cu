@@ -47,7 +47,7 @@ __global__ void k_dense_evaluate(int nrb, const DenseRb* __restrict__ rbs, const
     double sq = 0.0;
     for (int q = 0; q < fi.nres; ++q) sq += res[q] * res[q];
     double rho[3];
-    LossSpec ls{rb.loss_type, rb.loss_a};
+    LossSpec ls{rb.loss_type, rb.loss_a, rb.loss_b};
     loss_evaluate(ls, sq, rho);
     cost = 0.5 * rho[0];
     if (!(cost == cost)) atomicOr(fail_flag, 1);

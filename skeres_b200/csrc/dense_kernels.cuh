@@ -11,7 +11,7 @@ namespace sk {
 // One residual block of a generic (dense-path) problem, device side.
 struct DenseRb {
   int functor, row, loss_type, pad_;
-  double loss_a;
+  double loss_a, loss_b;
   double consts[SK_MAX_CONSTS];
   int col[SK_MAX_PARAMETER_BLOCKS];     // first column of each parameter block in the state vector
 };

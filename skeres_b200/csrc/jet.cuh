@@ -309,7 +309,7 @@ SK_HD bool evaluate_functor(int id, const double* c, const double* x, double* re
 }
 
 // ---- LossFunction::Evaluate (ceres/loss_function.cc) and Corrector (corrector.cc) -------------
-struct LossSpec { int type; double a; };
+struct LossSpec { int type; double a; double b = 0.0; };   // b: second parameter (TolerantLoss only)
 
 SK_HD void loss_evaluate(const LossSpec& l, double s, double* rho) {
   const double kMin = 2.2250738585072014e-308;
@@ -321,6 +321,16 @@ SK_HD void loss_evaluate(const LossSpec& l, double s, double* rho) {
     const double b = l.a * l.a, c = 1.0 / b;
     const double sum = 1.0 + s * c, inv = 1.0 / sum;
     rho[0] = b * log(sum); rho[1] = fmax(kMin, inv); rho[2] = -c * (inv * inv);
+  } else if (l.type == SK_LOSS_TOLERANT) {                  // ceres/loss_function.cc TolerantLoss::Evaluate
+    const double c = l.b * log(1.0 + exp(-l.a / l.b));
+    const double x = (s - l.a) / l.b;
+    if (x > 36.7) { rho[0] = s - l.a - c; rho[1] = 1.0; rho[2] = 0.0; }     // e^x would swamp the 1 (kLog2Pow53)
+    else {
+      const double ex = exp(x);
+      rho[0] = l.b * log(1.0 + ex) - c;
+      rho[1] = fmax(kMin, ex / (1.0 + ex));
+      rho[2] = 0.5 / (l.b * (1.0 + cosh(x)));
+    }
   } else { rho[0] = s; rho[1] = 1.0; rho[2] = 0.0; }
 }
 

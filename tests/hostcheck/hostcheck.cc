@@ -19,10 +19,10 @@ int hc_evaluate(int functor, const double* consts, const double* x, double* res,
 void hc_snavely_residual(const double* cam, const double* pt, double ox, double oy, double* res) {
   sk::snavely_residual(cam, pt, ox, oy, res);
 }
-void hc_loss(int type, double a, double s, double* rho) { sk::LossSpec l{type, a}; sk::loss_evaluate(l, s, rho); }
-void hc_correct(int type, double a, int nrow, int ncol, double* res, double* J) {
+void hc_loss(int type, double a, double b, double s, double* rho) { sk::LossSpec l{type, a, b}; sk::loss_evaluate(l, s, rho); }
+void hc_correct(int type, double a, double b, int nrow, int ncol, double* res, double* J) {
   double sq = 0; for (int i = 0; i < nrow; ++i) sq += res[i] * res[i];
-  double rho[3]; sk::LossSpec l{type, a}; sk::loss_evaluate(l, sq, rho);
+  double rho[3]; sk::LossSpec l{type, a, b}; sk::loss_evaluate(l, sq, rho);
   sk::Corrector c(sq, rho);
   c.correct_jacobian(nrow, ncol, ncol, res, J);
   c.correct_residuals(nrow, res);

@@ -36,6 +36,9 @@ def lib():
                                    C.c_char_p, C.c_int]
         L.oracle_evaluate.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_loss_evaluate.argtypes = [C.c_int, C.c_double, C.c_double, C.c_void_p]
+        L.oracle_loss_evaluate2.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p]
+        L.oracle_problem_add_residual_blocks2.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int,
+                                                          C.c_double, C.c_double, C.c_void_p]
         L.oracle_angle_axis_rotate_point.argtypes = [C.c_void_p] * 3
         L.oracle_angle_axis_to_rotation_matrix.argtypes = [C.c_void_p] * 2
         L.oracle_functor_info.argtypes = [C.c_int] + [C.c_void_p] * 4
@@ -87,9 +90,9 @@ def rotation_matrix(aa):
     return R.reshape(3, 3).T.copy()
 
 
-def loss(kind, a, s):
+def loss(kind, a, s, b=0.0):
     rho = np.zeros(3)
-    lib().oracle_loss_evaluate(kind, float(a), float(s), _p(rho))
+    lib().oracle_loss_evaluate2(kind, float(a), float(b), float(s), _p(rho))
     return rho
 
 
@@ -116,12 +119,12 @@ class OracleProblem:
             lib().oracle_problem_destroy(self._h)
             self._h = None
 
-    def add_residual_blocks(self, fid, consts, block_offsets, loss_type=_abi.LOSS_TRIVIAL, loss_a=0.0):
+    def add_residual_blocks(self, fid, consts, block_offsets, loss_type=_abi.LOSS_TRIVIAL, loss_a=0.0, loss_b=0.0):
         nres, sizes, nc = functor_info(fid)
         off = np.ascontiguousarray(block_offsets, dtype=np.int64).reshape(-1, len(sizes))
         n = off.shape[0]
         consts = np.ascontiguousarray(consts, dtype=np.float64).reshape(n, nc) if nc else np.zeros((n, 0))
-        ok = lib().oracle_problem_add_residual_blocks(self._h, fid, n, _p(consts), loss_type, float(loss_a), _p(off))
+        ok = lib().oracle_problem_add_residual_blocks2(self._h, fid, n, _p(consts), loss_type, float(loss_a), float(loss_b), _p(off))
         assert ok, "oracle_problem_add_residual_blocks failed"
         self.num_residual_blocks += n
         self.num_residuals += n * nres

@@ -136,6 +136,28 @@ def test_loss_functions_match_oracle(sk, oracle):
     for loss, kind, a in [(L.trivialLoss(), _abi.LOSS_TRIVIAL, 0.0), (L.huberLoss(0.7), _abi.LOSS_HUBER, 0.7), (L.cauchyLoss(0.5), _abi.LOSS_CAUCHY, 0.5)]:
         for s in [0.0, 0.2, 0.49, 3.0, 40.0]:
             assert np.allclose(loss.evaluate(s), oracle.loss(kind, a, s), rtol=1e-14, atol=0)
+    tol = L.tolerantLoss(0.8, 0.35)                      # rho'' > 0: the loss behind the Corrector's alpha branch
+    for s in [0.0, 0.05, 0.6, 0.8, 1.3, 5.0, 13.0, 0.8 + 40 * 0.35]:
+        assert np.allclose(tol.evaluate(s), oracle.loss(_abi.LOSS_TOLERANT, 0.8, s, 0.35), rtol=1e-12, atol=1e-300)
+    with pytest.raises(sk.SkeresError):
+        L.tolerantLoss(1.0, 0.0)                         # b > 0 (Ceres CHECKs the same)
+
+
+def test_ba_tolerant_loss_takes_the_alpha_branch(sk, oracle):
+    """Bundle adjustment with TolerantLoss(0.5, 0.3): squared residuals of ~0.5 px^2 sit where rho'' > 0, so the evaluator
+    kernel's Corrector runs its alpha != 0 branch on most observations (tests/test_host_logic.py checks the branch's algebra
+    on the same device code built for the host).  The solve must reach the oracle's optimum; rows are compared loosely."""
+    d = synth.make_bal("small", seed=8)
+    loss = sk.PredefinedLossFunctions.tolerantLoss(0.5, 0.3)
+    opts = dict(max_trust_region_radius=1e12)
+    p, so = oracle_ba(oracle, d, _abi.DENSE_SCHUR, loss=(_abi.LOSS_TOLERANT, 0.5, 0.3), **opts)
+    bal, s = gpu_ba(sk, d, _abi.DENSE_SCHUR, loss=loss, **opts)
+    assert s.termination_type == so.termination_type == _abi.CONVERGENCE
+    assert abs(s.initial_cost - so.initial_cost) <= 1e-11 * so.initial_cost           # evaluator + rho(s)
+    assert np.isclose(s.iterations[1].cost, so.iterations[1].cost, rtol=1e-8)         # first corrected step
+    assert abs(s.final_cost - so.final_cost) <= COST_RTOL * abs(so.final_cost)
+    plain = gpu_ba(sk, d, _abi.DENSE_SCHUR, **opts)[1]
+    assert s.initial_cost < 0.99 * plain.initial_cost and s.final_cost < 0.5 * plain.final_cost      # the loss really is in the path (oracle: 0.970, 0.365)
 
 
 # --------------------------------------------------------------------------------------------------- config 1: CurveFitting, DENSE_QR

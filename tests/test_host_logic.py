@@ -69,11 +69,16 @@ def test_functor_registry_and_unregistered_functor():
         pass
     with pytest.raises(api.SkeresError):
         Arbitrary(1, 2).toAutoDiffCostFunction()
-    for factory in (lambda: api.PredefinedLossFunctions.tukeyLoss(1.0), lambda: api.PredefinedLossFunctions.softLOneLoss(1.0),
-                    lambda: api.PredefinedLossFunctions.tolerantLoss(1.0, 2.0)):
+    for factory in (lambda: api.PredefinedLossFunctions.tukeyLoss(1.0), lambda: api.PredefinedLossFunctions.softLOneLoss(1.0)):
         with pytest.raises(api.SkeresError) as e:
             factory()
         assert e.value.status == _abi.ERR_UNSUPPORTED
+    tol = api.PredefinedLossFunctions.tolerantLoss(1.0, 2.0)        # registered (a host-side handle: no GPU needed to create it)
+    assert (tol.kind, tol.a, tol.b) == (_abi.LOSS_TOLERANT, 1.0, 2.0)
+    for bad in ((1.0, 0.0), (-0.5, 1.0)):                             # Ceres CHECKs a >= 0, b > 0
+        with pytest.raises(api.SkeresError) as e:
+            api.PredefinedLossFunctions.tolerantLoss(*bad)
+        assert e.value.status == _abi.ERR_INVALID_ARGUMENT
 
 
 def test_fails_loudly_without_a_gpu():
@@ -96,8 +101,8 @@ def hc():
     L.hc_layout_free.argtypes = [C.c_void_p]
     L.hc_evaluate.argtypes = [C.c_int] + [C.c_void_p] * 4
     L.hc_snavely_residual.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p]
-    L.hc_loss.argtypes = [C.c_int, C.c_double, C.c_double, C.c_void_p]
-    L.hc_correct.argtypes = [C.c_int, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.hc_loss.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p]
+    L.hc_correct.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.hc_invert_spd3.argtypes = [C.c_void_p, C.c_void_p]
     L.hc_invert_spd9.argtypes = [C.c_void_p, C.c_int]
     return L
@@ -383,25 +388,79 @@ def test_example_functors_device_code_matches_the_oracle(hc, oracle):
 
 def test_device_loss_and_corrector_match_the_oracle(hc, oracle):
     rng = np.random.default_rng(1)
-    for kind, a in [(_abi.LOSS_TRIVIAL, 0.0), (_abi.LOSS_HUBER, 0.7), (_abi.LOSS_CAUCHY, 0.5)]:
+    for kind, a, b in [(_abi.LOSS_TRIVIAL, 0.0, 0.0), (_abi.LOSS_HUBER, 0.7, 0.0), (_abi.LOSS_CAUCHY, 0.5, 0.0), (_abi.LOSS_TOLERANT, 1.5, 0.4),
+                       (_abi.LOSS_TOLERANT, 0.0, 2.0)]:
         for s in [0.0, 0.2, 3.0, 40.0]:
             rho = np.zeros(3)
-            hc.hc_loss(kind, a, s, p(rho))
-            assert np.allclose(rho, oracle.loss(kind, a, s), rtol=1e-15, atol=0)
+            hc.hc_loss(kind, a, b, s, p(rho))
+            assert np.allclose(rho, oracle.loss(kind, a, s, b), rtol=1e-15, atol=0)
     # Corrector through a one-block solve: compare the corrected residual/Jacobian implied by the oracle's gradient
     d = synth.make_bal("tiny", seed=3)
-    for kind, a in [(_abi.LOSS_HUBER, 1.0), (_abi.LOSS_CAUCHY, 2.0)]:
+    for kind, a, b in [(_abi.LOSS_HUBER, 1.0, 0.0), (_abi.LOSS_CAUCHY, 2.0, 0.0), (_abi.LOSS_TOLERANT, 0.3, 0.2)]:
         op = oracle.OracleProblem(d.parameters)
-        op.add_residual_blocks(_abi.FUNCTOR_SNAVELY_REPROJECTION_ERROR, d.observations.reshape(-1, 2), d.block_offsets(), kind, a)
+        op.add_residual_blocks(_abi.FUNCTOR_SNAVELY_REPROJECTION_ERROR, d.observations.reshape(-1, 2), d.block_offsets(), kind, a, b)
         cost, r, g, Jv = op.evaluate()
         op0 = oracle.OracleProblem(d.parameters)
         op0.add_residual_blocks(_abi.FUNCTOR_SNAVELY_REPROJECTION_ERROR, d.observations.reshape(-1, 2), d.block_offsets())
         _, r0, _, J0 = op0.evaluate()
         for i in rng.integers(0, d.num_observations, 25):
             res = r0[2 * i:2 * i + 2].copy(); J = J0[24 * i:24 * i + 18].copy()
-            hc.hc_correct(kind, a, 2, 9, p(res), p(J))
+            hc.hc_correct(kind, a, b, 2, 9, p(res), p(J))
             assert np.allclose(res, r[2 * i:2 * i + 2], rtol=1e-14, atol=1e-14)
             assert np.allclose(J, Jv[24 * i:24 * i + 18], rtol=1e-13, atol=1e-13)
+
+
+def test_tolerant_loss_and_the_alpha_branch_of_the_corrector(hc, oracle):
+    """TolerantLoss (ceres.i:175) is the one registered loss with rho'' > 0, i.e. the one that takes the Corrector through
+    its alpha != 0 branch (DESIGN.md parity gap 3, closed by this test).  Independent checks, not oracle-vs-device only:
+    rho against the closed form and its numerical derivatives; the corrected Jacobian and residual against the identities
+    they are built to satisfy (Triggs):  J~' J~ = J' (rho' I + 2 rho'' r r') J   and   J~' r~ = rho' J' r."""
+    a, b = 0.8, 0.35
+    c = b * np.log1p(np.exp(-a / b))
+    f = lambda s: b * np.log1p(np.exp((s - a) / b)) - c
+    for s in [0.0, 0.05, 0.6, 0.8, 1.3, 5.0, 13.0]:
+        rho = np.zeros(3)
+        hc.hc_loss(_abi.LOSS_TOLERANT, a, b, s, p(rho))
+        assert np.allclose(rho, oracle.loss(_abi.LOSS_TOLERANT, a, s, b), rtol=1e-15, atol=0)
+        h = 1e-5
+        assert np.isclose(rho[0], f(s), rtol=1e-13, atol=1e-15)
+        assert np.isclose(rho[1], (f(s + h) - f(s - h)) / (2 * h), rtol=1e-7, atol=1e-10)
+        h2 = 1e-3                                                                  # second difference: round-off ~ eps f / h^2
+        assert np.isclose(rho[2], (f(s + h2) - 2 * f(s) + f(s - h2)) / h2 ** 2, rtol=1e-4, atol=1e-8) and (rho[2] > 0 or s > a + 36.7 * b)
+    big = np.zeros(3)
+    hc.hc_loss(_abi.LOSS_TOLERANT, a, b, a + 40.0 * b, p(big))                     # the overflow guard: rho -> s - a - c, rho' = 1, rho'' = 0
+    assert np.allclose(big, [40.0 * b - c, 1.0, 0.0], rtol=1e-15)
+    assert f(0.0) == 0.0 or abs(f(0.0)) < 1e-16                                    # rho(0) = 0
+    rng = np.random.default_rng(9)
+    took_alpha = 0
+    for _ in range(40):
+        r = rng.normal(0, 0.7, 2); J = rng.normal(size=(2, 9))
+        sq = float(r @ r)
+        rho = oracle.loss(_abi.LOSS_TOLERANT, a, sq, b)
+        took_alpha += rho[2] > 0
+        res = r.copy(); Jc = np.ascontiguousarray(J.copy())
+        hc.hc_correct(_abi.LOSS_TOLERANT, a, b, 2, 9, p(res), p(Jc))
+        assert np.allclose(Jc.T @ Jc, J.T @ (rho[1] * np.eye(2) + 2.0 * rho[2] * np.outer(r, r)) @ J, rtol=1e-11, atol=1e-12)
+        assert np.allclose(Jc.T @ res, rho[1] * (J.T @ r), rtol=1e-11, atol=1e-12)
+    assert took_alpha == 40
+    # ... and the oracle's own Corrector (through a problem evaluation) satisfies the same identities
+    d = synth.make_bal("tiny", seed=3)
+    op = oracle.OracleProblem(d.parameters)
+    op.add_residual_blocks(_abi.FUNCTOR_SNAVELY_REPROJECTION_ERROR, d.observations.reshape(-1, 2), d.block_offsets(), _abi.LOSS_TOLERANT, 0.3, 0.2)
+    cost, rc, g, Jv = op.evaluate()
+    op0 = oracle.OracleProblem(d.parameters)
+    op0.add_residual_blocks(_abi.FUNCTOR_SNAVELY_REPROJECTION_ERROR, d.observations.reshape(-1, 2), d.block_offsets())
+    cost0, r0, g0, J0 = op0.evaluate()
+    want_cost = 0.0
+    for i in range(d.num_observations):
+        blocks = lambda v: np.hstack([v[24 * i:24 * i + 18].reshape(2, 9), v[24 * i + 18:24 * i + 24].reshape(2, 3)])   # [F | E], each row-major
+        r = r0[2 * i:2 * i + 2]; J = blocks(J0)
+        rho = oracle.loss(_abi.LOSS_TOLERANT, 0.3, float(r @ r), 0.2)
+        want_cost += 0.5 * rho[0]
+        Jt = blocks(Jv); rt = rc[2 * i:2 * i + 2]
+        assert np.allclose(Jt.T @ Jt, J.T @ (rho[1] * np.eye(2) + 2.0 * rho[2] * np.outer(r, r)) @ J, rtol=1e-10, atol=1e-9)
+        assert np.allclose(Jt.T @ rt, rho[1] * (J.T @ r), rtol=1e-10, atol=1e-9)
+    assert np.isclose(cost, want_cost, rtol=1e-13)
 
 
 def test_small_spd_inverses(hc):
