@@ -202,8 +202,9 @@ void BaSolver::eval_cost(const double* xv, const int* guard) {
 }
 
 // seg_a_ = segment partials of S_local * v, where v = `in` or (pcg_dir) the PCG direction z + beta p.
-// Multi-GPU: the partials are reduced per camera into ybuf_ and allreduced; returns the vector the
-// consumer kernels should read (nullptr = "reduce the segment partials yourself").
+// Multi-GPU: the partials are reduced per camera and exchanged -- through the peer window (the consumer kernels gather it
+// themselves: returns nullptr) or, as a fallback, into ybuf_ with an NCCL allreduce (returns ybuf_).  Single GPU: returns
+// nullptr = "reduce the segment partials yourself".
 const double* BaSolver::matvec(const double* in, bool pcg_dir, const int* guard) {
   {
     KScope k(prof_, SK_KF_SCHUR_MATVEC, 1 + (L_.n_giant ? 1 : 0));

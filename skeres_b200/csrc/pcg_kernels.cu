@@ -10,8 +10,12 @@
 //                          + D^2 p, and the p.q partials
 //   k_pcg_update  (warp per camera) alpha = rho / p.q; x += alpha p; r -= alpha q; Q partials;
 //                          z = M^-1 r (SchurJacobi block) and the r.z partials of the NEXT iteration
-// Every residual_reset_period-th iteration r is recomputed as b - S x (one more matvec + k_pcg_resid).
+// Every residual_reset_period-th iteration r is recomputed as b - S x (one more matvec + k_pcg_resid2).
 // All sums are fixed-order (per-warp partials reduced by one CTA), hence bit-reproducible.
+// Multi-GPU (points partitioned, cameras replicated): a fourth launch, k_cam_reduce9_warp, reduces this rank's partials per
+// camera into its NVLink peer window and publishes them; k_pcg_reduce / k_pcg_resid2 then wait for every rank's window and
+// add them in rank order (comm.cuh: PeerWindow) -- the exchange is part of the kernels on either side, not a collective call
+// between them.  Without peer mapping the reduced vector goes through an NCCL allreduce instead (y_in).
 #include "pcg_kernels.cuh"
 
 #include <cstdlib>
