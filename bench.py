@@ -268,7 +268,7 @@ def main():
     mv_bytes = matvec_algorithmic_bytes(per_gpu_obs, per_gpu_pts, n_cam)
     achieved = mv_bytes / (mv_ms * 1e-3) / 1e9 if mv_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "k_ba_matvec_tma (implicit Schur product, PCG inner kernel)", "achieved": achieved, "peak": hbm_peak,
-                "unit": "GB/s", "frac": achieved / hbm_peak,
+                "unit": "GB/s", "frac": achieved / hbm_peak, "frac_of_nominal_8000_GBps": achieved / 8000.0,
                 "traffic": (MATVEC_NCU_TRAFFIC["bytes_per_launch"] if (world == 1 and n_obs == MATVEC_NCU_TRAFFIC["n_obs"]) else None),
                 "traffic_source": MATVEC_NCU_TRAFFIC["source"], "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": mv_bytes, "avg_launch_ms": mv_ms, "launches": int(kl[3]),
