@@ -123,11 +123,21 @@ void build_ba_layout(int64_t n, const int64_t* cam_off, const int64_t* pt_off, c
   L.input_was_sorted = sorted;
   std::vector<int32_t> order;                                   // sorted position -> input index; empty = identity
   if (!sorted) {
+    // Counting sort by point (ids are dense), then every point's few observations by (camera, input index): all host
+    // threads, ~30x faster than one stable_sort over 5M keys, and the same order (ties keep their input order).
     order.resize((size_t)n);
-    std::iota(order.begin(), order.end(), 0);
-    std::vector<uint64_t> key((size_t)n);
-    for (int64_t i = 0; i < n; ++i) key[i] = ((uint64_t)(uint32_t)pt_id[i] << 32) | (uint32_t)cam_id[i];
-    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
+    std::vector<int32_t> start((size_t)n_pts_all + 1, 0);
+    parallel_for(n, [&](int64_t a, int64_t b) { for (int64_t i = a; i < b; ++i) __atomic_fetch_add(&start[(size_t)pt_id[i] + 1], 1, __ATOMIC_RELAXED); });
+    for (int64_t p = 0; p < n_pts_all; ++p) start[p + 1] += start[p];
+    std::vector<int32_t> next(start.begin(), start.end() - 1);
+    parallel_for(n, [&](int64_t a, int64_t b) {
+      for (int64_t i = a; i < b; ++i) order[(size_t)__atomic_fetch_add(&next[pt_id[i]], 1, __ATOMIC_RELAXED)] = (int32_t)i;
+    });
+    parallel_for(n_pts_all, [&](int64_t p0, int64_t p1) {
+      for (int64_t p = p0; p < p1; ++p)
+        std::sort(order.begin() + start[p], order.begin() + start[p + 1],
+                  [&](int32_t a, int32_t b) { return cam_id[a] != cam_id[b] ? cam_id[a] < cam_id[b] : a < b; });
+    });
   }
   auto src = [&](int64_t j) -> int64_t { return sorted ? j : (int64_t)order[j]; };
   lap("sort / sortedness");
