@@ -573,6 +573,12 @@ static LinSummary dense_qr_solve(const SolveCtx& c, const double* jvals, const d
 // SchurEliminator (internal/ceres/schur_eliminator_impl.h) — A.5.  lhs is either the dense reduced
 // camera matrix (upper block triangle filled) or only its diagonal blocks (SchurJacobi).
 // ------------------------------------------------------------------------------------------------
+// Rounding-sensitivity knob (tests only; tests/test_oracle_golden.py::test_schur_jacobi_rounding_sensitivity):
+// algebraically identical re-orderings of the Schur elimination.  0 = the restated Ceres order;
+// 1 = G^T (E^-1 G) instead of (G^T E^-1) G in ChunkOuterProduct; 2 = sum of F^T F and sum of G^T E^-1 G accumulated
+// separately per block and subtracted once at the end; 3 = e-blocks eliminated in reverse order.
+static int g_schur_variant = 0;
+
 struct ReducedMatrix {
   bool diagonal_only;
   int64_t nf = 0;                       // scalar size
@@ -615,7 +621,12 @@ struct Schur {
     }
     struct Slot { int32_t fb; int pos; };
     std::vector<Slot> layout; std::vector<double> buffer;
-    for (int32_t e = 0; e < P.num_e_blocks; ++e) {
+    const int variant = g_schur_variant;
+    std::vector<double> minus;                                   // variant 2: the subtracted part, accumulated on its own
+    if (variant == 2) minus.assign(S->diagonal_only ? S->blocks.size() : S->dense.size(), 0.0);
+    double* const lhs0 = S->diagonal_only ? S->blocks.data() : S->dense.data();
+    for (int32_t e_it = 0; e_it < P.num_e_blocks; ++e_it) {
+      const int32_t e = (variant == 3) ? (P.num_e_blocks - 1 - e_it) : e_it;
       const int es = P.pbs[e].size;
       double ete[81] = {0}, g[9] = {0};
       if (D) for (int i = 0; i < es; ++i) { const double d = D[P.pbs[e].col + i]; ete[i * es + i] = d * d; }
@@ -681,10 +692,21 @@ struct Schur {
           int64_t st; double* m = cell(S, b1, b2, &st);
           if (!m) continue;
           const double* B2 = &buffer[layout[i2].pos];
-          for (int i = 0; i < f1; ++i) for (int j = 0; j < f2; ++j) { double s = 0; for (int k = 0; k < es; ++k) s += b1t_inv[i * es + k] * B2[k * f2 + j]; m[i * st + j] -= s; }
+          if (variant == 1) {                                    // B1^T (inv B2)
+            double inv_b2[81];   // es x f2
+            for (int k = 0; k < es; ++k) for (int j = 0; j < f2; ++j) { double s = 0; for (int l = 0; l < es; ++l) s += inv[k * es + l] * B2[l * f2 + j]; inv_b2[k * f2 + j] = s; }
+            for (int i = 0; i < f1; ++i) for (int j = 0; j < f2; ++j) { double s = 0; for (int k = 0; k < es; ++k) s += B1[k * f1 + i] * inv_b2[k * f2 + j]; m[i * st + j] -= s; }
+            continue;
+          }
+          double* mm = (variant == 2) ? (minus.data() + (m - lhs0)) : m;
+          for (int i = 0; i < f1; ++i) for (int j = 0; j < f2; ++j) {
+            double s = 0; for (int k = 0; k < es; ++k) s += b1t_inv[i * es + k] * B2[k * f2 + j];
+            if (variant == 2) mm[i * st + j] += s; else mm[i * st + j] -= s;
+          }
         }
       }
     }
+    if (variant == 2) for (size_t i = 0; i < minus.size(); ++i) lhs0[i] -= minus[i];
     // NoEBlockRowsUpdate
     for (int64_t r = P.chunk_start[P.num_e_blocks]; r < P.num_rbs(); ++r) {
       const RB& rb = prob.rbs[P.row_rb[r]];
@@ -1236,6 +1258,8 @@ using namespace oracle;
 struct oracle_problem { Problem p; };
 
 extern "C" {
+
+void oracle_set_schur_rounding_variant(int v) { g_schur_variant = v; }
 
 void oracle_set_num_threads(int n) {
 #ifdef _OPENMP

@@ -26,6 +26,20 @@ def rel_param_diff(a, b, floor=1e-2):
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
 
 
+# Truncated (eta = 0.1) PCG with SCHUR_JACOBI / IDENTITY: the end point is not a well-conditioned function of the input
+# (tests/golden/make_rounding_envelope.py: the oracle moves by `envelope` against its OWN -ffp-contract=fast build and against
+# algebraically identical re-orderings of its eliminator; tests/test_oracle_golden.py pins that on the CPU).  Those perturb a
+# handful of operations by one rounding each; the device re-associates every sum (tiles, segments, trees), a seed one to two
+# orders of magnitude larger for the same amplification, hence the factor.  The 1e-5 bar itself is asserted on the converged
+# solves (test_ba_converged_linear_solves_meet_the_parameter_tolerance), on JACOBI and on the exact Schur solvers.
+ENVELOPE_FACTOR = 100.0
+
+
+def envelope_bound(case):
+    e = load("schur_jacobi_rounding_envelope.json")["cases"][case]
+    return max(PARAM_RTOL, ENVELOPE_FACTOR * e["fma"]["param_rel_diff"])
+
+
 def oracle_ba(oracle, d, lst, prec=_abi.SCHUR_JACOBI, loss=(_abi.LOSS_TRIVIAL, 0.0), **opts):
     p = oracle.OracleProblem(d.parameters)
     p.add_residual_blocks(_abi.FUNCTOR_SNAVELY_REPROJECTION_ERROR, d.observations.reshape(-1, 2), d.block_offsets(), *loss)
@@ -278,22 +292,37 @@ def test_example_functors_at_the_evaluate_boundary(sk, oracle):
         assert np.allclose(res, hand[fid][0], rtol=1e-14) and all(np.allclose(np.ravel(a), b, rtol=1e-14) for a, b in zip(jac, hand[fid][1]))
 
 
+def robust_curve_fit(sk, loss, max_it):
+    """RobustCurveFitting.scala:97-128 verbatim: its own data, one shared loss object, two DoubleArray(1) blocks from (0, 0)."""
+    d = load("robust_curve_fitting_data.json")
+    m, c = sk.DoubleArray(1), sk.DoubleArray(1)
+    problem = sk.Problem()
+    for xi, yi in zip(d["x"], d["y"]):
+        problem.addResidualBlock(sk.ExponentialResidual(xi, yi).toAutoDiffCostFunction(), loss, m.toPointer(), c.toPointer())
+    o = sk.Solver.Options()
+    o.setMaxNumIterations(max_it)
+    o.setLinearSolverType(_abi.DENSE_QR)
+    s = sk.Solver.Summary()
+    sk.ceres.solve(o, problem, s)
+    return np.array([m.get(0), c.get(0)]), s
+
+
 def test_robust_curve_fitting(sk, oracle):
-    """RobustCurveFitting.scala: outliers (:41-42) + CauchyLoss(0.5) (:107) — Corrector on the device."""
-    def spoil(y):
-        y = y.copy(); y[10] += 8.0; y[40] -= 6.0
-        return y
-    d = load("curve_fitting_data.json")
-    for make, kind, a in [(lambda: sk.PredefinedLossFunctions.cauchyLoss(0.5), _abi.LOSS_CAUCHY, 0.5),
+    """RobustCurveFitting.scala with the reference's own data (outliers at :41-42), CauchyLoss(0.5) (:107) and 25 iterations
+    (:117) -- the Corrector on the device.  Row by row against the oracle, and the published tutorial answer."""
+    d = load("robust_curve_fitting_data.json")
+    for make, kind, a in [(lambda: sk.PredefinedLossFunctions.cauchyLoss(d["cauchy_a"]), _abi.LOSS_CAUCHY, d["cauchy_a"]),
                           (lambda: sk.PredefinedLossFunctions.huberLoss(1.0), _abi.LOSS_HUBER, 1.0)]:
-        x, s, _ = curve_fit(sk, make(), spoil, max_it=50)
+        x, s = robust_curve_fit(sk, make(), d["max_num_iterations"])
         p = oracle.OracleProblem(np.zeros(2))
-        p.add_residual_blocks(_abi.FUNCTOR_EXPONENTIAL_RESIDUAL, np.stack([d["x"], spoil(np.array(d["y"]))], 1), np.tile([0, 1], (67, 1)), kind, a)
+        p.add_residual_blocks(_abi.FUNCTOR_EXPONENTIAL_RESIDUAL, np.stack([d["x"], d["y"]], 1), np.tile([0, 1], (67, 1)), kind, a)
         o = _abi.default_options()
-        o.linear_solver_type = _abi.DENSE_QR
+        o.linear_solver_type, o.max_num_iterations = _abi.DENSE_QR, d["max_num_iterations"]
         so = p.solve(o)
         assert_same_trajectory(s, so)
         assert rel_param_diff(x, p.params, 1e-6) <= PARAM_RTOL
+        if kind == _abi.LOSS_CAUCHY:
+            assert [float(f"{v:.6f}") for v in x] == [0.287605, 0.151213]      # the Ceres tutorial's robust fit
 
 
 def test_max_iterations_and_zero_iterations(sk):
@@ -324,10 +353,26 @@ def test_ba_iterative_schur_matches_oracle(sk, oracle, shape, seed):
     p, so = oracle_ba(oracle, d, _abi.ITERATIVE_SCHUR, _abi.SCHUR_JACOBI)
     bal, s = gpu_ba(sk, d, _abi.ITERATIVE_SCHUR, _abi.SCHUR_JACOBI)
     assert_same_trajectory(s, so, row_rtol=1e-6)
-    # An inexact (eta = 0.1) PCG step is sensitive to summation order after ~100 iterations, so on the largest case
-    # the parameters are compared on the cost they reach (1e-6) and loosely in value; small cases meet 1e-5.
-    tol = PARAM_RTOL if shape != "ladybug-49" else 2e-2
+    # small cases meet 1e-5; the Ladybug shape is held to the oracle's own rounding envelope (see envelope_bound) and to
+    # 1e-5 with converged solves (next test)
+    tol = PARAM_RTOL if shape != "ladybug-49" else envelope_bound("ladybug-49/SCHUR_JACOBI/eta0.1")
     assert rel_param_diff(bal.parameters.toArray(), p.params) <= tol
+
+
+@pytest.mark.parametrize("shape,seed,prec", [("ladybug-49", 1, _abi.SCHUR_JACOBI), ("ladybug-49", 1, _abi.JACOBI), ("small", 3, _abi.IDENTITY)])
+def test_ba_converged_linear_solves_meet_the_parameter_tolerance(sk, oracle, shape, seed, prec):
+    """The north star's parameter tolerance (1e-5 relative) where it is attainable: with the linear solves converged
+    (eta = 1e-10) every LM step is unique, so what is left between the device and the oracle is rounding, not the path a
+    truncated CG takes.  Same rows, PCG counts within 5 % (the Q-test flips within a few iterations once the decrease per
+    iteration is at rounding level), costs to 1e-9, parameters to 1e-5 -- SCHUR_JACOBI included."""
+    d = synth.make_bal(shape, seed=seed)
+    kw = dict(eta=1e-10, max_linear_solver_iterations=3000, max_num_iterations=3)
+    p, so = oracle_ba(oracle, d, _abi.ITERATIVE_SCHUR, prec, **kw)
+    bal, s = gpu_ba(sk, d, _abi.ITERATIVE_SCHUR, prec, **kw)
+    assert_same_trajectory(s, so, exact_rows=False, row_rtol=1e-9)
+    for a, b in zip(s.iterations, so.iterations):
+        assert abs(a.linear_solver_iterations - b.linear_solver_iterations) <= max(3, 0.05 * b.linear_solver_iterations)
+    assert rel_param_diff(bal.parameters.toArray(), p.params) <= PARAM_RTOL
 
 
 @pytest.mark.parametrize("shape,seed", [("tiny", 1), ("small", 2)])
@@ -361,10 +406,47 @@ def test_ba_identity_preconditioner(sk, oracle):
     assert_same_trajectory(s, so, exact_rows=False)
     for a, b in zip(s.iterations, so.iterations):
         assert abs(a.linear_solver_iterations - b.linear_solver_iterations) <= max(2, 0.1 * b.linear_solver_iterations)
-    # Parameters: NOT within the 1e-5 target here (measured 2.9e-3 on a B200). Same bound and same reason as the
-    # Ladybug ITERATIVE_SCHUR case: a truncated (eta = 0.1) CG solve depends on summation order; the cost reached
-    # (checked to 1e-6 above) is the well-defined quantity. Recorded as a parity gap in DESIGN.md section 2.
-    assert rel_param_diff(bal.parameters.toArray(), p.params) <= 2e-2
+    # Parameters: measured 2.9e-3 on a B200; the oracle's own rounding envelope for this run is 1e-4 (envelope_bound), and
+    # test_ba_converged_linear_solves_meet_the_parameter_tolerance holds the same problem to 1e-5 with converged solves.
+    assert rel_param_diff(bal.parameters.toArray(), p.params) <= envelope_bound("small-3/IDENTITY/eta0.1")
+
+
+# --------------------------------------------------------------------------------------------------- BASELINE-sized configs vs committed oracle rows
+def _digest_indices(n_cam, n_pt, kept):
+    pts = np.unique(np.linspace(0, n_pt - 1, kept).astype(np.int64))
+    return np.concatenate([np.arange(9 * n_cam, dtype=np.int64)] + [9 * n_cam + 3 * p + np.arange(3, dtype=np.int64) for p in pts])
+
+
+@pytest.mark.parametrize("fixture", ["oracle_venice_1778_rows.json", "oracle_final_13682_rows.json"])
+def test_baseline_sized_rows_follow_the_oracle_fixture(sk, fixture):
+    """BASELINE.json configs[2] (Venice-1778 shape, the headline) and configs[4] (Final-13682 shape) on ONE GPU against the
+    oracle's committed LM rows (tests/golden/make_oracle_ba_rows.py; the oracle needs 10 min / 1 h for them).  Row by row:
+    same step validity / acceptance, cost to 1e-8, radius to 1e-4, identical PCG iteration counts while a solve stays below
+    100 iterations and within 2 % beyond (the Q-test of a long truncated solve flips within a few iterations under a
+    different summation order; first such row on the Venice shape: row 8, 153 iterations); final cost to 1e-6."""
+    g = load(fixture)
+    c = g["case"]
+    d = synth.make_bal(c["shape"], seed=c["seed"])
+    assert float(np.sum(d.parameters) + np.sum(d.observations)) == g["input_checksum"], "synthetic input differs from the fixture's"
+    bal, s = gpu_ba(sk, d, _abi.ITERATIVE_SCHUR, _abi.SCHUR_JACOBI, max_num_iterations=c["max_num_iterations"])
+    rows = g["iterations"]
+    assert len(s.iterations) == len(rows) and s.termination_type == g["termination_type"]
+    assert abs(s.initial_cost - g["initial_cost"]) <= 1e-12 * g["initial_cost"]
+    for a, b in zip(s.iterations, rows):
+        assert (a.iteration, a.step_is_valid, a.step_is_successful) == (b["iteration"], b["step_is_valid"], b["step_is_successful"])
+        assert np.isclose(a.cost, b["cost"], rtol=1e-8), (a.iteration, a.cost, b["cost"])
+        assert np.isclose(a.trust_region_radius, b["trust_region_radius"], rtol=1e-4)
+        assert np.isclose(a.gradient_max_norm, b["gradient_max_norm"], rtol=1e-3, atol=1e-6)
+        n = b["linear_solver_iterations"]
+        if n < 100:
+            assert a.linear_solver_iterations == n, (a.iteration, a.linear_solver_iterations, n)
+        else:
+            assert abs(a.linear_solver_iterations - n) <= 0.02 * n, (a.iteration, a.linear_solver_iterations, n)
+    assert abs(s.final_cost - g["final_cost"]) <= COST_RTOL * g["final_cost"]
+    # parameters: cameras + 300 points kept in the fixture.  A truncated SCHUR_JACOBI run is held to cost, not to 1e-5 in
+    # parameters (envelope_bound above); the digest still catches a wrong block or a wrong scatter.
+    x = bal.parameters.toArray()[_digest_indices(g["n_cam"], g["n_pt"], g["param_digest_points"])]
+    assert rel_param_diff(x, np.array(g["param_digest"])) <= 5e-2
 
 
 LONG_TRACK_CASE = dict(n_cam=600, n_pt=1500, n_obs=12000, seed=5, long_tracks=(257, 600, 513))     # chunk tiles: 2, 3, 3

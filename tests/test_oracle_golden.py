@@ -294,6 +294,73 @@ def test_unsorted_input_gives_the_same_solve(oracle):
     assert np.allclose(outs[0][2], outs[1][2], rtol=1e-6, atol=1e-8)
 
 
+def test_robust_curve_fitting_reproduces_the_ceres_tutorial_answer(oracle):
+    """RobustCurveFitting.scala as written: its own 67 pairs with the two outliers (:41-42), CauchyLoss(0.5) (:107), 25
+    iterations, DENSE_QR, start (0, 0).  The reference example is the Ceres tutorial's robust_curve_fitting; the published
+    tutorial quotes the fit m = 0.287605, c = 0.151213 with the loss (and a visibly worse one without).  The two numbers
+    were written down from memory of the published docs BEFORE the oracle was run on this data; the oracle's Corrector +
+    Cauchy path reproduces them to all six digits."""
+    d = load("robust_curve_fitting_data.json")
+    assert d["outlier_indices"] == [19, 20] and len(d["x"]) == 67
+    p = oracle.OracleProblem(np.zeros(2))
+    p.add_residual_blocks(_abi.FUNCTOR_EXPONENTIAL_RESIDUAL, np.stack([d["x"], d["y"]], 1), np.tile([0, 1], (67, 1)), _abi.LOSS_CAUCHY, d["cauchy_a"])
+    o = _abi.default_options()
+    o.linear_solver_type, o.max_num_iterations = _abi.DENSE_QR, d["max_num_iterations"]
+    s = p.solve(o)
+    assert s.termination_type == _abi.CONVERGENCE
+    assert [float(f"{v:.6f}") for v in p.params] == [0.287605, 0.151213]
+    q = oracle.OracleProblem(np.zeros(2))                                  # without the loss the outliers drag the fit away
+    q.add_residual_blocks(_abi.FUNCTOR_EXPONENTIAL_RESIDUAL, np.stack([d["x"], d["y"]], 1), np.tile([0, 1], (67, 1)))
+    q.solve(o)
+    assert abs(q.params[0] - 0.3) > 2 * abs(p.params[0] - 0.3) and abs(q.params[1] - 0.1) > 2 * abs(p.params[1] - 0.1)
+
+
+def test_schur_jacobi_parameters_are_rounding_sensitive_at_the_default_eta(oracle):
+    """DESIGN.md section 2, parity gap 1.  An algebraically identical re-ordering of the oracle's own Schur eliminator
+    (G^T (E^-1 G) instead of (G^T E^-1) G) moves the parameters a truncated (eta = 0.1) ITERATIVE_SCHUR + SCHUR_JACOBI
+    solve of the Ladybug-49 shape ends at by ~6e-4 relative -- same LM rows, same PCG iteration counts, costs equal to
+    1e-9 -- so no implementation can meet a 1e-5 parameter tolerance against the oracle there without being bit-identical
+    to it.  With converged linear solves (eta = 1e-10) the same perturbation stays below 1e-6.  The measured values are
+    committed (tests/golden/schur_jacobi_rounding_envelope.json, made by make_rounding_envelope.py); the GPU parity tests
+    hold the device to the 1e-5 bar on the converged solves and to a multiple of this envelope on the truncated ones."""
+    import ctypes as C
+    env = load("schur_jacobi_rounding_envelope.json")["cases"]
+    L = oracle.lib()
+    L.oracle_set_schur_rounding_variant.argtypes = [C.c_int]
+    d = synth.make_bal("ladybug-49", seed=1)
+    rel = lambda a, b: float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-2)))
+
+    def solve(variant, **kw):
+        L.oracle_set_schur_rounding_variant(variant)
+        try:
+            p = oracle.OracleProblem(d.parameters)
+            p.add_residual_blocks(_abi.FUNCTOR_SNAVELY_REPROJECTION_ERROR, d.observations.reshape(-1, 2), d.block_offsets())
+            o = _abi.default_options()
+            o.linear_solver_type, o.preconditioner_type = _abi.ITERATIVE_SCHUR, _abi.SCHUR_JACOBI
+            for k, v in kw.items():
+                setattr(o, k, v)
+            summ = p.solve(o)
+            return p.params.copy(), summ
+        finally:
+            L.oracle_set_schur_rounding_variant(0)
+
+    x0, s0 = solve(0)
+    x1, s1 = solve(1)
+    assert [r.linear_solver_iterations for r in s0.iterations] == [r.linear_solver_iterations for r in s1.iterations]
+    assert abs(s0.final_cost - s1.final_cost) <= 1e-8 * s0.final_cost
+    gap = rel(x1, x0)
+    assert gap > 10 * 1e-5, gap                                            # an order of magnitude above the north star's tolerance
+    assert np.isclose(gap, env["ladybug-49/SCHUR_JACOBI/eta0.1"]["variant1"]["param_rel_diff"], rtol=1e-3)   # the committed fixture is this run
+    tight = dict(eta=1e-10, max_linear_solver_iterations=3000, max_num_iterations=3)
+    xt0, _ = solve(0, **tight)
+    xt1, _ = solve(1, **tight)
+    assert rel(xt1, xt0) < 1e-5
+    # every committed envelope: truncated SCHUR_JACOBI / IDENTITY far above 1e-5 on the larger cases, JACOBI far below
+    assert env["ladybug-49/SCHUR_JACOBI/eta0.1"]["envelope_param_rel_diff"] > 1e-4 > 1e-5 > env["ladybug-49/SCHUR_JACOBI/eta1e-10"]["envelope_param_rel_diff"]
+    assert env["ladybug-49/JACOBI/eta0.1"]["envelope_param_rel_diff"] < 1e-9
+    assert env["long-tracks/SCHUR_JACOBI/eta0.1"]["fma"]["param_rel_diff"] > 1e-2 and env["long-tracks/JACOBI/eta0.1"]["envelope_param_rel_diff"] < 1e-8
+
+
 # ---------------------------------------------------------------------------------------------------
 def test_loss_functions(oracle):
     """ceres/loss_function.h closed forms (A.2)."""
