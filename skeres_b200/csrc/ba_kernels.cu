@@ -431,11 +431,51 @@ __device__ __forceinline__ void seg_reduce9_s(const Tile& q, const TileMetaSmem&
   }
 }
 
+// ---- two-level sums of the implicit-Schur product --------------------------------------------------------------------
+// Round 1 formed every per-point sum and every per-(segment, component) sum as ONE serial chain of dependent shared-memory
+// loads (up to 16 resp. 40 long) walked by ~50 resp. ~150 of the 256 threads while the others waited at the next barrier:
+// 45 % of the warp samples of the kernel sat behind those two barriers (profiles/r01_v9_matvec_tma_ncu_source_lines.txt).
+// Here every sum is cut into fixed-size chunks (4 observations of a point, 8 of a segment), all threads of the CTA add one
+// chunk each as a small tree from independent loads, and a second short pass adds the chunk sums of a point / segment in
+// order.  The order of additions is fixed by the chunk tables alone, so the prefetching and the classic kernel still agree
+// bit for bit.  w is staged [observation][3], v in the segment order [position][9] (odd strides: conflict-free writes), so
+// that a chunk is one contiguous run and no permutation is read on the way.
+constexpr int VS = kSegRow;                // row stride of the segment-ordered staging of v
+__device__ __forceinline__ RecView rec_view(const BaDev& L, const unsigned char* base) { return ::sk::rec_view(base, L.rec_sp, L.rec_pp, L.rec_sc); }
+
+// pw[3 c + k] = sum over chunk c of w[.][k]; then u = (E^T E)^-1 (sum of the point's chunk sums).  Two barriers inside.
+__device__ __forceinline__ void point_sums_chunked(const RecView& R, int np, const double* w, double* pw, const double* ei,
+                                                   double* u, int UP) {
+  const int tid = threadIdx.x;
+  const int n3 = 3 * (int)R.pcptr[np];
+  for (int idx = tid; idx < n3; idx += T) pw[idx] = point_chunk_sum(R, w, idx);
+  __syncthreads();
+  if (tid < np) {
+    double a0, a1, a2;
+    point_combine(R, pw, tid, a0, a1, a2);
+    const double* m = ei + tid * 6;
+    u[tid] = m[0] * a0 + m[1] * a1 + m[2] * a2;
+    u[UP + tid] = m[1] * a0 + m[3] * a1 + m[4] * a2;
+    u[2 * UP + tid] = m[2] * a0 + m[4] * a1 + m[5] * a2;
+  }
+  __syncthreads();
+}
+
+// ps[9 c + k] = sum over chunk c of the segment-ordered v[.][k]; then seg_y[sb + s][k] = sum of the segment's chunk sums.
+__device__ __forceinline__ void seg_sums_chunked(const RecView& R, int ns, int sb, const double* vs, double* ps, double* seg_y) {
+  const int tid = threadIdx.x;
+  const int n9 = 9 * (int)R.scptr[ns];
+  for (int idx = tid; idx < n9; idx += T) ps[idx] = seg_chunk_sum(R, vs, idx);
+  __syncthreads();
+  for (int idx = tid; idx < ns * 9; idx += T) seg_y[(size_t)sb * 9 + idx] = seg_combine(R, ps, idx);
+}
+
 // Input vector: `p` itself, or (pcg != nullptr) the PCG direction z + beta p formed on the fly (p = z in iteration 1).
 __device__ __forceinline__ void l2_prefetch(const void* gsrc, unsigned bytes) {   // TMA prefetch into L2: no registers, no smem
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gsrc), "r"(bytes) : "memory");
 }
 
+template <bool CHUNKED>
 __global__ void __launch_bounds__(T, 768 / T) k_ba_matvec(BaDev L, const double2* __restrict__ J2, const double* __restrict__ p,
                                                     const double* __restrict__ zdir, const PcgDev* pcg,
                                                     const double* __restrict__ einv, double* __restrict__ seg_y,
@@ -455,6 +495,8 @@ __global__ void __launch_bounds__(T, 768 / T) k_ba_matvec(BaDev L, const double2
   meta.sptr = reinterpret_cast<int*>(ei + L.max_pt_tile * 6);        // [max_seg + 1]
   meta.pptr = meta.sptr + L.max_seg_tile + 1;                        // [max_pt + 1]
   meta.sperm = reinterpret_cast<unsigned short*>(meta.pptr + L.max_pt_tile + 1);   // [T]
+  double* ps = reinterpret_cast<double*>((reinterpret_cast<size_t>(meta.sperm + T) + 7) & ~(size_t)7);   // [seg_chunk_scratch] (CHUNKED)
+  const RecView R = rec_view(L, L.tile_rec + (size_t)blockIdx.x * L.rec_stride);   // CHUNKED: chunk tables straight from global memory
   const bool active = tid < q.no;
   const int i = q.ob + tid;
   const size_t O = (size_t)L.n_obs;
@@ -488,28 +530,33 @@ __global__ void __launch_bounds__(T, 768 / T) k_ba_matvec(BaDev L, const double2
 #pragma unroll
     for (int k = 0; k < 9; ++k) { const double xk = xs[slot * 9 + k]; t0 += Fv[k].x * xk; t1 += Fv[k].y * xk; }
 #pragma unroll
-    for (int k = 0; k < 3; ++k) w[k * T + tid] = Ev[k].x * t0 + Ev[k].y * t1;
+    for (int k = 0; k < 3; ++k) w[CHUNKED ? tid * 3 + k : k * T + tid] = Ev[k].x * t0 + Ev[k].y * t1;
   }
   __syncthreads();
-  if (tid < q.np) {
-    const int b = meta.pptr[tid], e = meta.pptr[tid + 1];
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-    for (int j = b; j < e; ++j) { a0 += w[j]; a1 += w[T + j]; a2 += w[2 * T + j]; }
-    const double* m = ei + tid * 6;
-    u[tid] = m[0] * a0 + m[1] * a1 + m[2] * a2;
-    u[T + tid] = m[1] * a0 + m[3] * a1 + m[4] * a2;
-    u[2 * T + tid] = m[2] * a0 + m[4] * a1 + m[5] * a2;
+  if (CHUNKED) point_sums_chunked(R, q.np, w, v, ei, u, T);
+  else {
+    if (tid < q.np) {
+      const int b = meta.pptr[tid], e = meta.pptr[tid + 1];
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+      for (int j = b; j < e; ++j) { a0 += w[j]; a1 += w[T + j]; a2 += w[2 * T + j]; }
+      const double* m = ei + tid * 6;
+      u[tid] = m[0] * a0 + m[1] * a1 + m[2] * a2;
+      u[T + tid] = m[1] * a0 + m[3] * a1 + m[4] * a2;
+      u[2 * T + tid] = m[2] * a0 + m[4] * a1 + m[5] * a2;
+    }
+    __syncthreads();
   }
-  __syncthreads();
   if (active) {
     const double u0 = u[ptl], u1 = u[T + ptl], u2 = u[2 * T + ptl];
     const double s0 = t0 - (Ev[0].x * u0 + Ev[1].x * u1 + Ev[2].x * u2);
     const double s1 = t1 - (Ev[0].y * u0 + Ev[1].y * u1 + Ev[2].y * u2);
+    double* vt = CHUNKED ? v + (int)R.srank[tid] * VS : v + tid;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) v[k * VLD + tid] = Fv[k].x * s0 + Fv[k].y * s1;
+    for (int k = 0; k < 9; ++k) vt[CHUNKED ? k : k * VLD] = Fv[k].x * s0 + Fv[k].y * s1;
   }
   __syncthreads();
-  seg_reduce9_s(q, meta, v, seg_y, 9, 0);
+  if (CHUNKED) seg_sums_chunked(R, q.ns, q.sb, v, ps, seg_y);
+  else seg_reduce9_s(q, meta, v, seg_y, 9, 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -544,24 +591,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
 }
 
-// Per-tile metadata record (device only; all sub-arrays 16-byte aligned, starts relative to the tile's first observation):
-//   u16 slot[T] | u16 ptl[T] | u16 sperm[T] | u16 pad[T] | i32 sptr[rec_sp] | i32 pptr[rec_pp] | i32 scam[rec_sp]
-struct RecView { const unsigned short* slot; const unsigned short* ptl; const unsigned short* sperm; const int* sptr; const int* pptr; const int* scam; };
-__device__ __forceinline__ RecView rec_view(const BaDev& L, const unsigned char* base) {
-  RecView r;
-  r.slot = reinterpret_cast<const unsigned short*>(base);
-  r.ptl = r.slot + T; r.sperm = r.ptl + T;
-  r.sptr = reinterpret_cast<const int*>(base + 8 * T);
-  r.pptr = r.sptr + L.rec_sp; r.scam = r.pptr + L.rec_pp;
-  return r;
-}
-
 #ifndef SK_TMA_CTAS
 #define SK_TMA_CTAS (512 / T)
 #endif
 // TMAP: the Jacobian of a tile arrives as two [12 planes][128 observations] boxes of a 2-D tensor map over the plane-major
 // array (2 TMA instructions per tile) instead of 12 one-plane bulk copies; Jbuf is then [2][12][T/2].
-template <bool TMAP>
+template <bool TMAP, bool CHUNKED>
 __global__ void __launch_bounds__(T, SK_TMA_CTAS) k_ba_matvec_tma(const __grid_constant__ CUtensorMap tmapJ, BaDev L, const double2* __restrict__ J2, const double* __restrict__ p,
                                                               const double* __restrict__ zdir, const PcgDev* pcg,
                                                               const double* __restrict__ einv, double* __restrict__ seg_y,
@@ -575,7 +610,8 @@ __global__ void __launch_bounds__(T, SK_TMA_CTAS) k_ba_matvec_tma(const __grid_c
   double* w = v + 9 * VLD;                                   // [3][T]
   const int UP = (L.max_pt_tile + 1) & ~1;
   double* u = w + 3 * T;                                     // [3][UP]
-  double* eibuf = u + 3 * UP + 1;                            // 2 x [max_pt][6]   (+1: 9 * VLD is odd)
+  double* ps = u + 3 * UP;                                   // [seg_chunk_scratch]  chunk sums of the segment sums (CHUNKED)
+  double* eibuf = ps + seg_chunk_scratch(L.max_seg_tile) + 1;   // 2 x [max_pt][6]   (+1: 9 * VLD is odd)
   unsigned char* recbuf = reinterpret_cast<unsigned char*>(eibuf + 2 * (size_t)L.max_pt_tile * 6);   // 2 x rec_stride bytes
   unsigned long long* bar_full = reinterpret_cast<unsigned long long*>(recbuf + 2 * (size_t)L.rec_stride);   // [2] Jacobian + einv
   unsigned long long* bar_rec = bar_full + 2;                                                                // [2] record
@@ -634,13 +670,14 @@ __global__ void __launch_bounds__(T, SK_TMA_CTAS) k_ba_matvec_tma(const __grid_c
     const bool active = tid < q.no;
     mbar_wait(bar_full + cur, par);                          // this tile's Jacobian and (E^T E)^-1 have landed
     double2 Fv[9], Ev[3];
-    int slot = 0, ptl = 0;
+    int slot = 0, ptl = 0, rank = 0;
     if (active) {
 #pragma unroll
       for (int k = 0; k < 9; ++k) Fv[k] = TMAP ? Jbuf[(tid >> 7) * kJPlanes * (T / 2) + k * (T / 2) + (tid & 127)] : Jbuf[k * T + tid];
 #pragma unroll
       for (int k = 0; k < 3; ++k) Ev[k] = TMAP ? Jbuf[(tid >> 7) * kJPlanes * (T / 2) + (9 + k) * (T / 2) + (tid & 127)] : Jbuf[(9 + k) * T + tid];
       slot = R.slot[tid]; ptl = R.ptl[tid];
+      if (CHUNKED) rank = R.srank[tid];
     }
     if (tid < q.ns * 9) xs[tid] = xpre;
     for (int idx = tid + T; idx < q.ns * 9; idx += T) xs[idx] = gather(R, idx);   // more than 28 segments: the rest, not prefetched
@@ -651,44 +688,51 @@ __global__ void __launch_bounds__(T, SK_TMA_CTAS) k_ba_matvec_tma(const __grid_c
 #pragma unroll
       for (int k = 0; k < 9; ++k) { const double xk = xs[slot * 9 + k]; t0 += Fv[k].x * xk; t1 += Fv[k].y * xk; }
 #pragma unroll
-      for (int k = 0; k < 3; ++k) w[k * T + tid] = Ev[k].x * t0 + Ev[k].y * t1;
+      for (int k = 0; k < 3; ++k) w[CHUNKED ? tid * 3 + k : k * T + tid] = Ev[k].x * t0 + Ev[k].y * t1;
     }
     __syncthreads();
-    if (tid < q.np) {
-      const int b = R.pptr[tid], e = R.pptr[tid + 1];
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-      for (int j = b; j < e; ++j) { a0 += w[j]; a1 += w[T + j]; a2 += w[2 * T + j]; }
-      const double* m = ei + tid * 6;
-      u[tid] = m[0] * a0 + m[1] * a1 + m[2] * a2;
-      u[UP + tid] = m[1] * a0 + m[3] * a1 + m[4] * a2;
-      u[2 * UP + tid] = m[2] * a0 + m[4] * a1 + m[5] * a2;
+    if (CHUNKED) point_sums_chunked(R, q.np, w, v, ei, u, UP);
+    else {
+      if (tid < q.np) {
+        const int b = R.pptr[tid], e = R.pptr[tid + 1];
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        for (int j = b; j < e; ++j) { a0 += w[j]; a1 += w[T + j]; a2 += w[2 * T + j]; }
+        const double* m = ei + tid * 6;
+        u[tid] = m[0] * a0 + m[1] * a1 + m[2] * a2;
+        u[UP + tid] = m[1] * a0 + m[3] * a1 + m[4] * a2;
+        u[2 * UP + tid] = m[2] * a0 + m[4] * a1 + m[5] * a2;
+      }
+      __syncthreads();
     }
-    __syncthreads();
     if (active) {
       const double u0 = u[ptl], u1 = u[UP + ptl], u2 = u[2 * UP + ptl];
       const double s0 = t0 - (Ev[0].x * u0 + Ev[1].x * u1 + Ev[2].x * u2);
       const double s1 = t1 - (Ev[0].y * u0 + Ev[1].y * u1 + Ev[2].y * u2);
+      double* vt = CHUNKED ? v + rank * VS : v + tid;
 #pragma unroll
-      for (int k = 0; k < 9; ++k) v[k * VLD + tid] = Fv[k].x * s0 + Fv[k].y * s1;
+      for (int k = 0; k < 9; ++k) vt[CHUNKED ? k : k * VLD] = Fv[k].x * s0 + Fv[k].y * s1;
     }
     __syncthreads();
     if (it + 1 < my_tiles) {                                 // start the next tile's input gather behind the segment sums
       mbar_wait(bar_rec + (cur ^ 1), (unsigned)(((it + 1) >> 1) & 1));
       if (tid < qn.ns * 9) xpre = gather(rec_view(L, recbuf + (size_t)(cur ^ 1) * L.rec_stride), tid);
     }
-    for (int idx = tid; idx < q.ns * 9; idx += T) {
-      const int s = idx / 9, k = idx - s * 9;
-      const int b = R.sptr[s], e = R.sptr[s + 1];
-      const double* vk = v + k * VLD;
-      double sum = 0.0;
-      int pos = b;
-      for (; pos + 4 <= e; pos += 4) {
-        const int i0 = R.sperm[pos], i1 = R.sperm[pos + 1], i2 = R.sperm[pos + 2], i3 = R.sperm[pos + 3];
-        const double x0 = vk[i0], x1 = vk[i1], x2 = vk[i2], x3 = vk[i3];
-        sum += x0; sum += x1; sum += x2; sum += x3;
+    if (CHUNKED) seg_sums_chunked(R, q.ns, q.sb, v, ps, seg_y);
+    else {
+      for (int idx = tid; idx < q.ns * 9; idx += T) {
+        const int s = idx / 9, k = idx - s * 9;
+        const int b = R.sptr[s], e = R.sptr[s + 1];
+        const double* vk = v + k * VLD;
+        double sum = 0.0;
+        int pos = b;
+        for (; pos + 4 <= e; pos += 4) {
+          const int i0 = R.sperm[pos], i1 = R.sperm[pos + 1], i2 = R.sperm[pos + 2], i3 = R.sperm[pos + 3];
+          const double x0 = vk[i0], x1 = vk[i1], x2 = vk[i2], x3 = vk[i3];
+          sum += x0; sum += x1; sum += x2; sum += x3;
+        }
+        for (; pos < e; ++pos) sum += vk[R.sperm[pos]];
+        seg_y[(size_t)(q.sb + s) * 9 + k] = sum;
       }
-      for (; pos < e; ++pos) sum += vk[R.sperm[pos]];
-      seg_y[(size_t)(q.sb + s) * 9 + k] = sum;
     }
     q = qn; qn = qnn;
   }
@@ -1089,13 +1133,14 @@ void launch_ba_matvec(const BaDev& L, const double2* J2, const double* p, const 
     k_ba_matvec_giant<<<L.n_giant, T, smem_g, s>>>(L, J2, p, zdir, pcg, einv, seg_y, guard);
     check_launch("k_ba_matvec_giant");
   }
+  const bool chunked = !L.matvec_serial_sums && L.tile_rec != nullptr;
   const size_t smem_tail = sizeof(double) * ((size_t)L.max_pt_tile * 6) + sizeof(int) * ((size_t)L.max_seg_tile + L.max_pt_tile + 2) +
-                           sizeof(unsigned short) * T + 16;
+                           sizeof(unsigned short) * T + 16 + sizeof(double) * (size_t)seg_chunk_scratch(L.max_seg_tile);
   const size_t smem = sizeof(double) * ((size_t)L.max_seg_tile * 9 + 9 * VLD + 6 * T) + smem_tail;
   if (!L.matvec_classic && L.tile_rec != nullptr) {
     // Default: persistent TMA-prefetching kernel, one wave of as many CTAs per SM as its shared memory allows.
     const size_t smem_p = sizeof(double2) * kJPlanes * T + sizeof(double) * ((size_t)((L.max_seg_tile * 9 + 1) & ~1) + 9 * VLD + 3 * T + 3 * (size_t)((L.max_pt_tile + 1) & ~1) + 1 +
-                          2 * (size_t)L.max_pt_tile * 6) + 2 * (size_t)L.rec_stride + 4 * sizeof(unsigned long long);
+                          (size_t)seg_chunk_scratch(L.max_seg_tile) + 2 * (size_t)L.max_pt_tile * 6) + 2 * (size_t)L.rec_stride + 4 * sizeof(unsigned long long);
     static int sms = 0, smem_max = 0;
     if (sms == 0) {
       int dev = 0; SK_CUDA(cudaGetDevice(&dev));
@@ -1103,9 +1148,9 @@ void launch_ba_matvec(const BaDev& L, const double2* J2, const double* p, const 
       SK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     }
     if (smem_p <= (size_t)smem_max) {
-      static size_t cfg_smem[2] = {0, 0}; static int per_sm[2] = {0, 0};   // function attributes / occupancy, redone when the size changes
-      const int v = tmapJ != nullptr ? 1 : 0;
-      auto kernel = v ? k_ba_matvec_tma<true> : k_ba_matvec_tma<false>;
+      static size_t cfg_smem[4] = {0, 0, 0, 0}; static int per_sm[4] = {0, 0, 0, 0};   // function attributes / occupancy, redone when the size changes
+      const int v = (tmapJ != nullptr ? 1 : 0) + (chunked ? 2 : 0);
+      auto kernel = v == 3 ? k_ba_matvec_tma<true, true> : v == 2 ? k_ba_matvec_tma<false, true> : v == 1 ? k_ba_matvec_tma<true, false> : k_ba_matvec_tma<false, false>;
       if (smem_p != cfg_smem[v]) {
         set_smem(kernel, smem_p);
         SK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -1115,7 +1160,7 @@ void launch_ba_matvec(const BaDev& L, const double2* J2, const double* p, const 
       if (per_sm[v] > 0) {
         const int grid = std::min(L.n_tiles, per_sm[v] * sms);
         static const CUtensorMap no_map{};
-        kernel<<<grid, T, smem_p, s>>>(v ? *tmapJ : no_map, L, J2, p, zdir, pcg, einv, seg_y, guard);
+        kernel<<<grid, T, smem_p, s>>>((v & 1) ? *tmapJ : no_map, L, J2, p, zdir, pcg, einv, seg_y, guard);
         check_launch("k_ba_matvec_tma");
         return;
       }
@@ -1124,10 +1169,15 @@ void launch_ba_matvec(const BaDev& L, const double2* J2, const double* p, const 
   // Classic kernel (one CTA per tile, Jacobian straight into registers): SKERES_MATVEC=classic, or when the per-tile
   // maxima of a problem make the prefetching kernel's shared memory exceed what one CTA may have.
   const size_t smem_v2 = smem;
-  set_smem(k_ba_matvec, smem_v2);
   // development knob: SKERES_MATVEC_PFDIST=<tiles> L2 prefetch distance (0 = off; measured +5 %, profiles/r01_v5_*)
   static const int pf_dist = [] { const char* e = getenv("SKERES_MATVEC_PFDIST"); return e ? atoi(e) : 0; }();
-  k_ba_matvec<<<L.n_tiles, T, smem_v2, s>>>(L, J2, p, zdir, pcg, einv, seg_y, guard, pf_dist);
+  if (chunked) {
+    set_smem(k_ba_matvec<true>, smem_v2);
+    k_ba_matvec<true><<<L.n_tiles, T, smem_v2, s>>>(L, J2, p, zdir, pcg, einv, seg_y, guard, pf_dist);
+  } else {
+    set_smem(k_ba_matvec<false>, smem_v2);
+    k_ba_matvec<false><<<L.n_tiles, T, smem_v2, s>>>(L, J2, p, zdir, pcg, einv, seg_y, guard, pf_dist);
+  }
   check_launch("k_ba_matvec");
 }
 

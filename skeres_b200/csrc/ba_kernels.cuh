@@ -3,6 +3,7 @@
 #include <cuda.h>   // CUtensorMap (type only; the encoder is fetched with cudaGetDriverEntryPoint, no libcuda link)
 
 #include "ba_layout.h"
+#include "ba_tile_rec.h"
 #include "common.cuh"
 #include "jet.cuh"
 
@@ -16,8 +17,10 @@ struct BaDev {
   const int* tile_np;                  // [T] > 0: points of a regular tile;  < 0: chunk tile, ordinal = -tile_np - 1
   const int* gp_tile_begin; const int* gp_tile_count; const int* gp_point;   // [n_giant]
   // per-tile metadata records for the prefetching matvec (ba_kernels.cu: RecView); nullptr when not built
-  const unsigned char* tile_rec; int rec_stride, rec_sp, rec_pp;
+  const unsigned char* tile_rec; int rec_stride, rec_sp, rec_pp, rec_sc;
   int matvec_classic;                  // 1: use k_ba_matvec instead of k_ba_matvec_tma (SKERES_MATVEC=classic, read per solver)
+  int matvec_serial_sums;              // 1: per-point / per-segment sums as one serial chain each (the round-1 order;
+                                       // SKERES_MATVEC_SUMS=serial, development A/B) instead of the chunked two-level sums
   const unsigned short* obs_slot; const unsigned short* obs_ptl; const unsigned short* seg_perm;
   const int* seg_ptr; const int* seg_cam; const int* cam_seg_ptr; const int* cam_seg;
   const double2* obs;   // [n_obs] observed (x, y)

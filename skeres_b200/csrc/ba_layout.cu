@@ -1,5 +1,6 @@
 // ba_layout.cu — host-side construction of the tiled BA layout (see ba_layout.h).
 #include "ba_layout.h"
+#include "ba_tile_rec.h"
 
 #include <algorithm>
 #include <chrono>
@@ -283,6 +284,49 @@ void build_ba_layout(int64_t n, const int64_t* cam_off, const int64_t* pt_off, c
   std::vector<int32_t> fill(L.cam_seg_ptr.begin(), L.cam_seg_ptr.end() - 1);
   for (int32_t s = 0; s < L.n_segs; ++s) L.cam_seg[fill[L.seg_cam[s]]++] = s;
   lap("camera -> segments");
+}
+
+// Per-tile metadata records of the implicit-Schur product (ba_tile_rec.h): everything a tile needs besides the Jacobian and
+// (E^T E)^-1, packed so that one bulk copy brings it on chip, plus the chunk tables of the two-level sums.
+void build_tile_records(const BaLayoutHost& H, TileRecDims* dims, std::vector<unsigned char>* out) {
+  const int T = kTileObs;
+  const TileRecDims D = tile_rec_dims(std::max(H.max_seg_tile, 1), std::max(H.max_pt_tile, 1));
+  const int sp = D.sp, pp = D.pp, sc = D.sc;
+  const size_t stride = (size_t)D.stride;
+  out->assign((size_t)std::max(H.n_tiles, 1) * stride, 0);
+  unsigned char* rec = out->data();
+  parallel_for(H.n_tiles, [&](int64_t t_begin, int64_t t_end) {
+  for (int64_t t = t_begin; t < t_end; ++t) {
+    unsigned char* base = rec + (size_t)t * stride;
+    uint16_t* slot = reinterpret_cast<uint16_t*>(base); uint16_t* ptl = slot + T; uint16_t* sperm = ptl + T; uint16_t* srank = sperm + T;
+    int32_t* sptr = reinterpret_cast<int32_t*>(base + 8 * T); int32_t* pptr = sptr + sp; int32_t* scam = pptr + pp;
+    uint16_t* pchunk = reinterpret_cast<uint16_t*>(scam + sp); uint16_t* pcptr = pchunk + T; uint16_t* schunk = pcptr + pp; uint16_t* scptr = schunk + sc;
+    const int ob = H.tile_obs[t], no = H.tile_obs[t + 1] - ob, pb = H.tile_pt[t], np = H.tile_np[t];
+    const int sb = H.tile_seg[t], ns = H.tile_seg[t + 1] - sb;
+    for (int j = 0; j < no; ++j) {
+      slot[j] = H.obs_slot[ob + j]; ptl[j] = H.obs_ptl[ob + j]; sperm[j] = H.seg_perm[ob + j];
+      srank[H.seg_perm[ob + j]] = (uint16_t)j;
+    }
+    for (int s = 0; s <= ns; ++s) sptr[s] = H.seg_ptr[sb + s] - ob;
+    for (int s = 0; s < ns; ++s) scam[s] = H.seg_cam[sb + s];
+    int nc = 0;
+    for (int s = 0; s < ns; ++s) {                           // segment s = positions [sptr[s], sptr[s + 1]) of the camera-sorted order
+      scptr[s] = (uint16_t)nc;
+      for (int b = sptr[s]; b < sptr[s + 1]; b += kSegChunk) schunk[nc++] = (uint16_t)(b | ((std::min(kSegChunk, sptr[s + 1] - b) - 1) << 8));
+    }
+    scptr[ns] = (uint16_t)nc;
+    if (H.tile_chunk[t] < 0) {                               // chunk tiles of long tracks have no per-point phase in the tile kernels
+      for (int q = 0; q <= np; ++q) pptr[q] = H.pt_ptr[pb + q] - ob;
+      nc = 0;
+      for (int q = 0; q < np; ++q) {
+        pcptr[q] = (uint16_t)nc;
+        for (int b = pptr[q]; b < pptr[q + 1]; b += kPtChunk) pchunk[nc++] = (uint16_t)(b | ((std::min(kPtChunk, pptr[q + 1] - b) - 1) << 8));
+      }
+      pcptr[np] = (uint16_t)nc;
+    }
+  }
+  });
+  *dims = D;
 }
 
 }  // namespace sk

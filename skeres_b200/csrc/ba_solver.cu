@@ -60,8 +60,9 @@ BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHo
   L_.obs = reinterpret_cast<const double2*>(d_obs_.p);
   L_.n_giant = H.n_giant; L_.n_chunks = H.n_chunks; L_.tile_np = d_tile_np_.p;
   L_.gp_tile_begin = d_gp_begin_.p; L_.gp_tile_count = d_gp_count_.p; L_.gp_point = d_gp_point_.p;
-  L_.tile_rec = nullptr; L_.rec_stride = L_.rec_sp = L_.rec_pp = 0;
+  L_.tile_rec = nullptr; L_.rec_stride = L_.rec_sp = L_.rec_pp = L_.rec_sc = 0;
   { const char* e = getenv("SKERES_MATVEC"); L_.matvec_classic = (e != nullptr && e[0] == 'c') ? 1 : 0; }
+  { const char* e = getenv("SKERES_MATVEC_SUMS"); L_.matvec_serial_sums = (e != nullptr && e[0] == 's') ? 1 : 0; }
   const int64_t nc = (int64_t)9 * H.n_cams, n = nc + (int64_t)3 * H.n_pts;
   allocate(n, nc);
   J2_.alloc((size_t)2 * kJPlanes * std::max(H.n_obs, 1)); r2_.alloc((size_t)2 * std::max(H.n_obs, 1));
@@ -99,30 +100,13 @@ BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHo
   }
 }
 
-// Per-tile metadata records for k_ba_matvec_pf: everything a tile needs besides the Jacobian and (E^T E)^-1, packed so
-// that it can be streamed into shared memory with 16-byte cp.async copies (layout: RecView in ba_kernels.cu).
+// Per-tile metadata records of the implicit-Schur product (ba_tile_rec.h), packed on the host and uploaded once.
 void BaSolver::build_tile_records() {
-  const auto& H = H_;
-  const int T = kTileObs;
-  const int sp = (std::max(H.max_seg_tile, 1) + 1 + 3) & ~3, pp = (std::max(H.max_pt_tile, 1) + 1 + 3) & ~3;
-  const size_t stride = (size_t)8 * T + 4 * ((size_t)2 * sp + pp);
-  std::vector<unsigned char> rec((size_t)std::max(H.n_tiles, 1) * stride, 0);
-  parallel_for(H.n_tiles, [&](int64_t t_begin, int64_t t_end) {
-  for (int64_t t = t_begin; t < t_end; ++t) {
-    unsigned char* base = rec.data() + (size_t)t * stride;
-    uint16_t* slot = reinterpret_cast<uint16_t*>(base); uint16_t* ptl = slot + T; uint16_t* sperm = ptl + T;
-    int32_t* sptr = reinterpret_cast<int32_t*>(base + 8 * T); int32_t* pptr = sptr + sp; int32_t* scam = pptr + pp;
-    const int ob = H.tile_obs[t], no = H.tile_obs[t + 1] - ob, pb = H.tile_pt[t], np = H.tile_np[t];
-    const int sb = H.tile_seg[t], ns = H.tile_seg[t + 1] - sb;
-    for (int j = 0; j < no; ++j) { slot[j] = H.obs_slot[ob + j]; ptl[j] = H.obs_ptl[ob + j]; sperm[j] = H.seg_perm[ob + j]; }
-    for (int s = 0; s <= ns; ++s) sptr[s] = H.seg_ptr[sb + s] - ob;
-    for (int s = 0; s < ns; ++s) scam[s] = H.seg_cam[sb + s];
-    if (H.tile_chunk[t] < 0) for (int q = 0; q <= np; ++q) pptr[q] = H.pt_ptr[pb + q] - ob;
-  }
-  });
+  TileRecDims dims; std::vector<unsigned char> rec;
+  sk::build_tile_records(H_, &dims, &rec);
   d_tile_rec_.upload(rec, stream_);
   SK_CUDA(cudaStreamSynchronize(stream_));
-  L_.tile_rec = d_tile_rec_.p; L_.rec_stride = (int)stride; L_.rec_sp = sp; L_.rec_pp = pp;
+  L_.tile_rec = d_tile_rec_.p; L_.rec_stride = dims.stride; L_.rec_sp = dims.sp; L_.rec_pp = dims.pp; L_.rec_sc = dims.sc;
 }
 
 void BaSolver::load_state() {

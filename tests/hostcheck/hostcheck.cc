@@ -4,10 +4,12 @@
 // the CPU-only build host.  The product never runs this code path: libskeres.so calls the same
 // functions from CUDA kernels only.
 #include <cstdint>
+#include <cmath>
 #include <cstring>
 #include <vector>
 
 #include "../../skeres_b200/csrc/ba_layout.h"
+#include "../../skeres_b200/csrc/ba_tile_rec.h"
 #include "../../skeres_b200/csrc/common.cuh"
 #include "../../skeres_b200/csrc/jet.cuh"
 
@@ -66,4 +68,65 @@ HC_COPY(tile_np, tile_np, int32_t) HC_COPY(tile_chunk, tile_chunk, int32_t) HC_C
 HC_COPY(gp_tile_count, gp_tile_count, int32_t) HC_COPY(gp_point, gp_point, int32_t)
 HC_COPY(cam_offset, cam_offset, int64_t) HC_COPY(pt_offset, pt_offset, int64_t)
 void hc_layout_obs(const HcLayout* h, double* out) { std::memcpy(out, h->L.obs_src, sizeof(double) * 2 * (size_t)h->L.n_obs); }   // caller's array still alive
+
+// Two-level sums of the implicit-Schur product (ba_tile_rec.h): runs the SAME per-item functions the kernels call, item by
+// item in place of thread by thread, over the records of every regular tile with pseudo-random staged values, and compares
+// with direct sums over the layout's own point / segment lists.  out[0] = max relative error of a point sum, out[1] = of a
+// segment sum, out[2] = number of sums checked, out[3] = 1 if every position lies in exactly one chunk of the right owner.
+void hc_check_two_level_sums(const HcLayout* h, uint64_t seed, double* out) {
+  const auto& H = h->L;
+  const int T = sk::kTileObs;
+  sk::TileRecDims D; std::vector<unsigned char> rec;
+  sk::build_tile_records(H, &D, &rec);
+  auto rnd = [&seed]() { seed = seed * 6364136223846793005ull + 1442695040888963407ull; return (double)((seed >> 11) & 0xfffff) / 1048576.0 - 0.5; };
+  double e_pt = 0, e_seg = 0, n = 0; bool cover = true;
+  std::vector<double> w(3 * T), pw(3 * T), vs((size_t)T * sk::kSegRow), ps((size_t)sk::seg_chunk_scratch(std::max(H.max_seg_tile, 1))), v(9 * T);
+  for (int t = 0; t < H.n_tiles; ++t) {
+    if (H.tile_chunk[t] >= 0) continue;
+    const sk::RecView R = sk::rec_view(rec.data() + (size_t)t * D.stride, D.sp, D.pp, D.sc);
+    const int ob = H.tile_obs[t], no = H.tile_obs[t + 1] - ob, np = H.tile_np[t], sb = H.tile_seg[t], ns = H.tile_seg[t + 1] - sb;
+    for (int i = 0; i < no; ++i) {
+      for (int k = 0; k < 3; ++k) w[i * 3 + k] = rnd();
+      for (int k = 0; k < 9; ++k) { v[i * 9 + k] = rnd(); vs[(size_t)R.srank[i] * sk::kSegRow + k] = v[i * 9 + k]; }
+    }
+    // chunk tables cover every position once
+    std::vector<int> seen(no, 0);
+    for (int p = 0; p < np; ++p)
+      for (int c = R.pcptr[p]; c < R.pcptr[p + 1]; ++c) {
+        const int st = R.pchunk[c] & 255, len = (R.pchunk[c] >> 8) + 1;
+        if (len > sk::kPtChunk || st < R.pptr[p] || st + len > R.pptr[p + 1]) cover = false;
+        for (int j = st; j < st + len; ++j) seen[j]++;
+      }
+    for (int i = 0; i < no; ++i) if (seen[i] != 1) cover = false;
+    std::fill(seen.begin(), seen.end(), 0);
+    for (int s = 0; s < ns; ++s)
+      for (int c = R.scptr[s]; c < R.scptr[s + 1]; ++c) {
+        const int st = R.schunk[c] & 255, len = (R.schunk[c] >> 8) + 1;
+        if (len > sk::kSegChunk || st < R.sptr[s] || st + len > R.sptr[s + 1]) cover = false;
+        for (int j = st; j < st + len; ++j) seen[j]++;
+      }
+    for (int i = 0; i < no; ++i) if (seen[i] != 1 || R.srank[R.sperm[i]] != i) cover = false;
+    // point sums
+    const int n3 = 3 * R.pcptr[np];
+    for (int idx = 0; idx < n3; ++idx) pw[idx] = sk::point_chunk_sum(R, w.data(), idx);
+    for (int p = 0; p < np; ++p) {
+      double a[3]; sk::point_combine(R, pw.data(), p, a[0], a[1], a[2]);
+      for (int k = 0; k < 3; ++k) {
+        double ref = 0, mag = 1e-300;
+        for (int j = H.pt_ptr[H.tile_pt[t] + p] - ob; j < H.pt_ptr[H.tile_pt[t] + p + 1] - ob; ++j) { ref += w[j * 3 + k]; mag += std::fabs(w[j * 3 + k]); }
+        e_pt = std::max(e_pt, std::fabs(a[k] - ref) / mag); n += 1;
+      }
+    }
+    // segment sums
+    const int n9 = 9 * R.scptr[ns];
+    for (int idx = 0; idx < n9; ++idx) ps[idx] = sk::seg_chunk_sum(R, vs.data(), idx);
+    for (int idx = 0; idx < 9 * ns; ++idx) {
+      const int s = idx / 9, k = idx % 9;
+      double ref = 0, mag = 1e-300;
+      for (int q = H.seg_ptr[sb + s]; q < H.seg_ptr[sb + s + 1]; ++q) { const double x = v[(size_t)H.seg_perm[q] * 9 + k]; ref += x; mag += std::fabs(x); }
+      e_seg = std::max(e_seg, std::fabs(sk::seg_combine(R, ps.data(), idx) - ref) / mag); n += 1;
+    }
+  }
+  out[0] = e_pt; out[1] = e_seg; out[2] = n; out[3] = cover ? 1.0 : 0.0;
+}
 }

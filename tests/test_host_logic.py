@@ -279,6 +279,38 @@ def test_ragged_tracks_fill_tiles(hc):
     check_layout(lay, cam_off, pt_off, obs)
 
 
+def _ragged_problem(seed, n_cam=300):
+    rng = np.random.default_rng(seed)
+    lens = np.concatenate([[256, 1, 255, 2, 17, 33], rng.integers(1, 40, 200), [256, 300], rng.integers(2, 9, 300)])
+    cam, pt = [], []
+    for j, k in enumerate(lens):
+        cam.extend(sorted(rng.choice(n_cam, size=k, replace=False))); pt.extend([j] * k)
+    return np.array(cam, dtype=np.int64) * 9, 9 * n_cam + np.array(pt, dtype=np.int64) * 3, rng.normal(size=2 * len(cam))
+
+
+@pytest.mark.parametrize("case", ["ladybug-49", "small", "ragged"])
+def test_two_level_sums_of_the_schur_product(hc, case):
+    """The per-tile records of the implicit-Schur product (ba_tile_rec.h) and the chunked two-level sums that read them:
+    the SAME per-item functions the kernels call (point_chunk_sum / point_combine / seg_chunk_sum / seg_combine), run item
+    by item on the host over every regular tile, give the per-point and per-(tile, camera) sums of the layout's own
+    lists, every position lies in exactly one chunk of its own point / segment, and srank inverts sperm."""
+    if case == "ragged":
+        cam_off, pt_off, obs = _ragged_problem(11)
+    else:
+        d = synth.make_bal(case, seed=2)
+        off = d.block_offsets()
+        cam_off, pt_off, obs = np.ascontiguousarray(off[:, 0]), np.ascontiguousarray(off[:, 1]), d.observations
+    st = C.c_int(); err = C.create_string_buffer(256)
+    h = hc.hc_layout_build(cam_off.size, p(cam_off), p(pt_off), p(obs), 0, 1, C.byref(st), err)
+    assert h and st.value == 0, err.value
+    out = np.zeros(4)
+    hc.hc_check_two_level_sums.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    hc.hc_check_two_level_sums(C.c_void_p(h), 12345, p(out))
+    hc.hc_layout_free(C.c_void_p(h))
+    assert out[3] == 1.0, "chunk tables do not partition the tile"
+    assert out[2] > 1000 and out[0] <= 4e-16 * 6 and out[1] <= 4e-16 * 10, out      # a handful of roundings apart, no more
+
+
 @pytest.mark.parametrize("world", [2, 3])
 @pytest.mark.parametrize("sparse_offsets", [False, True])
 def test_rank_local_ingestion_builds_the_same_layout(hc, world, sparse_offsets):
