@@ -17,6 +17,7 @@ namespace sk {
 static bool lst_is_explicit(int lst) { return lst == SK_DENSE_SCHUR || lst == SK_SPARSE_SCHUR; }
 
 namespace {
+__global__ void k_store_flag(const int* flag, double* out) { *out = *flag ? 1.0 : 0.0; }
 __global__ void k_gather_blocks(int nblocks, int bsize, const long long* __restrict__ offsets, const double* __restrict__ user,
                                 double* __restrict__ x) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -70,10 +71,14 @@ BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHo
   seg_a_.alloc((size_t)9 * std::max(H.n_segs, 1)); seg_b_.alloc((size_t)9 * std::max(H.n_segs, 1));
   tile_cost_.alloc(std::max(H.n_tiles, 1)); tile_mcc_.alloc(std::max(H.n_tiles, 1));
   tile_cost_.zero(s); tile_mcc_.zero(s);
-  rhs_.alloc(nc); px_.alloc(nc); pr_.alloc(nc); pp_.alloc(nc); pz_.alloc(nc); ybuf_.alloc(nc);
+  rhs_.alloc(nc + 1); px_.alloc(nc);   // rhs_[nc]: the ranks' summed Schur set-up failure flag (multi-GPU)
+  pr_.alloc(nc); pp_.alloc(nc); pz_.alloc(nc); ybuf_.alloc(nc);
   pcg_.alloc(1); pcg_h_.alloc(1);
   pcg_part_.alloc(4 * kMaxPartials);
+  pcg_.zero(s);
   if (comm_ && comm_->world > 1 && !(lst_is_explicit(opt.linear_solver_type))) peer_allreduce_create(comm_, (size_t)nc, s, &peer_);   // collective
+  if (!lst_is_explicit(opt.linear_solver_type)) flag_pcg_ = pcg_.p;          // a fatal linear-solver outcome reaches every rank (lm_kernels.cuh: SB_FLAG_LIN)
+  if (peer_.ok) flag_peer_error_ = peer_.win.error;
   SK_REQUIRE(cdiv(H.n_cams, 8) <= kMaxPartials, SK_ERR_UNSUPPORTED, "more than %d cameras", kMaxPartials * 256 / 9);
   const int lst = opt.linear_solver_type;
   explicit_schur_ = (lst == SK_DENSE_SCHUR || lst == SK_SPARSE_SCHUR);
@@ -111,6 +116,7 @@ void BaSolver::build_tile_records() {
 
 void BaSolver::load_state() {
   n_real_matvecs_ = 0;
+  if (peer_.ok) SK_CUDA(cudaMemsetAsync(peer_.win.error, 0, sizeof(int), stream_));   // a time-out is sticky within one solve only
   KScope k(prof_, SK_KF_LM, 2);
   k_gather_blocks<<<cdiv((int64_t)L_.n_cams * 9, 256), 256, 0, stream_>>>(L_.n_cams, 9, d_cam_off_.p, user_, x_.p);
   if (L_.n_pts) k_gather_blocks<<<cdiv((int64_t)L_.n_pts * 3, 256), 256, 0, stream_>>>(L_.n_pts, 3, d_pt_off_.p, user_, x_.p + nc_);
@@ -223,10 +229,14 @@ ReduceJob BaSolver::linear_solve(const PcgDev** pcg_out) {
     launch_cam_reduce(L_, 9, seg_b_.p, rhs_.p, nullptr, stream_);
     launch_cam_reduce(L_, 45, seg_M_.p, M45_.p, nullptr, stream_);
   }
-  if (comm_ && comm_->world > 1) {
-    KScope k(prof_, SK_KF_COMM);
+  const bool multi = comm_ && comm_->world > 1;
+  if (multi) {
+    // the set-up failure flag (a point's E^T E not positive definite on SOME rank) travels with the right-hand side: every rank
+    // must skip or run the PCG loop alike, or the per-iteration exchange loses its partners
+    KScope k(prof_, SK_KF_COMM, 2);
+    k_store_flag<<<1, 1, 0, stream_>>>(lin_error, rhs_.p + nc_);
     comm_group_start(comm_);
-    comm_allreduce_sum(comm_, rhs_.p, (size_t)nc_, stream_);
+    comm_allreduce_sum(comm_, rhs_.p, (size_t)nc_ + 1, stream_);
     comm_allreduce_sum(comm_, M45_.p, (size_t)45 * L_.n_cams, stream_);
     comm_group_end(comm_);
   }
@@ -239,7 +249,7 @@ ReduceJob BaSolver::linear_solve(const PcgDev** pcg_out) {
       KScope k(prof_, SK_KF_SCHUR_SETUP);
       launch_ba_precond_invert(L_, M45_.p, D_.p, Minv_.p, lin_error, stream_);
     }
-    pcg_solve(schur_jacobi ? Minv_.p : nullptr);
+    pcg_solve(schur_jacobi ? Minv_.p : nullptr, multi ? rhs_.p + nc_ : nullptr);
     *pcg_out = pcg_.p;
   }
   {
@@ -253,7 +263,7 @@ ReduceJob BaSolver::linear_solve(const PcgDev** pcg_out) {
 // ConjugateGradientsSolver::Solve on the implicit Schur complement; all scalars stay on the device
 // (pcg_kernels.cu).  The host enqueues iterations in batches and polls the state block between batches;
 // kernels of iterations after termination return immediately.
-void BaSolver::pcg_solve(const double* Minv) {
+void BaSolver::pcg_solve(const double* Minv, const double* global_lin_flag) {
   const int nb = pcg_blocks(L_.n_cams);
   PcgParams pp{opt_.min_linear_solver_iterations, opt_.max_linear_solver_iterations, opt_.eta};
   const int* active = &pcg_.p->active;
@@ -263,7 +273,7 @@ void BaSolver::pcg_solve(const double* Minv) {
   double* part_Q = pcg_part_.p + 3 * kMaxPartials;
   {
     KScope k(prof_, SK_KF_PCG_VECTOR, 2);
-    launch_pcg_begin(L_.n_cams, rhs_.p, Minv, px_.p, pr_.p, pz_.p, part_bb, part_rho, pcg_.p, &st_.p->lin_error, stream_);
+    launch_pcg_begin(L_.n_cams, rhs_.p, Minv, px_.p, pr_.p, pz_.p, part_bb, part_rho, pcg_.p, &st_.p->lin_error, global_lin_flag, stream_);
   }
   const int kBatch = 8, kResetPeriod = 10;
   int it = 0;
@@ -292,12 +302,9 @@ void BaSolver::pcg_solve(const double* Minv) {
     prof_.collect();
     done = pcg_h_.p->active == 0;
   }
-  if (peer_.ok) {
-    int perr = 0;
-    SK_CUDA(cudaMemcpyAsync(&perr, peer_.win.error, sizeof(int), cudaMemcpyDeviceToHost, stream_));
-    SK_CUDA(cudaStreamSynchronize(stream_));
-    SK_REQUIRE(perr == 0, SK_ERR_NCCL, "multi-GPU exchange timed out: a rank stopped or the ranks lost lockstep (rank %d)", comm_->rank);
-  }
+  // A peer-window time-out (a rank stopped, or the ranks lost lockstep) is not thrown here: the rank that saw it has marked its
+  // solve LIN_FATAL on the device, the flag reaches every rank with the next scalar allreduce (SB_FLAG_LIN) and all of them
+  // terminate with FAILURE together -- an exception on one rank would leave the others waiting in that allreduce.
   const int its = pcg_h_.p->iter;
   n_real_matvecs_ += (its + its / kResetPeriod) * (L_.n_giant ? 2 : 1);
 }

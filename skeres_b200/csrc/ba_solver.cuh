@@ -33,7 +33,7 @@ class BaSolver : public LmSolver {
 
  private:
   const double* matvec(const double* in, bool pcg_dir, const int* guard);
-  void pcg_solve(const double* Minv);
+  void pcg_solve(const double* Minv, const double* global_lin_flag);
   void build_pair_lists();
   void build_tile_records();
   void explicit_schur_solve();

@@ -151,6 +151,8 @@ void peer_allreduce_create(sk_comm* c, size_t count, cudaStream_t stream, PeerAl
   pa->win.error = reinterpret_cast<int*>(pa->mem.p + 2 * stride + flag_doubles);
   pa->win.done_count = reinterpret_cast<unsigned int*>(pa->win.error + 1);
   pa->win.stride = (long long)stride; pa->win.rank = rank; pa->win.world = world;
+  { const char* e = getenv("SKERES_PEER_TIMEOUT_S"); const double sec = e ? atof(e) : 60.0;
+    pa->win.timeout_ns = (unsigned long long)((sec > 0.0 ? sec : 60.0) * 1e9); }
   pa->ok = true;
   if (getenv("SKERES_TRACE_HOST")) fprintf(stderr, "[skeres] rank %d: peer window of %zu doubles mapped on %d ranks\n", rank, count, world);
 }

@@ -36,6 +36,7 @@ struct PeerWindow {
   int* error;                               // own error word
   unsigned int* done_count;                 // own: CTAs of the running producer kernel that have written their part
   long long stride;                         // doubles per parity slot
+  unsigned long long timeout_ns;            // bound of one wait for the peers (SKERES_PEER_TIMEOUT_S, default 60 s)
   int rank, world;                          // world == 0: no peer window (single GPU or NCCL path)
 };
 struct PeerAllreduce {

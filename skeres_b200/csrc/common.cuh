@@ -43,14 +43,20 @@ inline std::string fmt(const char* f, ...) {
 // Caching device allocator behind DBuf: freed blocks are kept per (device, rounded size) and handed to the next request of
 // that size, so that building a solver after another one was destroyed does not pay cudaMalloc / cudaFree of GB-sized
 // buffers again (measured 0.08-0.40 s per solver on a B200).  sk_release_cached_memory() returns everything to the driver;
-// SKERES_POOL_MAX_GB (default 64) bounds what is kept; SKERES_POOL_MAX_GB=0 disables caching.
+// SKERES_POOL_MAX_GB (default 16) bounds what is kept; SKERES_POOL_MAX_GB=0 disables caching.
+// A block is filed under the device it was ALLOCATED on (recorded by DBuf), whatever device is current when it is released --
+// a handle destroyed from another thread, or after sk_set_device to another GPU, must not hand device-A memory to a request
+// on device B.  A released block may still be read or written by kernels in flight (exception paths, handles destroyed right
+// after an asynchronous call), and the pool has no stream to order the next owner behind them: the owning device is
+// synchronised before the block is cached or freed.  Releases happen on tear-down paths only, never inside a solve.
 class DevicePool {
  public:
   static DevicePool& get() { static DevicePool* p = new DevicePool; return *p; }   // never destroyed: outlives the CUDA context teardown
   static size_t rounded(size_t bytes) { const size_t g = bytes >= (1u << 20) ? (size_t)(2u << 20) : (size_t)512; return (bytes + g - 1) / g * g; }
-  void* take(size_t bytes) {
+  void* take(size_t bytes, int* dev_out) {
     const size_t r = rounded(bytes);
     int dev = 0; cudaGetDevice(&dev);
+    *dev_out = dev;
     {
       std::lock_guard<std::mutex> g(mu_);
       auto it = free_.find({dev, r});
@@ -62,14 +68,18 @@ class DevicePool {
     if (e != cudaSuccess) throw Error(SK_ERR_CUDA, fmt("cudaMalloc of %zu bytes failed: %s", r, cudaGetErrorString(e)));
     return p;
   }
-  void give(void* p, size_t bytes) {
+  void give(void* p, size_t bytes, int dev) {
     const size_t r = rounded(bytes);
-    int dev = 0; cudaGetDevice(&dev);
+    int cur = 0; cudaGetDevice(&cur);
+    if (cur != dev) cudaSetDevice(dev);
+    cudaDeviceSynchronize();                           // nothing in flight may still touch the block (see above)
+    bool keep = false;
     {
       std::lock_guard<std::mutex> g(mu_);
-      if (cached_ + r <= max_cached_) { free_.insert({{dev, r}, p}); cached_ += r; return; }
+      if (cached_ + r <= max_cached_) { free_.insert({{dev, r}, p}); cached_ += r; keep = true; }
     }
-    cudaFree(p);
+    if (!keep) cudaFree(p);
+    if (cur != dev) cudaSetDevice(cur);
   }
   void release_all() {
     std::multimap<std::pair<int, size_t>, void*> drop;
@@ -81,7 +91,7 @@ class DevicePool {
   size_t cached_bytes() { std::lock_guard<std::mutex> g(mu_); return cached_; }
 
  private:
-  DevicePool() { const char* e = std::getenv("SKERES_POOL_MAX_GB"); max_cached_ = (size_t)((e ? atof(e) : 64.0) * (double)(1ull << 30)); }
+  DevicePool() { const char* e = std::getenv("SKERES_POOL_MAX_GB"); max_cached_ = (size_t)((e ? atof(e) : 16.0) * (double)(1ull << 30)); }
   std::mutex mu_;
   std::multimap<std::pair<int, size_t>, void*> free_;
   size_t cached_ = 0, max_cached_ = 0;
@@ -90,17 +100,17 @@ class DevicePool {
 // Device buffer with RAII; all device memory of the library is owned through these.
 template <class T>
 struct DBuf {
-  T* p = nullptr; size_t n = 0;
+  T* p = nullptr; size_t n = 0; int dev = 0;            // dev: the device the block lives on
   DBuf() = default;
   explicit DBuf(size_t count) { alloc(count); }
   DBuf(const DBuf&) = delete; DBuf& operator=(const DBuf&) = delete;
-  DBuf(DBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
-  DBuf& operator=(DBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+  DBuf(DBuf&& o) noexcept : p(o.p), n(o.n), dev(o.dev) { o.p = nullptr; o.n = 0; }
+  DBuf& operator=(DBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; dev = o.dev; o.p = nullptr; o.n = 0; } return *this; }
   ~DBuf() { release(); }
-  void release() { if (p) DevicePool::get().give(p, n * sizeof(T)); p = nullptr; n = 0; }
+  void release() { if (p) DevicePool::get().give(p, n * sizeof(T), dev); p = nullptr; n = 0; }
   void alloc(size_t count) {
     release(); n = count;
-    if (count) p = static_cast<T*>(DevicePool::get().take(count * sizeof(T)));
+    if (count) p = static_cast<T*>(DevicePool::get().take(count * sizeof(T), &dev));
   }
   void zero(cudaStream_t s) { if (n) SK_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
   void upload(const T* h, size_t count, cudaStream_t s) { if (count) SK_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s)); }

@@ -133,7 +133,12 @@ __global__ void k_fill(int64_t n, double value, double* __restrict__ out) {
 }
 
 struct ReduceJobs { ReduceJob j[8]; };
-__global__ void k_reduce_jobs(ReduceJobs jobs, double* sbuf, const int* guard) {
+__global__ void k_reduce_jobs(ReduceJobs jobs, double* sbuf, const int* guard, FlagSources fl) {
+  if (blockIdx.x == 0 && threadIdx.x == 0 && fl.st != nullptr) {     // before the guard: the flags are consumed either way
+    sbuf[SB_FLAG_EVAL] = fl.st->eval_failed ? 1.0 : 0.0;
+    const bool fatal = (fl.pcg != nullptr && fl.pcg->termination == LIN_FATAL) || (fl.peer_error != nullptr && *fl.peer_error != 0);
+    sbuf[SB_FLAG_LIN] = (fl.st->lin_error ? 1.0 : 0.0) + (fatal ? kFatalFlag : 0.0);
+  }
   if (guard != nullptr && *guard == 0) return;
   __shared__ double red[8];
   const ReduceJob jb = jobs.j[blockIdx.x];
@@ -174,7 +179,7 @@ __global__ void k_lm_iter0(LmDev* st, const double* sbuf, LmParams prm) {   // I
   memset(&row, 0, sizeof(row));
   row.iteration = 0; row.eta = prm.eta;
   st->g_finalize = 1;
-  if (st->eval_failed) {
+  if (st->eval_failed || sbuf[SB_FLAG_EVAL] != 0.0) {
     st->terminate = 1; st->termination_type = SK_FAILURE; st->term_reason = TR_EVALUATION_FAILED; st->g_finalize = 0; return;
   }
   st->x_cost = sbuf[SB_COST];
@@ -194,7 +199,9 @@ __global__ void k_lm_decide_a(LmDev* st, const PcgDev* pcg, const double* sbuf, 
   row.iteration = st->iteration;
   st->g_eval_cand = 0; st->g_accept = 0; st->g_finalize = 1;
   if (pcg != nullptr) { st->lin_iterations = pcg->iter; st->lin_termination = pcg->termination; }
-  if (st->lin_error) { st->lin_termination = LIN_FAILURE; st->lin_error = 0; }
+  const double lin_flags = sbuf[SB_FLAG_LIN];            // summed over the ranks: every rank takes the same branch
+  if (st->lin_error || lin_flags != 0.0) { st->lin_termination = LIN_FAILURE; st->lin_error = 0; }
+  if (lin_flags >= kFatalFlag) st->lin_termination = LIN_FATAL;
   row.linear_solver_iterations = st->lin_iterations;
   if (st->lin_termination == LIN_FATAL) {
     st->terminate = 1; st->termination_type = SK_FAILURE; st->term_reason = TR_LINEAR_SOLVER_FATAL; st->g_finalize = 0; return;
@@ -226,7 +233,7 @@ __global__ void k_lm_decide_b(LmDev* st, const double* sbuf, LmParams prm) {
   if (st->g_eval_cand == 0) return;
   sk_iteration_summary& row = st->row;
   double cand = sbuf[SB_COST];
-  if (st->eval_failed || !(cand == cand)) { cand = DBL_MAX; st->eval_failed = 0; }   // "step failed to evaluate"
+  if (st->eval_failed || sbuf[SB_FLAG_EVAL] != 0.0 || !(cand == cand)) { cand = DBL_MAX; st->eval_failed = 0; }   // "step failed to evaluate"
   st->cand_cost = cand;
   row.step_norm = sqrt(sbuf[SB_STEP_SQ_CAM] + sbuf[SB_STEP_SQ_PT]);
   const double step_size_tolerance = prm.parameter_tolerance * (st->x_norm + prm.parameter_tolerance);
@@ -255,7 +262,7 @@ __global__ void k_lm_decide_b(LmDev* st, const double* sbuf, LmParams prm) {
 __global__ void k_lm_post_accept(LmDev* st, const double* sbuf, LmParams prm) {
   if (st->g_accept == 0) return;
   sk_iteration_summary& row = st->row;
-  if (st->eval_failed) {
+  if (st->eval_failed || sbuf[SB_FLAG_EVAL] != 0.0) {
     st->terminate = 1; st->termination_type = SK_FAILURE; st->term_reason = TR_EVALUATION_FAILED; st->g_finalize = 0; return;
   }
   st->x_norm = sqrt(sbuf[SB_XNORM_SQ_CAM] + sbuf[SB_XNORM_SQ_PT]);
@@ -323,11 +330,11 @@ void launch_negate(int64_t n, const double* in, double* out, cudaStream_t s) {
 void launch_fill(int64_t n, double value, double* out, cudaStream_t s) {
   k_fill<<<vec_blocks(n), VT, 0, s>>>(n, value, out); check_launch("k_fill");
 }
-void launch_reduce_jobs(const ReduceJob* jobs, int njobs, double* sbuf, const int* guard, cudaStream_t s) {
+void launch_reduce_jobs(const ReduceJob* jobs, int njobs, double* sbuf, const int* guard, FlagSources flags, cudaStream_t s) {
   ReduceJobs j;
   SK_REQUIRE(njobs >= 1 && njobs <= 8, SK_ERR_INTERNAL, "bad reduce job count");
   for (int i = 0; i < njobs; ++i) j.j[i] = jobs[i];
-  k_reduce_jobs<<<njobs, VT, 0, s>>>(j, sbuf, guard); check_launch("k_reduce_jobs");
+  k_reduce_jobs<<<njobs, VT, 0, s>>>(j, sbuf, guard, flags); check_launch("k_reduce_jobs");
 }
 void launch_lm_init(LmDev* st, double r0, cudaStream_t s) { k_lm_init<<<1, 1, 0, s>>>(st, r0); check_launch("k_lm_init"); }
 void launch_lm_iter0(LmDev* st, const double* sbuf, LmParams prm, cudaStream_t s) { k_lm_iter0<<<1, 1, 0, s>>>(st, sbuf, prm); check_launch("k_lm_iter0"); }

@@ -11,17 +11,23 @@ namespace sk {
 
 enum Slot {                 // sbuf layout (doubles).  "pt" slots are summed across ranks (points are
   SB_COST = 0,              // partitioned); "cam" slots are identical on every rank.
-  SB_GRAD_SQ_PT = 1,        // slots [0,3) are fresh after a Jacobian evaluation,
-  SB_XNORM_SQ_PT = 2,
-  SB_MCC = 3,               // slots [3,5) after the linear solve + candidate,
-  SB_STEP_SQ_PT = 4,        // slot  [0,1) after the candidate cost.
-  SB_SUM_COUNT = 5,         // number of slots that go through the sum-allreduce
-  SB_STEP_SQ_CAM = 5,
-  SB_XNORM_SQ_CAM = 6,
-  SB_GRAD_SQ_CAM = 7,
-  SB_GRAD_MAX = 8,          // max-allreduced separately
+  SB_FLAG_EVAL = 1,         // != 0: an evaluation failed on some rank (every rank must take the same branch: a rank that
+                            // terminated alone would leave the others waiting in the next collective)
+  SB_GRAD_SQ_PT = 2,        // slots [0,4) are fresh after a Jacobian evaluation,
+  SB_XNORM_SQ_PT = 3,
+  SB_MCC = 4,               // slots [4,7) after the linear solve + candidate,
+  SB_STEP_SQ_PT = 5,        // slots [0,2) after the candidate cost.
+  SB_FLAG_LIN = 6,          // 1 per rank whose linear solve failed numerically + kFatalFlag per rank whose solve failed fatally
+  SB_SUM_COUNT = 7,         // number of slots that go through the sum-allreduces
+  SB_STEP_SQ_CAM = 7,
+  SB_XNORM_SQ_CAM = 8,
+  SB_GRAD_SQ_CAM = 9,
+  SB_GRAD_MAX = 10,         // slots [10,12) are max-allreduced
+  SB_TIME = 11,             // host wall-clock seconds since minimize() started, max over ranks (the time limit is then the
+                            // same decision on every rank)
   SB_COUNT = 16
 };
+constexpr double kFatalFlag = 1024.0;
 
 enum TermReason {
   TR_NONE = 0, TR_MAX_ITERATIONS, TR_GRADIENT_TOLERANCE, TR_MIN_RADIUS, TR_PARAMETER_TOLERANCE,
@@ -80,7 +86,11 @@ void launch_fill(int64_t n, double value, double* out, cudaStream_t s);
 
 // sbuf[slot] = fixed-order sum (or max) of part[0..n); one block per job, up to 8 jobs.
 struct ReduceJob { const double* part; int n; int slot; int is_max; };
-void launch_reduce_jobs(const ReduceJob* jobs, int njobs, double* sbuf, const int* guard, cudaStream_t s);
+// flags: after the jobs (and whatever the guard says) block 0 publishes the sticky failure flags of `st` (+ the linear solver's
+// fatal outcome: pcg termination, peer-window error word) into sbuf[SB_FLAG_EVAL] / sbuf[SB_FLAG_LIN], where the consumers
+// read them after the scalar allreduce.
+struct FlagSources { const LmDev* st; const PcgDev* pcg; const int* peer_error; };
+void launch_reduce_jobs(const ReduceJob* jobs, int njobs, double* sbuf, const int* guard, FlagSources flags, cudaStream_t s);
 
 // ---- scalar (single-thread) logic ---------------------------------------------------------------
 void launch_lm_init(LmDev* st, double initial_radius, cudaStream_t s);

@@ -40,7 +40,17 @@ void LmSolver::allocate(int64_t n, int64_t nc) {
 void LmSolver::reduce(std::initializer_list<ReduceJob> jobs, const int* guard) {
   std::vector<ReduceJob> v(jobs);
   KScope k(prof_, SK_KF_LM);
-  launch_reduce_jobs(v.data(), (int)v.size(), sbuf_.p, guard, stream_);
+  launch_reduce_jobs(v.data(), (int)v.size(), sbuf_.p, guard, FlagSources{st_.p, flag_pcg_, flag_peer_error_}, stream_);
+}
+
+// The sum / max allreduces that follow a Jacobian evaluation: cost, evaluation-failure flag, |g|^2 and |x|^2 of the point part;
+// max |g| and the elapsed host time.
+void LmSolver::allreduce_after_jacobian(double t_start) {
+  if (comm_ == nullptr || comm_->world <= 1) return;
+  time_h_.p[0] = wall() - t_start;
+  SK_CUDA(cudaMemcpyAsync(sbuf_.p + SB_TIME, time_h_.p, sizeof(double), cudaMemcpyHostToDevice, stream_));
+  comm_allreduce_sum(comm_, sbuf_.p, 4, stream_);
+  comm_allreduce_max(comm_, sbuf_.p + SB_GRAD_MAX, 2, stream_);
 }
 
 void LmSolver::minimize(sk_solver_summary* S, int max_num_iterations_override) {
@@ -56,9 +66,13 @@ void LmSolver::minimize(sk_solver_summary* S, int max_num_iterations_override) {
   if (!ev_start_) { SK_CUDA(cudaEventCreate(&ev_start_)); SK_CUDA(cudaEventCreate(&ev_stop_)); }
   SK_CUDA(cudaEventRecord(ev_start_, stream_));
   const int nb = vec_blocks(n_);
+  const bool multi = comm_ != nullptr && comm_->world > 1;
+  if (time_h_.n == 0) time_h_.alloc(2);
+  time_h_.p[0] = time_h_.p[1] = 0.0;
   std::vector<double> t_iter, t_cum;
   auto readback = [&]() -> const LmDev& {
     SK_CUDA(cudaMemcpyAsync(st_h_.p, st_.p, sizeof(LmDev), cudaMemcpyDeviceToHost, stream_));
+    if (multi) SK_CUDA(cudaMemcpyAsync(time_h_.p + 1, sbuf_.p + SB_TIME, sizeof(double), cudaMemcpyDeviceToHost, stream_));
     SK_CUDA(cudaStreamSynchronize(stream_));
     prof_.collect();
     return *st_h_.p;
@@ -93,8 +107,7 @@ void LmSolver::minimize(sk_solver_summary* S, int max_num_iterations_override) {
   reduce({cost_job(), {part_a_.p, nb, SB_GRAD_SQ_CAM, 0}, {part_a_.p + kMaxPartials, nb, SB_GRAD_SQ_PT, 0},
           {part_a_.p + 2 * kMaxPartials, nb, SB_GRAD_MAX, 1}, {part_b_.p, nb, SB_XNORM_SQ_CAM, 0},
           {part_b_.p + kMaxPartials, nb, SB_XNORM_SQ_PT, 0}}, nullptr);
-  comm_allreduce_sum(comm_, sbuf_.p, 3, stream_);
-  comm_allreduce_max(comm_, sbuf_.p + SB_GRAD_MAX, 1, stream_);
+  allreduce_after_jacobian(t_start);
   { KScope k(prof_, SK_KF_LM, 2); launch_lm_iter0(st_.p, sbuf_.p, prm_, stream_); launch_lm_finalize(st_.p, rows_.p, rows_cap_, prm_, stream_); }
   {
     const LmDev& h = readback();
@@ -105,7 +118,10 @@ void LmSolver::minimize(sk_solver_summary* S, int max_num_iterations_override) {
   // ---- main loop ---------------------------------------------------------------------------------
   while (!st_h_.p->terminate) {
     t_it = wall();
-    if (wall() - t_start > opt_.max_solver_time_in_seconds) {
+    // Multi-GPU: every rank must take this decision alike (a rank that left alone would leave the others waiting in the next
+    // collective), so it is taken on the maximum over the ranks of the elapsed time each rank recorded before the last scalar
+    // allreduce (SB_TIME), which came back with the state block.
+    if ((multi ? time_h_.p[1] : wall() - t_start) > opt_.max_solver_time_in_seconds) {
       st_h_.p->terminate = 1; st_h_.p->termination_type = SK_NO_CONVERGENCE; st_h_.p->term_reason = TR_MAX_TIME; break;
     }
     { KScope k(prof_, SK_KF_LM); launch_lm_diagonal(n_, cnorm2_.p, diagonal_.p, D_.p, st_.p, prm_, stream_); }
@@ -114,12 +130,12 @@ void LmSolver::minimize(sk_solver_summary* S, int max_num_iterations_override) {
     ++n_lin_solves_;
     { KScope k(prof_, SK_KF_LM); launch_candidate(n_, nc_, x_.p, step_.p, scale_.p, cand_.p, part_a_.p, stream_); }
     reduce({mcc_job, {part_a_.p, nb, SB_STEP_SQ_CAM, 0}, {part_a_.p + kMaxPartials, nb, SB_STEP_SQ_PT, 0}}, nullptr);
-    comm_allreduce_sum(comm_, sbuf_.p + SB_MCC, 2, stream_);
+    comm_allreduce_sum(comm_, sbuf_.p + SB_MCC, 3, stream_);       // model cost change, |step|^2 (points), linear-solver failure flags
     { KScope k(prof_, SK_KF_LM); launch_lm_decide_a(st_.p, pcg, sbuf_.p, prm_, stream_); }
     eval_cost(cand_.p, g_eval_cand);
     ++n_res_evals_;
     reduce({cost_job()}, g_eval_cand);
-    comm_allreduce_sum(comm_, sbuf_.p, 1, stream_);
+    comm_allreduce_sum(comm_, sbuf_.p, 2, stream_);                 // candidate cost, evaluation-failure flag
     { KScope k(prof_, SK_KF_LM); launch_lm_decide_b(st_.p, sbuf_.p, prm_, stream_); }
     // HandleSuccessfulStep (all guarded by g_accept)
     { KScope k(prof_, SK_KF_LM); launch_accept(n_, nc_, x_.p, cand_.p, part_b_.p, g_accept, stream_); }
@@ -128,8 +144,7 @@ void LmSolver::minimize(sk_solver_summary* S, int max_num_iterations_override) {
     reduce({cost_job(), {part_a_.p, nb, SB_GRAD_SQ_CAM, 0}, {part_a_.p + kMaxPartials, nb, SB_GRAD_SQ_PT, 0},
             {part_a_.p + 2 * kMaxPartials, nb, SB_GRAD_MAX, 1}, {part_b_.p, nb, SB_XNORM_SQ_CAM, 0},
             {part_b_.p + kMaxPartials, nb, SB_XNORM_SQ_PT, 0}}, g_accept);
-    comm_allreduce_sum(comm_, sbuf_.p, 3, stream_);
-    comm_allreduce_max(comm_, sbuf_.p + SB_GRAD_MAX, 1, stream_);
+    allreduce_after_jacobian(t_start);
     { KScope k(prof_, SK_KF_LM, 2); launch_lm_post_accept(st_.p, sbuf_.p, prm_, stream_); launch_lm_finalize(st_.p, rows_.p, rows_cap_, prm_, stream_); }
     const LmDev& h = readback();
     if (h.g_accept) ++n_jac_evals_;

@@ -41,7 +41,11 @@ class LmSolver {
 
   void allocate(int64_t n, int64_t nc);
   void reduce(std::initializer_list<ReduceJob> jobs, const int* guard);
-  void allreduce_scalars();            // multi-GPU: sum / max of the point-partitioned sbuf slots
+  void allreduce_after_jacobian(double t_start);   // multi-GPU: sum / max of the point-partitioned sbuf slots, flags, elapsed time
+  // where the reduce kernel finds the linear solver's fatal outcome (set by the back end; nullptr = none)
+  const PcgDev* flag_pcg_ = nullptr;
+  const int* flag_peer_error_ = nullptr;
+  HBuf<double> time_h_;                // [0] elapsed seconds written by this rank, [1] the maximum over the ranks read back
 
   sk_solver_options opt_;
   LmParams prm_{};

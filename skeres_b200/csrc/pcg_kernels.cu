@@ -99,18 +99,35 @@ __device__ __forceinline__ double ld_relaxed_sys(const double* p) {
   asm volatile("ld.relaxed.sys.global.f64 %0, [%1];\n" : "=d"(v) : "l"(p) : "memory");
   return v;
 }
-// Consumer side: every CTA waits until all ranks have published exchange `seq` (one polling thread per rank, bounded: a rank
-// that died or lost lockstep must not hang the GPU -- the error word is checked by the host after the solve).
-__device__ __forceinline__ void peer_wait(const PeerWindow& win, int parity, unsigned long long seq) {
+// Consumer side: every CTA waits until all ranks have published exchange `seq` (one polling thread per rank).  The wait is
+// bounded by wall-clock time (win.timeout_ns on %globaltimer; default 60 s, SKERES_PEER_TIMEOUT_S): ranks are separate
+// processes and a peer may legitimately stall for a while (lazy module load, a paused host thread), but a rank that died must
+// not hang the GPU.  Returns false -- in every thread of the CTA -- when this exchange, or an earlier one, timed out: the error
+// word is sticky, the caller then marks the solve LIN_FATAL instead of consuming unpublished data, and the flag reaches the
+// other ranks with the next scalar allreduce (lm_kernels.cuh: SB_FLAG_LIN).
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ bool peer_wait(const PeerWindow& win, int parity, unsigned long long seq) {
+  __shared__ int failed;
   if ((int)threadIdx.x < win.world) {
     const unsigned long long* f = win.flags[win.rank] + threadIdx.x * 2 + parity;
-    long long spins = 0;
+    const unsigned long long t0 = global_ns();
     while (ld_acquire_sys(f) < seq) {
       __nanosleep(40);
-      if (++spins > (1ll << 25)) { atomicExch(win.error, 1); break; }
+      if (*(volatile int*)win.error != 0) break;
+      if (global_ns() - t0 > win.timeout_ns) { atomicExch(win.error, 1); break; }
     }
   }
   __syncthreads();
+  if (threadIdx.x == 0) failed = *(volatile int*)win.error;
+  __syncthreads();
+  return failed == 0;
+}
+__device__ __forceinline__ void pcg_mark_fatal(PcgDev* st) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) { st->active = 0; st->termination = LIN_FATAL; }
 }
 // y[e] summed over the ranks' contributions in rank order (the same bits on every rank).
 __device__ __forceinline__ double peer_gather(const PeerWindow& win, int parity, size_t e) {
@@ -164,7 +181,7 @@ __global__ void k_pcg_begin(int n_cams, const double* __restrict__ rhs, const do
   if (threadIdx.x == 0) { part_bb[blockIdx.x] = s1; part_rho[blockIdx.x] = s2; }
 }
 
-__global__ void k_pcg_start2(PcgDev* st, const double* part_bb, int nparts, const int* lin_error) {
+__global__ void k_pcg_start2(PcgDev* st, const double* part_bb, int nparts, int* lin_error, const double* global_lin_flag) {
   __shared__ double red[8];
   const double bb = sum_fixed(part_bb, nparts, red);
   if (threadIdx.x != 0) return;
@@ -173,6 +190,7 @@ __global__ void k_pcg_start2(PcgDev* st, const double* part_bb, int nparts, cons
   st->Q0 = 0.0; st->Q1 = 0.0;                                   // Q0 = -x.(b + r) with x = 0
   st->iter = 0; st->active = 1; st->termination = LIN_NO_CONVERGENCE; st->pad_ = 0;   // pad_ = last finished iteration
   st->done_count = 0; st->pad2_ = 0;
+  if (global_lin_flag != nullptr && *global_lin_flag != 0.0) *lin_error |= 1;     // failed on some rank = failed for all
   if (*lin_error) { st->active = 0; st->termination = LIN_FAILURE; }
   else if (st->norm_b == 0.0) { st->active = 0; st->termination = LIN_SUCCESS; }
 }
@@ -273,7 +291,7 @@ __global__ void __launch_bounds__(WPB * WPC * 32) k_pcg_reduce(BaDev L, const do
                                                                 unsigned long long seq) {
   if (st->active == 0) return;
   const bool peer = win.world > 1;                     // y = sum over the ranks' windows (k_cam_reduce9_warp published them)
-  if (peer) peer_wait(win, parity, seq);
+  if (peer && !peer_wait(win, parity, seq)) { pcg_mark_fatal(const_cast<PcgDev*>(st)); return; }
   __shared__ double part[WPB][WPC][9];
   __shared__ double red[WPB];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -379,7 +397,7 @@ __global__ void k_pcg_resid2(BaDev L, const double* __restrict__ seg_y, const do
                              unsigned long long seq) {
   if (st->active == 0) return;
   const bool peer = win.world > 1;
-  if (peer) peer_wait(win, parity, seq);
+  if (peer && !peer_wait(win, parity, seq)) { pcg_mark_fatal(st); return; }
   __shared__ double red[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x * WPB + warp;
@@ -474,10 +492,10 @@ void launch_cam_reduce9_warp(const BaDev& L, const double* seg_y, double* y, con
 }
 
 void launch_pcg_begin(int n_cams, const double* rhs, const double* Minv, double* x, double* r, double* z, double* part_bb,
-                      double* part_rho, PcgDev* st, const int* lin_error, cudaStream_t s) {
+                      double* part_rho, PcgDev* st, int* lin_error, const double* global_lin_flag, cudaStream_t s) {
   const int nb = pcg_blocks(n_cams);
   k_pcg_begin<<<nb, WPB * 32, 0, s>>>(n_cams, rhs, Minv, x, r, z, part_bb, part_rho);
-  k_pcg_start2<<<1, 256, 0, s>>>(st, part_bb, nb, lin_error);
+  k_pcg_start2<<<1, 256, 0, s>>>(st, part_bb, nb, lin_error, global_lin_flag);
   check_launch("k_pcg_begin");
 }
 void launch_pcg_head(PcgDev* st, const double* part_rho, const double* part_pq, const double* part_Q, int nparts, PcgParams prm,
