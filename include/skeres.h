@@ -369,6 +369,11 @@ typedef struct sk_solver sk_solver;
 int sk_solver_create(const sk_solver_options* options, sk_problem* problem, sk_solver** out);
 int sk_solver_minimize(sk_solver* solver, int32_t max_num_iterations_override, sk_solver_summary* summary);
 int sk_solver_destroy(sk_solver* solver);
+/* Measurement aid (no reference counterpart): mean device time, in milliseconds, of `reps` back-to-back launches of the
+ * implicit Schur-complement product (ImplicitSchurComplement::RightMultiply) on the linearisation the last
+ * sk_solver_minimize call left behind, timed with CUDA events on the solver's stream.  ITERATIVE_SCHUR solvers only, after
+ * at least one LM iteration.  bench.py and tools/ use it to time the dominant kernel in isolation. */
+int sk_solver_time_schur_product(sk_solver* solver, int32_t reps, double* out_ms_per_launch);
 
 /* ------------------------------------------------------------------------------------------
  * Batched independent small problems (BASELINE.json configs[3]): n_problems CurveFitting-shaped

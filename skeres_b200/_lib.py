@@ -10,7 +10,8 @@ import os
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libskeres.so")
+# SKERES_LIB: development only -- an alternative build of the same library (kernel A/B variants under gpurun_variants/)
+LIB_PATH = os.environ.get("SKERES_LIB") or os.path.join(_HERE, "libskeres.so")
 
 
 class SkeresError(RuntimeError):
@@ -78,6 +79,7 @@ def _load():
         "sk_solve": (i32, [P(_abi.SolverOptions), vp, vp]),
         "sk_solver_create": (i32, [P(_abi.SolverOptions), vp, P(vp)]),
         "sk_solver_minimize": (i32, [vp, i32, vp]),
+        "sk_solver_time_schur_product": (i32, [vp, i32, P(dbl)]),
         "sk_solver_destroy": (i32, [vp]),
         "sk_curve_fit_batch_solve": (i32, [P(_abi.SolverOptions), i64, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
         "sk_bal_problem_from_file": (i32, [C.c_char_p, P(vp)]),

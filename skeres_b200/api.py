@@ -459,6 +459,12 @@ class PreparedSolver:
         check(lib.sk_solver_minimize(self._h, int(max_num_iterations), summary._h))
         return summary
 
+    def timeSchurProduct(self, reps=50):
+        """Measurement aid: mean device ms of one implicit Schur-complement product on the last linearisation."""
+        ms = C.c_double()
+        check(lib.sk_solver_time_schur_product(self._h, int(reps), C.byref(ms)))
+        return ms.value
+
     def close(self, _destroy=_destroy):
         if getattr(self, "_h", None):
             _destroy("sk_solver_destroy", self._h)

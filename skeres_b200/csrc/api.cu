@@ -617,6 +617,14 @@ int sk_solver_minimize(sk_solver* solver, int32_t max_num_iterations_override, s
 
 int sk_solver_destroy(sk_solver* solver) { SK_API_BEGIN delete solver; SK_API_END }
 
+int sk_solver_time_schur_product(sk_solver* solver, int32_t reps, double* out_ms_per_launch) {
+  SK_API_BEGIN
+  SK_REQUIRE(solver != nullptr && out_ms_per_launch != nullptr && reps > 0, SK_ERR_INVALID_ARGUMENT, "sk_solver_time_schur_product: bad argument");
+  SK_CUDA(cudaSetDevice(solver->device));
+  *out_ms_per_launch = solver->impl->time_linear_operator(reps);
+  SK_API_END
+}
+
 int sk_solve(const sk_solver_options* options, sk_problem* problem, sk_solver_summary* summary) {
   if (summary == nullptr) return fail(SK_ERR_INVALID_ARGUMENT, "sk_solve: null argument");
   sk_solver* s = nullptr;

@@ -62,7 +62,7 @@ BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHo
   L_.n_giant = H.n_giant; L_.n_chunks = H.n_chunks; L_.tile_np = d_tile_np_.p;
   L_.gp_tile_begin = d_gp_begin_.p; L_.gp_tile_count = d_gp_count_.p; L_.gp_point = d_gp_point_.p;
   L_.tile_rec = nullptr; L_.rec_stride = L_.rec_sp = L_.rec_pp = L_.rec_sc = 0;
-  { const char* e = getenv("SKERES_MATVEC"); L_.matvec_classic = (e != nullptr && e[0] == 'c') ? 1 : 0; }
+  { const char* e = getenv("SKERES_MATVEC"); L_.matvec_classic = (e != nullptr && e[0] == 'c') ? 1 : (e != nullptr && e[0] == 'r') ? 2 : 0; }
   { const char* e = getenv("SKERES_MATVEC_SUMS"); L_.matvec_serial_sums = (e != nullptr && e[0] == 's') ? 1 : 0; }
   const int64_t nc = (int64_t)9 * H.n_cams, n = nc + (int64_t)3 * H.n_pts;
   allocate(n, nc);
@@ -307,6 +307,24 @@ void BaSolver::pcg_solve(const double* Minv, const double* global_lin_flag) {
   // terminate with FAILURE together -- an exception on one rank would leave the others waiting in that allreduce.
   const int its = pcg_h_.p->iter;
   n_real_matvecs_ += (its + its / kResetPeriod) * (L_.n_giant ? 2 : 1);
+}
+
+double BaSolver::time_linear_operator(int reps) {
+  SK_REQUIRE(!explicit_schur_, SK_ERR_UNSUPPORTED, "the implicit Schur product exists for ITERATIVE_SCHUR solvers only");
+  SK_REQUIRE(n_jac_evals_ > 0, SK_ERR_INVALID_ARGUMENT, "sk_solver_time_schur_product: run sk_solver_minimize first (no linearisation yet)");
+  cudaEvent_t a, b;
+  SK_CUDA(cudaEventCreate(&a)); SK_CUDA(cudaEventCreate(&b));
+  launch_fill(nc_, 1.0, pp_.p, stream_);
+  const double2* J2 = reinterpret_cast<const double2*>(J2_.p);
+  for (int i = 0; i < 3; ++i) launch_ba_matvec(L_, J2, pp_.p, nullptr, nullptr, einv_.p, seg_a_.p, nullptr, stream_, have_tmapJ_ ? &tmapJ_ : nullptr);
+  SK_CUDA(cudaEventRecord(a, stream_));
+  for (int i = 0; i < reps; ++i) launch_ba_matvec(L_, J2, pp_.p, nullptr, nullptr, einv_.p, seg_a_.p, nullptr, stream_, have_tmapJ_ ? &tmapJ_ : nullptr);
+  SK_CUDA(cudaEventRecord(b, stream_));
+  SK_CUDA(cudaStreamSynchronize(stream_));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, a, b);
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  return (double)ms / reps;
 }
 
 BaSolver::~BaSolver() {

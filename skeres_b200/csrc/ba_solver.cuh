@@ -17,6 +17,7 @@ class BaSolver : public LmSolver {
   // Rank-local ingestion (sk_solver_options.residual_blocks_are_local): sums the per-rank observation / point counts for
   // the summary and checks that every rank built the same camera table.  Collective: every rank must call it.
   void exchange_local_totals();
+  double time_linear_operator(int reps) override;
 
   // ---- test / debug access (sk_debug_* entry points) ---------------------------------------------
   const BaDev& layout() const { return L_; }

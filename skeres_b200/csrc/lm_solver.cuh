@@ -23,6 +23,8 @@ class LmSolver {
   virtual ~LmSolver();
   // Runs the minimisation; state vector x must have been loaded by the back end.
   void minimize(sk_solver_summary* summary, int max_num_iterations_override = -1);
+  // sk_solver_time_schur_product: mean device ms of one application of the back end's iterative linear operator
+  virtual double time_linear_operator(int /*reps*/) { throw Error(SK_ERR_UNSUPPORTED, "this solver has no iterative linear operator to time"); }
 
  protected:
   // --- back-end hooks -----------------------------------------------------------------------------

@@ -19,8 +19,8 @@ comm = api.Communicator(ids[0], rank, world)
 shape = sys.argv[1] if len(sys.argv) > 1 else "ladybug-49"
 d = synth.make_bal(shape, seed=1)
 
-def solve(use_comm, local=False):
-    bal = api.BalProblem.fromArrays(d)
+def solve(use_comm, local=False, data=None):
+    bal = api.BalProblem.fromArrays(d if data is None else data)
     prob = bal.buildLocalProblem(rank, world) if local else bal.buildProblem()
     o = api.Solver.Options(); o.setLinearSolverType(_abi.ITERATIVE_SCHUR); o.setPreconditionerType(_abi.SCHUR_JACOBI)
     if use_comm: o.comm = comm
@@ -49,6 +49,16 @@ other = np.setdiff1d(np.arange(x.size), own)
 assert np.array_equal(xl[other], d.parameters[other]), "foreign points must stay untouched"
 assert (sl.num_residual_blocks, sl.num_parameter_blocks) == (s.num_residual_blocks, s.num_parameter_blocks)
 print(f"rank {rank}: rank-local ingestion OK ({o1 - o0} of {d.num_observations} observations ingested, {dtl:.3f}s vs {dt:.3f}s)", flush=True)
+# failure injection: a NaN coordinate in a point only the LAST rank owns.  Its evaluation fails on that rank alone;
+# every rank must report the same FAILURE and return -- a rank that terminated alone would leave the others in an allreduce.
+import copy
+dbad = copy.copy(d)
+dbad.parameters = d.parameters.copy()
+dbad.parameters[9 * d.num_cameras + 3 * (d.num_points - 1)] = float("nan")
+for local_mode in (False, True):
+    xb, sb, dtb = solve(True, local=local_mode, data=dbad)
+    assert sb.termination_type == _abi.FAILURE and len(sb.iterations) == 0, (rank, sb.termination_type, sb.message)
+print(f"rank {rank}: NaN on the last rank -> every rank terminates with FAILURE ({sb.message})", flush=True)
 if rank == 0:
     for g in gathered[1:]:
         assert g[0] == gathered[0][0], "ranks disagree on the solution"
