@@ -604,6 +604,17 @@ class BalProblem:
         return problem
 
 
+def build_share_problem(bal, loss=None):
+    """Multi-GPU ingestion from a rank's OWN share: `bal` holds only this rank's residual blocks (global camera / point
+    indices) and the full parameter array; every camera is declared (Problem::AddParameterBlock).  Solve with
+    Options.residual_blocks_are_local = 1 and a communicator."""
+    problem = Problem()
+    loss = loss if loss is not None else PredefinedLossFunctions.trivialLoss()
+    problem.addParameterBlocks(bal.parameters, 9 * np.arange(bal.numCameras, dtype=np.int64), 9)
+    problem.addResidualBlocks(_abi.FUNCTOR_SNAVELY_REPROJECTION_ERROR, bal.observations.reshape(-1, 2), loss, bal.parameters, bal.blockOffsets())
+    return problem
+
+
 def curve_fit_batch_solve(options, x, y, mc, want_details=True):
     """sk_curve_fit_batch_solve on device arrays x, y [n_obs][n], mc [2][n] (DoubleArray)."""
     n = mc.n // 2

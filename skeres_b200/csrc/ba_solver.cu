@@ -78,7 +78,23 @@ BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHo
   pcg_.zero(s);
   if (comm_ && comm_->world > 1 && !(lst_is_explicit(opt.linear_solver_type))) peer_allreduce_create(comm_, (size_t)nc, s, &peer_);   // collective
   if (!lst_is_explicit(opt.linear_solver_type)) flag_pcg_ = pcg_.p;          // a fatal linear-solver outcome reaches every rank (lm_kernels.cuh: SB_FLAG_LIN)
-  if (peer_.ok) flag_peer_error_ = peer_.win.error;
+  if (peer_.ok) {
+    flag_peer_error_ = peer_.win.error;
+    // which ranks contribute to which camera: bit r of cam_mask[c] = rank r holds observations of camera c (collective)
+    std::vector<double> touch((size_t)H.n_cams, 0.0);
+    for (int c = 0; c < H.n_cams; ++c) if (H.cam_seg_ptr[c + 1] > H.cam_seg_ptr[c]) touch[c] = (double)(1u << comm_->rank);
+    DBuf<double> d_touch(touch.size());
+    d_touch.upload(touch, s);
+    comm_allreduce_sum(comm_, d_touch.p, touch.size(), s);         // disjoint bits: the sum is the union, exact in a double
+    d_touch.download(touch.data(), touch.size(), s);
+    SK_CUDA(cudaStreamSynchronize(s));
+    std::vector<unsigned char> mask(touch.size());
+    for (size_t c = 0; c < touch.size(); ++c) mask[c] = (unsigned char)(unsigned)touch[c];
+    peer_.cam_mask.upload(mask, s);
+    SK_CUDA(cudaStreamSynchronize(s));
+    const char* e = getenv("SKERES_PEER_GATHER");                  // development: SKERES_PEER_GATHER=all reads every rank's window
+    peer_.win.cam_mask = (e != nullptr && e[0] == 'a') ? nullptr : peer_.cam_mask.p;
+  }
   SK_REQUIRE(cdiv(H.n_cams, 8) <= kMaxPartials, SK_ERR_UNSUPPORTED, "more than %d cameras", kMaxPartials * 256 / 9);
   const int lst = opt.linear_solver_type;
   explicit_schur_ = (lst == SK_DENSE_SCHUR || lst == SK_SPARSE_SCHUR);
@@ -312,19 +328,42 @@ void BaSolver::pcg_solve(const double* Minv, const double* global_lin_flag) {
 double BaSolver::time_linear_operator(int reps) {
   SK_REQUIRE(!explicit_schur_, SK_ERR_UNSUPPORTED, "the implicit Schur product exists for ITERATIVE_SCHUR solvers only");
   SK_REQUIRE(n_jac_evals_ > 0, SK_ERR_INVALID_ARGUMENT, "sk_solver_time_schur_product: run sk_solver_minimize first (no linearisation yet)");
+  // development: SKERES_TIME_MODE selects what surrounds the product (why is it slower inside the PCG loop than back to back?)
+  //   0 back to back | 1 a one-CTA kernel between products | 2 the second-level camera reduction between products
+  //   3 the camera reduction alone | 4 back to back with the PCG-style input (z + beta p) | 5 back to back, events around every launch
+  const int mode = [] { const char* e = getenv("SKERES_TIME_MODE"); return e ? atoi(e) : 0; }();
   cudaEvent_t a, b;
   SK_CUDA(cudaEventCreate(&a)); SK_CUDA(cudaEventCreate(&b));
   launch_fill(nc_, 1.0, pp_.p, stream_);
+  launch_fill(nc_, 0.5, pz_.p, stream_);
   const double2* J2 = reinterpret_cast<const double2*>(J2_.p);
-  for (int i = 0; i < 3; ++i) launch_ba_matvec(L_, J2, pp_.p, nullptr, nullptr, einv_.p, seg_a_.p, nullptr, stream_, have_tmapJ_ ? &tmapJ_ : nullptr);
-  SK_CUDA(cudaEventRecord(a, stream_));
-  for (int i = 0; i < reps; ++i) launch_ba_matvec(L_, J2, pp_.p, nullptr, nullptr, einv_.p, seg_a_.p, nullptr, stream_, have_tmapJ_ ? &tmapJ_ : nullptr);
-  SK_CUDA(cudaEventRecord(b, stream_));
-  SK_CUDA(cudaStreamSynchronize(stream_));
-  float ms = 0.f;
-  cudaEventElapsedTime(&ms, a, b);
+  const CUtensorMap* tm = have_tmapJ_ ? &tmapJ_ : nullptr;
+  auto product = [&]() {
+    if (mode == 4) launch_ba_matvec(L_, J2, pp_.p, pz_.p, pcg_.p, einv_.p, seg_a_.p, nullptr, stream_, tm);
+    else if (mode != 3) launch_ba_matvec(L_, J2, pp_.p, nullptr, nullptr, einv_.p, seg_a_.p, nullptr, stream_, tm);
+    if (mode == 1) launch_fill(1, 0.0, ybuf_.p, stream_);
+    if (mode == 2 || mode == 3) launch_cam_reduce(L_, 9, seg_a_.p, ybuf_.p, nullptr, stream_);
+  };
+  for (int i = 0; i < 3; ++i) product();
+  double total_ms = 0.0;
+  if (mode == 5) {
+    std::vector<cudaEvent_t> ev((size_t)2 * reps);
+    for (auto& e : ev) SK_CUDA(cudaEventCreate(&e));
+    for (int i = 0; i < reps; ++i) { SK_CUDA(cudaEventRecord(ev[2 * i], stream_)); product(); SK_CUDA(cudaEventRecord(ev[2 * i + 1], stream_)); }
+    SK_CUDA(cudaStreamSynchronize(stream_));
+    for (int i = 0; i < reps; ++i) { float ms = 0.f; cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]); total_ms += ms; }
+    for (auto& e : ev) cudaEventDestroy(e);
+  } else {
+    SK_CUDA(cudaEventRecord(a, stream_));
+    for (int i = 0; i < reps; ++i) product();
+    SK_CUDA(cudaEventRecord(b, stream_));
+    SK_CUDA(cudaStreamSynchronize(stream_));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    total_ms = ms;
+  }
   cudaEventDestroy(a); cudaEventDestroy(b);
-  return (double)ms / reps;
+  return total_ms / reps;
 }
 
 BaSolver::~BaSolver() {

@@ -37,12 +37,15 @@ struct PeerWindow {
   unsigned int* done_count;                 // own: CTAs of the running producer kernel that have written their part
   long long stride;                         // doubles per parity slot
   unsigned long long timeout_ns;            // bound of one wait for the peers (SKERES_PEER_TIMEOUT_S, default 60 s)
+  const unsigned char* cam_mask;            // [n_cams] bit r: rank r holds observations of the camera, i.e. contributes to its sums;
+                                            // the gather reads a camera only from those ranks (nullptr: from all)
   int rank, world;                          // world == 0: no peer window (single GPU or NCCL path)
 };
 struct PeerAllreduce {
   PeerWindow win{};
   void* opened[kMaxPeers] = {};
   DBuf<double> mem;
+  DBuf<unsigned char> cam_mask;             // see PeerWindow::cam_mask
   unsigned long long seq = 0;               // sequence number of the last exchange
   bool ok = false;
 };

@@ -129,15 +129,19 @@ __device__ __forceinline__ bool peer_wait(const PeerWindow& win, int parity, uns
 __device__ __forceinline__ void pcg_mark_fatal(PcgDev* st) {
   if (blockIdx.x == 0 && threadIdx.x == 0) { st->active = 0; st->termination = LIN_FATAL; }
 }
-// y[e] summed over the ranks' contributions in rank order (the same bits on every rank).
-__device__ __forceinline__ double peer_gather(const PeerWindow& win, int parity, size_t e) {
+// y[e] of camera c summed over the contributions of the ranks that hold observations of c, in rank order (the same bits on
+// every rank).  Points are partitioned, so a camera is seen by the few ranks whose points it observes: reading only those
+// windows (cam_mask) keeps the gather's NVLink volume at ~(cameras touched per rank) instead of (ranks x all cameras) --
+// measured round 1, N = 8: the all-windows gather was the part of the PCG iteration that grew with N (25 -> 94 us).
+__device__ __forceinline__ double peer_gather(const PeerWindow& win, int parity, int c, size_t e) {
+  const unsigned mask = win.cam_mask != nullptr ? (unsigned)win.cam_mask[c] : 0xffu;
   double x[kMaxPeers];
 #pragma unroll
   for (int r = 0; r < kMaxPeers; ++r)                     // all loads in flight before the first add (remote latency once, not world times)
-    x[r] = (r < win.world) ? ld_relaxed_sys(win.data[r] + (size_t)parity * win.stride + e) : 0.0;
+    x[r] = (r < win.world && ((mask >> r) & 1u)) ? ld_relaxed_sys(win.data[r] + (size_t)parity * win.stride + e) : 0.0;
   double acc = 0.0;
 #pragma unroll
-  for (int r = 0; r < kMaxPeers; ++r) if (r < win.world) acc += x[r];
+  for (int r = 0; r < kMaxPeers; ++r) if (r < win.world && ((mask >> r) & 1u)) acc += x[r];
   return acc;
 }
 // Producer side, at the end of the kernel that wrote this rank's contribution: the CTA that finishes last publishes `seq` to
@@ -310,7 +314,7 @@ __global__ void __launch_bounds__(WPB * WPC * 32) k_pcg_reduce(BaDev L, const do
   double pq = 0.0;
   if (c < L.n_cams && sub == 0 && lane < 9) {
     double acc;
-    if (peer) acc = peer_gather(win, parity, (size_t)c * 9 + lane);
+    if (peer) acc = peer_gather(win, parity, c, (size_t)c * 9 + lane);
     else if (y_in == nullptr) {
       acc = part[cl][0][lane];
 #pragma unroll
@@ -405,7 +409,7 @@ __global__ void k_pcg_resid2(BaDev L, const double* __restrict__ seg_y, const do
   if (c < L.n_cams) {
     const int k = lane % 9, j = lane / 9;
     double acc = 0.0;
-    if (peer) { if (lane < 9) acc = peer_gather(win, parity, (size_t)c * 9 + lane); }
+    if (peer) { if (lane < 9) acc = peer_gather(win, parity, c, (size_t)c * 9 + lane); }
     else if (y_in == nullptr) {
       if (lane < 27)
         for (int t = L.cam_seg_ptr[c] + j; t < L.cam_seg_ptr[c + 1]; t += 3) acc += seg_y[(size_t)L.cam_seg[t] * 9 + k];

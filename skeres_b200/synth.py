@@ -154,6 +154,23 @@ def make_bal(shape="ladybug-49", seed=1, noise_px=0.5, point_sigma=0.05, rot_sig
                    np.ascontiguousarray(obs.ravel()), x0, gt)
 
 
+def make_scene_share(rank, world, shape="venice-1778", seed=1) -> BalData:
+    """Rank `rank`'s share of a problem made of `world` DISJOINT copies of one scene (bench.py's weak-scaling workload): scene r
+    owns cameras [r C, (r + 1) C) and points [r P, (r + 1) P), so the point partition (contiguous, balanced by observation count)
+    gives every rank exactly one scene.  Because the copies are identical and do not share parameters, the LM trajectory and the
+    PCG iteration counts of the whole problem are those of one scene: the work per step is `world` times one scene's, step by
+    step -- a weak-scaling workload whose per-step work does not change with the number of GPUs.
+    Returns global camera / point indices for the local observations only, and the FULL start vector (cameras of every scene,
+    points of every scene), as the rank-local ingestion of the multi-GPU path expects."""
+    one = make_bal(shape, seed=seed)
+    C_, P_ = one.num_cameras, one.num_points
+    cams = np.tile(one.parameters[:9 * C_], world)
+    pts = np.tile(one.parameters[9 * C_:], world)
+    gt = np.concatenate([np.tile(one.ground_truth[:9 * C_], world), np.tile(one.ground_truth[9 * C_:], world)])
+    return BalData(C_ * world, P_ * world, (one.camera_index + rank * C_).astype(np.int32), (one.point_index + rank * P_).astype(np.int32),
+                   one.observations, np.concatenate([cams, pts]), gt)
+
+
 def write_bal_text(data: BalData, path):
     """BAL text layout parsed by BalProblem.fromFile (SimpleBundleAdjuster.scala:41-62)."""
     with open(path, "w") as fh:

@@ -11,6 +11,12 @@ o = api.Solver.Options(); o.setLinearSolverType(_abi.ITERATIVE_SCHUR); o.setPrec
 o.setMaxNumIterations(3)
 solver = api.PreparedSolver(o, prob)
 s = solver.minimize()
+modes = [int(m) for m in os.environ.get("TIME_MODES", "0").split(",")]
+for mode in modes[:-1]:
+    os.environ["SKERES_TIME_MODE"] = str(mode)
+    t = [solver.timeSchurProduct(200) for _ in range(3)]
+    print("time mode %d: %.4f ms per product (runs %s)" % (mode, min(t), ["%.4f" % m for m in t]))
+os.environ["SKERES_TIME_MODE"] = str(modes[-1])
 ms = [solver.timeSchurProduct(200) for _ in range(3)]
 nbytes = d.num_observations * 196 + d.num_points * 72 + d.num_cameras * 144
 print("variant matvec=%s sums=%s lib=%s : %.4f ms per product (runs %s) = %.0f GB/s algorithmic ; solve cost %.9e pcg %s" % (
