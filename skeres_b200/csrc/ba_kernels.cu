@@ -66,14 +66,16 @@ __device__ __forceinline__ void block_sum_all(double (&x)[N], double* red) {
 }
 
 // out[(sb+s)*ostride + ooff + k] = sum over segment s of v[k][local obs], fixed (point) order.
+// pos_map != nullptr: row pos_map[segment] instead of row `segment` (the camera-major rows of the implicit-Schur product).
 __device__ __forceinline__ void seg_reduce9(const BaDev& L, const Tile& q, const double* v, double* out,
-                                            int ostride, int ooff) {
+                                            int ostride, int ooff, const int* pos_map = nullptr) {
   for (int idx = threadIdx.x; idx < q.ns * 9; idx += blockDim.x) {
     const int s = idx / 9, k = idx - s * 9;
     const int b = L.seg_ptr[q.sb + s], e = L.seg_ptr[q.sb + s + 1];
     double sum = 0.0;
     for (int pos = b; pos < e; ++pos) sum += v[k * VLD + L.seg_perm[pos]];
-    out[(size_t)(q.sb + s) * ostride + ooff + k] = sum;
+    const int row = pos_map != nullptr ? pos_map[q.sb + s] : q.sb + s;
+    out[(size_t)row * ostride + ooff + k] = sum;
   }
 }
 
@@ -421,13 +423,13 @@ __global__ void k_ba_precond_invert(BaDev L, const double* __restrict__ M45, con
 
 // ------------------------------------------------------------------------------------------------
 // seg_reduce9 with the metadata already in shared memory.
-__device__ __forceinline__ void seg_reduce9_s(const Tile& q, const TileMetaSmem& m, const double* v, double* out, int ostride, int ooff) {
+__device__ __forceinline__ void seg_reduce9_s(const Tile& q, const TileMetaSmem& m, const double* v, double* out, const int* spos) {
   for (int idx = threadIdx.x; idx < q.ns * 9; idx += T) {
     const int s = idx / 9, k = idx - s * 9;
     const int b = m.sptr[s], e = m.sptr[s + 1];
     double sum = 0.0;
     for (int pos = b; pos < e; ++pos) sum += v[k * VLD + m.sperm[pos]];
-    out[(size_t)(q.sb + s) * ostride + ooff + k] = sum;
+    out[(size_t)spos[s] * 9 + k] = sum;
   }
 }
 
@@ -469,7 +471,7 @@ __device__ __forceinline__ void seg_sums_chunked(const RecView& R, int ns, int s
   const int n9 = 9 * (int)R.scptr[ns];
   for (int idx = tid; idx < n9; idx += NT) ps[idx] = seg_chunk_sum(R, vs, idx);
   __syncthreads();
-  for (int idx = tid; idx < ns * 9; idx += NT) seg_y[(size_t)sb * 9 + idx] = seg_combine(R, ps, idx);
+  for (int idx = tid; idx < ns * 9; idx += NT) { const int s = idx / 9; seg_y[(size_t)R.spos[s] * 9 + (idx - 9 * s)] = seg_combine(R, ps, idx); }
 }
 
 // Arithmetic of one observation inside the implicit-Schur product, with every rounding spelled out: the three product kernels
@@ -542,7 +544,7 @@ __global__ void __launch_bounds__(T, 768 / T) k_ba_matvec(BaDev L, const double2
   for (int idx = tid; idx < q.ns * 9; idx += T) {
     const int s = idx / 9, k = idx - s * 9;
     const size_t e = (size_t)L.seg_cam[q.sb + s] * 9 + k;
-    xs[idx] = (pcg == nullptr) ? p[e] : ((pcg->iter == 1) ? zdir[e] : (zdir[e] + pcg->beta * p[e]));
+    xs[idx] = (pcg == nullptr) ? p[e] : ((pcg->iter == 1) ? zdir[e] : __fma_rn(pcg->beta, p[e], zdir[e]));
   }
   __syncthreads();
   double t0 = 0.0, t1 = 0.0;
@@ -576,7 +578,7 @@ __global__ void __launch_bounds__(T, 768 / T) k_ba_matvec(BaDev L, const double2
   }
   __syncthreads();
   if (CHUNKED) seg_sums_chunked(R, q.ns, q.sb, v, ps, seg_y);
-  else seg_reduce9_s(q, meta, v, seg_y, 9, 0);
+  else seg_reduce9_s(q, meta, v, seg_y, R.spos);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -674,18 +676,26 @@ __global__ void __launch_bounds__(T, SK_TMA_CTAS) k_ba_matvec_tma(const __grid_c
   // PCG direction z + beta p formed on the fly (p = z in iteration 1); the two scalars are read once, not per tile
   const bool dir_is_z = pcg != nullptr && pcg->iter == 1;
   const double beta = (pcg != nullptr && !dir_is_z) ? pcg->beta : 0.0;
-  auto gather = [&](const RecView& R, int idx) {             // element idx of the tile's input vector [ns][9]
+  // Element idx of the tile's input vector [ns][9] as its two RAW operands: the direction is z + beta p (or z, or p alone).
+  // The multiply-add is left to the consumer on purpose: the operands are fetched one tile ahead, behind the segment sums,
+  // and an arithmetic instruction placed right after the loads would make every warp wait for that L2 round trip on the spot
+  // (measured: +34 us per product, 0.2033 -> 0.2374 ms, with the fused form -- profiles/r02_matvec_timing_modes.md).
+  const double* va = (pcg == nullptr) ? p : zdir;            // first operand
+  const bool two = pcg != nullptr && !dir_is_z;              // second operand p, scaled by beta
+  auto gather2 = [&](const RecView& R, int idx, double& a, double& b) {
     const int s = idx / 9, k = idx - s * 9;
     const size_t e = (size_t)R.scam[s] * 9 + k;
-    return (pcg == nullptr) ? p[e] : (dir_is_z ? zdir[e] : (zdir[e] + beta * p[e]));
+    a = va[e];
+    b = two ? p[e] : 0.0;
   };
+  auto combine = [&](double a, double b) { return two ? __fma_rn(beta, b, a) : a; };
   Tile q = header(0);
   Tile qn = q;
   if (my_tiles > 1) qn = header(1);
   if (tid == 0) issue(q, blockIdx.x, 0);
   mbar_wait(bar_rec, 0);
-  double xpre = 0.0;                                         // element `tid` of the current tile's input vector
-  if (tid < q.ns * 9) xpre = gather(rec_view(L, recbuf), tid);
+  double xpre = 0.0, xpre2 = 0.0;                            // operands of element `tid` of the current tile's input vector
+  if (tid < q.ns * 9) gather2(rec_view(L, recbuf), tid, xpre, xpre2);
   for (int it = 0; it < my_tiles; ++it) {
     const int cur = it & 1;
     const unsigned par = (unsigned)((it >> 1) & 1);
@@ -705,8 +715,8 @@ __global__ void __launch_bounds__(T, SK_TMA_CTAS) k_ba_matvec_tma(const __grid_c
       slot = R.slot[tid]; ptl = R.ptl[tid];
       if (CHUNKED) rank = R.srank[tid];
     }
-    if (tid < q.ns * 9) xs[tid] = xpre;
-    for (int idx = tid + T; idx < q.ns * 9; idx += T) xs[idx] = gather(R, idx);   // more than 28 segments: the rest, not prefetched
+    if (tid < q.ns * 9) xs[tid] = combine(xpre, xpre2);
+    for (int idx = tid + T; idx < q.ns * 9; idx += T) { double a, b; gather2(R, idx, a, b); xs[idx] = combine(a, b); }   // more than 28 segments: the rest, not prefetched
     __syncthreads();                                         // xs complete; everyone has taken its Jacobian out of Jbuf
     if (tid == 0 && it + 1 < my_tiles) issue(qn, blockIdx.x + (it + 1) * gridDim.x, cur ^ 1);
     double t0 = 0.0, t1 = 0.0;
@@ -720,7 +730,7 @@ __global__ void __launch_bounds__(T, SK_TMA_CTAS) k_ba_matvec_tma(const __grid_c
     __syncthreads(); __syncthreads(); __syncthreads();
     if (it + 1 < my_tiles) {
       mbar_wait(bar_rec + (cur ^ 1), (unsigned)(((it + 1) >> 1) & 1));
-      if (tid < qn.ns * 9) xpre = gather(rec_view(L, recbuf + (size_t)(cur ^ 1) * L.rec_stride), tid);
+      if (tid < qn.ns * 9) gather2(rec_view(L, recbuf + (size_t)(cur ^ 1) * L.rec_stride), tid, xpre, xpre2);
     }
     if (tid < q.ns * 9) seg_y[(size_t)q.sb * 9 + tid] = w[tid];
     q = qn; qn = qnn;
@@ -757,7 +767,7 @@ __global__ void __launch_bounds__(T, SK_TMA_CTAS) k_ba_matvec_tma(const __grid_c
     __syncthreads();
     if (it + 1 < my_tiles) {                                 // start the next tile's input gather behind the segment sums
       mbar_wait(bar_rec + (cur ^ 1), (unsigned)(((it + 1) >> 1) & 1));
-      if (tid < qn.ns * 9) xpre = gather(rec_view(L, recbuf + (size_t)(cur ^ 1) * L.rec_stride), tid);
+      if (tid < qn.ns * 9) gather2(rec_view(L, recbuf + (size_t)(cur ^ 1) * L.rec_stride), tid, xpre, xpre2);
     }
     if (CHUNKED) seg_sums_chunked(R, q.ns, q.sb, v, ps, seg_y);
     else {
@@ -773,7 +783,7 @@ __global__ void __launch_bounds__(T, SK_TMA_CTAS) k_ba_matvec_tma(const __grid_c
           sum += x0; sum += x1; sum += x2; sum += x3;
         }
         for (; pos < (SK_ABLATE >= 1 ? b + 1 : e); ++pos) sum += vk[R.sperm[pos]];
-        seg_y[(size_t)(q.sb + s) * 9 + k] = sum;
+        seg_y[(size_t)R.spos[s] * 9 + k] = sum;
       }
     }
     q = qn; qn = qnn;
@@ -840,11 +850,15 @@ __global__ void __launch_bounds__(T2, 2) k_ba_matvec_rows(const __grid_constant_
   };
   const bool dir_is_z = pcg != nullptr && pcg->iter == 1;
   const double beta = (pcg != nullptr && !dir_is_z) ? pcg->beta : 0.0;
-  auto gather = [&](const RecView& R, int idx) {
+  const double* va = (pcg == nullptr) ? p : zdir;            // see k_ba_matvec_tma: raw operands now, multiply-add at the consumer
+  const bool two = pcg != nullptr && !dir_is_z;
+  auto gather2 = [&](const RecView& R, int idx, double& a, double& b) {
     const int s = idx / 9, k = idx - s * 9;
     const size_t e = (size_t)R.scam[s] * 9 + k;
-    return (pcg == nullptr) ? p[e] : (dir_is_z ? zdir[e] : (zdir[e] + beta * p[e]));
+    a = va[e];
+    b = two ? p[e] : 0.0;
   };
+  auto combine = [&](double a, double b) { return two ? __fma_rn(beta, b, a) : a; };
   // element (plane k, observation i, row) of the staged Jacobian
   const int jbase = TMAP ? (((i >> 7) * kJPlanes * (T / 2) + (i & 127)) * 2 + row) : (i * 2 + row);
   constexpr int jstride = TMAP ? T : 2 * T;                  // doubles between planes
@@ -853,8 +867,8 @@ __global__ void __launch_bounds__(T2, 2) k_ba_matvec_rows(const __grid_constant_
   if (my_tiles > 1) qn = header(1);
   if (tid == 0) issue(q, blockIdx.x, 0);
   mbar_wait(bar_rec, 0);
-  double xpre = 0.0;
-  if (tid < q.ns * 9) xpre = gather(rec_view(L, recbuf), tid);
+  double xpre = 0.0, xpre2 = 0.0;
+  if (tid < q.ns * 9) gather2(rec_view(L, recbuf), tid, xpre, xpre2);
   for (int it = 0; it < my_tiles; ++it) {
     const int cur = it & 1;
     const unsigned par = (unsigned)((it >> 1) & 1);
@@ -879,8 +893,8 @@ __global__ void __launch_bounds__(T2, 2) k_ba_matvec_rows(const __grid_constant_
 #pragma unroll
       for (int k = 0; k < 3; ++k) E[k] = 0.0;
     }
-    if (tid < q.ns * 9) xs[tid] = xpre;
-    for (int idx = tid + T2; idx < q.ns * 9; idx += T2) xs[idx] = gather(R, idx);
+    if (tid < q.ns * 9) xs[tid] = combine(xpre, xpre2);
+    for (int idx = tid + T2; idx < q.ns * 9; idx += T2) { double a, b; gather2(R, idx, a, b); xs[idx] = combine(a, b); }
     __syncthreads();                                         // xs complete; everyone has taken its Jacobian out of Jbuf
     if (tid == 0 && it + 1 < my_tiles) issue(qn, blockIdx.x + (it + 1) * gridDim.x, cur ^ 1);
     const double t = row_dot9(F, xs + slot * 9);             // inactive lanes: slot 0, F = 0 (they still take part in the shuffles)
@@ -915,7 +929,7 @@ __global__ void __launch_bounds__(T2, 2) k_ba_matvec_rows(const __grid_constant_
     __syncthreads();
     if (it + 1 < my_tiles) {
       mbar_wait(bar_rec + (cur ^ 1), (unsigned)(((it + 1) >> 1) & 1));
-      if (tid < qn.ns * 9) xpre = gather(rec_view(L, recbuf + (size_t)(cur ^ 1) * L.rec_stride), tid);
+      if (tid < qn.ns * 9) gather2(rec_view(L, recbuf + (size_t)(cur ^ 1) * L.rec_stride), tid, xpre, xpre2);
     }
     if (CHUNKED) seg_sums_chunked<T2>(R, q.ns, q.sb, v, ps, seg_y);
     else {
@@ -931,7 +945,7 @@ __global__ void __launch_bounds__(T2, 2) k_ba_matvec_rows(const __grid_constant_
           sum += x0; sum += x1; sum += x2; sum += x3;
         }
         for (; pos < e; ++pos) sum += vk[R.sperm[pos]];
-        seg_y[(size_t)(q.sb + s) * 9 + k] = sum;
+        seg_y[(size_t)R.spos[s] * 9 + k] = sum;
       }
     }
     q = qn; qn = qnn;
@@ -1155,7 +1169,7 @@ __global__ void __launch_bounds__(T) k_ba_matvec_giant(BaDev L, const double2* _
       for (int idx = tid; idx < q.ns * 9; idx += T) {
         const int s = idx / 9, k = idx - s * 9;
         const size_t e = (size_t)L.seg_cam[q.sb + s] * 9 + k;
-        xs[idx] = (pcg == nullptr) ? p[e] : ((pcg->iter == 1) ? zdir[e] : (zdir[e] + pcg->beta * p[e]));
+        xs[idx] = (pcg == nullptr) ? p[e] : ((pcg->iter == 1) ? zdir[e] : __fma_rn(pcg->beta, p[e], zdir[e]));
       }
       __syncthreads();
       double t0 = 0.0, t1 = 0.0;
@@ -1180,7 +1194,7 @@ __global__ void __launch_bounds__(T) k_ba_matvec_giant(BaDev L, const double2* _
           for (int k = 0; k < 9; ++k) v[k * VLD + tid] = Fv[k].x * s0 + Fv[k].y * s1;
         }
         __syncthreads();
-        seg_reduce9(L, q, v, seg_y, 9, 0);
+        seg_reduce9(L, q, v, seg_y, 9, 0, L.seg_pos);
         __syncthreads();
       }
     }

@@ -19,10 +19,11 @@ struct BaDev {
   // per-tile metadata records for the prefetching matvec (ba_kernels.cu: RecView); nullptr when not built
   const unsigned char* tile_rec; int rec_stride, rec_sp, rec_pp, rec_sc;
   int matvec_classic;                  // 0: k_ba_matvec_tma; 1: k_ba_matvec (SKERES_MATVEC=classic); 2: k_ba_matvec_rows (SKERES_MATVEC=rows); read per solver
-  int matvec_serial_sums;              // 1: per-point / per-segment sums as one serial chain each (the round-1 order;
-                                       // SKERES_MATVEC_SUMS=serial, development A/B) instead of the chunked two-level sums
+  int matvec_serial_sums;              // 1 (default): per-point / per-segment sums as one serial chain each; 0: the chunked
+                                       // two-level sums (SKERES_MATVEC_SUMS=chunked)
   const unsigned short* obs_slot; const unsigned short* obs_ptl; const unsigned short* seg_perm;
   const int* seg_ptr; const int* seg_cam; const int* cam_seg_ptr; const int* cam_seg;
+  const int* seg_pos;                  // [S] inverse of cam_seg: the implicit-Schur product stores a segment's partial at its camera-major position
   const double2* obs;   // [n_obs] observed (x, y)
 };
 
@@ -65,7 +66,8 @@ void launch_ba_schur_setup(const BaDev& L, const double2* J2, const double2* r2,
 void launch_ba_precond_invert(const BaDev& L, const double* M45 /*[C][45]*/, const double* D, double* Minv,
                               int* error_flag, cudaStream_t s);
 
-// Implicit Schur product partials: seg_y[S][9] of  F^T (F p - E (E^T E)^-1 E^T F p)
+// Implicit Schur product partials: seg_y[S][9] of  F^T (F p - E (E^T E)^-1 E^T F p), stored CAMERA-major (row seg_pos[s]): the
+// partials of camera c are rows [cam_seg_ptr[c], cam_seg_ptr[c + 1]) -- contiguous for the second-level sums (pcg_kernels.cu)
 struct PcgDev;
 void launch_ba_matvec(const BaDev& L, const double2* J2, const double* p, const double* zdir, const PcgDev* pcg, const double* einv,
                       double* seg_y, const int* guard, cudaStream_t s, const CUtensorMap* tmapJ = nullptr);

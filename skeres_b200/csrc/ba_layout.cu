@@ -295,12 +295,14 @@ void build_tile_records(const BaLayoutHost& H, TileRecDims* dims, std::vector<un
   const size_t stride = (size_t)D.stride;
   out->assign((size_t)std::max(H.n_tiles, 1) * stride, 0);
   unsigned char* rec = out->data();
+  std::vector<int32_t> seg_pos((size_t)H.n_segs);            // inverse of cam_seg: position of a segment in the camera-major list
+  for (int32_t t = 0; t < H.n_segs; ++t) seg_pos[H.cam_seg[t]] = t;
   parallel_for(H.n_tiles, [&](int64_t t_begin, int64_t t_end) {
   for (int64_t t = t_begin; t < t_end; ++t) {
     unsigned char* base = rec + (size_t)t * stride;
     uint16_t* slot = reinterpret_cast<uint16_t*>(base); uint16_t* ptl = slot + T; uint16_t* sperm = ptl + T; uint16_t* srank = sperm + T;
-    int32_t* sptr = reinterpret_cast<int32_t*>(base + 8 * T); int32_t* pptr = sptr + sp; int32_t* scam = pptr + pp;
-    uint16_t* pchunk = reinterpret_cast<uint16_t*>(scam + sp); uint16_t* pcptr = pchunk + T; uint16_t* schunk = pcptr + pp; uint16_t* scptr = schunk + sc;
+    int32_t* sptr = reinterpret_cast<int32_t*>(base + 8 * T); int32_t* pptr = sptr + sp; int32_t* scam = pptr + pp; int32_t* spos = scam + sp;
+    uint16_t* pchunk = reinterpret_cast<uint16_t*>(spos + sp); uint16_t* pcptr = pchunk + T; uint16_t* schunk = pcptr + pp; uint16_t* scptr = schunk + sc;
     const int ob = H.tile_obs[t], no = H.tile_obs[t + 1] - ob, pb = H.tile_pt[t], np = H.tile_np[t];
     const int sb = H.tile_seg[t], ns = H.tile_seg[t + 1] - sb;
     for (int j = 0; j < no; ++j) {
@@ -308,7 +310,7 @@ void build_tile_records(const BaLayoutHost& H, TileRecDims* dims, std::vector<un
       srank[H.seg_perm[ob + j]] = (uint16_t)j;
     }
     for (int s = 0; s <= ns; ++s) sptr[s] = H.seg_ptr[sb + s] - ob;
-    for (int s = 0; s < ns; ++s) scam[s] = H.seg_cam[sb + s];
+    for (int s = 0; s < ns; ++s) { scam[s] = H.seg_cam[sb + s]; spos[s] = seg_pos[sb + s]; }
     int nc = 0;
     for (int s = 0; s < ns; ++s) {                           // segment s = positions [sptr[s], sptr[s + 1]) of the camera-sorted order
       scptr[s] = (uint16_t)nc;

@@ -43,6 +43,9 @@ BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHo
   d_pt_ptr_.upload(H.pt_ptr, s); d_obs_slot_.upload(H.obs_slot, s); d_obs_ptl_.upload(H.obs_ptl, s);
   d_seg_perm_.upload(H.seg_perm, s); d_seg_ptr_.upload(H.seg_ptr, s); d_seg_cam_.upload(H.seg_cam, s);
   d_cam_seg_ptr_.upload(H.cam_seg_ptr, s); d_cam_seg_.upload(H.cam_seg, s);
+  std::vector<int> seg_pos((size_t)H.n_segs);
+  for (int t = 0; t < H.n_segs; ++t) seg_pos[H.cam_seg[t]] = t;
+  d_seg_pos_.upload(seg_pos, s);
   d_obs_.alloc((size_t)2 * H.n_obs); d_obs_.upload(H.obs_src, (size_t)2 * H.n_obs, s);   // possibly the caller's own array
   // device encoding of the tile kind: > 0 points of a regular tile, < 0 chunk tile of a long track (ordinal = -v - 1)
   std::vector<int> tile_np_enc((size_t)H.n_tiles);
@@ -57,13 +60,15 @@ BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHo
   L_.max_seg_tile = std::max(H.max_seg_tile, 1); L_.max_pt_tile = std::max(H.max_pt_tile, 1);
   L_.tile_obs = d_tile_obs_.p; L_.tile_pt = d_tile_pt_.p; L_.tile_seg = d_tile_seg_.p; L_.pt_ptr = d_pt_ptr_.p;
   L_.obs_slot = d_obs_slot_.p; L_.obs_ptl = d_obs_ptl_.p; L_.seg_perm = d_seg_perm_.p; L_.seg_ptr = d_seg_ptr_.p;
-  L_.seg_cam = d_seg_cam_.p; L_.cam_seg_ptr = d_cam_seg_ptr_.p; L_.cam_seg = d_cam_seg_.p;
+  L_.seg_cam = d_seg_cam_.p; L_.cam_seg_ptr = d_cam_seg_ptr_.p; L_.cam_seg = d_cam_seg_.p; L_.seg_pos = d_seg_pos_.p;
   L_.obs = reinterpret_cast<const double2*>(d_obs_.p);
   L_.n_giant = H.n_giant; L_.n_chunks = H.n_chunks; L_.tile_np = d_tile_np_.p;
   L_.gp_tile_begin = d_gp_begin_.p; L_.gp_tile_count = d_gp_count_.p; L_.gp_point = d_gp_point_.p;
   L_.tile_rec = nullptr; L_.rec_stride = L_.rec_sp = L_.rec_pp = L_.rec_sc = 0;
   { const char* e = getenv("SKERES_MATVEC"); L_.matvec_classic = (e != nullptr && e[0] == 'c') ? 1 : (e != nullptr && e[0] == 'r') ? 2 : 0; }
-  { const char* e = getenv("SKERES_MATVEC_SUMS"); L_.matvec_serial_sums = (e != nullptr && e[0] == 's') ? 1 : 0; }
+  // per-point / per-segment sums of the product: serial chains (default: measured 1.5 % faster back to back, r02) or the chunked
+  // two-level sums (SKERES_MATVEC_SUMS=chunked)
+  { const char* e = getenv("SKERES_MATVEC_SUMS"); L_.matvec_serial_sums = (e != nullptr && e[0] == 'c') ? 0 : 1; }
   const int64_t nc = (int64_t)9 * H.n_cams, n = nc + (int64_t)3 * H.n_pts;
   allocate(n, nc);
   J2_.alloc((size_t)2 * kJPlanes * std::max(H.n_obs, 1)); r2_.alloc((size_t)2 * std::max(H.n_obs, 1));

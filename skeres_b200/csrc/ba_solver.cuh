@@ -48,7 +48,7 @@ class BaSolver : public LmSolver {
   bool local_blocks_ = false;          // this rank was given only its own residual blocks (no publication of foreign points)
   int64_t total_obs_ = 0, total_param_blocks_ = 0, total_params_ = 0;
   std::vector<int64_t> all_pt_off_;
-  DBuf<int> d_tile_obs_, d_tile_pt_, d_tile_seg_, d_pt_ptr_, d_seg_ptr_, d_seg_cam_, d_cam_seg_ptr_, d_cam_seg_;
+  DBuf<int> d_tile_obs_, d_tile_pt_, d_tile_seg_, d_pt_ptr_, d_seg_ptr_, d_seg_cam_, d_cam_seg_ptr_, d_cam_seg_, d_seg_pos_;
   DBuf<int> d_tile_np_, d_gp_begin_, d_gp_count_, d_gp_point_;   // long tracks (ba_layout.h)
   CUtensorMap tmapJ_{}; bool have_tmapJ_ = false;                // 2-D TMA view of J2_ (prefetching matvec)
   DBuf<unsigned char> d_tile_rec_;                               // per-tile metadata records (prefetching matvec)

@@ -22,16 +22,18 @@ constexpr int kPtChunk = 4, kSegChunk = 8;
 constexpr int kSegRow = 9;                 // row stride of the segment-ordered staging of v (odd: conflict-free scatter)
 
 // Record of one tile (all starts relative to the tile's first observation):
-//   u16 slot[T] | u16 ptl[T] | u16 sperm[T] | u16 srank[T] | i32 sptr[sp] | i32 pptr[pp] | i32 scam[sp]
+//   u16 slot[T] | u16 ptl[T] | u16 sperm[T] | u16 srank[T] | i32 sptr[sp] | i32 pptr[pp] | i32 scam[sp] | i32 spos[sp]
 //   | u16 pchunk[T] | u16 pcptr[pp] | u16 schunk[sc] | u16 scptr[sp]
 // slot / ptl = tile-local segment and point of an observation; sperm = tile-local observation ids in (segment, point) order,
 // srank its inverse; sptr / pptr = first position of every segment (in sperm order) / first observation of every point;
-// scam = camera of a segment; pchunk / schunk = chunks of the two-level sums (first position | (length - 1) << 8);
+// scam = camera of a segment, spos = where the segment's partial sum goes: its position in the CAMERA-major list of all
+// segments (BaLayoutHost::cam_seg), so that the partials of one camera are contiguous for the second-level sums;
+// pchunk / schunk = chunks of the two-level sums (first position | (length - 1) << 8);
 // pcptr / scptr = first chunk of every point / segment.
 struct TileRecDims { int stride, sp, pp, sc; };
 struct RecView {
   const unsigned short* slot; const unsigned short* ptl; const unsigned short* sperm; const unsigned short* srank;
-  const int* sptr; const int* pptr; const int* scam;
+  const int* sptr; const int* pptr; const int* scam; const int* spos;
   const unsigned short* pchunk; const unsigned short* pcptr; const unsigned short* schunk; const unsigned short* scptr;
 };
 SK_HD RecView rec_view(const unsigned char* base, int sp, int pp, int sc) {
@@ -40,8 +42,8 @@ SK_HD RecView rec_view(const unsigned char* base, int sp, int pp, int sc) {
   r.slot = reinterpret_cast<const unsigned short*>(base);
   r.ptl = r.slot + T; r.sperm = r.ptl + T; r.srank = r.sperm + T;
   r.sptr = reinterpret_cast<const int*>(base + 8 * T);
-  r.pptr = r.sptr + sp; r.scam = r.pptr + pp;
-  r.pchunk = reinterpret_cast<const unsigned short*>(r.scam + sp);
+  r.pptr = r.sptr + sp; r.scam = r.pptr + pp; r.spos = r.scam + sp;
+  r.pchunk = reinterpret_cast<const unsigned short*>(r.spos + sp);
   r.pcptr = r.pchunk + T; r.schunk = r.pcptr + pp; r.scptr = r.schunk + sc;
   return r;
 }
@@ -50,7 +52,7 @@ inline TileRecDims tile_rec_dims(int max_seg_tile, int max_pt_tile) {
   TileRecDims d;
   d.sp = (max_seg_tile + 1 + 3) & ~3; d.pp = (max_pt_tile + 1 + 3) & ~3;
   d.sc = (T / kSegChunk + max_seg_tile + 1 + 7) & ~7;
-  d.stride = (int)(((size_t)8 * T + 4 * ((size_t)2 * d.sp + d.pp) + 2 * ((size_t)T + d.pp + d.sc + d.sp) + 15) & ~(size_t)15);
+  d.stride = (int)(((size_t)8 * T + 4 * ((size_t)3 * d.sp + d.pp) + 2 * ((size_t)T + d.pp + d.sc + d.sp) + 15) & ~(size_t)15);
   return d;
 }
 // Packs the records of all tiles (host, threaded).  out: n_tiles * dims.stride bytes.

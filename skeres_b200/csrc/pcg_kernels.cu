@@ -273,18 +273,18 @@ __device__ bool pcg_last_block(PcgDev* st) {
 // one GPU), 2 or 1 when the cameras of a larger problem are spread over more ranks and each rank holds few partials per camera
 // -- four warps walking two partials each made these kernels six waves of near-empty CTAs at 14,224 cameras.
 
-// acc = seg_y[cam_seg[t]][k] + seg_y[cam_seg[t + 3 WPC]][k] + ... in that order, four partials in flight (the walk is a
-// chain of dependent index -> value loads out of L2 otherwise).
+// acc = seg_y[t][k] + seg_y[t + 3 WPC][k] + ... in that order, four partials in flight.  The product kernels store a segment's
+// partial at its camera-major position (BaDev::seg_pos), so a camera's partials are the contiguous rows [cam_seg_ptr[c],
+// cam_seg_ptr[c + 1]) in tile order: no index is read on the way.
 template <int WPC>
 __device__ __forceinline__ double walk_segments(const BaDev& L, const double* __restrict__ seg_y, int t, int e, int k) {
   constexpr int S = 3 * WPC;
   double acc = 0.0;
   for (; t + 3 * S < e; t += 4 * S) {
-    const int s0 = L.cam_seg[t], s1 = L.cam_seg[t + S], s2 = L.cam_seg[t + 2 * S], s3 = L.cam_seg[t + 3 * S];
-    const double x0 = seg_y[(size_t)s0 * 9 + k], x1 = seg_y[(size_t)s1 * 9 + k], x2 = seg_y[(size_t)s2 * 9 + k], x3 = seg_y[(size_t)s3 * 9 + k];
+    const double x0 = seg_y[(size_t)t * 9 + k], x1 = seg_y[(size_t)(t + S) * 9 + k], x2 = seg_y[(size_t)(t + 2 * S) * 9 + k], x3 = seg_y[(size_t)(t + 3 * S) * 9 + k];
     acc += x0; acc += x1; acc += x2; acc += x3;
   }
-  for (; t < e; t += S) acc += seg_y[(size_t)L.cam_seg[t] * 9 + k];
+  for (; t < e; t += S) acc += seg_y[(size_t)t * 9 + k];
   return acc;
 }
 
@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(WPB * WPC * 32) k_pcg_reduce(BaDev L, const do
     } else acc = y_in[(size_t)c * 9 + lane];
     const size_t e = (size_t)c * 9 + lane;
     const double zk = z[e];
-    const double pk = (st->iter == 1) ? zk : (zk + st->beta * p[e]);
+    const double pk = (st->iter == 1) ? zk : __fma_rn(st->beta, p[e], zk);
     const double d = D[e];
     const double qk = (d * d) * pk + acc;
     p[e] = pk; z[e] = qk;
@@ -412,7 +412,7 @@ __global__ void k_pcg_resid2(BaDev L, const double* __restrict__ seg_y, const do
     if (peer) { if (lane < 9) acc = peer_gather(win, parity, c, (size_t)c * 9 + lane); }
     else if (y_in == nullptr) {
       if (lane < 27)
-        for (int t = L.cam_seg_ptr[c] + j; t < L.cam_seg_ptr[c + 1]; t += 3) acc += seg_y[(size_t)L.cam_seg[t] * 9 + k];
+        for (int t = L.cam_seg_ptr[c] + j; t < L.cam_seg_ptr[c + 1]; t += 3) acc += seg_y[(size_t)t * 9 + k];
       const double a1 = __shfl_down_sync(0xffffffffu, acc, 9), a2 = __shfl_down_sync(0xffffffffu, acc, 18);
       acc = (acc + a1) + a2;
     } else if (lane < 9) acc = y_in[(size_t)c * 9 + lane];

@@ -80,6 +80,8 @@ void hc_check_two_level_sums(const HcLayout* h, uint64_t seed, double* out) {
   sk::build_tile_records(H, &D, &rec);
   auto rnd = [&seed]() { seed = seed * 6364136223846793005ull + 1442695040888963407ull; return (double)((seed >> 11) & 0xfffff) / 1048576.0 - 0.5; };
   double e_pt = 0, e_seg = 0, n = 0; bool cover = true;
+  std::vector<int> seg_pos((size_t)H.n_segs);
+  for (int t = 0; t < H.n_segs; ++t) seg_pos[H.cam_seg[t]] = t;
   std::vector<double> w(3 * T), pw(3 * T), vs((size_t)T * sk::kSegRow), ps((size_t)sk::seg_chunk_scratch(std::max(H.max_seg_tile, 1))), v(9 * T);
   for (int t = 0; t < H.n_tiles; ++t) {
     if (H.tile_chunk[t] >= 0) continue;
@@ -106,6 +108,7 @@ void hc_check_two_level_sums(const HcLayout* h, uint64_t seed, double* out) {
         for (int j = st; j < st + len; ++j) seen[j]++;
       }
     for (int i = 0; i < no; ++i) if (seen[i] != 1 || R.srank[R.sperm[i]] != i) cover = false;
+    for (int s = 0; s < ns; ++s) if (R.spos[s] != seg_pos[sb + s] || R.scam[s] != H.seg_cam[sb + s]) cover = false;   // camera-major output row
     // point sums
     const int n3 = 3 * R.pcptr[np];
     for (int idx = 0; idx < n3; ++idx) pw[idx] = sk::point_chunk_sum(R, w.data(), idx);

@@ -475,20 +475,24 @@ def test_ba_long_tracks_iterative_schur(sk, oracle, case, prec, max_it):
 
 @pytest.mark.parametrize("case", [LONG_TRACK_CASE, LONG_TRACK_SMALL])
 def test_ba_long_tracks_schur_jacobi_full_run(sk, oracle, case):
-    """Full SCHUR_JACOBI runs.  Once a PCG solve needs 50+ iterations the two sides drift apart (row costs 5e-6, radii
-    4e-4, parameters 1.6e-2 measured) -- on the same problem WITHOUT long tracks just as much (5.6e-7 after one
-    iteration), and not at all with JACOBI: the block F'F - G'(E'E)^-1 G is formed by cancellation, so its inverse
-    depends on summation order and a truncated (eta 0.1) solve inherits that.  DESIGN.md parity gap 1.  What is
-    well-defined is checked: termination, iteration structure, PCG counts within 10 %, costs."""
+    """Full SCHUR_JACOBI runs at Ceres' default eta on the long-track problems: the least well-conditioned cases of the suite.
+    The oracle itself does not reproduce its own run here under a rounding-level perturbation -- against its -ffp-contract=fast
+    build the parameters move by 4e-2, and with the eliminator's two sums merely accumulated separately it takes 13 LM rows
+    instead of 7 and ends 9e-5 away in cost (tests/golden/schur_jacobi_rounding_envelope.json, "long-tracks").  So rows are
+    compared one by one only up to the first PCG solve of 50+ iterations (before it the two sides agree to 1e-9); after it what
+    is asserted is what survives such perturbations: both sides converge, and to the same cost within 10 x the envelope."""
     d = synth.make_bal(**case)
     p, so = oracle_ba(oracle, d, _abi.ITERATIVE_SCHUR, _abi.SCHUR_JACOBI)
     bal, s = gpu_ba(sk, d, _abi.ITERATIVE_SCHUR, _abi.SCHUR_JACOBI)
-    assert s.termination_type == so.termination_type == _abi.CONVERGENCE and len(s.iterations) == len(so.iterations)
+    assert s.termination_type == so.termination_type == _abi.CONVERGENCE
     for a, b in zip(s.iterations, so.iterations):
         assert (a.step_is_valid, a.step_is_successful) == (b.step_is_valid, b.step_is_successful)
-        assert abs(a.linear_solver_iterations - b.linear_solver_iterations) <= max(2, 0.1 * b.linear_solver_iterations)
-        assert np.isclose(a.cost, b.cost, rtol=2e-5)                    # measured worst row: 5.4e-6
-    assert abs(s.final_cost - so.final_cost) <= COST_RTOL * abs(so.final_cost)   # measured 6.8e-8 / 4.9e-9
+        assert np.isclose(a.cost, b.cost, rtol=1e-9) and a.linear_solver_iterations == b.linear_solver_iterations
+        if b.linear_solver_iterations >= 50:
+            break
+    env = load("schur_jacobi_rounding_envelope.json")["cases"]["long-tracks/SCHUR_JACOBI/eta0.1"]
+    bound = 10.0 * max(v["final_cost_rel_diff"] for v in env.values() if isinstance(v, dict))
+    assert abs(s.final_cost - so.final_cost) <= max(COST_RTOL, bound) * abs(so.final_cost)
 
 
 def test_ba_long_tracks_first_iteration_is_exact(sk, oracle):
