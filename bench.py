@@ -81,7 +81,7 @@ def source_hash():
     """sha256 (first 16 hex digits) of the sources of the dominant kernel: the key of profiles/matvec_traffic.json."""
     import hashlib
     h = hashlib.sha256()
-    for f in ("ba_kernels.cu", "ba_tile_rec.h", "ba_kernels.cuh"):
+    for f in ("ba_product.cuh", "pcg_fused.cu", "pcg_device.cuh", "ba_tile_rec.h", "ba_kernels.cuh"):
         h.update(open(os.path.join(ROOT, "skeres_b200", "csrc", f), "rb").read())
     return h.hexdigest()[:16]
 
@@ -356,28 +356,53 @@ def main():
         dev_s = float(t.item())
     value = n_obs * done / dev_s
     hbm_peak, peak_src = load_peaks()
-    mv_launches = max(kl[3], 1)
-    mv_ms = kms[3] / mv_launches
     mv_bytes = matvec_algorithmic_bytes(o1, p1, n_cam)        # per GPU: its observations and points, every camera
-    achieved = mv_bytes / (mv_ms * 1e-3) / 1e9 if mv_ms > 0 else 0.0
+    KF = {n: i for i, n in enumerate(_abi.KF_NAMES)}
+    products = int(kl[KF["schur_matvec"]])                    # implicit-Schur products executed in the timed region
+    fused = kl[KF["pcg_solve"]] > 0                           # the PCG loop ran as one persistent kernel per linear solve
+    if fused:
+        # dominant kernel = k_pcg_solve: CUDA events around each launch (one per linear solve); its algorithmic bytes are those of
+        # the products it executed.  The product phase alone (first CTA's device clock, incl. the grid barrier that ends it) is
+        # reported next to it.
+        dom_ms, dom_launches = float(kms[KF["pcg_solve"]]), int(kl[KF["pcg_solve"]])
+        dom_name = "k_pcg_solve (persistent fused PCG solve: implicit Schur products + vector phases behind grid barriers, one launch per linear solve)"
+        mv_ms = dom_ms / max(products, 1)                     # per product, vector phases and barriers included
+        product_phase_ms = float(kms[KF["schur_matvec"]]) / max(products, 1)
+        vector_phase_ms = float(kms[KF["pcg_vector"]]) / max(products, 1)
+    else:
+        dom_ms, dom_launches = float(kms[KF["schur_matvec"]]), products
+        dom_name = "k_ba_matvec_tma (implicit Schur product, PCG inner kernel)"
+        mv_ms = dom_ms / max(products, 1)
+        product_phase_ms = vector_phase_ms = None
+    achieved = products * mv_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     path_bytes = path_algorithmic_bytes(o1, p1, n_cam, A["jac"], A["cost"], A["lin"], int(kl[3]))
     path_gbs = path_bytes / dev_s / 1e9 if dev_s > 0 else 0.0
     traffic, traffic_src = ncu_traffic(o1) if world == 1 else (None, "single-GPU capture only")
-    pcg_ms = None if fam_ms is None or fam_launches[3] == 0 else float((fam_ms[3] + fam_ms[4] + fam_ms[8]) / fam_launches[3])
-    roofline = {"bound": "hbm", "kernel": "k_ba_matvec_tma (implicit Schur product, PCG inner kernel)", "achieved": achieved, "peak": hbm_peak,
+    if fused:
+        pcg_ms = mv_ms
+    else:
+        pcg_ms = None if fam_ms is None or fam_launches[3] == 0 else float((fam_ms[3] + fam_ms[4] + fam_ms[8]) / fam_launches[3])
+    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": hbm_peak,
                 "unit": "GB/s", "frac": achieved / hbm_peak, "frac_of_nominal_8000_GBps": achieved / 8000.0,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": mv_bytes, "avg_launch_ms": mv_ms, "launches": int(kl[3]),
+                "algorithmic_bytes_per_launch": products * mv_bytes / max(dom_launches, 1), "avg_launch_ms": dom_ms / max(dom_launches, 1),
+                "launches": dom_launches,
+                "algorithmic_bytes_per_product": mv_bytes, "products": products, "ms_per_product": mv_ms,
+                "product_phase_ms": product_phase_ms, "vector_phase_ms_per_product": vector_phase_ms,
+                "product_phase_frac": None if not product_phase_ms else mv_bytes / (product_phase_ms * 1e-3) / 1e9 / hbm_peak,
+                "phase_note": "inside k_pcg_solve: time its first CTA spent in the product passes (incl. the grid barrier that ends each) / in the "
+                              "vector phases, on the device clock (globaltimer); CUDA events cannot split one launch" if fused else None,
                 "avg_launch_ms_back_to_back": mv_alone_ms,
-                "share_of_step_device_time": float(kms[3] / (dev_s * 1e3)) if dev_s > 0 else None,
-                "events_in_timed_region": "k_ba_matvec only",
+                "share_of_step_device_time": float(dom_ms / (dev_s * 1e3)) if dev_s > 0 else None,
+                "events_in_timed_region": "k_pcg_solve only" if fused else "k_ba_matvec only",
                 # the whole per-iteration path (evaluate + eliminate + PCG + back-substitution + LM control), per GPU:
                 # algorithmic bytes of every evaluation / set-up / product executed in the timed region over its device time
                 "path_frac": path_gbs / hbm_peak, "path_achieved_gbs": path_gbs, "path_algorithmic_bytes": path_bytes,
                 "path_counts": {"jacobian_evaluations": A["jac"], "residual_evaluations": A["cost"], "linear_solves": A["lin"], "schur_products": int(kl[3])},
                 "matvecs_per_step": float(kl[3]) / max(done, 1),
                 "pcg_iteration_ms": pcg_ms,
-                "pcg_iteration_ms_note": "(implicit Schur product + PCG vector kernels + exchange) device time per executed product, instrumented pass; "
+                "pcg_iteration_ms_note": "(implicit Schur product + PCG vector phases + exchange) device time per executed product"
+                                         + (" = k_pcg_solve event time / products, timed region; " if fused else ", instrumented pass; ") +
                                          "comparable across N because the N-scene workload executes the same products per step at every N",
                 "kernel_family_ms": None if fam_ms is None else {_abi.KF_NAMES[i]: float(fam_ms[i]) for i in range(_abi.KF_COUNT)},
                 "kernel_family_launches": None if fam_launches is None else {_abi.KF_NAMES[i]: int(fam_launches[i]) for i in range(_abi.KF_COUNT)},

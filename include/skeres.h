@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SKERES_ABI_VERSION 2
+#define SKERES_ABI_VERSION 3
 
 typedef enum sk_status {
   SK_OK = 0,
@@ -309,7 +309,12 @@ typedef enum sk_kernel_family {
   SK_KF_DENSE = 6,             /* dense QR / Cholesky                                          */
   SK_KF_LM = 7,                /* LM diagonal, step acceptance, radius update, small vector ops */
   SK_KF_COMM = 8,              /* NCCL allreduce                                               */
-  SK_KF_COUNT = 9
+  SK_KF_PCG_SOLVE = 9,         /* fused PCG solve: one persistent kernel per linear solve (products + vector phases).
+                                  When it runs, kernel_launches[SK_KF_SCHUR_MATVEC] counts the products executed INSIDE it and
+                                  (profile_kernels) kernel_ms[SK_KF_SCHUR_MATVEC] / [SK_KF_PCG_VECTOR] hold the time its first CTA
+                                  spent in the product / vector phases (device clock), kernel_ms[SK_KF_PCG_SOLVE] the CUDA-event
+                                  time of the launches */
+  SK_KF_COUNT = 10
 } sk_kernel_family;
 
 typedef struct sk_solver_summary_data {

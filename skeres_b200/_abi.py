@@ -5,7 +5,7 @@ test-side oracle binding (`tests/oracle_lib.py`) can share them.
 """
 import ctypes as C
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # sk_status
 OK, ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_UNSUPPORTED, ERR_NCCL, ERR_IO, ERR_INTERNAL = range(7)
@@ -44,7 +44,7 @@ TERMINATION_NAMES = {
 }
 
 KF_NAMES = ["evaluate_jacobian", "evaluate_cost", "schur_setup", "schur_matvec", "pcg_vector",
-            "back_substitute", "dense", "lm", "comm"]
+            "back_substitute", "dense", "lm", "comm", "pcg_solve"]
 KF_COUNT = len(KF_NAMES)
 
 COMM_UNIQUE_ID_BYTES = 128

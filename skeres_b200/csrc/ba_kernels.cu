@@ -22,26 +22,12 @@
 #include <cstdlib>
 #include <utility>
 
+#include "ba_product.cuh"
 #include "lm_kernels.cuh"
 
 namespace sk {
 
 namespace {
-
-constexpr int T = kTileObs;
-constexpr int VLD = T + 1;   // padded leading dimension of the per-observation staging planes
-
-struct Tile { int ob, no, pb, np, sb, ns, chunk; };   // chunk >= 0: chunk tile of a long track (np == 1), else -1
-
-__device__ __forceinline__ Tile load_tile(const BaDev& L, int t) {
-  Tile q;
-  q.ob = L.tile_obs[t]; q.no = L.tile_obs[t + 1] - q.ob;
-  q.pb = L.tile_pt[t];
-  const int np = L.tile_np[t];
-  q.np = np < 0 ? 1 : np; q.chunk = np < 0 ? -np - 1 : -1;
-  q.sb = L.tile_seg[t]; q.ns = L.tile_seg[t + 1] - q.sb;
-  return q;
-}
 
 // Sums of N per-thread values over the CTA, returned to EVERY thread (fixed shuffle tree, then the 8 warp totals in
 // warp order): used by the long-track kernels, which accumulate per-point sums chunk by chunk.  red: [N][8] doubles.
@@ -433,70 +419,6 @@ __device__ __forceinline__ void seg_reduce9_s(const Tile& q, const TileMetaSmem&
   }
 }
 
-// ---- two-level sums of the implicit-Schur product --------------------------------------------------------------------
-// Round 1 formed every per-point sum and every per-(segment, component) sum as ONE serial chain of dependent shared-memory
-// loads (up to 16 resp. 40 long) walked by ~50 resp. ~150 of the 256 threads while the others waited at the next barrier:
-// 45 % of the warp samples of the kernel sat behind those two barriers (profiles/r01_v9_matvec_tma_ncu_source_lines.txt).
-// Here every sum is cut into fixed-size chunks (4 observations of a point, 8 of a segment), all threads of the CTA add one
-// chunk each as a small tree from independent loads, and a second short pass adds the chunk sums of a point / segment in
-// order.  The order of additions is fixed by the chunk tables alone, so the prefetching and the classic kernel still agree
-// bit for bit.  w is staged [observation][3], v in the segment order [position][9] (odd strides: conflict-free writes), so
-// that a chunk is one contiguous run and no permutation is read on the way.
-constexpr int VS = kSegRow;                // row stride of the segment-ordered staging of v
-__device__ __forceinline__ RecView rec_view(const BaDev& L, const unsigned char* base) { return ::sk::rec_view(base, L.rec_sp, L.rec_pp, L.rec_sc); }
-
-// pw[3 c + k] = sum over chunk c of w[.][k]; then u = (E^T E)^-1 (sum of the point's chunk sums).  Two barriers inside.
-template <int NT = T>
-__device__ __forceinline__ void point_sums_chunked(const RecView& R, int np, const double* w, double* pw, const double* ei,
-                                                   double* u, int UP) {
-  const int tid = threadIdx.x;
-  const int n3 = 3 * (int)R.pcptr[np];
-  for (int idx = tid; idx < n3; idx += NT) pw[idx] = point_chunk_sum(R, w, idx);
-  __syncthreads();
-  if (tid < np) {
-    double a0, a1, a2;
-    point_combine(R, pw, tid, a0, a1, a2);
-    const double* m = ei + tid * 6;
-    u[tid] = m[0] * a0 + m[1] * a1 + m[2] * a2;
-    u[UP + tid] = m[1] * a0 + m[3] * a1 + m[4] * a2;
-    u[2 * UP + tid] = m[2] * a0 + m[4] * a1 + m[5] * a2;
-  }
-  __syncthreads();
-}
-
-// ps[9 c + k] = sum over chunk c of the segment-ordered v[.][k]; then seg_y[sb + s][k] = sum of the segment's chunk sums.
-template <int NT = T>
-__device__ __forceinline__ void seg_sums_chunked(const RecView& R, int ns, int sb, const double* vs, double* ps, double* seg_y) {
-  const int tid = threadIdx.x;
-  const int n9 = 9 * (int)R.scptr[ns];
-  for (int idx = tid; idx < n9; idx += NT) ps[idx] = seg_chunk_sum(R, vs, idx);
-  __syncthreads();
-  for (int idx = tid; idx < ns * 9; idx += NT) { const int s = idx / 9; seg_y[(size_t)R.spos[s] * 9 + (idx - 9 * s)] = seg_combine(R, ps, idx); }
-}
-
-// Arithmetic of one observation inside the implicit-Schur product, with every rounding spelled out: the three product kernels
-// (one thread per observation: k_ba_matvec, k_ba_matvec_tma; one thread per residual ROW: k_ba_matvec_rows) must agree bit for
-// bit, so nothing is left to the compiler's choice of multiply-add contraction.  A row's dot products are FMA chains; what
-// combines the two rows of an observation is one rounded product per row and one rounded sum (row 0 first) -- the form a pair
-// of lanes can evaluate with one shuffle.
-__device__ __forceinline__ double row_dot9(const double (&F)[9], const double* x) {        // F . x, FMA chain from 0
-  double t = 0.0;
-#pragma unroll
-  for (int k = 0; k < 9; ++k) t = __fma_rn(F[k], x[k], t);
-  return t;
-}
-__device__ __forceinline__ double row_minus_Eu(double t, const double (&E)[3], double u0, double u1, double u2) {   // t - E . u
-  return __dsub_rn(t, __fma_rn(E[2], u2, __fma_rn(E[1], u1, __dmul_rn(E[0], u0))));
-}
-__device__ __forceinline__ double two_rows(double a0, double b0, double a1, double b1) {   // a0 b0 + a1 b1, three roundings
-  return __dadd_rn(__dmul_rn(a0, b0), __dmul_rn(a1, b1));
-}
-
-// Input vector: `p` itself, or (pcg != nullptr) the PCG direction z + beta p formed on the fly (p = z in iteration 1).
-__device__ __forceinline__ void l2_prefetch(const void* gsrc, unsigned bytes) {   // TMA prefetch into L2: no registers, no smem
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gsrc), "r"(bytes) : "memory");
-}
-
 template <bool CHUNKED>
 __global__ void __launch_bounds__(T, 768 / T) k_ba_matvec(BaDev L, const double2* __restrict__ J2, const double* __restrict__ p,
                                                     const double* __restrict__ zdir, const PcgDev* pcg,
@@ -582,48 +504,13 @@ __global__ void __launch_bounds__(T, 768 / T) k_ba_matvec(BaDev L, const double2
 }
 
 // ------------------------------------------------------------------------------------------------
-// Persistent, fully prefetching variant of k_ba_matvec.  Same arithmetic in the same order (results agree with
-// k_ba_matvec up to the compiler's choice of multiply-add contraction), but each CTA walks a strided list of tiles and,
-// while it computes tile i from registers, the TMA engine streams EVERYTHING tile i+1 needs into shared memory:
-// the 12 Jacobian planes (12 bulk copies of <= 4 KB), the tile's metadata record (one bulk copy; packed per tile by
-// BaSolver::build_tile_records, layout: RecView) and the (E^T E)^-1 blocks of its points (one bulk copy).  One thread
-// issues the 14 copies; completion is tracked by mbarriers, so the copy costs no LSU issue slots -- with per-thread
-// cp.async the issue of the copies and the read-back took a third of a tile's time (profiles/r01_v5_matvec_*.md).
-// The gather of the input vector for tile i+1 is started into registers while tile i runs its segment sums.
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
-  asm volatile(
-      "{\n.reg .pred p;\nWAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(smem_u32(b)), "r"(parity) : "memory");
-}
-// One box of a 2-D tensor map (inner coordinate c0, outer c1) into shared memory, completion on an mbarrier.
-__device__ __forceinline__ void tma_box_2d(void* dst, const CUtensorMap* map, int c0, int c1, unsigned long long* b) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::
-               "r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(smem_u32(b)) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* b) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::
-               "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
-}
-
+// Persistent, fully prefetching variant of k_ba_matvec (ba_product.cuh: ProductPass).  Same arithmetic in the same order:
+// the two kernels give bit-identical solves (test_matvec_kernels_agree_bitwise).
+// TMAP: the Jacobian of a tile arrives as two [12 planes][128 observations] boxes of a 2-D tensor map over the plane-major
+// array (2 TMA instructions per tile) instead of 12 one-plane bulk copies.
 #ifndef SK_TMA_CTAS
 #define SK_TMA_CTAS (512 / T)
 #endif
-// Development only (never defined in the product build): timing ablations of k_ba_matvec_tma, results are WRONG by design.
-//   SK_ABLATE 1: the per-point and per-segment sums do no work (barriers kept)   2: ... and no arithmetic per observation
-//   3: only the copy pipeline: wait, Jacobian out of shared memory, one barrier, next copy
-#ifndef SK_ABLATE
-#define SK_ABLATE 0
-#endif
-// TMAP: the Jacobian of a tile arrives as two [12 planes][128 observations] boxes of a 2-D tensor map over the plane-major
-// array (2 TMA instructions per tile) instead of 12 one-plane bulk copies; Jbuf is then [2][12][T/2].
 template <bool TMAP, bool CHUNKED>
 __global__ void __launch_bounds__(T, SK_TMA_CTAS) k_ba_matvec_tma(const __grid_constant__ CUtensorMap tmapJ, BaDev L, const double2* __restrict__ J2, const double* __restrict__ p,
                                                               const double* __restrict__ zdir, const PcgDev* pcg,
@@ -631,325 +518,12 @@ __global__ void __launch_bounds__(T, SK_TMA_CTAS) k_ba_matvec_tma(const __grid_c
                                                               const int* guard) {
   if (guard != nullptr && *guard == 0) return;
   extern __shared__ __align__(128) double sm[];
-  const int tid = threadIdx.x;
-  double2* Jbuf = reinterpret_cast<double2*>(sm);            // [12][T] next tile's Jacobian
-  double* xs = sm + 2 * kJPlanes * T;                        // [max_seg][9]
-  double* v = xs + ((L.max_seg_tile * 9 + 1) & ~1);          // [9][VLD]   (xs padded to an even count: 16-byte alignment below)
-  double* w = v + 9 * VLD;                                   // [3][T]
-  const int UP = (L.max_pt_tile + 1) & ~1;
-  double* u = w + 3 * T;                                     // [3][UP]
-  double* ps = u + 3 * UP;                                   // [seg_chunk_scratch]  chunk sums of the segment sums (CHUNKED)
-  double* eibuf = ps + seg_chunk_scratch(L.max_seg_tile) + 1;   // 2 x [max_pt][6]   (+1: 9 * VLD is odd)
-  unsigned char* recbuf = reinterpret_cast<unsigned char*>(eibuf + 2 * (size_t)L.max_pt_tile * 6);   // 2 x rec_stride bytes
-  unsigned long long* bar_full = reinterpret_cast<unsigned long long*>(recbuf + 2 * (size_t)L.rec_stride);   // [2] Jacobian + einv
-  unsigned long long* bar_rec = bar_full + 2;                                                                // [2] record
-  const size_t O = (size_t)L.n_obs;
-  const int my_tiles = ((int)blockIdx.x < L.n_tiles) ? (L.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  if (my_tiles == 0) return;
-  if (tid == 0) {
-    mbar_init(bar_full, 1); mbar_init(bar_full + 1, 1); mbar_init(bar_rec, 1); mbar_init(bar_rec + 1, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-  }
-  __syncthreads();
-  auto header = [&](int it) {                                // chunk tiles of long tracks are empty work items here
-    Tile q = load_tile(L, blockIdx.x + it * gridDim.x);
-    if (q.chunk >= 0) { q.no = 0; q.np = 0; q.ns = 0; }
-    return q;
-  };
-  auto issue = [&](const Tile& q, int t, int buf) {          // thread 0: everything tile t needs, into ring slot `buf`
-    mbar_expect_tx(bar_rec + buf, (unsigned)L.rec_stride);
-    bulk_g2s(recbuf + (size_t)buf * L.rec_stride, L.tile_rec + (size_t)t * L.rec_stride, (unsigned)L.rec_stride, bar_rec + buf);
-    if (TMAP) {
-      static_assert(T == 256, "the tensor-map box is 128 observations: two boxes per tile");
-      const int boxes = (q.no + T / 2 - 1) / (T / 2);          // a box past the tile's end only brings the next tile's data
-      mbar_expect_tx(bar_full + buf, (unsigned)(boxes * kJPlanes * (T / 2) * 16 + q.np * 48));
-      for (int h = 0; h < boxes; ++h) tma_box_2d(Jbuf + h * kJPlanes * (T / 2), &tmapJ, 2 * (q.ob + h * (T / 2)), 0, bar_full + buf);
-    } else {
-      mbar_expect_tx(bar_full + buf, (unsigned)(q.no * kJPlanes * 16 + q.np * 48));
-      if (q.no > 0) {
-#pragma unroll
-        for (int k = 0; k < kJPlanes; ++k) bulk_g2s(Jbuf + k * T, J2 + k * O + q.ob, (unsigned)q.no * 16u, bar_full + buf);
-      }
-    }
-    if (q.np > 0) bulk_g2s(eibuf + (size_t)buf * L.max_pt_tile * 6, einv + (size_t)q.pb * 6, (unsigned)q.np * 48u, bar_full + buf);
-  };
+  ProductPass<TMAP, CHUNKED, false> P;
+  P.init(L, sm);
   // PCG direction z + beta p formed on the fly (p = z in iteration 1); the two scalars are read once, not per tile
   const bool dir_is_z = pcg != nullptr && pcg->iter == 1;
   const double beta = (pcg != nullptr && !dir_is_z) ? pcg->beta : 0.0;
-  // Element idx of the tile's input vector [ns][9] as its two RAW operands: the direction is z + beta p (or z, or p alone).
-  // The multiply-add is left to the consumer on purpose: the operands are fetched one tile ahead, behind the segment sums,
-  // and an arithmetic instruction placed right after the loads would make every warp wait for that L2 round trip on the spot
-  // (measured: +34 us per product, 0.2033 -> 0.2374 ms, with the fused form -- profiles/r02_matvec_timing_modes.md).
-  const double* va = (pcg == nullptr) ? p : zdir;            // first operand
-  const bool two = pcg != nullptr && !dir_is_z;              // second operand p, scaled by beta
-  auto gather2 = [&](const RecView& R, int idx, double& a, double& b) {
-    const int s = idx / 9, k = idx - s * 9;
-    const size_t e = (size_t)R.scam[s] * 9 + k;
-    a = va[e];
-    b = two ? p[e] : 0.0;
-  };
-  auto combine = [&](double a, double b) { return two ? __fma_rn(beta, b, a) : a; };
-  Tile q = header(0);
-  Tile qn = q;
-  if (my_tiles > 1) qn = header(1);
-  if (tid == 0) issue(q, blockIdx.x, 0);
-  mbar_wait(bar_rec, 0);
-  double xpre = 0.0, xpre2 = 0.0;                            // operands of element `tid` of the current tile's input vector
-  if (tid < q.ns * 9) gather2(rec_view(L, recbuf), tid, xpre, xpre2);
-  for (int it = 0; it < my_tiles; ++it) {
-    const int cur = it & 1;
-    const unsigned par = (unsigned)((it >> 1) & 1);
-    Tile qnn = qn;
-    if (it + 2 < my_tiles) qnn = header(it + 2);             // plain loads, consumed in the next iteration
-    const RecView R = rec_view(L, recbuf + (size_t)cur * L.rec_stride);
-    const double* ei = eibuf + (size_t)cur * L.max_pt_tile * 6;
-    const bool active = tid < q.no;
-    mbar_wait(bar_full + cur, par);                          // this tile's Jacobian and (E^T E)^-1 have landed
-    double2 Fv[9], Ev[3];
-    int slot = 0, ptl = 0, rank = 0;
-    if (active) {
-#pragma unroll
-      for (int k = 0; k < 9; ++k) Fv[k] = TMAP ? Jbuf[(tid >> 7) * kJPlanes * (T / 2) + k * (T / 2) + (tid & 127)] : Jbuf[k * T + tid];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) Ev[k] = TMAP ? Jbuf[(tid >> 7) * kJPlanes * (T / 2) + (9 + k) * (T / 2) + (tid & 127)] : Jbuf[(9 + k) * T + tid];
-      slot = R.slot[tid]; ptl = R.ptl[tid];
-      if (CHUNKED) rank = R.srank[tid];
-    }
-    if (tid < q.ns * 9) xs[tid] = combine(xpre, xpre2);
-    for (int idx = tid + T; idx < q.ns * 9; idx += T) { double a, b; gather2(R, idx, a, b); xs[idx] = combine(a, b); }   // more than 28 segments: the rest, not prefetched
-    __syncthreads();                                         // xs complete; everyone has taken its Jacobian out of Jbuf
-    if (tid == 0 && it + 1 < my_tiles) issue(qn, blockIdx.x + (it + 1) * gridDim.x, cur ^ 1);
-    double t0 = 0.0, t1 = 0.0;
-#if SK_ABLATE >= 3
-    if (active) { double a = 0.0; for (int k = 0; k < 9; ++k) a += Fv[k].x + Fv[k].y; for (int k = 0; k < 3; ++k) a += Ev[k].x + Ev[k].y; if (a == 1.2345e300) seg_y[tid] = a + slot + ptl + rank; }
-    q = qn; qn = qnn;
-    continue;
-#endif
-#if SK_ABLATE >= 2
-    if (active) { double a = 0.0; for (int k = 0; k < 9; ++k) a += Fv[k].x + Fv[k].y; for (int k = 0; k < 3; ++k) a += Ev[k].x + Ev[k].y; w[tid] = a; }
-    __syncthreads(); __syncthreads(); __syncthreads();
-    if (it + 1 < my_tiles) {
-      mbar_wait(bar_rec + (cur ^ 1), (unsigned)(((it + 1) >> 1) & 1));
-      if (tid < qn.ns * 9) gather2(rec_view(L, recbuf + (size_t)(cur ^ 1) * L.rec_stride), tid, xpre, xpre2);
-    }
-    if (tid < q.ns * 9) seg_y[(size_t)q.sb * 9 + tid] = w[tid];
-    q = qn; qn = qnn;
-    continue;
-#endif
-    if (active) {
-#pragma unroll
-      for (int k = 0; k < 9; ++k) { const double xk = xs[slot * 9 + k]; t0 = __fma_rn(Fv[k].x, xk, t0); t1 = __fma_rn(Fv[k].y, xk, t1); }
-#pragma unroll
-      for (int k = 0; k < 3; ++k) w[CHUNKED ? tid * 3 + k : k * T + tid] = two_rows(Ev[k].x, t0, Ev[k].y, t1);
-    }
-    __syncthreads();
-    if (CHUNKED) point_sums_chunked(R, q.np, w, v, ei, u, UP);
-    else {
-      if (tid < q.np) {
-        const int b = R.pptr[tid], e = R.pptr[tid + 1];
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-        for (int j = b; j < (SK_ABLATE >= 1 ? b + 1 : e); ++j) { a0 += w[j]; a1 += w[T + j]; a2 += w[2 * T + j]; }
-        const double* m = ei + tid * 6;
-        u[tid] = m[0] * a0 + m[1] * a1 + m[2] * a2;
-        u[UP + tid] = m[1] * a0 + m[3] * a1 + m[4] * a2;
-        u[2 * UP + tid] = m[2] * a0 + m[4] * a1 + m[5] * a2;
-      }
-      __syncthreads();
-    }
-    if (active) {
-      const double u0 = u[ptl], u1 = u[UP + ptl], u2 = u[2 * UP + ptl];
-      const double s0 = __dsub_rn(t0, __fma_rn(Ev[2].x, u2, __fma_rn(Ev[1].x, u1, __dmul_rn(Ev[0].x, u0))));
-      const double s1 = __dsub_rn(t1, __fma_rn(Ev[2].y, u2, __fma_rn(Ev[1].y, u1, __dmul_rn(Ev[0].y, u0))));
-      double* vt = CHUNKED ? v + rank * VS : v + tid;
-#pragma unroll
-      for (int k = 0; k < 9; ++k) vt[CHUNKED ? k : k * VLD] = two_rows(Fv[k].x, s0, Fv[k].y, s1);
-    }
-    __syncthreads();
-    if (it + 1 < my_tiles) {                                 // start the next tile's input gather behind the segment sums
-      mbar_wait(bar_rec + (cur ^ 1), (unsigned)(((it + 1) >> 1) & 1));
-      if (tid < qn.ns * 9) gather2(rec_view(L, recbuf + (size_t)(cur ^ 1) * L.rec_stride), tid, xpre, xpre2);
-    }
-    if (CHUNKED) seg_sums_chunked(R, q.ns, q.sb, v, ps, seg_y);
-    else {
-      for (int idx = tid; idx < q.ns * 9; idx += T) {
-        const int s = idx / 9, k = idx - s * 9;
-        const int b = R.sptr[s], e = R.sptr[s + 1];
-        const double* vk = v + k * VLD;
-        double sum = 0.0;
-        int pos = b;
-        for (; pos + 4 <= (SK_ABLATE >= 1 ? b : e); pos += 4) {
-          const int i0 = R.sperm[pos], i1 = R.sperm[pos + 1], i2 = R.sperm[pos + 2], i3 = R.sperm[pos + 3];
-          const double x0 = vk[i0], x1 = vk[i1], x2 = vk[i2], x3 = vk[i3];
-          sum += x0; sum += x1; sum += x2; sum += x3;
-        }
-        for (; pos < (SK_ABLATE >= 1 ? b + 1 : e); ++pos) sum += vk[R.sperm[pos]];
-        seg_y[(size_t)R.spos[s] * 9 + k] = sum;
-      }
-    }
-    q = qn; qn = qnn;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_ba_matvec_tma with one thread per residual ROW of an observation: 512 threads per tile, lanes 2i and 2i + 1 hold the x and
-// the y row of observation i (12 doubles of the Jacobian each instead of 24).  The two rows of an observation are independent
-// up to the sums -- t_r = F_r x, s_r = t_r - E_r u -- and what combines them (w = E_0^T t_0 + E_1^T t_1, v = F_0^T s_0 + F_1^T s_1)
-// is one product per lane and one shuffle.  Half the registers per thread, so twice the warps are resident per SM (32 instead of
-// 16) with the same shared memory: the round-1 kernel was bound by its warps' own latency at 25 % warp occupancy with nothing
-// saturated (profiles/r01_v11_summary.md).  Same pipeline (TMA ring, mbarriers, record), same sums, same bits as the
-// thread-per-observation kernels.
-constexpr int T2 = 2 * T;
-template <bool TMAP, bool CHUNKED>
-__global__ void __launch_bounds__(T2, 2) k_ba_matvec_rows(const __grid_constant__ CUtensorMap tmapJ, BaDev L, const double2* __restrict__ J2,
-                                                           const double* __restrict__ p, const double* __restrict__ zdir, const PcgDev* pcg,
-                                                           const double* __restrict__ einv, double* __restrict__ seg_y, const int* guard) {
-  if (guard != nullptr && *guard == 0) return;
-  extern __shared__ __align__(128) double sm[];
-  const int tid = threadIdx.x;
-  const int i = tid >> 1, row = tid & 1;                     // observation of the tile, residual row
-  double2* Jbuf = reinterpret_cast<double2*>(sm);            // [12][T] next tile's Jacobian
-  const double* Jrows = reinterpret_cast<const double*>(sm); // the same, as rows: element (plane, obs, row)
-  double* xs = sm + 2 * kJPlanes * T;                        // [max_seg][9]
-  double* v = xs + ((L.max_seg_tile * 9 + 1) & ~1);          // [9][VLD]
-  double* w = v + 9 * VLD;                                   // [3][T]
-  const int UP = (L.max_pt_tile + 1) & ~1;
-  double* u = w + 3 * T;                                     // [3][UP]
-  double* ps = u + 3 * UP;                                   // [seg_chunk_scratch]
-  double* eibuf = ps + seg_chunk_scratch(L.max_seg_tile) + 1;   // 2 x [max_pt][6]
-  unsigned char* recbuf = reinterpret_cast<unsigned char*>(eibuf + 2 * (size_t)L.max_pt_tile * 6);   // 2 x rec_stride bytes
-  unsigned long long* bar_full = reinterpret_cast<unsigned long long*>(recbuf + 2 * (size_t)L.rec_stride);
-  unsigned long long* bar_rec = bar_full + 2;
-  const size_t O = (size_t)L.n_obs;
-  const int my_tiles = ((int)blockIdx.x < L.n_tiles) ? (L.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  if (my_tiles == 0) return;
-  if (tid == 0) {
-    mbar_init(bar_full, 1); mbar_init(bar_full + 1, 1); mbar_init(bar_rec, 1); mbar_init(bar_rec + 1, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-  }
-  __syncthreads();
-  auto header = [&](int it) {
-    Tile q = load_tile(L, blockIdx.x + it * gridDim.x);
-    if (q.chunk >= 0) { q.no = 0; q.np = 0; q.ns = 0; }
-    return q;
-  };
-  auto issue = [&](const Tile& q, int t, int buf) {
-    mbar_expect_tx(bar_rec + buf, (unsigned)L.rec_stride);
-    bulk_g2s(recbuf + (size_t)buf * L.rec_stride, L.tile_rec + (size_t)t * L.rec_stride, (unsigned)L.rec_stride, bar_rec + buf);
-    if (TMAP) {
-      const int boxes = (q.no + T / 2 - 1) / (T / 2);
-      mbar_expect_tx(bar_full + buf, (unsigned)(boxes * kJPlanes * (T / 2) * 16 + q.np * 48));
-      for (int h = 0; h < boxes; ++h) tma_box_2d(Jbuf + h * kJPlanes * (T / 2), &tmapJ, 2 * (q.ob + h * (T / 2)), 0, bar_full + buf);
-    } else {
-      mbar_expect_tx(bar_full + buf, (unsigned)(q.no * kJPlanes * 16 + q.np * 48));
-      if (q.no > 0) {
-#pragma unroll
-        for (int k = 0; k < kJPlanes; ++k) bulk_g2s(Jbuf + k * T, J2 + k * O + q.ob, (unsigned)q.no * 16u, bar_full + buf);
-      }
-    }
-    if (q.np > 0) bulk_g2s(eibuf + (size_t)buf * L.max_pt_tile * 6, einv + (size_t)q.pb * 6, (unsigned)q.np * 48u, bar_full + buf);
-  };
-  const bool dir_is_z = pcg != nullptr && pcg->iter == 1;
-  const double beta = (pcg != nullptr && !dir_is_z) ? pcg->beta : 0.0;
-  const double* va = (pcg == nullptr) ? p : zdir;            // see k_ba_matvec_tma: raw operands now, multiply-add at the consumer
-  const bool two = pcg != nullptr && !dir_is_z;
-  auto gather2 = [&](const RecView& R, int idx, double& a, double& b) {
-    const int s = idx / 9, k = idx - s * 9;
-    const size_t e = (size_t)R.scam[s] * 9 + k;
-    a = va[e];
-    b = two ? p[e] : 0.0;
-  };
-  auto combine = [&](double a, double b) { return two ? __fma_rn(beta, b, a) : a; };
-  // element (plane k, observation i, row) of the staged Jacobian
-  const int jbase = TMAP ? (((i >> 7) * kJPlanes * (T / 2) + (i & 127)) * 2 + row) : (i * 2 + row);
-  constexpr int jstride = TMAP ? T : 2 * T;                  // doubles between planes
-  Tile q = header(0);
-  Tile qn = q;
-  if (my_tiles > 1) qn = header(1);
-  if (tid == 0) issue(q, blockIdx.x, 0);
-  mbar_wait(bar_rec, 0);
-  double xpre = 0.0, xpre2 = 0.0;
-  if (tid < q.ns * 9) gather2(rec_view(L, recbuf), tid, xpre, xpre2);
-  for (int it = 0; it < my_tiles; ++it) {
-    const int cur = it & 1;
-    const unsigned par = (unsigned)((it >> 1) & 1);
-    Tile qnn = qn;
-    if (it + 2 < my_tiles) qnn = header(it + 2);
-    const RecView R = rec_view(L, recbuf + (size_t)cur * L.rec_stride);
-    const double* ei = eibuf + (size_t)cur * L.max_pt_tile * 6;
-    const bool active = i < q.no;
-    mbar_wait(bar_full + cur, par);
-    double F[9], E[3];
-    int slot = 0, ptl = 0, rank = 0;
-    if (active) {
-#pragma unroll
-      for (int k = 0; k < 9; ++k) F[k] = Jrows[jbase + k * jstride];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) E[k] = Jrows[jbase + (9 + k) * jstride];
-      slot = R.slot[i]; ptl = R.ptl[i];
-      if (CHUNKED) rank = R.srank[i];
-    } else {
-#pragma unroll
-      for (int k = 0; k < 9; ++k) F[k] = 0.0;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) E[k] = 0.0;
-    }
-    if (tid < q.ns * 9) xs[tid] = combine(xpre, xpre2);
-    for (int idx = tid + T2; idx < q.ns * 9; idx += T2) { double a, b; gather2(R, idx, a, b); xs[idx] = combine(a, b); }
-    __syncthreads();                                         // xs complete; everyone has taken its Jacobian out of Jbuf
-    if (tid == 0 && it + 1 < my_tiles) issue(qn, blockIdx.x + (it + 1) * gridDim.x, cur ^ 1);
-    const double t = row_dot9(F, xs + slot * 9);             // inactive lanes: slot 0, F = 0 (they still take part in the shuffles)
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const double m = __dmul_rn(E[k], t), o = __shfl_xor_sync(0xffffffffu, m, 1);
-      if (row == 0 && active) w[CHUNKED ? i * 3 + k : k * T + i] = __dadd_rn(m, o);      // row 0 first
-    }
-    __syncthreads();
-    if (CHUNKED) point_sums_chunked<T2>(R, q.np, w, v, ei, u, UP);
-    else {
-      if (tid < q.np) {
-        const int b = R.pptr[tid], e = R.pptr[tid + 1];
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-        for (int j = b; j < e; ++j) { a0 += w[j]; a1 += w[T + j]; a2 += w[2 * T + j]; }
-        const double* m = ei + tid * 6;
-        u[tid] = m[0] * a0 + m[1] * a1 + m[2] * a2;
-        u[UP + tid] = m[1] * a0 + m[3] * a1 + m[4] * a2;
-        u[2 * UP + tid] = m[2] * a0 + m[4] * a1 + m[5] * a2;
-      }
-      __syncthreads();
-    }
-    {
-      const double s = row_minus_Eu(t, E, u[ptl], u[UP + ptl], u[2 * UP + ptl]);
-      double* vt = CHUNKED ? v + rank * VS : v + i;
-#pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        const double m = __dmul_rn(F[k], s), o = __shfl_xor_sync(0xffffffffu, m, 1);
-        if (row == 0 && active) vt[CHUNKED ? k : k * VLD] = __dadd_rn(m, o);
-      }
-    }
-    __syncthreads();
-    if (it + 1 < my_tiles) {
-      mbar_wait(bar_rec + (cur ^ 1), (unsigned)(((it + 1) >> 1) & 1));
-      if (tid < qn.ns * 9) gather2(rec_view(L, recbuf + (size_t)(cur ^ 1) * L.rec_stride), tid, xpre, xpre2);
-    }
-    if (CHUNKED) seg_sums_chunked<T2>(R, q.ns, q.sb, v, ps, seg_y);
-    else {
-      for (int idx = tid; idx < q.ns * 9; idx += T2) {
-        const int s = idx / 9, k = idx - s * 9;
-        const int b = R.sptr[s], e = R.sptr[s + 1];
-        const double* vk = v + k * VLD;
-        double sum = 0.0;
-        int pos = b;
-        for (; pos + 4 <= e; pos += 4) {
-          const int i0 = R.sperm[pos], i1 = R.sperm[pos + 1], i2 = R.sperm[pos + 2], i3 = R.sperm[pos + 3];
-          const double x0 = vk[i0], x1 = vk[i1], x2 = vk[i2], x3 = vk[i3];
-          sum += x0; sum += x1; sum += x2; sum += x3;
-        }
-        for (; pos < e; ++pos) sum += vk[R.sperm[pos]];
-        seg_y[(size_t)R.spos[s] * 9 + k] = sum;
-      }
-    }
-    q = qn; qn = qnn;
-  }
+  P.run(&tmapJ, L, J2, (pcg == nullptr) ? p : zdir, p, beta, pcg != nullptr && !dir_is_z, einv, seg_y, false);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1353,8 +927,7 @@ void launch_ba_matvec(const BaDev& L, const double2* J2, const double* p, const 
   const size_t smem = sizeof(double) * ((size_t)L.max_seg_tile * 9 + 9 * VLD + 6 * T) + smem_tail;
   if (L.matvec_classic != 1 && L.tile_rec != nullptr) {
     // Default: persistent TMA-prefetching kernel, one wave of as many CTAs per SM as its shared memory allows.
-    const size_t smem_p = sizeof(double2) * kJPlanes * T + sizeof(double) * ((size_t)((L.max_seg_tile * 9 + 1) & ~1) + 9 * VLD + 3 * T + 3 * (size_t)((L.max_pt_tile + 1) & ~1) + 1 +
-                          (size_t)seg_chunk_scratch(L.max_seg_tile) + 2 * (size_t)L.max_pt_tile * 6) + 2 * (size_t)L.rec_stride + 4 * sizeof(unsigned long long);
+    const size_t smem_p = ProductPass<true, false, false>::smem_bytes(L);
     static int sms = 0, smem_max = 0;
     if (sms == 0) {
       int dev = 0; SK_CUDA(cudaGetDevice(&dev));
@@ -1362,25 +935,22 @@ void launch_ba_matvec(const BaDev& L, const double2* J2, const double* p, const 
       SK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     }
     if (smem_p <= (size_t)smem_max) {
-      static size_t cfg_smem[8] = {0}; static int per_sm[8] = {0};   // function attributes / occupancy, redone when the size changes
-      const bool rows = L.matvec_classic == 2;                    // one thread per residual row (512 threads per tile)
-      const int v = (tmapJ != nullptr ? 1 : 0) + (chunked ? 2 : 0) + (rows ? 4 : 0);
+      static size_t cfg_smem[4] = {0}; static int per_sm[4] = {0};   // function attributes / occupancy, redone when the size changes
+      const int v = (tmapJ != nullptr ? 1 : 0) + (chunked ? 2 : 0);
       using Kernel = void (*)(const CUtensorMap, BaDev, const double2*, const double*, const double*, const PcgDev*, const double*, double*, const int*);
-      static const Kernel kernels[8] = {k_ba_matvec_tma<false, false>, k_ba_matvec_tma<true, false>, k_ba_matvec_tma<false, true>, k_ba_matvec_tma<true, true>,
-                                        k_ba_matvec_rows<false, false>, k_ba_matvec_rows<true, false>, k_ba_matvec_rows<false, true>, k_ba_matvec_rows<true, true>};
+      static const Kernel kernels[4] = {k_ba_matvec_tma<false, false>, k_ba_matvec_tma<true, false>, k_ba_matvec_tma<false, true>, k_ba_matvec_tma<true, true>};
       const Kernel kernel = kernels[v];
-      const int nthreads = rows ? T2 : T;
       if (smem_p != cfg_smem[v]) {
         set_smem(kernel, smem_p);
         SK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        SK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[v], kernel, nthreads, smem_p));
+        SK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[v], kernel, T, smem_p));
         cfg_smem[v] = smem_p;
       }
       if (per_sm[v] > 0) {
         const int grid = std::min(L.n_tiles, per_sm[v] * sms);
         static const CUtensorMap no_map{};
-        kernel<<<grid, nthreads, smem_p, s>>>((v & 1) ? *tmapJ : no_map, L, J2, p, zdir, pcg, einv, seg_y, guard);
-        check_launch(rows ? "k_ba_matvec_rows" : "k_ba_matvec_tma");
+        kernel<<<grid, T, smem_p, s>>>((v & 1) ? *tmapJ : no_map, L, J2, p, zdir, pcg, einv, seg_y, guard);
+        check_launch("k_ba_matvec_tma");
         return;
       }
     }

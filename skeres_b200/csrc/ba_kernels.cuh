@@ -18,7 +18,7 @@ struct BaDev {
   const int* gp_tile_begin; const int* gp_tile_count; const int* gp_point;   // [n_giant]
   // per-tile metadata records for the prefetching matvec (ba_kernels.cu: RecView); nullptr when not built
   const unsigned char* tile_rec; int rec_stride, rec_sp, rec_pp, rec_sc;
-  int matvec_classic;                  // 0: k_ba_matvec_tma; 1: k_ba_matvec (SKERES_MATVEC=classic); 2: k_ba_matvec_rows (SKERES_MATVEC=rows); read per solver
+  int matvec_classic;                  // 0: k_ba_matvec_tma / the fused PCG solve; 1: k_ba_matvec (SKERES_MATVEC=classic); read per solver
   int matvec_serial_sums;              // 1 (default): per-point / per-segment sums as one serial chain each; 0: the chunked
                                        // two-level sums (SKERES_MATVEC_SUMS=chunked)
   const unsigned short* obs_slot; const unsigned short* obs_ptl; const unsigned short* seg_perm;

@@ -10,10 +10,12 @@
 #include <cstdlib>
 
 #include "dense_kernels.cuh"
+#include "pcg_fused.cuh"
 #include "pcg_kernels.cuh"
 
 namespace sk {
 
+constexpr int kResidualResetPeriod = 10;   // ConjugateGradientsSolver: r = b - S x recomputed every 10th iteration
 static bool lst_is_explicit(int lst) { return lst == SK_DENSE_SCHUR || lst == SK_SPARSE_SCHUR; }
 
 namespace {
@@ -65,7 +67,7 @@ BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHo
   L_.n_giant = H.n_giant; L_.n_chunks = H.n_chunks; L_.tile_np = d_tile_np_.p;
   L_.gp_tile_begin = d_gp_begin_.p; L_.gp_tile_count = d_gp_count_.p; L_.gp_point = d_gp_point_.p;
   L_.tile_rec = nullptr; L_.rec_stride = L_.rec_sp = L_.rec_pp = L_.rec_sc = 0;
-  { const char* e = getenv("SKERES_MATVEC"); L_.matvec_classic = (e != nullptr && e[0] == 'c') ? 1 : (e != nullptr && e[0] == 'r') ? 2 : 0; }
+  { const char* e = getenv("SKERES_MATVEC"); L_.matvec_classic = (e != nullptr && e[0] == 'c') ? 1 : 0; }
   // per-point / per-segment sums of the product: serial chains (default: measured 1.5 % faster back to back, r02) or the chunked
   // two-level sums (SKERES_MATVEC_SUMS=chunked)
   { const char* e = getenv("SKERES_MATVEC_SUMS"); L_.matvec_serial_sums = (e != nullptr && e[0] == 'c') ? 0 : 1; }
@@ -115,6 +117,15 @@ BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHo
                SK_ERR_UNSUPPORTED, "ITERATIVE_SCHUR supports the JACOBI, SCHUR_JACOBI and IDENTITY preconditioners on the device (got %d)",
                opt.preconditioner_type);
     seg_M_.alloc((size_t)45 * std::max(H.n_segs, 1)); M45_.alloc((size_t)45 * H.n_cams); Minv_.alloc((size_t)81 * H.n_cams);
+    // SKERES_PCG=fused: the whole PCG loop as one persistent kernel (pcg_fused.cu) unless the problem has tracks longer than a tile,
+    // a development variant of the product is selected, or (multi-GPU) the peer window is unavailable.  Bit-identical to the
+    // kernel sequence but, as measured so far (profiles/r02_v2_*), slower: not the default yet.
+    const char* e = getenv("SKERES_PCG");
+    const bool multi = comm_ && comm_->world > 1;
+    fused_pcg_ = (e != nullptr && e[0] == 'f') && L_.matvec_classic == 0 && L_.matvec_serial_sums == 1 && (!multi || peer_.ok) &&
+                 pcg_solve_supported(L_, have_tmapJ_);
+    grid_bar_.alloc(1); phase_ns_.alloc(2);
+    grid_bar_.zero(s); phase_ns_.zero(s);
   } else {
     SK_REQUIRE(nc <= 16384, SK_ERR_UNSUPPORTED,
                "DENSE_SCHUR / SPARSE_SCHUR keep the reduced camera matrix dense on the device: at most 1820 cameras (got %d); use ITERATIVE_SCHUR",
@@ -137,6 +148,7 @@ void BaSolver::build_tile_records() {
 
 void BaSolver::load_state() {
   n_real_matvecs_ = 0;
+  if (phase_ns_.n) phase_ns_.zero(stream_);
   if (peer_.ok) SK_CUDA(cudaMemsetAsync(peer_.win.error, 0, sizeof(int), stream_));   // a time-out is sticky within one solve only
   KScope k(prof_, SK_KF_LM, 2);
   k_gather_blocks<<<cdiv((int64_t)L_.n_cams * 9, 256), 256, 0, stream_>>>(L_.n_cams, 9, d_cam_off_.p, user_, x_.p);
@@ -184,6 +196,24 @@ void BaSolver::fill_summary(sk_solver_summary_data* d) {
   // matvec launches that did work: launches issued after PCG termination inside a batch return at once and
   // would dilute the per-launch average the roofline figure is built from
   if (!explicit_schur_) d->kernel_launches[SK_KF_SCHUR_MATVEC] = n_real_matvecs_;
+  if (fused_pcg_ && prof_.enabled) {
+    // where the fused solves spent their time, on the device clock of their first CTA (pcg_fused.cu)
+    unsigned long long ns[2] = {0, 0};
+    SK_CUDA(cudaMemcpyAsync(ns, phase_ns_.p, sizeof(ns), cudaMemcpyDeviceToHost, stream_));
+    SK_CUDA(cudaStreamSynchronize(stream_));
+    d->kernel_ms[SK_KF_SCHUR_MATVEC] += 1e-6 * (double)ns[0];
+    d->kernel_ms[SK_KF_PCG_VECTOR] += 1e-6 * (double)ns[1];
+  }
+}
+
+// The iteration count of the LM iteration's linear solve has come back with the state block: the fused solve ran
+// its + its / 10 products (and as many peer-window exchanges) without the host counting them.
+void BaSolver::note_linear_iterations(int its) {
+  if (!fused_in_flight_) return;
+  fused_in_flight_ = false;
+  const int64_t products = (int64_t)its + its / kResidualResetPeriod;
+  n_real_matvecs_ += products;
+  if (peer_.ok) peer_.seq += (unsigned long long)products;
 }
 
 ReduceJob BaSolver::cost_job() { return {tile_cost_.p, L_.n_tiles, SB_COST, 0}; }
@@ -294,9 +324,23 @@ void BaSolver::pcg_solve(const double* Minv, const double* global_lin_flag) {
   double* part_Q = pcg_part_.p + 3 * kMaxPartials;
   {
     KScope k(prof_, SK_KF_PCG_VECTOR, 2);
-    launch_pcg_begin(L_.n_cams, rhs_.p, Minv, px_.p, pr_.p, pz_.p, part_bb, part_rho, pcg_.p, &st_.p->lin_error, global_lin_flag, stream_);
+    launch_pcg_begin(L_.n_cams, rhs_.p, Minv, px_.p, pr_.p, pz_.p, part_bb, part_rho, pcg_.p, &st_.p->lin_error, global_lin_flag,
+                     fused_pcg_ ? grid_bar_.p : nullptr, stream_);
   }
-  const int kBatch = 8, kResetPeriod = 10;
+  if (fused_pcg_) {
+    // One launch for the whole solve; nothing is read back here -- the outcome travels with the LM iteration's state block.
+    PcgSolveArgs a{};
+    a.L = L_; a.J2 = reinterpret_cast<const double2*>(J2_.p); a.einv = einv_.p; a.seg_y = seg_a_.p;
+    a.D = D_.p; a.Minv = Minv; a.b = rhs_.p; a.x = px_.p; a.p = pp_.p; a.r = pr_.p; a.z = pz_.p;
+    a.part_pq = part_pq; a.part_Q = part_Q; a.part_rho = part_rho; a.st = pcg_.p; a.prm = pp; a.reset_period = kResidualResetPeriod;
+    a.grid_bar = grid_bar_.p; a.phase_ns = prof_.enabled ? phase_ns_.p : nullptr;
+    if (peer_.ok) { a.win = peer_.win; a.seq_base = peer_.seq; }
+    KScope k(prof_, SK_KF_PCG_SOLVE);
+    launch_pcg_solve(a, have_tmapJ_ ? &tmapJ_ : nullptr, stream_);
+    fused_in_flight_ = true;
+    return;
+  }
+  const int kBatch = 8, kResetPeriod = kResidualResetPeriod;
   int it = 0;
   bool done = false;
   while (!done && it < pp.max_iterations) {

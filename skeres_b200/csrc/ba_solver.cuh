@@ -31,6 +31,7 @@ class BaSolver : public LmSolver {
   void load_state() override;
   void store_state() override;
   void fill_summary(sk_solver_summary_data* d) override;
+  void note_linear_iterations(int iterations) override;
 
  private:
   const double* matvec(const double* in, bool pcg_dir, const int* guard);
@@ -60,6 +61,10 @@ class BaSolver : public LmSolver {
   DBuf<double> rhs_, px_, pr_, pp_, pz_, ybuf_, pcg_part_, S_;
   DBuf<PcgDev> pcg_;
   HBuf<PcgDev> pcg_h_;
+  // fused PCG solve (pcg_fused.cu): the default for ITERATIVE_SCHUR; SKERES_PCG=sequence keeps the kernel sequence
+  bool fused_pcg_ = false, fused_in_flight_ = false;
+  DBuf<unsigned int> grid_bar_;
+  DBuf<unsigned long long> phase_ns_;
   // explicit Schur: for every camera pair (c1 < c2) sharing points, the list of observation pairs
   DBuf<int> pair_ptr_, pair_c1_, pair_c2_, pair_o1_, pair_o2_, pair_pt_;
   int n_pair_groups_ = 0;

@@ -20,7 +20,7 @@ LmSolver::LmSolver(const sk_solver_options& opt, cudaStream_t stream) : opt_(opt
   prm_.function_tolerance = opt.function_tolerance; prm_.gradient_tolerance = opt.gradient_tolerance;
   prm_.parameter_tolerance = opt.parameter_tolerance; prm_.eta = opt.eta; prm_.fixed_cost = 0.0;
   prof_.enabled = opt.profile_kernels != 0;
-  prof_.family_mask = (opt.profile_kernels == 2) ? (1u << SK_KF_SCHUR_MATVEC) : ~0u;
+  prof_.family_mask = (opt.profile_kernels == 2) ? ((1u << SK_KF_SCHUR_MATVEC) | (1u << SK_KF_PCG_SOLVE)) : ~0u;
   prof_.stream = stream;
 }
 
@@ -149,6 +149,7 @@ void LmSolver::minimize(sk_solver_summary* S, int max_num_iterations_override) {
     const LmDev& h = readback();
     if (h.g_accept) ++n_jac_evals_;
     n_lin_iters_ += h.lin_iterations;
+    note_linear_iterations(h.lin_iterations);
     const double now = wall();
     if (h.g_finalize) { t_iter.push_back(now - t_it); t_cum.push_back(now - t_start + d.preprocessor_time_in_seconds); print_row(h.row, t_iter.back(), t_cum.back()); }
   }

@@ -40,6 +40,7 @@ class LmSolver {
   virtual void load_state() = 0;       // user parameter arrays -> x
   virtual void store_state() = 0;      // x -> user parameter arrays
   virtual void fill_summary(sk_solver_summary_data* d) = 0;
+  virtual void note_linear_iterations(int /*iterations*/) {}   // after the readback of an LM iteration: what its linear solve took
 
   void allocate(int64_t n, int64_t nc);
   void reduce(std::initializer_list<ReduceJob> jobs, const int* guard);

@@ -13,8 +13,9 @@ int pcg_blocks(int n_cams);   // CTAs (= partial sums) of the warp-per-camera ke
 void launch_cam_reduce9_warp(const BaDev& L, const double* seg_y, double* y, const int* guard, cudaStream_t s,
                              const PeerWindow* win = nullptr, unsigned long long seq = 0);
 void launch_pcg_begin(int n_cams, const double* rhs, const double* Minv, double* x, double* r, double* z, double* part_bb,
-                      double* part_rho, PcgDev* st, int* lin_error, const double* global_lin_flag, cudaStream_t s);
+                      double* part_rho, PcgDev* st, int* lin_error, const double* global_lin_flag, unsigned int* grid_bar, cudaStream_t s);
 // global_lin_flag: multi-GPU, != 0 when the Schur set-up failed on some rank (then it failed for all: *lin_error is raised).
+// grid_bar: the fused solve's grid-barrier counter, zeroed here (nullptr: kernel sequence only).
 void launch_pcg_head(PcgDev* st, const double* part_rho, const double* part_pq, const double* part_Q, int nparts, PcgParams prm,
                      int finish_only, cudaStream_t s);
 void launch_pcg_reduce(const BaDev& L, const double* seg_y, const double* y_in, const double* D, double* z, double* p, double* part_pq,

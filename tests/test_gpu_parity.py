@@ -551,20 +551,57 @@ def test_ba_medium_tracks_iterative_schur(sk, oracle):
 @pytest.mark.parametrize("sums", ["chunked", "serial"])
 @pytest.mark.parametrize("case", [dict(shape="small", seed=2), LONG_TRACK_SMALL, MEDIUM_TRACK_CASE])
 def test_matvec_kernels_agree_bitwise(sk, monkeypatch, case, sums):
-    """The default implicit-Schur product (persistent TMA-prefetching k_ba_matvec_tma) and the classic one-CTA-per-tile
-    kernel add in the same order -- fixed by the chunk tables of the tile records for the default two-level sums, by the
-    point / segment lists for the round-1 serial chains (SKERES_MATVEC_SUMS=serial): every LM row and every parameter must
-    be identical, not merely close."""
+    """The persistent TMA-prefetching implicit-Schur product (k_ba_matvec_tma) and the classic one-CTA-per-tile kernel add in
+    the same order -- fixed by the point / segment lists for the serial chains (the default), by the chunk tables of the tile
+    records for the two-level sums (SKERES_MATVEC_SUMS=chunked): every LM row and every parameter must be identical, not
+    merely close.  Both run inside the kernel SEQUENCE of the PCG loop here (SKERES_PCG=sequence)."""
     d = synth.make_bal(**case)
     runs = []
-    monkeypatch.setenv("SKERES_MATVEC_SUMS", sums)             # both read when a solver is constructed
-    for mode in ("classic", "tma", "rows"):                    # "rows": one thread per residual row (k_ba_matvec_rows)
+    monkeypatch.setenv("SKERES_MATVEC_SUMS", sums)             # all read when a solver is constructed
+    monkeypatch.setenv("SKERES_PCG", "sequence")
+    for mode in ("classic", "tma"):
         monkeypatch.setenv("SKERES_MATVEC", mode)
         bal, s = gpu_ba(sk, d, _abi.ITERATIVE_SCHUR, _abi.SCHUR_JACOBI)
         runs.append(([r.cost for r in s.iterations], [r.linear_solver_iterations for r in s.iterations], bal.parameters.toArray()))
     for other in runs[1:]:
         assert runs[0][0] == other[0] and runs[0][1] == other[1]
         assert np.array_equal(runs[0][2], other[2])
+
+
+@pytest.mark.parametrize("case,prec,kw", [(dict(shape="small", seed=2), _abi.SCHUR_JACOBI, {}), (dict(shape="ladybug-49", seed=1), _abi.SCHUR_JACOBI, {}),
+                                          (MEDIUM_TRACK_CASE, _abi.JACOBI, {}), (dict(shape="small", seed=3), _abi.IDENTITY, {}),
+                                          (dict(shape="ladybug-49", seed=1), _abi.SCHUR_JACOBI, dict(eta=1e-10, max_linear_solver_iterations=3000, max_num_iterations=3)),
+                                          (dict(shape="tiny", seed=1), _abi.SCHUR_JACOBI, dict(max_linear_solver_iterations=3))])
+def test_fused_pcg_matches_kernel_sequence_bitwise(sk, monkeypatch, case, prec, kw):
+    """The fused PCG solve (one persistent cooperative kernel per linear solve: products, vector phases and termination tests
+    behind grid barriers, pcg_fused.cu) is built from the device functions of the kernel sequence (pcg_kernels.cu) and must
+    reproduce it bit for bit: LM rows, PCG iteration counts -- through residual resets every 10th iteration, the iteration
+    cap and solves of hundreds of iterations -- and parameters.  The sequence is run with one warp per camera in its
+    second-level sums (SKERES_PCG_WPC=1), the order the fused kernel uses."""
+    d = synth.make_bal(**case)
+    runs = []
+    monkeypatch.setenv("SKERES_PCG_WPC", "1")
+    for mode in ("sequence", "fused"):
+        monkeypatch.setenv("SKERES_PCG", mode)
+        bal, s = gpu_ba(sk, d, _abi.ITERATIVE_SCHUR, prec, **kw)
+        fams = s.kernel_times()
+        assert (fams["pcg_solve"][1] > 0) == (mode == "fused"), fams       # the path that was asked for is the one that ran
+        runs.append(([r.cost for r in s.iterations], [r.linear_solver_iterations for r in s.iterations], bal.parameters.toArray(),
+                     fams["schur_matvec"][1]))
+    assert runs[0][0] == runs[1][0] and runs[0][1] == runs[1][1]
+    assert np.array_equal(runs[0][2], runs[1][2])
+    assert runs[0][3] == runs[1][3]                                         # products executed: counted by the host / derived from the readback
+
+
+def test_fused_pcg_needs_no_host_polling(sk, monkeypatch):
+    """north_star (4): one readback per LM iteration.  With the fused solve a linear solve is ONE launch whatever its
+    iteration count, so the launches of a whole solve are a fixed number per LM iteration."""
+    monkeypatch.setenv("SKERES_PCG", "fused")
+    d = synth.make_bal("ladybug-49", seed=1)
+    bal, s = gpu_ba(sk, d, _abi.ITERATIVE_SCHUR, _abi.SCHUR_JACOBI)
+    fams = s.kernel_times()
+    assert fams["pcg_solve"][1] == s.num_linear_solves and fams["pcg_vector"][1] == 2 * s.num_linear_solves   # begin + start2 only
+    assert sum(r.linear_solver_iterations for r in s.iterations) > 200
 
 
 def test_two_level_sums_follow_the_serial_sums(sk, monkeypatch):
