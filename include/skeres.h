@@ -242,7 +242,7 @@ typedef struct sk_comm sk_comm;
 typedef struct sk_solver_options {
   int32_t minimizer_type;               /* TRUST_REGION */
   int32_t trust_region_strategy_type;   /* LEVENBERG_MARQUARDT */
-  int32_t linear_solver_type;           /* SPARSE_NORMAL_CHOLESKY in Ceres; callers always set it */
+  int32_t linear_solver_type;           /* SPARSE_NORMAL_CHOLESKY (Ceres default): runs on the dense QR back end, like DENSE_NORMAL_CHOLESKY */
   int32_t preconditioner_type;          /* JACOBI */
   int32_t max_num_iterations;           /* 50 */
   int32_t max_num_consecutive_invalid_steps; /* 5 */

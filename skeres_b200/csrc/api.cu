@@ -594,8 +594,12 @@ int sk_solver_create(const sk_solver_options* options, sk_problem* problem, sk_s
   s->device = g_device;
   SK_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
   if (is_schur(o.linear_solver_type)) s->impl = prepare_ba(o, problem, s->stream);
-  else if (o.linear_solver_type == SK_DENSE_QR) s->impl = prepare_dense(o, problem, s->stream);
-  else throw Error(SK_ERR_UNSUPPORTED, fmt("linear_solver_type %d has no device implementation (supported: DENSE_QR, DENSE_SCHUR, SPARSE_SCHUR, ITERATIVE_SCHUR)", o.linear_solver_type));
+  // DENSE_NORMAL_CHOLESKY and SPARSE_NORMAL_CHOLESKY -- the latter is Ceres' DEFAULT linear_solver_type, which HelloWorld.scala and
+  // HelloWorldNumericDiff.scala never change -- solve the same damped normal equations as DENSE_QR: they run on the dense QR back
+  // end (same step up to rounding; within that back end's size limits).
+  else if (o.linear_solver_type == SK_DENSE_QR || o.linear_solver_type == SK_DENSE_NORMAL_CHOLESKY || o.linear_solver_type == SK_SPARSE_NORMAL_CHOLESKY)
+    s->impl = prepare_dense(o, problem, s->stream);
+  else throw Error(SK_ERR_UNSUPPORTED, fmt("linear_solver_type %d has no device implementation (supported: DENSE_QR, DENSE_NORMAL_CHOLESKY, SPARSE_NORMAL_CHOLESKY, DENSE_SCHUR, SPARSE_SCHUR, ITERATIVE_SCHUR)", o.linear_solver_type));
   s->preprocessor_s = wall() - t0;
   *out = s.release();
   SK_API_END

@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(T, SK_TMA_CTAS) k_ba_matvec_tma(const __grid_c
   // PCG direction z + beta p formed on the fly (p = z in iteration 1); the two scalars are read once, not per tile
   const bool dir_is_z = pcg != nullptr && pcg->iter == 1;
   const double beta = (pcg != nullptr && !dir_is_z) ? pcg->beta : 0.0;
-  P.run(&tmapJ, L, J2, (pcg == nullptr) ? p : zdir, p, beta, pcg != nullptr && !dir_is_z, einv, seg_y, false);
+  P.run(&tmapJ, L, J2, (pcg == nullptr) ? p : zdir, p, beta, pcg != nullptr && !dir_is_z, einv, seg_y, false, sm);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -115,11 +115,35 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 // the next pass.  COHERENT: the input vector was written by other CTAs of the SAME launch -- read it at L2 (ld.global.cg).
 template <bool TMAP, bool CHUNKED, bool COHERENT>
 struct ProductPass {
-  double2* Jbuf; double* xs; double* v; double* w; double* u; double* ps; double* eibuf; unsigned char* recbuf;
-  unsigned long long* bar_full; unsigned long long* bar_rec;
-  int UP, my_tiles;
+  // Only the ring position lives across passes; the carve-up of the shared memory is recomputed by every pass into locals (a
+  // kernel that keeps ten more pointers alive across its other phases runs out of registers at 2 CTAs / SM and the compiler
+  // then re-derives them inside the inner loops: measured 0.316 instead of 0.206 ms per product, profiles/r02_v2_*).
   unsigned done;          // tiles this CTA has consumed so far, over all passes: tile `it` of a pass sits at ring position done + it
   bool chained;           // the first tile of the coming pass has already been issued (by the previous pass)
+
+  struct Smem {
+    double2* Jbuf; double* xs; double* v; double* w; double* u; double* ps; double* eibuf; unsigned char* recbuf;
+    unsigned long long* bar_full; unsigned long long* bar_rec;
+    int UP;
+  };
+  static __device__ __forceinline__ Smem carve(const BaDev& L, double* sm) {
+    Smem m;
+    m.Jbuf = reinterpret_cast<double2*>(sm);                 // [12][T] next tile's Jacobian (TMAP: [2][12][T/2])
+    m.xs = sm + 2 * kJPlanes * T;                            // [max_seg][9]
+    m.v = m.xs + ((L.max_seg_tile * 9 + 1) & ~1);            // [9][VLD]   (xs padded to an even count: 16-byte alignment below)
+    m.w = m.v + 9 * VLD;                                     // [3][T]
+    m.UP = (L.max_pt_tile + 1) & ~1;
+    m.u = m.w + 3 * T;                                       // [3][UP]
+    m.ps = m.u + 3 * m.UP;                                   // [seg_chunk_scratch]  chunk sums of the segment sums (CHUNKED)
+    m.eibuf = m.ps + seg_chunk_scratch(L.max_seg_tile) + 1;  // 2 x [max_pt][6]   (+1: 9 * VLD is odd)
+    m.recbuf = reinterpret_cast<unsigned char*>(m.eibuf + 2 * (size_t)L.max_pt_tile * 6);   // 2 x rec_stride bytes
+    m.bar_full = reinterpret_cast<unsigned long long*>(m.recbuf + 2 * (size_t)L.rec_stride);   // [2] Jacobian + einv
+    m.bar_rec = m.bar_full + 2;                                                                 // [2] record
+    return m;
+  }
+  static __device__ __forceinline__ int tiles_of_cta(const BaDev& L) {
+    return ((int)blockIdx.x < L.n_tiles) ? (L.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  }
 
   static size_t smem_bytes(const BaDev& L) {
     return sizeof(double2) * kJPlanes * T +
@@ -128,35 +152,27 @@ struct ProductPass {
            2 * (size_t)L.rec_stride + 4 * sizeof(unsigned long long);
   }
 
-  // Carves the dynamic shared memory and initialises the mbarriers; ends with a CTA barrier.
+  // Initialises the mbarriers; ends with a CTA barrier.
   __device__ __forceinline__ void init(const BaDev& L, double* sm) {
-    Jbuf = reinterpret_cast<double2*>(sm);                   // [12][T] next tile's Jacobian (TMAP: [2][12][T/2])
-    xs = sm + 2 * kJPlanes * T;                              // [max_seg][9]
-    v = xs + ((L.max_seg_tile * 9 + 1) & ~1);                // [9][VLD]   (xs padded to an even count: 16-byte alignment below)
-    w = v + 9 * VLD;                                         // [3][T]
-    UP = (L.max_pt_tile + 1) & ~1;
-    u = w + 3 * T;                                           // [3][UP]
-    ps = u + 3 * UP;                                         // [seg_chunk_scratch]  chunk sums of the segment sums (CHUNKED)
-    eibuf = ps + seg_chunk_scratch(L.max_seg_tile) + 1;      // 2 x [max_pt][6]   (+1: 9 * VLD is odd)
-    recbuf = reinterpret_cast<unsigned char*>(eibuf + 2 * (size_t)L.max_pt_tile * 6);   // 2 x rec_stride bytes
-    bar_full = reinterpret_cast<unsigned long long*>(recbuf + 2 * (size_t)L.rec_stride);   // [2] Jacobian + einv
-    bar_rec = bar_full + 2;                                                                 // [2] record
-    my_tiles = ((int)blockIdx.x < L.n_tiles) ? (L.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     done = 0; chained = false;
     if (threadIdx.x == 0) {
-      mbar_init(bar_full, 1); mbar_init(bar_full + 1, 1); mbar_init(bar_rec, 1); mbar_init(bar_rec + 1, 1);
+      const Smem m = carve(L, sm);
+      mbar_init(m.bar_full, 1); mbar_init(m.bar_full + 1, 1); mbar_init(m.bar_rec, 1); mbar_init(m.bar_rec + 1, 1);
       asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
   }
 
-  __device__ __forceinline__ Tile header(const BaDev& L, int it) const {   // chunk tiles of long tracks are empty work items here
+  static __device__ __forceinline__ Tile header(const BaDev& L, int it) {   // chunk tiles of long tracks are empty work items here
     Tile q = load_tile(L, blockIdx.x + it * gridDim.x);
     if (q.chunk >= 0) { q.no = 0; q.np = 0; q.ns = 0; }
     return q;
   }
   // thread 0: everything tile t needs, into ring slot `buf`
-  __device__ __forceinline__ void issue(const CUtensorMap* tmapJ, const BaDev& L, const double2* J2, const double* einv, const Tile& q, int t, int buf) const {
+  static __device__ __forceinline__ void issue(const Smem& m, const CUtensorMap* tmapJ, const BaDev& L, const double2* J2, const double* einv,
+                                               const Tile& q, int t, int buf) {
+    double2* Jbuf = m.Jbuf; double* eibuf = m.eibuf; unsigned char* recbuf = m.recbuf;
+    unsigned long long* bar_full = m.bar_full; unsigned long long* bar_rec = m.bar_rec;
     const size_t O = (size_t)L.n_obs;
     mbar_expect_tx(bar_rec + buf, (unsigned)L.rec_stride);
     bulk_g2s(recbuf + (size_t)buf * L.rec_stride, L.tile_rec + (size_t)t * L.rec_stride, (unsigned)L.rec_stride, bar_rec + buf);
@@ -180,9 +196,15 @@ struct ProductPass {
   // multiply-add is left to the consumer on purpose: an arithmetic instruction placed right after the loads would make every warp
   // wait for that L2 round trip on the spot (measured: +34 us per product with the fused form, profiles/r02_v1_summary.md).
   __device__ __forceinline__ void run(const CUtensorMap* tmapJ, const BaDev& L, const double2* J2, const double* va, const double* vb,
-                                      double beta, bool two, const double* einv, double* seg_y, bool chain_next) {
+                                      double beta, bool two, const double* einv, double* seg_y, bool chain_next, double* sm) {
+    const int my_tiles = tiles_of_cta(L);
     if (my_tiles == 0) return;
     const int tid = threadIdx.x;
+    const Smem m = carve(L, sm);
+    double2* const Jbuf = m.Jbuf; double* const xs = m.xs; double* const v = m.v; double* const w = m.w; double* const u = m.u;
+    double* const ps = m.ps; double* const eibuf = m.eibuf; unsigned char* const recbuf = m.recbuf;
+    unsigned long long* const bar_full = m.bar_full; unsigned long long* const bar_rec = m.bar_rec;
+    const int UP = m.UP;
     auto gather2 = [&](const RecView& R, int idx, double& a, double& b) {
       const int s = idx / 9, k = idx - s * 9;
       const size_t e = (size_t)R.scam[s] * 9 + k;
@@ -194,7 +216,7 @@ struct ProductPass {
     const Tile q0 = q;
     Tile qn = q;
     if (my_tiles > 1) qn = header(L, 1);
-    if (!chained && tid == 0) issue(tmapJ, L, J2, einv, q, blockIdx.x, (int)(done & 1u));
+    if (!chained && tid == 0) issue(m, tmapJ, L, J2, einv, q, blockIdx.x, (int)(done & 1u));
     mbar_wait(bar_rec + (done & 1u), (done >> 1) & 1u);
     double xpre = 0.0, xpre2 = 0.0;                            // operands of element `tid` of the current tile's input vector
     if (tid < q.ns * 9) gather2(rec_view(L, recbuf + (size_t)(done & 1u) * L.rec_stride), tid, xpre, xpre2);
@@ -222,8 +244,8 @@ struct ProductPass {
       for (int idx = tid + T; idx < q.ns * 9; idx += T) { double a, b; gather2(R, idx, a, b); xs[idx] = combine(a, b); }   // more than 28 segments: the rest, not prefetched
       __syncthreads();                                         // xs complete; everyone has taken its Jacobian out of Jbuf
       if (tid == 0) {
-        if (it + 1 < my_tiles) issue(tmapJ, L, J2, einv, qn, blockIdx.x + (it + 1) * gridDim.x, cur ^ 1);
-        else if (chain_next) issue(tmapJ, L, J2, einv, q0, blockIdx.x, cur ^ 1);   // first tile of the next pass
+        if (it + 1 < my_tiles) issue(m, tmapJ, L, J2, einv, qn, blockIdx.x + (it + 1) * gridDim.x, cur ^ 1);
+        else if (chain_next) issue(m, tmapJ, L, J2, einv, q0, blockIdx.x, cur ^ 1);   // first tile of the next pass
       }
       double t0 = 0.0, t1 = 0.0;
       if (active) {
@@ -282,10 +304,11 @@ struct ProductPass {
   }
 
   // Before the kernel ends: a chained first tile that no pass will consume must have landed (no copy may outlive the CTA).
-  __device__ __forceinline__ void drain() {
-    if (my_tiles == 0 || !chained) return;
-    mbar_wait(bar_rec + (done & 1u), (done >> 1) & 1u);
-    mbar_wait(bar_full + (done & 1u), (done >> 1) & 1u);
+  __device__ __forceinline__ void drain(const BaDev& L, double* sm) {
+    if (tiles_of_cta(L) == 0 || !chained) return;
+    const Smem m = carve(L, sm);
+    mbar_wait(m.bar_rec + (done & 1u), (done >> 1) & 1u);
+    mbar_wait(m.bar_full + (done & 1u), (done >> 1) & 1u);
     chained = false;
   }
 };

@@ -117,12 +117,12 @@ BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHo
                SK_ERR_UNSUPPORTED, "ITERATIVE_SCHUR supports the JACOBI, SCHUR_JACOBI and IDENTITY preconditioners on the device (got %d)",
                opt.preconditioner_type);
     seg_M_.alloc((size_t)45 * std::max(H.n_segs, 1)); M45_.alloc((size_t)45 * H.n_cams); Minv_.alloc((size_t)81 * H.n_cams);
-    // SKERES_PCG=fused: the whole PCG loop as one persistent kernel (pcg_fused.cu) unless the problem has tracks longer than a tile,
-    // a development variant of the product is selected, or (multi-GPU) the peer window is unavailable.  Bit-identical to the
-    // kernel sequence but, as measured so far (profiles/r02_v2_*), slower: not the default yet.
+    // The whole PCG loop as one persistent kernel (pcg_fused.cu) unless the problem has tracks longer than a tile, a development
+    // variant of the product is selected, or (multi-GPU) the peer window is unavailable; SKERES_PCG=sequence forces the kernel
+    // sequence (bit-identical with SKERES_PCG_WPC=1; measured 0.2303 ms per PCG iteration against 0.2211 fused, profiles/r02_v2_*).
     const char* e = getenv("SKERES_PCG");
     const bool multi = comm_ && comm_->world > 1;
-    fused_pcg_ = (e != nullptr && e[0] == 'f') && L_.matvec_classic == 0 && L_.matvec_serial_sums == 1 && (!multi || peer_.ok) &&
+    fused_pcg_ = !(e != nullptr && e[0] == 's') && L_.matvec_classic == 0 && L_.matvec_serial_sums == 1 && (!multi || peer_.ok) &&
                  pcg_solve_supported(L_, have_tmapJ_);
     grid_bar_.alloc(1); phase_ns_.alloc(2);
     grid_bar_.zero(s); phase_ns_.zero(s);

@@ -186,19 +186,30 @@ __device__ __forceinline__ void pcg_head_step(PcgDev* st, const double* part_rho
   }
 }
 
-// acc = seg_y[t][k] + seg_y[t + 3 WPC][k] + ... in that order, eight partials in flight.  The product kernels store a segment's
-// partial at its camera-major position (BaDev::seg_pos), so a camera's partials are the contiguous rows [cam_seg_ptr[c],
-// cam_seg_ptr[c + 1]) in tile order: no index is read on the way.  L2 loads: the partials come from other CTAs.
+// acc = seg_y[t][k] + seg_y[t + 3 WPC][k] + ... in that order, sixteen partials in flight (the adds stay one chain in t order:
+// only the loads are batched -- a camera of the Venice shape owns ~190 partials, 63 per segment lane, and every batch costs
+// one L2 round trip).  The product kernels store a segment's partial at its camera-major position (BaDev::seg_pos), so a
+// camera's partials are the contiguous rows [cam_seg_ptr[c], cam_seg_ptr[c + 1]) in tile order: no index is read on the way.
+// L2 loads: the partials come from other CTAs.
 template <int WPC>
 __device__ __forceinline__ double walk_segments(const double* seg_y, int t, int e, int k) {
   constexpr int S = 3 * WPC;
+  constexpr int B = 16;
   double acc = 0.0;
-  for (; t + 7 * S < e; t += 8 * S) {
-    double x[8];
+  for (; t + (B - 1) * S < e; t += B * S) {
+    double x[B];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = __ldcg(seg_y + (size_t)(t + i * S) * 9 + k);
+    for (int i = 0; i < B; ++i) x[i] = __ldcg(seg_y + (size_t)(t + i * S) * 9 + k);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc += x[i];
+    for (int i = 0; i < B; ++i) acc += x[i];
+  }
+  if (t + 3 * S < e) {
+    double x[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = __ldcg(seg_y + (size_t)(t + i * S) * 9 + k);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc += x[i];
+    t += 4 * S;
   }
   for (; t < e; t += S) acc += __ldcg(seg_y + (size_t)t * 9 + k);
   return acc;

@@ -43,14 +43,16 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// Barrier over all CTAs of the (co-resident) grid.  `target` counts the arrivals expected so far; the counter only grows.
-__device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int& target) {
+// Barrier over all CTAs of the (co-resident) grid.  `*target` (shared memory, thread 0's) counts the arrivals expected so far;
+// the counter only grows.
+__device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int* target) {
   __syncthreads();                                   // the CTA's writes happen before thread 0's fence (cumulativity)
   if (threadIdx.x == 0) {
-    target += gridDim.x;
+    const unsigned int t = *target + gridDim.x;
+    *target = t;
     __threadfence();
     atomicAdd(bar, 1u);
-    while (ld_acquire_gpu(bar) < target) { }
+    while (ld_acquire_gpu(bar) < t) { }
   }
   __syncthreads();
 }
@@ -62,92 +64,105 @@ __device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int& targe
 #ifndef SK_FUSED_CHAIN
 #define SK_FUSED_CHAIN 1         // 0: every pass starts its copy pipeline from cold
 #endif
+
+// Everything the loop keeps between its phases lives in shared memory, not in registers: the product pass needs every register
+// of the 128 that two CTAs per SM allow (see ProductPass).
+struct SolveCtl {
+  PcgDev s;                                          // this CTA's copy of the scalar state: identical in every CTA at every barrier
+  unsigned long long seq;                            // peer-window exchanges so far
+  unsigned long long t_last, ns_product, ns_vector;  // CTA 0, thread 0: device-clock accounting of the phases
+  unsigned int bar_target;
+  int peer_failed;
+  int reset_pass;                                    // the coming pass multiplies x (residual reset), not the direction
+  double red[8];
+  double bc;
+};
+
+// ONE call site of the product pass.  With two (direction product / residual-reset product of x) ptxas ran out of registers at
+// the 128 that two CTAs per SM allow and issued every shared-memory load of the per-point / per-segment sums right in front of
+// the add that consumes it instead of a batch of loads ahead (SASS: "LDS DADD LDS DADD ..." against "LDS x 11, then LDS / DADD
+// interleaved" in the stand-alone product kernel): 0.316 ms per product instead of 0.206 ms (profiles/r02_v2_*).  The loop
+// below therefore runs one pass per trip and selects its operands from the state: a residual reset is a trip of its own.
 template <bool TMAP>
 __global__ void __launch_bounds__(T, 2) k_pcg_solve(const __grid_constant__ CUtensorMap tmapJ, const PcgSolveArgs A) {
   extern __shared__ __align__(128) double sm[];
-  __shared__ PcgDev s;                               // this CTA's copy of the scalar state: identical in every CTA at every barrier
-  __shared__ double red[8];
-  __shared__ double bc;
-  __shared__ int peer_failed;
+  __shared__ SolveCtl ctl;
   const int tid = threadIdx.x;
-  if (tid == 0) s = *A.st;
+  if (tid == 0) {
+    ctl.s = *A.st; ctl.seq = A.seq_base; ctl.bar_target = 0; ctl.ns_product = 0; ctl.ns_vector = 0; ctl.t_last = global_ns();
+    ctl.reset_pass = 0;
+  }
   __syncthreads();
-  if (s.active == 0) return;                         // the set-up failed or b == 0 (k_pcg_start2): the same decision in every CTA
+  if (ctl.s.active == 0) return;                     // the set-up failed or b == 0 (k_pcg_start2): the same decision in every CTA
   const BaDev& L = A.L;
   const int nparts = (L.n_cams + WPB - 1) / WPB;
   const bool peer = A.win.world > 1;
+  const bool stamps = A.phase_ns != nullptr && blockIdx.x == 0 && tid == 0;
   ProductPass<TMAP, false, SK_FUSED_COHERENT != 0> P;
   P.init(L, sm);
-  unsigned int bar_target = 0;
-  unsigned long long seq = A.seq_base;
-  unsigned long long t_last = 0, ns_product = 0, ns_vector = 0;
-  const bool stamp = A.phase_ns != nullptr && blockIdx.x == 0 && tid == 0;
-  if (stamp) t_last = global_ns();
 
-  // One implicit-Schur product + (multi-GPU) the exchange of its camera-sized result; returns the window parity to gather from.
-  auto product = [&](const double* va, const double* vb, double beta, bool two) -> int {
-    if (stamp) { const unsigned long long t = global_ns(); ns_vector += t - t_last; t_last = t; }
-    P.run(&tmapJ, L, A.J2, va, vb, beta, two, A.einv, A.seg_y, SK_FUSED_CHAIN != 0);
-    grid_sync(A.grid_bar, bar_target);
+  pcg_head_step(&ctl.s, A.part_rho, A.part_pq, A.part_Q, nparts, A.prm, 0);   // opens iteration 1 (what k_pcg_head does in the sequence)
+  __syncthreads();
+  while (ctl.s.active) {
+    // ---- one implicit-Schur product: of the direction z + beta p (p = z in iteration 1), or -- residual reset -- of x
+    const bool reset_pass = ctl.reset_pass != 0;
+    if (stamps) { const unsigned long long t = global_ns(); ctl.ns_vector += t - ctl.t_last; ctl.t_last = t; }
+    P.run(&tmapJ, L, A.J2, reset_pass ? A.x : A.z, A.p, ctl.s.beta, !reset_pass && ctl.s.iter != 1, A.einv, A.seg_y, SK_FUSED_CHAIN != 0, sm);
+    grid_sync(A.grid_bar, &ctl.bar_target);
     int parity = 0;
-    if (peer) {
-      ++seq; parity = (int)(seq & 1ull);
+    if (peer) {                                      // exchange of the camera-sized result over the NVLink peer window
+      if (tid == 0) ++ctl.seq;
+      __syncthreads();
+      const unsigned long long seq = ctl.seq;
+      parity = (int)(seq & 1ull);
       double* y = A.win.data[A.win.rank] + (size_t)parity * A.win.stride;
-      for (int vb_ = blockIdx.x; vb_ < nparts; vb_ += gridDim.x) cam_reduce9_block<1>(L, vb_, A.seg_y, y);
-      grid_sync(A.grid_bar, bar_target);             // this rank's contribution is complete
+      for (int vb = blockIdx.x; vb < nparts; vb += gridDim.x) cam_reduce9_block<1>(L, vb, A.seg_y, y);
+      grid_sync(A.grid_bar, &ctl.bar_target);        // this rank's contribution is complete
       if (blockIdx.x == 0) peer_store_flags(A.win, parity, seq);
       peer_wait(A.win, parity, seq);                 // a time-out raises win.error; checked by all CTAs after the next barrier
     }
-    if (stamp) { const unsigned long long t = global_ns(); ns_product += t - t_last; t_last = t; }
-    return parity;
-  };
-  // After a grid barrier that follows an exchange: did any CTA's wait time out?  (Same answer in every CTA.)
-  auto exchange_failed = [&]() -> bool {
-    if (!peer) return false;
-    if (tid == 0) peer_failed = *(volatile int*)A.win.error;
-    __syncthreads();
-    const bool f = peer_failed != 0;
-    __syncthreads();
-    if (f && tid == 0) { s.active = 0; s.termination = LIN_FATAL; }
-    __syncthreads();
-    return f;
-  };
-
-  pcg_head_step(&s, A.part_rho, A.part_pq, A.part_Q, nparts, A.prm, 0);   // opens iteration 1 (what k_pcg_head does in the sequence)
-  __syncthreads();
-  while (s.active) {
-    const int it = s.iter;
-    const double beta = s.beta, rho = s.rho;
-    const int parity = product(A.z, A.p, beta, it != 1);
-    for (int vb = blockIdx.x; vb < nparts; vb += gridDim.x)
-      pcg_reduce_block<1>(L, vb, A.seg_y, nullptr, A.D, A.z, A.p, A.part_pq, it, beta, A.win, parity);
-    grid_sync(A.grid_bar, bar_target);
-    if (exchange_failed()) break;
-    const double pq = sum_fixed_all(A.part_pq, nparts, red, &bc);
-    const bool ok = (pq > 0.0) && !isinf(pq);
-    const double alpha = rho / pq;
-    const bool go = ok && !isinf(alpha);
-    const int recompute = (it % A.reset_period == 0) ? 1 : 0;
-    for (int vb = blockIdx.x; vb < nparts; vb += gridDim.x)
-      pcg_update_block(L.n_cams, vb, A.Minv, A.b, A.x, A.p, A.r, A.z, alpha, go, recompute, A.part_Q, A.part_rho);
-    if (recompute) {                                 // r = b - S x from one more product
-      grid_sync(A.grid_bar, bar_target);
-      const int par2 = product(A.x, nullptr, 0.0, false);
+    if (stamps) { const unsigned long long t = global_ns(); ctl.ns_product += t - ctl.t_last; ctl.t_last = t; }
+    // ---- vector phases
+    bool finish = true;                              // this trip ends the iteration (head step)
+    if (!reset_pass) {
+      const int it = ctl.s.iter; const double beta = ctl.s.beta;
       for (int vb = blockIdx.x; vb < nparts; vb += gridDim.x)
-        pcg_resid_block(L, vb, A.seg_y, nullptr, A.D, A.Minv, A.b, A.x, A.r, A.z, A.part_Q, A.part_rho, A.win, par2);
+        pcg_reduce_block<1>(L, vb, A.seg_y, nullptr, A.D, A.z, A.p, A.part_pq, it, beta, A.win, parity);
+      grid_sync(A.grid_bar, &ctl.bar_target);
+      const int recompute = (it % A.reset_period == 0) ? 1 : 0;
+      const double pq = sum_fixed_all(A.part_pq, nparts, ctl.red, &ctl.bc);
+      const bool ok = (pq > 0.0) && !isinf(pq);
+      const double alpha = ctl.s.rho / pq;
+      const bool go = ok && !isinf(alpha);
+      for (int vb = blockIdx.x; vb < nparts; vb += gridDim.x)
+        pcg_update_block(L.n_cams, vb, A.Minv, A.b, A.x, A.p, A.r, A.z, alpha, go, recompute, A.part_Q, A.part_rho);
+      if (recompute) finish = false;                 // r = b - S x from one more product: the next trip
+    } else {
+      for (int vb = blockIdx.x; vb < nparts; vb += gridDim.x)
+        pcg_resid_block(L, vb, A.seg_y, nullptr, A.D, A.Minv, A.b, A.x, A.r, A.z, A.part_Q, A.part_rho, A.win, parity);
     }
-    grid_sync(A.grid_bar, bar_target);
-    if (recompute && exchange_failed()) break;
-    pcg_head_step(&s, A.part_rho, A.part_pq, A.part_Q, nparts, A.prm, 0);   // finishes `it`, opens it + 1
+    grid_sync(A.grid_bar, &ctl.bar_target);
+    if (peer) {                                      // did any CTA's wait time out?  (same answer in every CTA: read after the barrier)
+      if (tid == 0) ctl.peer_failed = *(volatile int*)A.win.error;
+      __syncthreads();
+      if (ctl.peer_failed != 0) {
+        __syncthreads();
+        if (tid == 0) { ctl.s.active = 0; ctl.s.termination = LIN_FATAL; }
+        __syncthreads();
+        break;
+      }
+    }
+    if (tid == 0) ctl.reset_pass = finish ? 0 : 1;
+    if (finish) pcg_head_step(&ctl.s, A.part_rho, A.part_pq, A.part_Q, nparts, A.prm, 0);   // finishes this iteration, opens the next
     __syncthreads();
   }
-  P.drain();
+  P.drain(L, sm);
   if (blockIdx.x == 0 && tid == 0) {
-    s.done_count = 0;
-    *A.st = s;
-    if (stamp) {
-      ns_vector += global_ns() - t_last;
-      atomicAdd(A.phase_ns, ns_product); atomicAdd(A.phase_ns + 1, ns_vector);
+    ctl.s.done_count = 0;
+    *A.st = ctl.s;
+    if (A.phase_ns != nullptr) {
+      ctl.ns_vector += global_ns() - ctl.t_last;
+      atomicAdd(A.phase_ns, ctl.ns_product); atomicAdd(A.phase_ns + 1, ctl.ns_vector);
     }
   }
 }

@@ -221,11 +221,17 @@ def test_hello_world_example(sk, oracle):
     problem = sk.Problem()
     problem.addResidualBlock(sk.HelloCostFunctor().toAutoDiffCostFunction(), sk.PredefinedLossFunctions.trivialLoss(), x.toPointer())
     options = sk.Solver.Options()
-    with pytest.raises(sk.SkeresError):                      # the example keeps Ceres' default SPARSE_NORMAL_CHOLESKY: no device path
-        sk.ceres.solve(options, problem, sk.Solver.Summary())
+    # the example keeps Ceres' default SPARSE_NORMAL_CHOLESKY (HelloWorld.scala:27-31 never sets a solver): it runs on the dense
+    # back end, same rows as DENSE_QR
+    assert options.linear_solver_type == _abi.SPARSE_NORMAL_CHOLESKY
+    s0 = sk.Solver.Summary()
+    sk.ceres.solve(options, problem, s0)
+    assert abs(x.get(0) - 10.0) < 1e-7 and s0.linear_solver_type_used == _abi.SPARSE_NORMAL_CHOLESKY
+    x.set(0, 0.5)
     options.setLinearSolverType(_abi.DENSE_QR)
     s = sk.Solver.Summary()
     sk.ceres.solve(options, problem, s)
+    assert [r.cost for r in s0.iterations] == [r.cost for r in s.iterations]
     p = oracle.OracleProblem(np.array([0.5]))
     p.add_residual_blocks(_abi.FUNCTOR_HELLO_WORLD, np.zeros((1, 0)), np.array([[0]]))
     o = _abi.default_options()
@@ -753,7 +759,7 @@ def test_unsupported_requests_fail_loudly(sk):
     d = synth.make_bal("tiny", seed=1)
     bal = sk.BalProblem.fromArrays(d)
     problem = bal.buildProblem()
-    for setter in (lambda o: o.setLinearSolverType(_abi.SPARSE_NORMAL_CHOLESKY), lambda o: o.setMinimizerType(_abi.LINE_SEARCH),
+    for setter in (lambda o: o.setLinearSolverType(_abi.CGNR), lambda o: o.setMinimizerType(_abi.LINE_SEARCH),
                    lambda o: (o.setLinearSolverType(_abi.ITERATIVE_SCHUR), o.setPreconditionerType(_abi.CLUSTER_JACOBI))):
         o = sk.Solver.Options()
         o.setLinearSolverType(_abi.DENSE_SCHUR)
