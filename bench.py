@@ -32,8 +32,19 @@ import time
 
 import numpy as np
 
-# stdout carries exactly ONE JSON line: NCCL's version banner (printed when the box sets NCCL_DEBUG) goes to stderr
+# stdout carries exactly ONE JSON line.  NCCL's version banner (printed when the box sets NCCL_DEBUG) is written by native code
+# straight to file descriptor 1 -- NCCL_DEBUG_FILE does not catch torch's bundled NCCL in every case (seen on a 2-GPU box) -- so
+# descriptor 1 is pointed at stderr for the whole run and the JSON line goes to a duplicate of the original stdout.
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+sys.stdout.flush()
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -235,7 +246,7 @@ def main():
                                            "; CPU oracle = Ceres-algorithm restatement (libceres is not buildable here)"},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "rows_timed": R, "row_seconds": row_s, "final_cost": s.final_cost, "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ this repo's CUDA arm
@@ -458,7 +469,7 @@ def main():
                 "multi_vs_single": multi_vs_single,
                 "clocks": clocks, "final_cost_last_solve": last.final_cost if last is not None else None,
                 "pcg_iterations_last_solve": [r.linear_solver_iterations for r in last.iterations] if last is not None else None}
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0

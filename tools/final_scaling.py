@@ -99,7 +99,9 @@ def main():
     if rank == 0:
         o_gpu, p_gpu = d.num_observations / world, d.num_points / world
         mv_bytes = o_gpu * 196 + p_gpu * 72 + d.num_cameras * 144
-        mv_ms = kms[3] / max(kl[3], 1)
+        fused = kl[9] > 0                                   # the PCG loop ran as one persistent kernel per linear solve (pcg_fused.cu)
+        mv_ms = kms[3] / max(kl[3], 1)                      # fused: the product phases on the device clock of the first CTA
+        pcg_ms = float(kms[9] / max(kl[3], 1)) if fused else float((fam_ms[3] + fam_ms[4] + fam_ms[8]) / max(fam_l[3], 1))
         hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
         line = {"metric": "BA LM observations/s (n_obs x LM iterations per second; ITERATIVE_SCHUR + SCHUR_JACOBI)", "value": d.num_observations * its / dev_s,
                 "unit": "obs*iter/s", "n_gpus": world, "steps": K, "warmup": W, "steps_timed": its, "ms_per_step": 1e3 * dev_s / max(its, 1), "scaling": "strong",
@@ -107,9 +109,9 @@ def main():
                 "config": {"workload": f"synthetic {args.shape}-shaped BAL ({d.num_cameras} cameras, {d.num_points} points, {d.num_observations} observations), "
                                        "ITERATIVE_SCHUR + SCHUR_JACOBI, trivial loss, seed 1", "parallelism": f"point-partitioned x{world}, cameras replicated, rank-local ingestion"},
                 "pcg_iterations": [r.linear_solver_iterations for r in s.iterations], "final_cost": s.final_cost,
-                "roofline": {"bound": "hbm", "kernel": "k_ba_matvec_tma", "avg_launch_ms": float(mv_ms), "launches": int(kl[3]), "algorithmic_bytes_per_launch": mv_bytes,
+                "roofline": {"bound": "hbm", "kernel": "product phase of k_pcg_solve" if fused else "k_ba_matvec_tma", "avg_launch_ms": float(mv_ms), "launches": int(kl[3]), "algorithmic_bytes_per_launch": mv_bytes,
                              "achieved": mv_bytes / (mv_ms * 1e-3) / 1e9 if mv_ms > 0 else 0.0, "peak": hbm, "frac": (mv_bytes / (mv_ms * 1e-3) / 1e9 / hbm) if mv_ms > 0 else 0.0,
-                             "pcg_iteration_ms": float((fam_ms[3] + fam_ms[4] + fam_ms[8]) / max(fam_l[3], 1)),
+                             "pcg_iteration_ms": pcg_ms, "vector_phase_ms_per_product": float(kms[4] / max(kl[3], 1)) if fused else None,
                              "kernel_family_ms": {_abi.KF_NAMES[i]: float(fam_ms[i]) for i in range(_abi.KF_COUNT)},
                              "kernel_family_launches": {_abi.KF_NAMES[i]: int(fam_l[i]) for i in range(_abi.KF_COUNT)}},
                 "multi_vs_single": mvs, "host_seconds": {"generate": t_gen, "ingest_and_prepare": t_prep}}
