@@ -140,6 +140,22 @@ typedef enum sk_functor_id {
 int sk_functor_info(int functor_id, int* num_residuals, int* num_parameter_blocks,
                     int block_sizes[SK_MAX_PARAMETER_BLOCKS], int* num_consts);
 
+/* A user-defined functor, handed over as CUDA source and compiled at run time (NVRTC, sm_100a) over the device Jet<N>: what
+ * `class MyFunctor extends CostFunctor(kNumResiduals, N0, N1, ...) { def apply[T: Field : Trig : NRoot : Order : ClassTag](x: Array[T]*): Array[T] }`
+ * followed by `.toAutoDiffCostFunction` is on the JVM (CostFunctor.scala:31-51; evaluated there by AutodiffCostFunction.scala:74-134
+ * with one JNI up-call per residual block).  `cuda_source` must define
+ *     template <class T> __device__ bool NAME(const double* consts, T const* const* x, T* residuals);
+ * with x[k] = parameter block k (block_sizes[k] values) and the return value = the functor's success flag (false = the empty-array
+ * convention of CostFunctor.scala:15-26).  T is double or sk::Jet<N0 + N1 + ...>: +, -, *, /, comparisons with doubles, sqrt, exp,
+ * log, sin, cos are overloaded (jet.cuh, the operator set spire gives a Jet); `consts` are the per-residual-block constants given to
+ * sk_cost_function_create (the constructor arguments of the Scala functor).
+ * Returns a functor id (>= 1000) usable wherever a built-in id is: sk_functor_info, sk_cost_function_create / _evaluate,
+ * sk_problem_add_residual_block(s) with the dense back end (DENSE_QR and the normal-Cholesky types).  Compiling needs no device;
+ * the module is loaded on first use.  SK_ERR_INVALID_ARGUMENT with the compiler log in sk_last_error() when the source does not
+ * compile; SK_ERR_UNSUPPORTED when libnvrtc is not available.  Limits: <= 16 residuals, <= 10 blocks, <= 32 parameters in total. */
+int sk_functor_register_source(const char* name, const char* cuda_source, int num_residuals, int num_parameter_blocks,
+                               const int* block_sizes, int num_consts, int* out_functor_id);
+
 typedef struct sk_cost_function sk_cost_function;
 int sk_cost_function_create(int functor_id, const double* consts, int num_consts,
                             sk_cost_function** out);

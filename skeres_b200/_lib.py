@@ -52,6 +52,7 @@ def _load():
         "sk_loss_destroy": (i32, [vp]),
         "sk_loss_evaluate": (i32, [vp, dbl, P(dbl)]),
         "sk_functor_info": (i32, [i32, P(i32), P(i32), P(i32), P(i32)]),
+        "sk_functor_register_source": (i32, [C.c_char_p, C.c_char_p, i32, i32, P(i32), i32, P(i32)]),
         "sk_cost_function_create": (i32, [i32, vp, i32, P(vp)]),
         "sk_cost_function_destroy": (i32, [vp]),
         "sk_cost_function_num_residuals": (i32, [vp]),

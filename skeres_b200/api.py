@@ -249,6 +249,33 @@ class AutoDiffCostFunctor:
         return cf
 
 
+class SourceCostFunctor(AutoDiffCostFunctor):
+    """A functor written by the user, as CUDA source over T = double / Jet<N> (sk_functor_register_source): the device
+    counterpart of subclassing CostFunctor on the JVM (CostFunctor.scala:31-51).
+
+        F = SourceCostFunctor.define("MyResidual", SRC, 1, [1, 1], num_consts=2)     # compile once (NVRTC)
+        cost = F(x_i, y_i).toAutoDiffCostFunction()                                   # per residual block: its constants
+    """
+    @staticmethod
+    def define(name, cuda_source, kNumResiduals, N, num_consts=0):
+        sizes = (C.c_int * len(N))(*N)
+        fid = C.c_int(0)
+        check(lib.sk_functor_register_source(name.encode(), cuda_source.encode(), int(kNumResiduals), len(N), sizes, int(num_consts), C.byref(fid)))
+
+        class _Defined(SourceCostFunctor):
+            functor_id = fid.value
+
+            def __init__(self, *consts):
+                assert len(consts) == num_consts, f"{name} takes {num_consts} constants"
+                super().__init__(kNumResiduals, *N)
+                self._consts = [float(c) for c in consts]
+
+            def consts(self):
+                return self._consts
+        _Defined.__name__ = name
+        return _Defined
+
+
 class SnavelyReprojectionError(AutoDiffCostFunctor):
     """SimpleBundleAdjuster.scala:79-119."""
     functor_id = _abi.FUNCTOR_SNAVELY_REPROJECTION_ERROR

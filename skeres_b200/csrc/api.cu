@@ -16,6 +16,7 @@
 #include "comm.cuh"
 #include "dense_solver.cuh"
 #include "jet.cuh"
+#include "user_functor.cuh"
 
 using namespace sk;
 
@@ -69,13 +70,10 @@ void ensure_device() {
 
 double wall() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-struct EvalArgs {
-  int functor; int has_jac;
-  double consts[SK_MAX_CONSTS];
-  const double* params[SK_MAX_PARAMETER_BLOCKS];
-  double* jac[SK_MAX_PARAMETER_BLOCKS];
-  double* residuals;
-};
+// Sizes of a functor: one of the built-in device functors (jet.cuh) or one compiled at run time from source (user_functor.cu).
+bool lookup_functor(int id, FunctorInfo* fi) { return id >= kUserFunctorBase ? user_functor_info(id, fi) : functor_info(id, fi); }
+const char* const kNoFunctor = "functor id %d is neither a built-in device functor nor one registered from source (sk_functor_register_source); "
+                               "arbitrary JVM functors cannot run on the GPU and there is no CPU fallback";
 
 // AutoDiffCostFunction.evaluate (AutodiffCostFunction.scala:74-134) for one residual block.
 __global__ void k_evaluate_single(EvalArgs a, int* ok_out) {
@@ -206,20 +204,25 @@ int sk_functor_info(int functor_id, int* num_residuals, int* num_parameter_block
                     int* num_consts) {
   SK_API_BEGIN
   FunctorInfo fi;
-  SK_REQUIRE(functor_info(functor_id, &fi), SK_ERR_UNSUPPORTED,
-             "functor id %d is not a registered device functor (arbitrary JVM functors cannot run on the GPU; there is no CPU fallback)", functor_id);
+  SK_REQUIRE(lookup_functor(functor_id, &fi), SK_ERR_UNSUPPORTED, kNoFunctor, functor_id);
   if (num_residuals) *num_residuals = fi.nres;
   if (num_parameter_blocks) *num_parameter_blocks = fi.nblk;
   if (num_consts) *num_consts = fi.nconsts;
   if (block_sizes) for (int i = 0; i < SK_MAX_PARAMETER_BLOCKS; ++i) block_sizes[i] = fi.sizes[i];
   SK_API_END
 }
+int sk_functor_register_source(const char* name, const char* cuda_source, int num_residuals, int num_parameter_blocks, const int* block_sizes,
+                               int num_consts, int* out_functor_id) {
+  SK_API_BEGIN
+  SK_REQUIRE(out_functor_id != nullptr, SK_ERR_INVALID_ARGUMENT, "sk_functor_register_source: null output");
+  *out_functor_id = register_user_functor(name, cuda_source, num_residuals, num_parameter_blocks, block_sizes, num_consts);
+  SK_API_END
+}
 int sk_cost_function_create(int functor_id, const double* consts, int num_consts, sk_cost_function** out) {
   SK_API_BEGIN
   SK_REQUIRE(out != nullptr, SK_ERR_INVALID_ARGUMENT, "sk_cost_function_create: null output");
   FunctorInfo fi;
-  SK_REQUIRE(functor_info(functor_id, &fi), SK_ERR_UNSUPPORTED,
-             "functor id %d is not a registered device functor (arbitrary JVM functors cannot run on the GPU; there is no CPU fallback)", functor_id);
+  SK_REQUIRE(lookup_functor(functor_id, &fi), SK_ERR_UNSUPPORTED, kNoFunctor, functor_id);
   SK_REQUIRE(num_consts == fi.nconsts && (consts != nullptr || num_consts == 0), SK_ERR_INVALID_ARGUMENT,
              "functor %d takes %d constants, got %d", functor_id, fi.nconsts, num_consts);
   std::unique_ptr<sk_cost_function> f(new sk_cost_function);
@@ -251,7 +254,8 @@ int sk_cost_function_evaluate(const sk_cost_function* f, const sk_double_pointer
   check_block(residuals.array, residuals.offset, f->info.nres, "residuals");
   a.residuals = residuals.array->d.p + residuals.offset;
   DBuf<int> d_ok(1);
-  k_evaluate_single<<<1, 1>>>(a, d_ok.p);
+  if (f->functor_id >= kUserFunctorBase) launch_user_evaluate_single(f->functor_id, a, d_ok.p, nullptr);
+  else k_evaluate_single<<<1, 1>>>(a, d_ok.p);
   check_launch("k_evaluate_single");
   SK_CUDA(cudaMemcpy(ok, d_ok.p, sizeof(int), cudaMemcpyDeviceToHost));
   SK_API_END
@@ -343,8 +347,7 @@ int sk_problem_add_residual_blocks(sk_problem* p, int functor_id, int64_t n, con
   SK_REQUIRE(p != nullptr && array != nullptr && block_offsets != nullptr && n >= 0, SK_ERR_INVALID_ARGUMENT,
              "sk_problem_add_residual_blocks: null argument");
   FunctorInfo fi;
-  SK_REQUIRE(functor_info(functor_id, &fi), SK_ERR_UNSUPPORTED,
-             "functor id %d is not a registered device functor (arbitrary JVM functors cannot run on the GPU; there is no CPU fallback)", functor_id);
+  SK_REQUIRE(lookup_functor(functor_id, &fi), SK_ERR_UNSUPPORTED, kNoFunctor, functor_id);
   SK_REQUIRE(consts != nullptr || fi.nconsts == 0 || n == 0, SK_ERR_INVALID_ARGUMENT, "missing constants");
   {
     int64_t bad = -1;                                          // lowest offending residual block, whatever the thread count

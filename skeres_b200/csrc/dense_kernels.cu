@@ -2,6 +2,7 @@
 // evaluator (A.2), DenseQRSolver (A.8: unpivoted Householder QR of [J; D] with Eigen's reflector
 // convention), the off-diagonal part of SchurEliminator::Eliminate (A.5) and Eigen LLT.
 #include "dense_kernels.cuh"
+#include "user_functor.cuh"
 
 #include "lm_kernels.cuh"
 
@@ -34,7 +35,7 @@ __global__ void k_dense_evaluate(int nrb, const DenseRb* __restrict__ rbs, const
   __shared__ double red[32];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double cost = 0.0;
-  if (i < nrb) {
+  if (i < nrb && rbs[i].functor < kUserFunctorBase) {     // run-time compiled functors: their own kernels (user_functor.cu)
     const DenseRb rb = rbs[i];
     FunctorInfo fi;
     functor_info(rb.functor, &fi);

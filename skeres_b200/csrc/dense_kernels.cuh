@@ -4,17 +4,10 @@
 #pragma once
 #include "ba_kernels.cuh"
 #include "common.cuh"
+#include "eval_abi.cuh"
 #include "jet.cuh"
 
 namespace sk {
-
-// One residual block of a generic (dense-path) problem, device side.
-struct DenseRb {
-  int functor, row, loss_type, pad_;
-  double loss_a, loss_b;
-  double consts[SK_MAX_CONSTS];
-  int col[SK_MAX_PARAMETER_BLOCKS];     // first column of each parameter block in the state vector
-};
 
 // Residuals + (unscaled) dense Jacobian J (m x n column-major, ld = m); b = corrected residuals.
 // Entries of J not covered by a residual block must already be zero (structure is fixed).

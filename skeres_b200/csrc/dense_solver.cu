@@ -8,6 +8,7 @@
 #include <map>
 
 #include "ba_solver.cuh"
+#include "user_functor.cuh"
 
 namespace sk {
 
@@ -30,6 +31,9 @@ DenseSolver::DenseSolver(const sk_solver_options& opt, cudaStream_t stream, cons
   SK_REQUIRE(n >= 1 && n <= 4096, SK_ERR_UNSUPPORTED, "DENSE_QR on the device supports 1..4096 parameters (got %lld)", (long long)n);
   SK_REQUIRE((double)(m_ + n) * (double)(n + 1) < 2.5e8, SK_ERR_UNSUPPORTED, "dense problem too large for DENSE_QR (%d x %lld)", m_, (long long)n);
   allocate(n, n);
+  for (const DenseRb& rb : rbs) if (rb.functor >= kUserFunctorBase) user_functors_.push_back(rb.functor);
+  std::sort(user_functors_.begin(), user_functors_.end());
+  user_functors_.erase(std::unique(user_functors_.begin(), user_functors_.end()), user_functors_.end());
   d_rbs_.upload(rbs, stream_);
   d_ptrs_.upload(scalar_ptrs, stream_);
   J_.alloc((size_t)m_ * n); J_.zero(stream_);
@@ -51,15 +55,25 @@ void DenseSolver::fill_summary(sk_solver_summary_data* d) {
 }
 ReduceJob DenseSolver::cost_job() { return {block_cost_.p, cdiv(nrb_, 128), SB_COST, 0}; }
 
+// The built-in functors in one launch (it writes every cost slot), then one launch per run-time compiled functor, in id order,
+// each adding its residual blocks' cost to the slots: a fixed order, hence reproducible.
+void DenseSolver::evaluate(const double* xv, bool with_jacobian, const int* guard) {
+  launch_dense_evaluate(nrb_, d_rbs_.p, xv, with_jacobian, with_jacobian ? J_.p : nullptr, m_, with_jacobian ? b_.p : nullptr, block_cost_.p,
+                        &st_.p->eval_failed, guard, stream_);
+  for (int id : user_functors_)
+    launch_user_dense_evaluate(id, with_jacobian, nrb_, d_rbs_.p, xv, with_jacobian ? J_.p : nullptr, m_, with_jacobian ? b_.p : nullptr,
+                               block_cost_.p, &st_.p->eval_failed, guard, stream_);
+}
+
 void DenseSolver::eval_jacobian(bool scale_valid, bool /*store*/, const int* guard) {
-  KScope k(prof_, SK_KF_EVALUATE_JACOBIAN, 3);
-  launch_dense_evaluate(nrb_, d_rbs_.p, x_.p, true, J_.p, m_, b_.p, block_cost_.p, &st_.p->eval_failed, guard, stream_);
+  KScope k(prof_, SK_KF_EVALUATE_JACOBIAN, 3 + (int)user_functors_.size());
+  evaluate(x_.p, true, guard);
   launch_dense_gradient(m_, (int)n_, J_.p, b_.p, grad_.p, guard, stream_);
   launch_dense_scale_norms(m_, (int)n_, J_.p, scale_valid ? scale_.p : nullptr, cnorm2_.p, guard, stream_);
 }
 void DenseSolver::eval_cost(const double* xv, const int* guard) {
-  KScope k(prof_, SK_KF_EVALUATE_COST);
-  launch_dense_evaluate(nrb_, d_rbs_.p, xv, false, nullptr, m_, nullptr, block_cost_.p, &st_.p->eval_failed, guard, stream_);
+  KScope k(prof_, SK_KF_EVALUATE_COST, 1 + (int)user_functors_.size());
+  evaluate(xv, false, guard);
 }
 ReduceJob DenseSolver::linear_solve(const PcgDev** pcg_out) {
   *pcg_out = nullptr;

@@ -1,5 +1,6 @@
 // dense_solver.cuh — DENSE_QR back end of the LM driver for small generic problems.
 #pragma once
+#include <vector>
 #include "dense_kernels.cuh"
 #include "lm_solver.cuh"
 
@@ -22,7 +23,9 @@ class DenseSolver : public LmSolver {
   void fill_summary(sk_solver_summary_data* d) override;
 
  private:
+  void evaluate(const double* xv, bool with_jacobian, const int* guard);
   int nrb_, m_, nparam_blocks_;
+  std::vector<int> user_functors_;        // run-time compiled functors among the residual blocks (user_functor.cu), ascending
   DBuf<DenseRb> d_rbs_;
   DBuf<double*> d_ptrs_;
   DBuf<double> J_, b_, W_, block_cost_, mcc_part_;

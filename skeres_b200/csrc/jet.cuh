@@ -75,6 +75,18 @@ template <int N> SK_HD void jsincos(const Jet<N>& x, Jet<N>* s, Jet<N>* c) {
   SK_JET_LOOP { s->v[i] = ca * x.v[i]; c->v[i] = -sa * x.v[i]; }
 }
 template <int N> SK_HD Jet<N> jexp(const Jet<N>& x) { Jet<N> r; const double e = exp(x.a); r.a = e; SK_JET_LOOP r.v[i] = e * x.v[i]; return r; }
+template <int N> SK_HD Jet<N> jlog(const Jet<N>& x) { Jet<N> r; const double inv = 1.0 / x.a; r.a = log(x.a); SK_JET_LOOP r.v[i] = x.v[i] * inv; return r; }
+// The names a functor written for T = double uses (spire's Trig / NRoot instances on Jet, package.scala): found by argument-dependent
+// lookup when T = Jet<N>, so that ONE functor body serves both instantiations -- also for functors compiled at run time.
+using ::sqrt; using ::exp; using ::log; using ::sin; using ::cos;      // keep the double versions visible next to the overloads
+template <int N> SK_HD Jet<N> sqrt(const Jet<N>& x) { return jsqrt(x); }
+template <int N> SK_HD Jet<N> exp(const Jet<N>& x) { return jexp(x); }
+template <int N> SK_HD Jet<N> log(const Jet<N>& x) { return jlog(x); }
+template <int N> SK_HD Jet<N> sin(const Jet<N>& x) { Jet<N> s, c; jsincos(x, &s, &c); return s; }
+template <int N> SK_HD Jet<N> cos(const Jet<N>& x) { Jet<N> s, c; jsincos(x, &s, &c); return c; }
+template <int N> SK_HD bool operator<(const Jet<N>& x, double y) { return x.a < y; }
+template <int N> SK_HD bool operator>(const Jet<N>& x, const Jet<N>& y) { return x.a > y.a; }
+template <int N> SK_HD bool operator<(const Jet<N>& x, const Jet<N>& y) { return x.a < y.a; }
 SK_HD double jsqrt(double x) { return sqrt(x); }
 SK_HD void jsincos(double x, double* s, double* c) {
 #ifdef __CUDA_ARCH__

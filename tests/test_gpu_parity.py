@@ -95,6 +95,68 @@ def test_golden_vectors_host_abi(sk):
         assert ok and jacs[0] is None and jacs[1].ravel().tolist() == case["jacobians"][1]
 
 
+def test_user_functors_from_source(sk):
+    """the three AutodiffCostFuntionSpec functors supplied AS SOURCE STRINGS (sk_functor_register_source:
+    NVRTC over the device Jet<N>) reproduce the reference's golden vectors exactly, through the same NULL-jacobians and
+    NULL-row branches as the built-in registrations."""
+    import user_functor_sources as U
+    for (name, src, nres, sizes, nconsts), case in zip(U.SPEC, load("autodiff_spec_vectors.json")["cases"]):
+        F = sk.SourceCostFunctor.define(name, src, nres, sizes, nconsts)
+        cf = F(*case["consts"]).toAutoDiffCostFunction()
+        assert cf.functor_id >= 1000 and cf.kNumResiduals == nres and cf.N == sizes
+        ok, res, jacs = cf.evaluate_host(case["parameters"], want_jacobians=False)
+        assert ok and res.tolist() == case["residuals"] and jacs is None
+        ok, res, jacs = cf.evaluate_host(case["parameters"])
+        assert ok and res.tolist() == case["residuals"]
+        for j, want in zip(jacs, case["jacobians"]):
+            assert j.ravel().tolist() == want
+        ok, res, jacs = cf.evaluate_host(case["parameters"], skip_blocks=(0,))
+        assert ok and jacs[0] is None and jacs[1].ravel().tolist() == case["jacobians"][1]
+
+
+def test_user_functor_solves_curve_fitting_like_the_builtin(sk):
+    """CurveFitting.scala with ExponentialResidual given as source: every LM row equals the built-in functor's run (the
+    same arithmetic on the same duals), including the published final (0.291861, 0.131439); and a problem that MIXES
+    built-in and run-time functors gives the same rows again."""
+    import user_functor_sources as U
+    d = load("curve_fitting_data.json")
+    F = sk.SourceCostFunctor.define("UserExponentialResidual", U.EXPONENTIAL, 1, [1, 1], 2)
+
+    def fit(make):
+        m, c = sk.DoubleArray(1), sk.DoubleArray(1)
+        problem = sk.Problem()
+        for i, (xi, yi) in enumerate(zip(d["x"], d["y"])):
+            problem.addResidualBlock(make(i, xi, yi).toAutoDiffCostFunction(), sk.PredefinedLossFunctions.trivialLoss(), m.toPointer(), c.toPointer())
+        o = sk.Solver.Options()
+        o.setMaxNumIterations(25); o.setLinearSolverType(_abi.DENSE_QR)
+        s = sk.Solver.Summary()
+        sk.ceres.solve(o, problem, s)
+        return [m.get(0), c.get(0)], s
+    x0, s0 = fit(lambda i, x, y: sk.ExponentialResidual(x, y))
+    x1, s1 = fit(lambda i, x, y: F(x, y))
+    x2, s2 = fit(lambda i, x, y: F(x, y) if i % 2 else sk.ExponentialResidual(x, y))
+    for xs, s in ((x1, s1), (x2, s2)):
+        assert len(s.iterations) == len(s0.iterations) == 14 and s.termination_type == s0.termination_type
+        for a, b in zip(s.iterations, s0.iterations):
+            assert (a.step_is_successful, a.linear_solver_iterations) == (b.step_is_successful, b.linear_solver_iterations)
+            assert np.isclose(a.cost, b.cost, rtol=1e-13) and np.isclose(a.trust_region_radius, b.trust_region_radius, rtol=1e-12)
+        assert np.allclose(xs, x0, rtol=1e-12)
+    assert [float(f"{v:.6f}") for v in x1] == [0.291861, 0.131439]
+
+
+def test_user_functor_is_rejected_by_the_schur_solvers(sk):
+    import user_functor_sources as U
+    F = sk.SourceCostFunctor.define("UserExponentialResidual", U.EXPONENTIAL, 1, [1, 1], 2)
+    m, c = sk.DoubleArray(1), sk.DoubleArray(1)
+    problem = sk.Problem()
+    problem.addResidualBlock(F(1.0, 2.0).toAutoDiffCostFunction(), None, m.toPointer(), c.toPointer())
+    o = sk.Solver.Options()
+    o.setLinearSolverType(_abi.ITERATIVE_SCHUR)
+    with pytest.raises(sk.SkeresError) as e:
+        sk.ceres.solve(o, problem, sk.Solver.Summary())
+    assert e.value.status == _abi.ERR_UNSUPPORTED
+
+
 def test_golden_vectors_device_pointers(sk):
     """The same through device DoubleArrays / DoublePointers, as the Scala spec does with RichDoubleMatrix."""
     case = load("autodiff_spec_vectors.json")["cases"][1]

@@ -569,3 +569,30 @@ def test_local_range_equals_partition_points(world):
         for r in range(world):
             assert bal.localRange(r, world) == (int(ptr[begin[r]]), int(ptr[begin[r + 1]])), (r, world)
         assert bal.localRange(0, world)[0] == 0 and bal.localRange(world - 1, world)[1] == d.num_observations
+
+
+def test_user_functor_sources_compile_without_a_gpu():
+    """sk_functor_register_source: NVRTC turns the functor source plus the library's own jet.cuh into
+    sm_100a kernels; compiling needs no device (the module is loaded at first use), so the generated translation unit is
+    checked here.  A source that does not compile comes back as INVALID_ARGUMENT with the compiler's log."""
+    import ctypes as C
+    import user_functor_sources as U
+    from skeres_b200 import _abi
+    from skeres_b200._lib import lib
+    ids = []
+    for name, src, nres, sizes, nconsts in U.SPEC + [("UserExponentialResidual", U.EXPONENTIAL, 1, [1, 1], 2)]:
+        fid = C.c_int(0)
+        st = lib.sk_functor_register_source(name.encode(), src.encode(), nres, len(sizes), (C.c_int * len(sizes))(*sizes), nconsts, C.byref(fid))
+        assert st == _abi.OK, lib.sk_last_error().decode()
+        assert fid.value >= 1000 and fid.value not in ids
+        ids.append(fid.value)
+        nr, nb, nc = C.c_int(), C.c_int(), C.c_int()
+        bs = (C.c_int * 10)()
+        assert lib.sk_functor_info(fid.value, C.byref(nr), C.byref(nb), bs, C.byref(nc)) == _abi.OK
+        assert (nr.value, nb.value, nc.value, list(bs)[:len(sizes)]) == (nres, len(sizes), nconsts, sizes)
+    fid = C.c_int(0)
+    bad = "template <class T> __device__ bool Broken(const double* c, T const* const* x, T* r) { r[0] = undefined_symbol; return true; }"
+    st = lib.sk_functor_register_source(b"Broken", bad.encode(), 1, 1, (C.c_int * 1)(1), 0, C.byref(fid))
+    assert st == _abi.ERR_INVALID_ARGUMENT and "undefined_symbol" in lib.sk_last_error().decode()
+    st = lib.sk_functor_register_source(b"not an identifier", bad.encode(), 1, 1, (C.c_int * 1)(1), 0, C.byref(fid))
+    assert st == _abi.ERR_INVALID_ARGUMENT
