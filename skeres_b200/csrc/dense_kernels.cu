@@ -194,8 +194,9 @@ __global__ void k_schur_offdiag(BaDev L, const int* __restrict__ pair_ptr, const
   if (t >= 81) return;
   const int a = t / 9, b = t - a * 9;
   const size_t O = (size_t)L.n_obs;
-  double val = 0.0;
-  for (int q = pair_ptr[g]; q < pair_ptr[g + 1]; ++q) {
+  // entry (a, b) of G_o1^T (E^T E)^-1 G_o2 for one shared point; four points in flight at a time (the loads of a point hang off
+  // its three indices: one after the other they cost two global round trips per point), added in list order as before
+  auto term = [&](int q) {
     const int o1 = pair_o1[q], o2 = pair_o2[q];
     const double* m = einv + (size_t)pair_pt[q] * 6;
     const double2 fa = J2[a * O + o1], fb = J2[b * O + o2];
@@ -209,8 +210,19 @@ __global__ void k_schur_offdiag(BaDev L, const int* __restrict__ pair_ptr, const
     const double h0 = m[0] * g2[0] + m[1] * g2[1] + m[2] * g2[2];
     const double h1 = m[1] * g2[0] + m[3] * g2[1] + m[4] * g2[2];
     const double h2 = m[2] * g2[0] + m[4] * g2[1] + m[5] * g2[2];
-    val += g1[0] * h0 + g1[1] * h1 + g1[2] * h2;
+    return g1[0] * h0 + g1[1] * h1 + g1[2] * h2;
+  };
+  double val = 0.0;
+  int q = pair_ptr[g];
+  const int qe = pair_ptr[g + 1];
+  for (; q + 4 <= qe; q += 4) {
+    double tq[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) tq[u] = term(q + u);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) val += tq[u];
   }
+  for (; q < qe; ++q) val += term(q);
   const size_t nc = (size_t)L.n_cams * 9;
   const size_t r = (size_t)pair_c1[g] * 9 + a, c = (size_t)pair_c2[g] * 9 + b;
   S[r * nc + c] = -val;
@@ -220,96 +232,147 @@ __global__ void k_schur_offdiag(BaDev L, const int* __restrict__ pair_ptr, const
 // ---- blocked Cholesky (lower), both triangles kept consistent (upper = L^T) ------------------------
 constexpr int NB = 32;
 
-__global__ void k_chol_diag(int n, int k0, int kb, double* __restrict__ A, int* error_flag) {
-  __shared__ double T[NB][NB + 1];
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  if (tx < kb && ty < kb) T[ty][tx] = A[(size_t)(k0 + ty) * n + k0 + tx];
-  __syncthreads();
+// In-place lower Cholesky of the kb x kb block T (shared memory, row stride NB + 1) by ONE warp, left-looking: column j is
+// L_ij = (A_ij - sum_{k<j} L_ik L_jk) / L_jj with lane i = row i (L_jk is a broadcast read, L_ik conflict-free at the odd stride).
+// No CTA barrier inside (round 1 factored the block with 1024 threads and three barriers per column).  A register-resident
+// right-looking variant (row per lane, L_kj by shuffle, fully unrolled) measured SLOWER: 56.6 against 35.0 us per panel kernel
+// (profiles/r02_v3_dense_path.md).  A pivot that is not > 0 raises bit 4 of *error_flag.
+__device__ __forceinline__ void chol_block_warp(double (*T)[NB + 1], int kb, int* error_flag, bool report) {
+  const int i = threadIdx.x & 31;
   for (int j = 0; j < kb; ++j) {
-    if (tx == 0 && ty == 0) {
-      const double d = T[j][j];
-      if (!(d > 0.0)) { atomicOr(error_flag, 4); T[j][j] = 1.0; } else T[j][j] = sqrt(d);
-    }
-    __syncthreads();
-    if (ty == 0 && tx > j && tx < kb) T[tx][j] = T[tx][j] / T[j][j];
-    __syncthreads();
-    if (tx > j && ty > j && tx < kb && ty < kb && ty >= tx) T[ty][tx] -= T[ty][j] * T[tx][j];
-    __syncthreads();
-  }
-  if (tx < kb && ty < kb) {
-    const double v = (ty >= tx) ? T[ty][tx] : T[tx][ty];      // lower = L, upper = L^T
-    A[(size_t)(k0 + ty) * n + k0 + tx] = v;
+    double s = (i >= j && i < kb) ? T[i][j] : 0.0;
+    for (int k = 0; k < j; ++k) s -= ((i >= j && i < kb) ? T[i][k] : 0.0) * T[j][k];
+    double d = __shfl_sync(0xffffffffu, s, j);
+    if (!(d > 0.0)) { if (report && i == 0) atomicOr(error_flag, 4); d = 1.0; }
+    const double r = sqrt(d);
+    if (i == j) T[i][j] = r;
+    else if (i > j && i < kb) T[i][j] = s / r;
+    __syncwarp();
   }
 }
 
-// L_ik = A_ik L_kk^-T for the rows below the diagonal block; also mirrors into the upper triangle.
-__global__ void k_chol_panel(int n, int k0, int kb, double* __restrict__ A) {
+// Diagonal block of panel k0 (factored redundantly by every CTA: no launch and no trip through memory in between; CTA 0
+// writes it back, lower = L and upper = L^T) and L_ik = A_ik L_kk^-T for the CTA's 32 rows below it, mirrored into the upper
+// triangle.  blockDim = (32, 32): the 32 threads that share ty are one warp and own one row of the panel; the row's triangular
+// solve runs j = 0 .. kb-1 with the dot product over t < j spread over the warp's lanes (fixed shuffle tree).
+// gridDim.x = max(1, row blocks below the panel).
+__global__ void __launch_bounds__(1024) k_chol_panel(int n, int k0, int kb, double* __restrict__ A, int* error_flag) {
   __shared__ double Lk[NB][NB + 1];
   __shared__ double X[NB][NB + 1];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int r0 = k0 + kb + blockIdx.x * NB;
-  if (tx < kb && ty < kb) Lk[ty][tx] = A[(size_t)(k0 + ty) * n + k0 + tx];
+  Lk[ty][tx] = (tx < kb && ty < kb) ? A[(size_t)(k0 + ty) * n + k0 + tx] : 0.0;
   const int row = r0 + ty;
-  if (row < n && tx < kb) X[ty][tx] = A[(size_t)row * n + k0 + tx];
+  X[ty][tx] = (row < n && tx < kb) ? A[(size_t)row * n + k0 + tx] : 0.0;
   __syncthreads();
-  if (tx == 0 && row < n) {
+  if (ty == 0) chol_block_warp(Lk, kb, error_flag, blockIdx.x == 0);
+  __syncthreads();
+  if (blockIdx.x == 0 && tx < kb && ty < kb) A[(size_t)(k0 + ty) * n + k0 + tx] = (ty >= tx) ? Lk[ty][tx] : Lk[tx][ty];
+  if (row < n) {
+    double xj_mine = X[ty][tx];                            // lane tx keeps X[ty][tx]; finished entries are final
     for (int j = 0; j < kb; ++j) {
-      double s = X[ty][j];
-      for (int t = 0; t < j; ++t) s -= X[ty][t] * Lk[j][t];
-      X[ty][j] = s / Lk[j][j];
+      double part = (tx < j) ? xj_mine * Lk[j][tx] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      if (tx == j) xj_mine = (xj_mine - part) / Lk[j][j];
+    }
+    if (tx < kb) {
+      A[(size_t)row * n + k0 + tx] = xj_mine;
+      A[(size_t)(k0 + tx) * n + row] = xj_mine;
     }
   }
-  __syncthreads();
-  if (row < n && tx < kb) {
-    const double v = X[ty][tx];
-    A[(size_t)row * n + k0 + tx] = v;
-    A[(size_t)(k0 + tx) * n + row] = v;
-  }
 }
 
-// A_ij -= sum_t L_i,k0+t L_j,k0+t for the trailing lower tiles.
-__global__ void k_chol_update(int n, int k0, int kb, double* __restrict__ A) {
+// ---- FP64 tensor-core tile product -------------------------------------------------------------------------------------------
+// D(8x8) += A(8x4) * B(4x8): mma.sync.aligned.m8n8k4.row.col.f64 (DMMA).  Lane l supplies a = A[l / 4][l % 4] and
+// b = B[l % 4][l / 4] and holds d0 = D[l / 4][2 (l % 4)], d1 = D[l / 4][2 (l % 4) + 1].
+__device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// A_ij -= sum_t L_i,k0+t L_j,k0+t for the trailing lower tiles: the one real dense contraction of the hot path (north_star (3)),
+// (n - k0)^2 / 2 * kb multiply-adds per panel, on the FP64 tensor pipe.  One CTA of 16 warps per 32 x 32 tile of the trailing
+// matrix; warp (wi, wj) owns the 8 x 8 sub-tile and walks the panel's kb columns four at a time.
+__global__ void __launch_bounds__(512) k_chol_update(int n, int k0, int kb, double* __restrict__ A) {
   const int bi = blockIdx.y, bj = blockIdx.x;
   if (bj > bi) return;
-  __shared__ double Li[NB][NB + 1];
-  __shared__ double Lj[NB][NB + 1];
-  const int tx = threadIdx.x, ty = threadIdx.y;
+  __shared__ double Li[NB][NB + 4];                        // +4: the (row, 4 consecutive k) fragment loads hit distinct banks
+  __shared__ double Lj[NB][NB + 4];
+  const int tid = threadIdx.x;
   const int base = k0 + kb;
-  const int i = base + bi * NB + ty, jrow = base + bj * NB + ty;
-  if (tx < kb) {
-    Li[ty][tx] = (i < n) ? A[(size_t)i * n + k0 + tx] : 0.0;
-    Lj[ty][tx] = (jrow < n) ? A[(size_t)jrow * n + k0 + tx] : 0.0;
+  for (int e = tid; e < NB * NB; e += 512) {
+    const int r = e / NB, c = e - r * NB;
+    const int i = base + bi * NB + r, j = base + bj * NB + r;
+    Li[r][c] = (c < kb && i < n) ? A[(size_t)i * n + k0 + c] : 0.0;
+    Lj[r][c] = (c < kb && j < n) ? A[(size_t)j * n + k0 + c] : 0.0;
   }
   __syncthreads();
-  const int j = base + bj * NB + tx;
-  if (i < n && j < n && j <= i) {
-    double s = 0.0;
-    for (int t = 0; t < kb; ++t) s += Li[ty][t] * Lj[tx][t];
-    A[(size_t)i * n + j] -= s;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int wi = warp >> 2, wj = warp & 3;
+  const int fr = lane >> 2, fk = lane & 3;
+  double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+  for (int ks = 0; ks < NB; ks += 4) dmma_8x8x4(d0, d1, Li[wi * 8 + fr][ks + fk], Lj[wj * 8 + fr][ks + fk]);
+  const int i = base + bi * NB + wi * 8 + fr;
+  const int j = base + bj * NB + wj * 8 + 2 * fk;
+  if (i < n) {
+    if (j < n && j <= i) A[(size_t)i * n + j] -= d0;
+    if (j + 1 < n && j + 1 <= i) A[(size_t)i * n + j + 1] -= d1;
   }
 }
 
-// Forward (L y = b, using the mirrored upper triangle row-wise) and backward (L^T z = y) substitution.
+// Forward (L y = b) and backward (L^T z = y) substitution in blocks of 32 unknowns: the diagonal block is solved by one warp out
+// of shared memory (lane i keeps unknown i, one shuffle per step), then all threads subtract the block's contribution from the
+// unknowns still open (coalesced rows of the mirrored triangle).  Two CTA barriers per 32 unknowns (round 1: two per unknown).
 __global__ void __launch_bounds__(1024) k_chol_solve(int n, const double* __restrict__ A, const double* __restrict__ rhs,
                                                      double* __restrict__ z) {
-  __shared__ double piv;
+  __shared__ double Dg[NB][NB + 1];
+  __shared__ double zb[NB];
   const int tid = threadIdx.x, nthr = blockDim.x;
   for (int i = tid; i < n; i += nthr) z[i] = rhs[i];
   __syncthreads();
-  for (int j = 0; j < n; ++j) {
-    if (tid == 0) { piv = z[j] / A[(size_t)j * n + j]; z[j] = piv; }
+  // forward: L y = b
+  for (int k0 = 0; k0 < n; k0 += NB) {
+    const int kb = min(NB, n - k0);
+    for (int e = tid; e < NB * NB; e += nthr) { const int r = e / NB, c = e - r * NB; Dg[r][c] = (r < kb && c < kb) ? A[(size_t)(k0 + r) * n + k0 + c] : 0.0; }
     __syncthreads();
-    const double yj = piv;
-    const double* urow = A + (size_t)j * n;              // U[j][i] = L[i][j]
-    for (int i = j + 1 + tid; i < n; i += nthr) z[i] -= urow[i] * yj;
+    if (tid < 32) {
+      double zi = (tid < kb) ? z[k0 + tid] : 0.0;
+      for (int j = 0; j < kb; ++j) {
+        const double zj = __shfl_sync(0xffffffffu, zi, j) / Dg[j][j];
+        if (tid == j) zi = zj;
+        else if (tid > j && tid < kb) zi -= Dg[tid][j] * zj;               // L[i][j], i > j
+      }
+      if (tid < kb) { z[k0 + tid] = zi; zb[tid] = zi; }
+    }
+    __syncthreads();
+    for (int i = k0 + kb + tid; i < n; i += nthr) {
+      double s = 0.0;
+      for (int j = 0; j < kb; ++j) s += A[(size_t)(k0 + j) * n + i] * zb[j];  // U[k0 + j][i] = L[i][k0 + j]: coalesced over i
+      z[i] -= s;
+    }
     __syncthreads();
   }
-  for (int j = n - 1; j >= 0; --j) {
-    if (tid == 0) { piv = z[j] / A[(size_t)j * n + j]; z[j] = piv; }
+  // backward: L^T z = y
+  for (int k1 = n; k1 > 0; k1 -= NB) {
+    const int k0 = max(0, k1 - NB), kb = k1 - k0;
+    for (int e = tid; e < NB * NB; e += nthr) { const int r = e / NB, c = e - r * NB; Dg[r][c] = (r < kb && c < kb) ? A[(size_t)(k0 + r) * n + k0 + c] : 0.0; }
     __syncthreads();
-    const double zj = piv;
-    const double* lrow = A + (size_t)j * n;              // L[j][i], i < j  == U[i][j]
-    for (int i = tid; i < j; i += nthr) z[i] -= lrow[i] * zj;
+    if (tid < 32) {
+      double zi = (tid < kb) ? z[k0 + tid] : 0.0;
+      for (int j = kb - 1; j >= 0; --j) {
+        const double zj = __shfl_sync(0xffffffffu, zi, j) / Dg[j][j];
+        if (tid == j) zi = zj;
+        else if (tid < j) zi -= Dg[j][tid] * zj;                            // L^T[i][j] = L[j][i], i < j
+      }
+      if (tid < kb) { z[k0 + tid] = zi; zb[tid] = zi; }
+    }
+    __syncthreads();
+    for (int i = tid; i < k0; i += nthr) {
+      double s = 0.0;
+      for (int j = 0; j < kb; ++j) s += A[(size_t)(k0 + j) * n + i] * zb[j];  // L[k0 + j][i], i < k0: coalesced over i
+      z[i] -= s;
+    }
     __syncthreads();
   }
 }
@@ -351,16 +414,12 @@ void launch_schur_offdiag(const BaDev& L, int n_groups, const int* pair_ptr, con
 }
 int launch_cholesky_solve(int n, double* S, const double* rhs, double* z, int* error_flag, cudaStream_t s) {
   int launches = 0;
-  const dim3 tb(NB, NB);
   for (int k0 = 0; k0 < n; k0 += NB) {
     const int kb = std::min(NB, n - k0);
-    k_chol_diag<<<1, tb, 0, s>>>(n, k0, kb, S, error_flag); ++launches;
     const int rem = n - k0 - kb;
-    if (rem > 0) {
-      const int nt = cdiv(rem, NB);
-      k_chol_panel<<<nt, tb, 0, s>>>(n, k0, kb, S); ++launches;
-      k_chol_update<<<dim3(nt, nt), tb, 0, s>>>(n, k0, kb, S); ++launches;
-    }
+    const int nt = cdiv(rem, NB);
+    k_chol_panel<<<std::max(nt, 1), dim3(NB, NB), 0, s>>>(n, k0, kb, S, error_flag); ++launches;       // diagonal block + the rows below it
+    if (rem > 0) { k_chol_update<<<dim3(nt, nt), 512, 0, s>>>(n, k0, kb, S); ++launches; }   // trailing update on the FP64 tensor pipe
   }
   k_chol_solve<<<1, 1024, 0, s>>>(n, S, rhs, z); ++launches;
   check_launch("cholesky");
