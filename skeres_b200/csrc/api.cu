@@ -28,8 +28,8 @@ struct sk_cost_function { int functor_id; FunctorInfo info; double consts[SK_MAX
 struct ResidualGroup {              // n residual blocks of one functor / loss over one array per block slot
   int functor_id; FunctorInfo info; LossSpec loss;
   std::vector<sk_double_array*> arrays;   // per residual block per parameter block (size n * nblk)
-  std::vector<double> consts;             // n * nconsts
-  std::vector<int64_t> offsets;           // n * nblk
+  RawVector<double> consts;                // n * nconsts   (RawVector: filled by parallel copies, never zeroed first)
+  RawVector<int64_t> offsets;              // n * nblk
   int64_t n = 0;
 };
 struct DeclaredBlocks { sk_double_array* array; int32_t size; std::vector<int64_t> offsets; };   // AddParameterBlock
@@ -622,7 +622,21 @@ int sk_solver_minimize(sk_solver* solver, int32_t max_num_iterations_override, s
   SK_API_END
 }
 
-int sk_solver_destroy(sk_solver* solver) { SK_API_BEGIN delete solver; SK_API_END }
+int sk_solver_destroy(sk_solver* solver) {
+  SK_API_BEGIN
+  if (solver != nullptr && getenv("SKERES_TRACE_HOST")) {
+    const double t0 = wall();
+    solver->impl.reset();
+    const double t1 = wall();
+    if (solver->stream) { cudaStreamDestroy(solver->stream); solver->stream = nullptr; }
+    const double t2 = wall();
+    fprintf(stderr, "[skeres] sk_solver_destroy: solver %.3f s (pool: sync %.3f s, free %.3f s over %ld blocks), stream %.3f s\n", t1 - t0,
+            DevicePool::get().t_sync, DevicePool::get().t_free, DevicePool::get().n_give, t2 - t1);
+    DevicePool::get().t_sync = DevicePool::get().t_free = 0.0; DevicePool::get().n_give = 0;
+  }
+  delete solver;
+  SK_API_END
+}
 
 int sk_solver_time_schur_product(sk_solver* solver, int32_t reps, double* out_ms_per_launch) {
   SK_API_BEGIN

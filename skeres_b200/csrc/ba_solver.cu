@@ -135,6 +135,7 @@ BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHo
     S_.alloc((size_t)nc * nc);
     seg_M_.alloc((size_t)45 * std::max(H.n_segs, 1)); M45_.alloc((size_t)45 * H.n_cams);
   }
+  release_host_layout();
 }
 
 // Per-tile metadata records of the implicit-Schur product (ba_tile_rec.h), packed on the host and uploaded once.
@@ -415,14 +416,24 @@ double BaSolver::time_linear_operator(int reps) {
   return total_ms / reps;
 }
 
-BaSolver::~BaSolver() {
-  peer_allreduce_destroy(&peer_);
+// The host copy of the layout is hundreds of MB at Venice scale and nothing reads its per-observation arrays once the device
+// copies exist.  Returning it to the OS takes up to 80 ms, so it is handed to a detached thread (plain host memory, no CUDA
+// calls) -- at the END OF CONSTRUCTION, where it overlaps the first LM iterations, not at destruction, where it delayed the
+// caller and (through the process's mmap lock) whatever else the tear-down unmaps.  Counts and the camera table stay.
+void BaSolver::release_host_layout() {
   if ((size_t)H_.n_obs < (size_t)1 << 20) return;            // small: freed in place with the other members
   try {
     auto* drop = new BaLayoutHost(std::move(H_));
+    H_ = BaLayoutHost{};
+    H_.n_obs = drop->n_obs; H_.n_pts = drop->n_pts; H_.n_cams = drop->n_cams; H_.n_tiles = drop->n_tiles; H_.n_segs = drop->n_segs;
+    H_.max_seg_tile = drop->max_seg_tile; H_.max_pt_tile = drop->max_pt_tile; H_.n_giant = drop->n_giant; H_.n_chunks = drop->n_chunks;
+    H_.input_was_sorted = drop->input_was_sorted;
+    H_.cam_offset = drop->cam_offset;                         // exchange_local_totals
     std::thread([drop] { delete drop; }).detach();
-  } catch (...) {}                                          // no thread: H_ (or *drop, leaked at worst) is freed the usual way
+  } catch (...) {}                                            // no thread: *drop is leaked at worst, H_ keeps what it has
 }
+
+BaSolver::~BaSolver() { peer_allreduce_destroy(&peer_); }
 
 void BaSolver::exchange_local_totals() {
   local_blocks_ = true;

@@ -10,8 +10,6 @@ class BaSolver : public LmSolver {
   // user_params: device pointer of the user's parameter DoubleArray (all blocks live in it).
   BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHost&& layout, double* user_params,
            int64_t user_n, LossSpec loss);
-  // The host copy of the layout is hundreds of MB at Venice scale; unmapping it took up to 80 ms of sk_solver_destroy, so it
-  // is handed to a detached thread (plain host memory, no CUDA calls).
   ~BaSolver() override;
   void fill_totals(int64_t total_obs, int64_t total_blocks, int64_t total_params, std::vector<int64_t>&& all_pt_off);
   // Rank-local ingestion (sk_solver_options.residual_blocks_are_local): sums the per-rank observation / point counts for
@@ -21,7 +19,6 @@ class BaSolver : public LmSolver {
 
   // ---- test / debug access (sk_debug_* entry points) ---------------------------------------------
   const BaDev& layout() const { return L_; }
-  const BaLayoutHost& host_layout() const { return H_; }
 
  protected:
   void eval_jacobian(bool scale_valid, bool store, const int* guard) override;
@@ -37,6 +34,7 @@ class BaSolver : public LmSolver {
   const double* matvec(const double* in, bool pcg_dir, const int* guard);
   void pcg_solve(const double* Minv, const double* global_lin_flag);
   void build_pair_lists();
+  void release_host_layout();
   void build_tile_records();
   void explicit_schur_solve();
 

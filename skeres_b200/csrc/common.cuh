@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -72,13 +73,18 @@ class DevicePool {
     const size_t r = rounded(bytes);
     int cur = 0; cudaGetDevice(&cur);
     if (cur != dev) cudaSetDevice(dev);
+    const auto t0 = std::chrono::steady_clock::now();
     cudaDeviceSynchronize();                           // nothing in flight may still touch the block (see above)
+    const auto t1 = std::chrono::steady_clock::now();
     bool keep = false;
     {
       std::lock_guard<std::mutex> g(mu_);
       if (cached_ + r <= max_cached_) { free_.insert({{dev, r}, p}); cached_ += r; keep = true; }
     }
     if (!keep) cudaFree(p);
+    t_sync += std::chrono::duration<double>(t1 - t0).count();
+    t_free += std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
+    ++n_give;
     if (cur != dev) cudaSetDevice(cur);
   }
   void release_all() {
@@ -89,6 +95,7 @@ class DevicePool {
     cudaSetDevice(cur);
   }
   size_t cached_bytes() { std::lock_guard<std::mutex> g(mu_); return cached_; }
+  double t_sync = 0.0, t_free = 0.0; long n_give = 0;   // development trace (SKERES_TRACE_HOST): where tear-down time goes
 
  private:
   DevicePool() { const char* e = std::getenv("SKERES_POOL_MAX_GB"); max_cached_ = (size_t)((e ? atof(e) : 16.0) * (double)(1ull << 30)); }
@@ -118,15 +125,40 @@ struct DBuf {
   void download(T* h, size_t count, cudaStream_t s) const { if (count) SK_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s)); }
 };
 
-// Pinned host buffer (readback targets).
+// Pinned host buffer (readback targets).  Freed blocks are kept per size and reused: cudaFreeHost unmaps pinned pages and was
+// seen to stall a solver's tear-down for up to 0.45 s when another thread was returning large host vectors to the OS at the
+// same time (both need the process's mmap lock); the buffers are a few hundred bytes each.
+class PinnedPool {
+ public:
+  static PinnedPool& get() { static PinnedPool* p = new PinnedPool; return *p; }
+  void* take(size_t bytes) {
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      auto it = free_.find(bytes);
+      if (it != free_.end()) { void* p = it->second; free_.erase(it); return p; }
+    }
+    void* p = nullptr;
+    SK_CUDA(cudaMallocHost(&p, bytes));
+    return p;
+  }
+  void give(void* p, size_t bytes) {
+    std::lock_guard<std::mutex> g(mu_);
+    if (free_.size() < 256) { free_.insert({bytes, p}); return; }
+    cudaFreeHost(p);
+  }
+ private:
+  std::mutex mu_;
+  std::multimap<size_t, void*> free_;
+};
 template <class T>
 struct HBuf {
   T* p = nullptr; size_t n = 0;
   HBuf() = default;
   explicit HBuf(size_t count) { alloc(count); }
   HBuf(const HBuf&) = delete; HBuf& operator=(const HBuf&) = delete;
-  ~HBuf() { if (p) cudaFreeHost(p); }
-  void alloc(size_t count) { if (p) cudaFreeHost(p); p = nullptr; n = count; if (count) SK_CUDA(cudaMallocHost((void**)&p, count * sizeof(T))); }
+  ~HBuf() { release(); }
+  void release() { if (p) PinnedPool::get().give(p, n * sizeof(T)); p = nullptr; n = 0; }
+  void alloc(size_t count) { release(); n = count; if (count) p = static_cast<T*>(PinnedPool::get().take(count * sizeof(T))); }
 };
 
 // Per-solve launch accounting + optional CUDA-event timing per kernel family.
