@@ -105,6 +105,23 @@ JNIEXPORT jlong JNICALL FN(costFunctionCreate)(JNIEnv* env, jclass cls, jint fun
   return ok(env, sk_cost_function_create((int)functor, c, (int)n, &f)) ? J(f) : 0;
 }
 JNIEXPORT void JNICALL FN(costFunctionDestroy)(JNIEnv* env, jclass cls, jlong h) { (void)cls; ok(env, sk_cost_function_destroy(H(sk_cost_function, h))); }
+/* A functor given as CUDA source over T = double / Jet<N> (sk_functor_register_source): the device counterpart of subclassing
+ * CostFunctor on the JVM.  Returns the functor id to pass to costFunctionCreate. */
+JNIEXPORT jint JNICALL FN(functorRegisterSource)(JNIEnv* env, jclass cls, jstring name, jstring source, jint numResiduals, jintArray blockSizes,
+                                                 jint numConsts) {
+  int id = -1, sizes[SK_MAX_PARAMETER_BLOCKS] = {0};
+  const char* cname; const char* csrc;
+  jsize nblk = blockSizes ? (*env)->GetArrayLength(env, blockSizes) : 0;
+  (void)cls;
+  if (name == NULL || source == NULL || nblk < 1 || nblk > SK_MAX_PARAMETER_BLOCKS) { ok(env, SK_ERR_INVALID_ARGUMENT); return -1; }
+  (*env)->GetIntArrayRegion(env, blockSizes, 0, nblk, (jint*)sizes);
+  cname = (*env)->GetStringUTFChars(env, name, NULL);
+  csrc = (*env)->GetStringUTFChars(env, source, NULL);
+  ok(env, (cname && csrc) ? sk_functor_register_source(cname, csrc, (int)numResiduals, (int)nblk, sizes, (int)numConsts, &id) : SK_ERR_INTERNAL);
+  if (csrc) (*env)->ReleaseStringUTFChars(env, source, csrc);
+  if (cname) (*env)->ReleaseStringUTFChars(env, name, cname);
+  return (jint)id;
+}
 /* bool evaluate(parameters, residuals, jacobians) on device-resident blocks: arrays/offsets describe the DoublePointers;
  * jacobianArrays == null <=> jacobians.isNull, a 0 handle inside it <=> jacobians.getRow(i).isNull (:80, :118) */
 JNIEXPORT jboolean JNICALL FN(costFunctionEvaluate)(JNIEnv* env, jclass cls, jlong h, jlongArray paramArrays, jlongArray paramOffsets,

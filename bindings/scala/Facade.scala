@@ -49,6 +49,25 @@ abstract class AutoDiffCostFunctor(val kNumResiduals: Int, val N: Int*) {
   def toAutoDiffCostFunction: CostFunction = new CostFunction(Native.costFunctionCreate(functorId, consts))
 }
 
+/** A functor whose body is handed to the library as CUDA source (sk_functor_register_source) and compiled once for the device:
+  * the port of `def apply[T](x: Array[T]*): Array[T]` is
+  * `template <class T> __device__ bool Name(const double* consts, T const* const* x, T* residuals)`.
+  * {{{
+  *   val Exp = SourceCostFunctor.define("ExponentialResidual", src, 1, Seq(1, 1), numConsts = 2)
+  *   problem.addResidualBlock(Exp(x, y).toAutoDiffCostFunction, loss, m.toPointer, c.toPointer)
+  * }}} */
+object SourceCostFunctor {
+  final class Defined(val functorId: Int, kNumResiduals: Int, N: Seq[Int], numConsts: Int) {
+    def apply(cs: Double*): AutoDiffCostFunctor = {
+      require(cs.length == numConsts, s"functor takes $numConsts constants")
+      val id = functorId
+      new AutoDiffCostFunctor(kNumResiduals, N: _*) { def functorId: Int = id; override def consts: Array[Double] = cs.toArray }
+    }
+  }
+  def define(name: String, cudaSource: String, kNumResiduals: Int, N: Seq[Int], numConsts: Int = 0): Defined =
+    new Defined(Native.functorRegisterSource(name, cudaSource, kNumResiduals, N.toArray, numConsts), kNumResiduals, N, numConsts)
+}
+
 /** Problem.scala:16-33. */
 final class Problem extends AutoCloseable {
   val handle: Long = Native.problemCreate()

@@ -23,6 +23,7 @@ object Native {
 
   @native def costFunctionCreate(functorId: Int, consts: Array[Double]): Long
   @native def costFunctionDestroy(h: Long): Unit
+  @native def functorRegisterSource(name: String, cudaSource: String, numResiduals: Int, blockSizes: Array[Int], numConsts: Int): Int
   @native def costFunctionEvaluate(h: Long, paramArrays: Array[Long], paramOffsets: Array[Long], residualArray: Long,
                                    residualOffset: Long, jacobianArrays: Array[Long], jacobianOffsets: Array[Long]): Boolean
 

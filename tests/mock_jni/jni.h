@@ -7,7 +7,7 @@
 #include <stdint.h>
 typedef int32_t jint; typedef int64_t jlong; typedef int8_t jbyte; typedef uint8_t jboolean; typedef double jdouble; typedef jint jsize;
 typedef struct _jobject* jobject; typedef jobject jclass; typedef jobject jstring; typedef jobject jarray; typedef jarray jdoubleArray;
-typedef jarray jlongArray; typedef jarray jbyteArray;
+typedef jarray jlongArray; typedef jarray jbyteArray; typedef jarray jintArray;
 #define JNI_FALSE 0
 #define JNI_TRUE 1
 #define JNI_ABORT 2
@@ -23,6 +23,7 @@ struct JNINativeInterface_ {
   void (*ReleasePrimitiveArrayCritical)(JNIEnv*, jarray, void*, jint);
   void (*GetDoubleArrayRegion)(JNIEnv*, jdoubleArray, jsize, jsize, jdouble*);
   void (*GetLongArrayRegion)(JNIEnv*, jlongArray, jsize, jsize, jlong*);
+  void (*GetIntArrayRegion)(JNIEnv*, jintArray, jsize, jsize, jint*);
   void (*GetByteArrayRegion)(JNIEnv*, jbyteArray, jsize, jsize, jbyte*);
   void (*SetByteArrayRegion)(JNIEnv*, jbyteArray, jsize, jsize, const jbyte*);
   jbyteArray (*NewByteArray)(JNIEnv*, jsize);
