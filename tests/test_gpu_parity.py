@@ -639,7 +639,9 @@ def test_matvec_kernels_agree_bitwise(sk, monkeypatch, case, sums):
 @pytest.mark.parametrize("case,prec,kw", [(dict(shape="small", seed=2), _abi.SCHUR_JACOBI, {}), (dict(shape="ladybug-49", seed=1), _abi.SCHUR_JACOBI, {}),
                                           (MEDIUM_TRACK_CASE, _abi.JACOBI, {}), (dict(shape="small", seed=3), _abi.IDENTITY, {}),
                                           (dict(shape="ladybug-49", seed=1), _abi.SCHUR_JACOBI, dict(eta=1e-10, max_linear_solver_iterations=3000, max_num_iterations=3)),
-                                          (dict(shape="tiny", seed=1), _abi.SCHUR_JACOBI, dict(max_linear_solver_iterations=3))])
+                                          (dict(shape="tiny", seed=1), _abi.SCHUR_JACOBI, dict(max_linear_solver_iterations=3)),
+                                          # more virtual blocks of 8 cameras (313) than persistent CTAs (196 tiles): two blocks per round
+                                          (dict(n_cam=2500, n_pt=8000, n_obs=50000, seed=7), _abi.SCHUR_JACOBI, dict(max_num_iterations=6))])
 def test_fused_pcg_matches_kernel_sequence_bitwise(sk, monkeypatch, case, prec, kw):
     """The fused PCG solve (one persistent cooperative kernel per linear solve: products, vector phases and termination tests
     behind grid barriers, pcg_fused.cu) is built from the device functions of the kernel sequence (pcg_kernels.cu) and must
