@@ -857,6 +857,62 @@ __global__ void k_ba_export_jacobian(BaDev L, const double2* __restrict__ J2, do
   for (int k = 0; k < 3; ++k) { const double2 e = J2[(9 + k) * O + i]; E[(size_t)i * 6 + k] = e.x; E[(size_t)i * 6 + 3 + k] = e.y; }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Per-tile metadata records of the implicit-Schur product (ba_tile_rec.h), packed ON THE DEVICE from the layout arrays that are
+// uploaded anyway: one CTA per tile.  Byte for byte what the host builder (ba_layout.cu: build_tile_records, kept for the
+// host-side checks and as SKERES_TILE_REC=host) writes into a zero-filled buffer; packing 19,539 records of the Venice shape
+// took 35 ms on the host and another 66 MB of upload -- a third of the solver's set-up time.
+__global__ void __launch_bounds__(T) k_ba_build_tile_records(BaDev L, unsigned char* __restrict__ rec, int stride, int sp, int pp, int sc) {
+  const int t = blockIdx.x, tid = threadIdx.x;
+  unsigned char* base = rec + (size_t)t * stride;
+  unsigned short* slot = reinterpret_cast<unsigned short*>(base); unsigned short* ptl = slot + T; unsigned short* sperm = ptl + T;
+  unsigned short* srank = sperm + T;
+  int* sptr = reinterpret_cast<int*>(base + 8 * T); int* pptr = sptr + sp; int* scam = pptr + pp; int* spos = scam + sp;
+  unsigned short* pchunk = reinterpret_cast<unsigned short*>(spos + sp); unsigned short* pcptr = pchunk + T; unsigned short* schunk = pcptr + pp;
+  unsigned short* scptr = schunk + sc;
+  const int ob = L.tile_obs[t], no = L.tile_obs[t + 1] - ob, pb = L.tile_pt[t];
+  const int npe = L.tile_np[t];                            // > 0: points of a regular tile; < 0: chunk tile of a long track
+  const int sb = L.tile_seg[t], ns = L.tile_seg[t + 1] - sb;
+  __shared__ int s_sptr[T + 1], s_pptr[T + 1], s_cnt[T + 1];
+  if (tid < no) {
+    const unsigned short sp_ = L.seg_perm[ob + tid];
+    slot[tid] = L.obs_slot[ob + tid]; ptl[tid] = L.obs_ptl[ob + tid]; sperm[tid] = sp_;
+    srank[sp_] = (unsigned short)tid;
+  }
+  for (int s = tid; s <= ns; s += T) { const int v = L.seg_ptr[sb + s] - ob; sptr[s] = v; s_sptr[s] = v; }
+  for (int s = tid; s < ns; s += T) { scam[s] = L.seg_cam[sb + s]; spos[s] = L.seg_pos[sb + s]; }
+  __syncthreads();
+  // chunk tables of the two-level sums: first chunk of every segment = exclusive prefix sum of the segments' chunk counts
+  if (tid == 0) {
+    int nc = 0;
+    for (int s = 0; s < ns; ++s) { s_cnt[s] = nc; nc += (s_sptr[s + 1] - s_sptr[s] + kSegChunk - 1) / kSegChunk; }
+    s_cnt[ns] = nc;
+  }
+  __syncthreads();
+  for (int s = tid; s <= ns; s += T) scptr[s] = (unsigned short)s_cnt[s];
+  for (int s = tid; s < ns; s += T) {
+    int nc = s_cnt[s];
+    for (int b = s_sptr[s]; b < s_sptr[s + 1]; b += kSegChunk) schunk[nc++] = (unsigned short)(b | ((min(kSegChunk, s_sptr[s + 1] - b) - 1) << 8));
+  }
+  if (npe > 0) {                                           // chunk tiles of long tracks have no per-point phase in the tile kernels
+    const int np = npe;
+    __syncthreads();
+    for (int q = tid; q <= np; q += T) { const int v = L.pt_ptr[pb + q] - ob; pptr[q] = v; s_pptr[q] = v; }
+    __syncthreads();
+    if (tid == 0) {
+      int nc = 0;
+      for (int q = 0; q < np; ++q) { s_cnt[q] = nc; nc += (s_pptr[q + 1] - s_pptr[q] + kPtChunk - 1) / kPtChunk; }
+      s_cnt[np] = nc;
+    }
+    __syncthreads();
+    for (int q = tid; q <= np; q += T) pcptr[q] = (unsigned short)s_cnt[q];
+    for (int q = tid; q < np; q += T) {
+      int nc = s_cnt[q];
+      for (int b = s_pptr[q]; b < s_pptr[q + 1]; b += kPtChunk) pchunk[nc++] = (unsigned short)(b | ((min(kPtChunk, s_pptr[q + 1] - b) - 1) << 8));
+    }
+  }
+}
+
 template <class K>
 void set_smem(K kernel, size_t bytes) {
   if (bytes > 48 * 1024) SK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -1005,6 +1061,13 @@ void launch_ba_back_substitute(const BaDev& L, const double2* J2, const double2*
     k_ba_back_substitute_giant<<<L.n_giant, T, smem_g, s>>>(L, J2, r2, z, einv, step, tile_mcc);
   }
   check_launch("k_ba_back_substitute");
+}
+
+void launch_ba_build_tile_records(const BaDev& L, unsigned char* rec, const TileRecDims& d, cudaStream_t s) {
+  if (L.n_tiles == 0) return;
+  SK_CUDA(cudaMemsetAsync(rec, 0, (size_t)L.n_tiles * d.stride, s));
+  k_ba_build_tile_records<<<L.n_tiles, T, 0, s>>>(L, rec, d.stride, d.sp, d.pp, d.sc);
+  check_launch("k_ba_build_tile_records");
 }
 
 void launch_ba_export_jacobian(const BaDev& L, const double2* J2, double* F, double* E, cudaStream_t s) {

@@ -74,6 +74,10 @@ void launch_ba_matvec(const BaDev& L, const double2* J2, const double* p, const 
 // tmapJ: 2-D tensor map over the stored Jacobian (make_jacobian_tensor_map), or nullptr = one bulk copy per plane.
 bool make_jacobian_tensor_map(const double2* J2, int n_obs, CUtensorMap* out);   // false when the problem is too small for the box
 
+// Packs the per-tile metadata records (ba_tile_rec.h) on the device: rec = n_tiles * d.stride bytes, d = tile_rec_dims(...).
+// Needs L.seg_pos and the layout arrays; byte-identical to the host builder.
+void launch_ba_build_tile_records(const BaDev& L, unsigned char* rec, const TileRecDims& d, cudaStream_t s);
+
 // Back-substitution + model cost change. z = reduced solution [9C] (not negated).
 //   step[9C + 3p + k] = -y_p ; tile_mcc[t] = sum_i m_i . (r_i + m_i / 2), m = J * step
 void launch_ba_back_substitute(const BaDev& L, const double2* J2, const double2* r2, const double* z,

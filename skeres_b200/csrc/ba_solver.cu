@@ -140,10 +140,18 @@ BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHo
 
 // Per-tile metadata records of the implicit-Schur product (ba_tile_rec.h), packed on the host and uploaded once.
 void BaSolver::build_tile_records() {
-  TileRecDims dims; std::vector<unsigned char> rec;
-  sk::build_tile_records(H_, &dims, &rec);
-  d_tile_rec_.upload(rec, stream_);
-  SK_CUDA(cudaStreamSynchronize(stream_));
+  const char* e = getenv("SKERES_TILE_REC");               // development / tests: SKERES_TILE_REC=host packs them on the host
+  if (e != nullptr && e[0] == 'h') {
+    TileRecDims dims; std::vector<unsigned char> rec;
+    sk::build_tile_records(H_, &dims, &rec);
+    d_tile_rec_.upload(rec, stream_);
+    SK_CUDA(cudaStreamSynchronize(stream_));
+    L_.tile_rec = d_tile_rec_.p; L_.rec_stride = dims.stride; L_.rec_sp = dims.sp; L_.rec_pp = dims.pp; L_.rec_sc = dims.sc;
+    return;
+  }
+  const TileRecDims dims = tile_rec_dims(std::max(H_.max_seg_tile, 1), std::max(H_.max_pt_tile, 1));
+  d_tile_rec_.alloc((size_t)std::max(H_.n_tiles, 1) * dims.stride);
+  launch_ba_build_tile_records(L_, d_tile_rec_.p, dims, stream_);
   L_.tile_rec = d_tile_rec_.p; L_.rec_stride = dims.stride; L_.rec_sp = dims.sp; L_.rec_pp = dims.pp; L_.rec_sc = dims.sc;
 }
 

@@ -663,6 +663,23 @@ def test_fused_pcg_matches_kernel_sequence_bitwise(sk, monkeypatch, case, prec, 
     assert runs[0][3] == runs[1][3]                                         # products executed: counted by the host / derived from the readback
 
 
+@pytest.mark.parametrize("sums", ["serial", "chunked"])
+@pytest.mark.parametrize("case", [dict(shape="ladybug-49", seed=1), MEDIUM_TRACK_CASE, LONG_TRACK_SMALL])
+def test_device_built_tile_records_equal_the_host_builder(sk, monkeypatch, case, sums):
+    """The per-tile metadata records of the implicit-Schur product are packed by a kernel (k_ba_build_tile_records); the host
+    builder (ba_layout.cu, checked against a direct evaluation by tests/hostcheck) stays as SKERES_TILE_REC=host.  Every field
+    of a record steers the product -- slots, point / segment starts, permutations, camera ids, output rows and, for the
+    two-level sums, the chunk tables -- so identical LM rows and identical parameters, bit for bit, mean identical records."""
+    d = synth.make_bal(**case)
+    monkeypatch.setenv("SKERES_MATVEC_SUMS", sums)
+    runs = []
+    for where in ("host", "device"):
+        monkeypatch.setenv("SKERES_TILE_REC", where)
+        bal, s = gpu_ba(sk, d, _abi.ITERATIVE_SCHUR, _abi.SCHUR_JACOBI, max_num_iterations=5)
+        runs.append(([r.cost for r in s.iterations], [r.linear_solver_iterations for r in s.iterations], bal.parameters.toArray()))
+    assert runs[0][0] == runs[1][0] and runs[0][1] == runs[1][1] and np.array_equal(runs[0][2], runs[1][2])
+
+
 def test_fused_pcg_needs_no_host_polling(sk, monkeypatch):
     """north_star (4): one readback per LM iteration.  With the fused solve a linear solve is ONE launch whatever its
     iteration count, so the launches of a whole solve are a fixed number per LM iteration."""
