@@ -500,7 +500,13 @@ static std::unique_ptr<LmSolver> prepare_ba(const sk_solver_options& opt, sk_pro
   const ResidualGroup* single = nullptr;                    // one bulk group (the usual case): read its arrays in place
   for (auto& g : p->groups) if (g.n == n) single = &g;
   double tp1 = tp0;
-  if (single != nullptr) {
+  // The usual case -- one bulk group, one GPU or rank-local blocks, implicit Schur solver -- is built by kernels from the uploaded
+  // residual-block table (ba_layout_device.cu); anything that path does not cover falls through to the host builder.
+  BaLayoutDevice dev;
+  const bool try_device = single != nullptr && world == 1 && opt.linear_solver_type == SK_ITERATIVE_SCHUR;
+  if (try_device && build_ba_layout_device(n, single->offsets.data(), single->consts.data(), extra, stream, &H, &dev)) {
+  } else if (single != nullptr) {
+    H = BaLayoutHost{};
     build_ba_layout(n, single->offsets.data(), single->offsets.data() + 1, single->consts.data(), rank, world, &H, 2, extra);
   } else {
     std::vector<int64_t> cam_off((size_t)n), pt_off((size_t)n);
@@ -522,7 +528,7 @@ static std::unique_ptr<LmSolver> prepare_ba(const sk_solver_options& opt, sk_pro
     total_points = (int64_t)all_pt.size();
   }
   const int64_t n_cams = H.n_cams;
-  std::unique_ptr<BaSolver> solver(new BaSolver(opt, stream, std::move(H), array->d.p, array->n, loss));
+  std::unique_ptr<BaSolver> solver(new BaSolver(opt, stream, std::move(H), array->d.p, array->n, loss, &dev));
   solver->fill_totals(n, n_cams + total_points, 9 * n_cams + 3 * total_points, std::move(all_pt));
   if (local && opt.comm != nullptr && opt.comm->world > 1) solver->exchange_local_totals();
   if (trace) fprintf(stderr, "[skeres] preprocess: flatten %.3f s, layout %.3f s, device set-up %.3f s\n", tp1 - tp0, tp2 - tp1, wall() - tp2);

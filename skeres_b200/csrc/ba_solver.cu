@@ -37,10 +37,21 @@ __global__ void k_scatter_blocks(int nblocks, int bsize, const long long* __rest
 }  // namespace
 
 BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHost&& layout, double* user_params,
-                   int64_t user_n, LossSpec loss)
+                   int64_t user_n, LossSpec loss, BaLayoutDevice* dev)
     : LmSolver(opt, stream), H_(std::move(layout)), user_(user_params), user_n_(user_n), loss_(loss) {
   const auto& H = H_;
   cudaStream_t s = stream_;
+  if (dev != nullptr && dev->valid) {
+    // built on the device: nothing to upload
+    d_tile_obs_ = std::move(dev->tile_obs); d_tile_pt_ = std::move(dev->tile_pt); d_tile_seg_ = std::move(dev->tile_seg);
+    d_pt_ptr_ = std::move(dev->pt_ptr); d_obs_slot_ = std::move(dev->obs_slot); d_obs_ptl_ = std::move(dev->obs_ptl);
+    d_seg_perm_ = std::move(dev->seg_perm); d_seg_ptr_ = std::move(dev->seg_ptr); d_seg_cam_ = std::move(dev->seg_cam);
+    d_cam_seg_ptr_ = std::move(dev->cam_seg_ptr); d_cam_seg_ = std::move(dev->cam_seg); d_seg_pos_ = std::move(dev->seg_pos);
+    d_obs_ = std::move(dev->obs); d_tile_np_ = std::move(dev->tile_np);
+    d_cam_off_ = std::move(dev->cam_off); d_pt_off_ = std::move(dev->pt_off);
+    d_gp_begin_.alloc(1); d_gp_count_.alloc(1); d_gp_point_.alloc(1);
+    chunk_pt_.alloc(6);
+  } else {
   d_tile_obs_.upload(H.tile_obs, s); d_tile_pt_.upload(H.tile_pt, s); d_tile_seg_.upload(H.tile_seg, s);
   d_pt_ptr_.upload(H.pt_ptr, s); d_obs_slot_.upload(H.obs_slot, s); d_obs_ptl_.upload(H.obs_ptl, s);
   d_seg_perm_.upload(H.seg_perm, s); d_seg_ptr_.upload(H.seg_ptr, s); d_seg_cam_.upload(H.seg_cam, s);
@@ -58,6 +69,7 @@ BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHo
   std::vector<long long> co(H.cam_offset.begin(), H.cam_offset.end()), po(H.pt_offset.begin(), H.pt_offset.end());
   d_cam_off_.upload(co, s); d_pt_off_.upload(po, s);
   SK_CUDA(cudaStreamSynchronize(s));   // host vectors above are temporaries / pageable
+  }
   L_.n_obs = H.n_obs; L_.n_pts = H.n_pts; L_.n_cams = H.n_cams; L_.n_tiles = H.n_tiles; L_.n_segs = H.n_segs;
   L_.max_seg_tile = std::max(H.max_seg_tile, 1); L_.max_pt_tile = std::max(H.max_pt_tile, 1);
   L_.tile_obs = d_tile_obs_.p; L_.tile_pt = d_tile_pt_.p; L_.tile_seg = d_tile_seg_.p; L_.pt_ptr = d_pt_ptr_.p;
@@ -141,7 +153,7 @@ BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHo
 // Per-tile metadata records of the implicit-Schur product (ba_tile_rec.h), packed on the host and uploaded once.
 void BaSolver::build_tile_records() {
   const char* e = getenv("SKERES_TILE_REC");               // development / tests: SKERES_TILE_REC=host packs them on the host
-  if (e != nullptr && e[0] == 'h') {
+  if (e != nullptr && e[0] == 'h' && !H_.obs_slot.empty()) {
     TileRecDims dims; std::vector<unsigned char> rec;
     sk::build_tile_records(H_, &dims, &rec);
     d_tile_rec_.upload(rec, stream_);

@@ -1,6 +1,7 @@
 // ba_solver.cuh — bundle-adjustment back end of the LM driver (see ba_solver.cu).
 #pragma once
 #include "ba_kernels.cuh"
+#include "ba_layout_device.cuh"
 #include "lm_solver.cuh"
 
 namespace sk {
@@ -8,8 +9,10 @@ namespace sk {
 class BaSolver : public LmSolver {
  public:
   // user_params: device pointer of the user's parameter DoubleArray (all blocks live in it).
+  // dev != nullptr && dev->valid: the layout arrays are already on the device (ba_layout_device.cu) and are adopted; `layout`
+  // then carries counts, per-tile maxima and the camera table only.
   BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHost&& layout, double* user_params,
-           int64_t user_n, LossSpec loss);
+           int64_t user_n, LossSpec loss, BaLayoutDevice* dev = nullptr);
   ~BaSolver() override;
   void fill_totals(int64_t total_obs, int64_t total_blocks, int64_t total_params, std::vector<int64_t>&& all_pt_off);
   // Rank-local ingestion (sk_solver_options.residual_blocks_are_local): sums the per-rank observation / point counts for

@@ -680,6 +680,23 @@ def test_device_built_tile_records_equal_the_host_builder(sk, monkeypatch, case,
     assert runs[0][0] == runs[1][0] and runs[0][1] == runs[1][1] and np.array_equal(runs[0][2], runs[1][2])
 
 
+@pytest.mark.parametrize("case", [dict(shape="tiny", seed=1), dict(shape="ladybug-49", seed=1), MEDIUM_TRACK_CASE,
+                                  dict(n_cam=2500, n_pt=8000, n_obs=50000, seed=7), dict(n_cam=300, n_pt=60000, n_obs=400000, seed=3)])
+def test_device_built_layout_equals_the_host_builder(sk, monkeypatch, case):
+    """the layout (dense ids, point CSR, tiles, tile-local camera segments, camera -> segment lists) is built by
+    kernels from the uploaded residual-block table (ba_layout_device.cu); the host builder (ba_layout.cu) stays as
+    SKERES_LAYOUT=host and for what the device path hands back (unsorted input, long tracks, explicit Schur solvers).  Every
+    array of the layout steers the kernels, so bit-identical LM rows and parameters mean identical layouts."""
+    d = synth.make_bal(**case)
+    runs = []
+    for where in ("host", "device"):
+        monkeypatch.setenv("SKERES_LAYOUT", where)
+        bal, s = gpu_ba(sk, d, _abi.ITERATIVE_SCHUR, _abi.SCHUR_JACOBI, max_num_iterations=5)
+        runs.append(([r.cost for r in s.iterations], [r.linear_solver_iterations for r in s.iterations], bal.parameters.toArray(),
+                     (s.num_residual_blocks, s.num_parameter_blocks, s.num_parameters)))
+    assert runs[0][0] == runs[1][0] and runs[0][1] == runs[1][1] and np.array_equal(runs[0][2], runs[1][2]) and runs[0][3] == runs[1][3]
+
+
 def test_fused_pcg_needs_no_host_polling(sk, monkeypatch):
     """north_star (4): one readback per LM iteration.  With the fused solve a linear solve is ONE launch whatever its
     iteration count, so the launches of a whole solve are a fixed number per LM iteration."""
