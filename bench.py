@@ -98,9 +98,10 @@ def source_hash():
 
 
 def ncu_traffic(n_obs):
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of THIS kernel source on THIS
-    workload (profiles/matvec_traffic.json, keyed by source_hash()); None -- with the reason -- when the kernel has changed since
-    the last capture or the workload is another one.  bench.py cannot run ncu itself."""
+    """DRAM bytes PER PRODUCT of the dominant kernel from the committed `ncu --set full` capture of THIS kernel source on THIS
+    workload (profiles/matvec_traffic.json, keyed by source_hash(): dram__bytes_read.sum + dram__bytes_write.sum of one
+    k_pcg_solve launch divided by the products it executed); None -- with the reason -- when the kernel has changed since the
+    last capture or the workload is another one.  bench.py cannot run ncu itself."""
     path = os.path.join(ROOT, "profiles", "matvec_traffic.json")
     key = source_hash()
     try:
@@ -111,7 +112,7 @@ def ncu_traffic(n_obs):
         return None, f"no ncu capture committed for kernel source {key} (profiles/matvec_traffic.json)"
     if int(t["n_obs"]) != int(n_obs):
         return None, f"ncu capture is for n_obs = {t['n_obs']}"
-    return float(t["bytes_per_launch"]), t["source"]
+    return float(t["bytes_per_product"]), t["source"]
 
 
 def matvec_algorithmic_bytes(n_obs, n_pts, n_cams):
@@ -388,14 +389,16 @@ def main():
     achieved = products * mv_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     path_bytes = path_algorithmic_bytes(o1, p1, n_cam, A["jac"], A["cost"], A["lin"], int(kl[3]))
     path_gbs = path_bytes / dev_s / 1e9 if dev_s > 0 else 0.0
-    traffic, traffic_src = ncu_traffic(o1) if world == 1 else (None, "single-GPU capture only")
+    traffic_pp, traffic_src = ncu_traffic(o1) if world == 1 else (None, "single-GPU capture only")
     if fused:
         pcg_ms = mv_ms
     else:
         pcg_ms = None if fam_ms is None or fam_launches[3] == 0 else float((fam_ms[3] + fam_ms[4] + fam_ms[8]) / fam_launches[3])
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": hbm_peak,
                 "unit": "GB/s", "frac": achieved / hbm_peak, "frac_of_nominal_8000_GBps": achieved / 8000.0,
-                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                # per launch like `achieved`: the capture's bytes per product x the products per launch of this run
+                "traffic": None if traffic_pp is None else traffic_pp * products / max(dom_launches, 1),
+                "traffic_per_product": traffic_pp, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": products * mv_bytes / max(dom_launches, 1), "avg_launch_ms": dom_ms / max(dom_launches, 1),
                 "launches": dom_launches,
                 "algorithmic_bytes_per_product": mv_bytes, "products": products, "ms_per_product": mv_ms,
