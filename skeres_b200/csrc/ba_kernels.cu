@@ -273,21 +273,22 @@ __host__ __device__ constexpr int upper_col(int idx) {
 
 // Entry IDX (0..44) of the packed upper 9x9 block one observation contributes: F^T F - G^T (E^T E)^-1 G, indices folded at
 // compile time so that F, G, H stay in registers.
+// Entry (k, l) of an observation's contribution to its camera's diagonal block of the reduced matrix,
+//   F^T F - G^T (E^T E)^-1 G  with  G = E^T F      (SchurEliminator)
+// written as F^T P F with the 2 x 2 projector P = I - E (E^T E)^-1 E^T of the observation: 18 values (Pf = P F) instead of the 54
+// of G and H = (E^T E)^-1 G stay alive across the three staging rounds -- the kernel spilled 196 bytes at the 128 registers that
+// two CTAs per SM allow -- and an entry costs two multiply-adds instead of five.  JACOBI (ftf_only): P = I.
 template <int IDX>
-__device__ __forceinline__ double block_entry(const double2 (&Fv)[9], const double (&G)[3][9], const double (&H)[3][9], int ftf_only) {
+__device__ __forceinline__ double block_entry(const double2 (&Fv)[9], const double2 (&Pf)[9]) {
   constexpr int k = upper_row(IDX), l = upper_col(IDX);
-  const double ftf = Fv[k].x * Fv[l].x + Fv[k].y * Fv[l].y;
-  return ftf_only ? ftf : (ftf - (G[0][k] * H[0][l] + G[1][k] * H[1][l] + G[2][k] * H[2][l]));
+  return Fv[k].x * Pf[l].x + Fv[k].y * Pf[l].y;
 }
-// Stages entries FIRST + 0, 1, ... into consecutive planes starting at vt (= plane base + thread's column).
 template <int FIRST, int... Is>
-__device__ __forceinline__ void stage_block_entries(double* vt, const double2 (&Fv)[9], const double (&G)[3][9], const double (&H)[3][9],
-                                                    int ftf_only, std::integer_sequence<int, Is...>) {
-  ((vt[Is * VLD] = block_entry<FIRST + Is>(Fv, G, H, ftf_only)), ...);
+__device__ __forceinline__ void stage_block_entries(double* vt, const double2 (&Fv)[9], const double2 (&Pf)[9], std::integer_sequence<int, Is...>) {
+  ((vt[Is * VLD] = block_entry<FIRST + Is>(Fv, Pf)), ...);
 }
 
 constexpr int kSetupPlanes = 18;     // staged planes per round of k_ba_schur_setup: 9 rhs + 45 block entries = 3 rounds of 18
-
 __global__ void __launch_bounds__(T, 2) k_ba_schur_setup(BaDev L, const double2* __restrict__ J2, const double2* __restrict__ r2,
                                                       const double* __restrict__ D, double* __restrict__ einv,
                                                       double* __restrict__ seg_rhs, double* __restrict__ seg_M,
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(T, 2) k_ba_schur_setup(BaDev L, const double2*
     pinv[tid * 9 + 8] = inv[2] * g[0] + inv[4] * g[1] + inv[5] * g[2];
   }
   __syncthreads();
-  double G[3][9], H[3][9];
+  double2 Pf[9];
   if (active) {
     const double* pi = pinv + ptl * 9;
     // reduced rhs: F^T (r - E (E^T E)^-1 E^T r)
@@ -366,27 +367,30 @@ __global__ void __launch_bounds__(T, 2) k_ba_schur_setup(BaDev L, const double2*
     const double q1 = r.y - (Ev[0].y * pi[6] + Ev[1].y * pi[7] + Ev[2].y * pi[8]);
 #pragma unroll
     for (int k = 0; k < 9; ++k) v[k * VLD + tid] = Fv[k].x * q0 + Fv[k].y * q1;
-    // G = E^T F (3 x 9), H = (E^T E)^-1 G
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-#pragma unroll
-      for (int a = 0; a < 3; ++a) G[a][k] = Ev[a].x * Fv[k].x + Ev[a].y * Fv[k].y;
-      H[0][k] = pi[0] * G[0][k] + pi[1] * G[1][k] + pi[2] * G[2][k];
-      H[1][k] = pi[1] * G[0][k] + pi[3] * G[1][k] + pi[4] * G[2][k];
-      H[2][k] = pi[2] * G[0][k] + pi[4] * G[1][k] + pi[5] * G[2][k];
+    // P = I - E (E^T E)^-1 E^T (2 x 2, symmetric): T_a = sum_b inv[a][b] e_b, M = sum_a e_a T_a^T
+    double p00 = 1.0, p01 = 0.0, p11 = 1.0;
+    if (!ftf_only) {
+      const double t0x = pi[0] * Ev[0].x + pi[1] * Ev[1].x + pi[2] * Ev[2].x, t0y = pi[0] * Ev[0].y + pi[1] * Ev[1].y + pi[2] * Ev[2].y;
+      const double t1x = pi[1] * Ev[0].x + pi[3] * Ev[1].x + pi[4] * Ev[2].x, t1y = pi[1] * Ev[0].y + pi[3] * Ev[1].y + pi[4] * Ev[2].y;
+      const double t2x = pi[2] * Ev[0].x + pi[4] * Ev[1].x + pi[5] * Ev[2].x, t2y = pi[2] * Ev[0].y + pi[4] * Ev[1].y + pi[5] * Ev[2].y;
+      p00 = 1.0 - (Ev[0].x * t0x + Ev[1].x * t1x + Ev[2].x * t2x);
+      p01 = -(Ev[0].x * t0y + Ev[1].x * t1y + Ev[2].x * t2y);
+      p11 = 1.0 - (Ev[0].y * t0y + Ev[1].y * t1y + Ev[2].y * t2y);
     }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Pf[k] = make_double2(p00 * Fv[k].x + p01 * Fv[k].y, p01 * Fv[k].x + p11 * Fv[k].y);
     // round 0: planes 0..8 = reduced rhs (above), planes 9..17 = block entries 0..8
-    stage_block_entries<0>(v + 9 * VLD + tid, Fv, G, H, ftf_only, std::make_integer_sequence<int, 9>());
+    stage_block_entries<0>(v + 9 * VLD + tid, Fv, Pf, std::make_integer_sequence<int, 9>());
   }
   __syncthreads();
   seg_reduce_planes<kSetupPlanes>(q, meta, v, 9, seg_rhs, 9, seg_M, 45, 0);
   // rounds 1, 2: block entries 9..26 and 27..44
   __syncthreads();
-  if (active) stage_block_entries<9>(v + tid, Fv, G, H, ftf_only, std::make_integer_sequence<int, kSetupPlanes>());
+  if (active) stage_block_entries<9>(v + tid, Fv, Pf, std::make_integer_sequence<int, kSetupPlanes>());
   __syncthreads();
   seg_reduce_planes<kSetupPlanes>(q, meta, v, 0, seg_M, 45, seg_M, 45, 9);
   __syncthreads();
-  if (active) stage_block_entries<9 + kSetupPlanes>(v + tid, Fv, G, H, ftf_only, std::make_integer_sequence<int, kSetupPlanes>());
+  if (active) stage_block_entries<9 + kSetupPlanes>(v + tid, Fv, Pf, std::make_integer_sequence<int, kSetupPlanes>());
   __syncthreads();
   seg_reduce_planes<kSetupPlanes>(q, meta, v, 0, seg_M, 45, seg_M, 45, 9 + kSetupPlanes);
 }
