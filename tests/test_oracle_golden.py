@@ -250,6 +250,36 @@ def test_first_schur_step_equals_dense_normal_equations(oracle, lst):
     assert np.allclose(p.params - x0, delta, rtol=1e-7, atol=1e-9)
 
 
+@pytest.mark.parametrize("shape,seed", [("tiny", 1), ("small", 2), ("small", 5)])
+@pytest.mark.parametrize("linear,lst,prec", [("dense", _abi.DENSE_SCHUR, _abi.JACOBI), ("pcg", _abi.ITERATIVE_SCHUR, _abi.SCHUR_JACOBI),
+                                             ("pcg", _abi.ITERATIVE_SCHUR, _abi.JACOBI)])
+def test_whole_trajectories_against_an_independent_numpy_solver(oracle, shape, seed, linear, lst, prec):
+    """not one LM step but whole solves.  tests/numpy_lm.py states the trust-region loop, the LM strategy,
+    the explicit Schur complement and Ceres' conjugate-gradients solver with the SchurJacobi / Jacobi preconditioner in dense
+    numpy -- sharing only the functor evaluation with the oracle -- and the oracle's C++ restatement (Schur eliminator, implicit
+    products, fixed-order sums) must follow it row for row: costs to 1e-11, the same radii, the same accepted / rejected steps
+    and the same number of PCG iterations in every linear solve."""
+    import numpy_lm
+    d = synth.make_bal(shape, seed=seed)
+
+    def evaluate(x):
+        q = oracle.OracleProblem(x)
+        q.add_residual_blocks(_abi.FUNCTOR_SNAVELY_REPROJECTION_ERROR, d.observations.reshape(-1, 2), d.block_offsets())
+        c, r, _, Jv = q.evaluate()
+        return c, r, numpy_lm.dense_jacobian(d, Jv)
+    rows, x = numpy_lm.solve(d, evaluate, linear=linear, preconditioner="schur_jacobi" if prec == _abi.SCHUR_JACOBI else "jacobi")
+    p = oracle.OracleProblem(d.parameters)
+    p.add_residual_blocks(_abi.FUNCTOR_SNAVELY_REPROJECTION_ERROR, d.observations.reshape(-1, 2), d.block_offsets())
+    o = _abi.default_options()
+    o.linear_solver_type, o.preconditioner_type = lst, prec
+    s = p.solve(o)
+    assert s.termination_type == _abi.CONVERGENCE and len(rows) == len(s.iterations) >= 3
+    for a, b in zip(rows, s.iterations):
+        assert np.isclose(a[0], b.cost, rtol=1e-11) and np.isclose(a[1], b.trust_region_radius, rtol=1e-9)
+        assert bool(a[2]) == bool(b.step_is_successful) and a[3] == b.linear_solver_iterations
+    assert np.isclose(evaluate(x)[0], evaluate(p.params)[0], rtol=1e-11)       # neither side applies the step that met the tolerance
+
+
 def test_iterative_schur_converges_to_the_exact_schur_optimum(oracle):
     costs = {}
     for lst, prec in [(_abi.DENSE_SCHUR, _abi.JACOBI), (_abi.ITERATIVE_SCHUR, _abi.SCHUR_JACOBI), (_abi.ITERATIVE_SCHUR, _abi.JACOBI),
