@@ -79,8 +79,11 @@ sk_comm* comm_create(const char* id128, int rank, int world) {
   return c;
 }
 
+static void peer_allreduce_close(PeerAllreduce* pa);
 void comm_destroy(sk_comm* c) {
   if (!c) return;
+  for (void* p : c->peer_cache) { PeerAllreduce* pa = static_cast<PeerAllreduce*>(p); peer_allreduce_close(pa); delete pa; }
+  c->peer_cache.clear();
   if (c->nccl_comm) api().CommDestroy(c->nccl_comm);
   delete c;
 }
@@ -103,10 +106,25 @@ void comm_group_start(sk_comm* c) { if (c && c->world > 1) check(api().GroupStar
 void comm_group_end(sk_comm* c) { if (c && c->world > 1) check(api().GroupEnd(), "ncclGroupEnd"); }
 
 // ---- peer window ---------------------------------------------------------------------------------------------------------
+static void peer_allreduce_close(PeerAllreduce* pa) {
+  for (int r = 0; r < kMaxPeers; ++r)
+    if (pa->opened[r]) { cudaIpcCloseMemHandle(pa->opened[r]); pa->opened[r] = nullptr; }
+  pa->ok = false; pa->win = PeerWindow{};
+}
+
 void peer_allreduce_create(sk_comm* c, size_t count, cudaStream_t stream, PeerAllreduce* pa) {
-  pa->ok = false; pa->win = PeerWindow{}; pa->seq = 0;
+  pa->ok = false; pa->win = PeerWindow{}; pa->seq = 0; pa->owner = nullptr; pa->count = count;
   if (!c || c->world <= 1 || c->world > kMaxPeers) return;
   { const char* e = getenv("SKERES_PEER_ALLREDUCE"); if (e && e[0] == '0') return; }
+  for (size_t i = 0; i < c->peer_cache.size(); ++i) {       // a window of this size left by an earlier solver: no collective needed
+    PeerAllreduce* cached = static_cast<PeerAllreduce*>(c->peer_cache[i]);
+    if (cached->count != count) continue;
+    c->peer_cache.erase(c->peer_cache.begin() + (long)i);
+    *pa = std::move(*cached);
+    delete cached;
+    pa->win.cam_mask = nullptr;
+    return;
+  }
   const int world = c->world, rank = c->rank;
   const size_t stride = (count + 15) & ~(size_t)15;
   const size_t flag_doubles = (size_t)kMaxPeers * 2, tail_doubles = 2;            // flags, then error + done_count
@@ -146,21 +164,26 @@ void peer_allreduce_create(sk_comm* c, size_t count, cudaStream_t stream, PeerAl
   comm_allreduce_sum(c, d.p, 1, stream);
   d.download(m.data(), 1, stream);
   SK_CUDA(cudaStreamSynchronize(stream));
-  if (m[0] != (double)world) { peer_allreduce_destroy(pa); return; }
+  if (m[0] != (double)world) { peer_allreduce_close(pa); return; }
   for (int r = 0; r < world; ++r) pa->win.flags[r] = reinterpret_cast<unsigned long long*>(pa->win.data[r] + 2 * stride);
   pa->win.error = reinterpret_cast<int*>(pa->mem.p + 2 * stride + flag_doubles);
   pa->win.done_count = reinterpret_cast<unsigned int*>(pa->win.error + 1);
   pa->win.stride = (long long)stride; pa->win.rank = rank; pa->win.world = world;
   { const char* e = getenv("SKERES_PEER_TIMEOUT_S"); const double sec = e ? atof(e) : 60.0;
     pa->win.timeout_ns = (unsigned long long)((sec > 0.0 ? sec : 60.0) * 1e9); }
-  pa->ok = true;
+  pa->ok = true; pa->owner = c;
   if (getenv("SKERES_TRACE_HOST")) fprintf(stderr, "[skeres] rank %d: peer window of %zu doubles mapped on %d ranks\n", rank, count, world);
 }
 
 void peer_allreduce_destroy(PeerAllreduce* pa) {
-  for (int r = 0; r < kMaxPeers; ++r)
-    if (pa->opened[r]) { cudaIpcCloseMemHandle(pa->opened[r]); pa->opened[r] = nullptr; }
-  pa->ok = false; pa->win = PeerWindow{};
+  if (pa->ok && pa->owner != nullptr && pa->owner->peer_cache.size() < 4) {     // keep it mapped for the next solver of this size
+    sk_comm* c = pa->owner;
+    c->peer_cache.push_back(new PeerAllreduce(std::move(*pa)));
+    pa->ok = false; pa->win = PeerWindow{};
+    for (int r = 0; r < kMaxPeers; ++r) pa->opened[r] = nullptr;
+    return;
+  }
+  peer_allreduce_close(pa);
 }
 
 }  // namespace sk

@@ -2,11 +2,14 @@
 // libnccl and the library has no link-time dependency on it (inside a torch process the already
 // loaded libnccl.so.2 is reused).
 #pragma once
+#include <vector>
+
 #include "common.cuh"
 
 struct sk_comm {
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;
+  std::vector<void*> peer_cache;   // sk::PeerAllreduce* of destroyed solvers, kept mapped for the next solver of the same size
 };
 
 namespace sk {
@@ -48,9 +51,15 @@ struct PeerAllreduce {
   DBuf<unsigned char> cam_mask;             // see PeerWindow::cam_mask
   unsigned long long seq = 0;               // sequence number of the last exchange
   bool ok = false;
+  sk_comm* owner = nullptr;                 // the communicator whose cache takes the window back
+  size_t count = 0;                         // doubles per contribution it was created for
 };
 // Collective over `c`: allocates the window for `count` doubles and exchanges the IPC handles (through one NCCL allreduce).
 // Leaves pa->ok == false (NCCL allreduce stays in use) when peer mapping is unavailable or SKERES_PEER_ALLREDUCE=0.
+// Windows are recycled: peer_allreduce_destroy hands a mapped window back to its communicator and the next create of the same
+// size takes it without any collective -- closing an IPC mapping synchronises the ranks and took 0.2-0.5 s of every
+// sk_solver_destroy (profiles/r02_v9_*), more than the whole set-up of a solver.  Every rank must create and destroy solvers in
+// the same order (they do: a solve is collective), so that all of them hit or miss the cache alike.  comm_destroy closes them.
 void peer_allreduce_create(sk_comm* c, size_t count, cudaStream_t stream, PeerAllreduce* pa);
 void peer_allreduce_destroy(PeerAllreduce* pa);
 void comm_group_end(sk_comm* c);
