@@ -377,5 +377,104 @@ __device__ __forceinline__ void cam_reduce9_block(const BaDev& L, int vb, const 
   if (c < L.n_cams && sub == 0 && lane < 9) y[(size_t)c * 9 + lane] = acc;
 }
 
+// ---- three virtual blocks per round, by lane groups ---------------------------------------------------------------------------
+// At many cameras (13,682 of the Final shape, 14,224 of eight Venice scenes) the fused solve's persistent grid needs seven rounds
+// of virtual blocks per vector phase, each a chain of dependent L2 round trips, while a warp uses 9 of its 32 lanes for a camera.
+// Here lanes 0-8, 9-17 and 18-26 of warp w serve camera w of THREE blocks (va, va + step, va + 2 step; a block >= nparts is
+// skipped): the same arithmetic per camera, the same trees (a shuffle that would reach into the neighbouring group is masked
+// -- the one-block form adds the zeros of its idle lanes there), the same slots: the same bits, a third of the rounds, no extra
+// registers.  256 threads.  Used where no walk over segment partials is involved: the update, and the reduce when the camera
+// sums come from the peer windows.
+__device__ __forceinline__ double group_sum9(double v, int i) {       // sum over the 9 lanes of a group, valid in its first lane
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) { const double t = __shfl_down_sync(0xffffffffu, v, o); if (i + o < 9) v += t; }
+  return v;
+}
+// slot[vb_g] = the 8 warps' group sums of block g combined as block_sum_fixed combines its 8 warp totals.  red: [3][N][8].
+template <int N>
+__device__ __forceinline__ void block3_slots(const double (&v)[N], int g, int i, double (*red)[N][8], const int (&vb)[3], int nparts,
+                                             double* const (&out)[N]) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (g < 3 && i == 0) {
+#pragma unroll
+    for (int n = 0; n < N; ++n) red[g][n][warp] = v[n];
+  }
+  __syncthreads();
+  if (warp < 3) {
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      double r = (lane < 8) ? red[warp][n][lane] : 0.0;
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
+      if (lane == 0 && vb[warp] < nparts) out[n][vb[warp]] = r;
+    }
+  }
+  __syncthreads();                                      // red may be rewritten by the next round
+}
+
+__device__ __forceinline__ void pcg_reduce_block3_peer(const BaDev& L, int va, int step, int nparts, const double* D, double* z, double* p,
+                                                       double* part_pq, int iter, double beta, const PeerWindow& win, int parity) {
+  __shared__ double red[3][1][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane / 9, i = lane - 9 * g;
+  const int vb[3] = {va, va + step, va + 2 * step};
+  const int v = g < 3 ? vb[g] : nparts;
+  const int c = v * WPB + warp;
+  double pq[1] = {0.0};
+  if (g < 3 && v < nparts && c < L.n_cams) {
+    const size_t e = (size_t)c * 9 + i;
+    const double acc = peer_gather(win, parity, c, e);
+    const double zk = __ldcg(z + e);
+    const double pk = (iter == 1) ? zk : __fma_rn(beta, __ldcg(p + e), zk);
+    const double d = D[e];
+    const double qk = __fma_rn(__dmul_rn(d, d), pk, acc);
+    p[e] = pk; z[e] = qk;
+    pq[0] = __dmul_rn(pk, qk);
+  }
+  pq[0] = group_sum9(pq[0], i);
+  double* const out[1] = {part_pq};
+  block3_slots<1>(pq, g, i, red, vb, nparts, out);
+}
+
+__device__ __forceinline__ void pcg_update_block3(int n_cams, int va, int step, int nparts, const double* Minv, const double* b, double* x,
+                                                  const double* p, double* r, double* z, double alpha, bool go, int recompute,
+                                                  double* part_Q, double* part_rho) {
+  __shared__ double red[3][2][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane / 9, i = lane - 9 * g;
+  const int vb[3] = {va, va + step, va + 2 * step};
+  const int v = g < 3 ? vb[g] : nparts;
+  const int c = v * WPB + warp;
+  const bool on = go && g < 3 && v < nparts && c < n_cams;
+  double s12[2] = {0.0, 0.0};
+  double rk = 0.0;
+  const size_t e = on ? (size_t)c * 9 + i : 0;
+  if (on) {
+    const double xk = __fma_rn(alpha, __ldcg(p + e), __ldcg(x + e));
+    x[e] = xk;
+    if (!recompute) {
+      rk = __fma_rn(-alpha, __ldcg(z + e), __ldcg(r + e));
+      r[e] = rk;
+      s12[0] = __dmul_rn(xk, __dadd_rn(b[e], rk));
+    }
+  }
+  if (!recompute) {
+    double zk = rk;
+    if (Minv != nullptr) {
+      zk = 0.0;
+      const int base = (g < 3 ? g : 0) * 9;
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        const double rj = __shfl_sync(0xffffffffu, rk, base + j);
+        if (on) zk = __fma_rn(Minv[(size_t)c * 81 + i * 9 + j], rj, zk);
+      }
+    }
+    if (on) { z[e] = zk; s12[1] = __dmul_rn(rk, zk); }
+    s12[0] = group_sum9(s12[0], i); s12[1] = group_sum9(s12[1], i);
+    double* const out[2] = {part_Q, part_rho};
+    block3_slots<2>(s12, g, i, red, vb, nparts, out);
+  }
+}
+
 }  // namespace
 }  // namespace sk

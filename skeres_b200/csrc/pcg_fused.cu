@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(T, 2) k_pcg_solve(const __grid_constant__ CUte
   const BaDev& L = A.L;
   const int nparts = (L.n_cams + WPB - 1) / WPB;
   const bool peer = A.win.world > 1;
+  const bool packed = nparts > (int)gridDim.x;       // more virtual blocks than CTAs: three blocks per round by lane groups (pcg_device.cuh)
   const bool stamps = A.phase_ns != nullptr && blockIdx.x == 0 && tid == 0;
   ProductPass<TMAP, false, SK_FUSED_COHERENT != 0> P;
   P.init(L, sm);
@@ -126,16 +127,24 @@ __global__ void __launch_bounds__(T, 2) k_pcg_solve(const __grid_constant__ CUte
     bool finish = true;                              // this trip ends the iteration (head step)
     if (!reset_pass) {
       const int it = ctl.s.iter; const double beta = ctl.s.beta;
-      for (int vb = blockIdx.x; vb < nparts; vb += gridDim.x)
-        pcg_reduce_block<1>(L, vb, A.seg_y, nullptr, A.D, A.z, A.p, A.part_pq, it, beta, A.win, parity);
+      if (packed && peer)
+        for (int vb = blockIdx.x; vb < nparts; vb += 3 * gridDim.x)
+          pcg_reduce_block3_peer(L, vb, (int)gridDim.x, nparts, A.D, A.z, A.p, A.part_pq, it, beta, A.win, parity);
+      else
+        for (int vb = blockIdx.x; vb < nparts; vb += gridDim.x)
+          pcg_reduce_block<1>(L, vb, A.seg_y, nullptr, A.D, A.z, A.p, A.part_pq, it, beta, A.win, parity);
       grid_sync(A.grid_bar, &ctl.bar_target);
       const int recompute = (it % A.reset_period == 0) ? 1 : 0;
       const double pq = sum_fixed_all(A.part_pq, nparts, ctl.red, &ctl.bc);
       const bool ok = (pq > 0.0) && !isinf(pq);
       const double alpha = ctl.s.rho / pq;
       const bool go = ok && !isinf(alpha);
-      for (int vb = blockIdx.x; vb < nparts; vb += gridDim.x)
-        pcg_update_block(L.n_cams, vb, A.Minv, A.b, A.x, A.p, A.r, A.z, alpha, go, recompute, A.part_Q, A.part_rho);
+      if (packed)
+        for (int vb = blockIdx.x; vb < nparts; vb += 3 * gridDim.x)
+          pcg_update_block3(L.n_cams, vb, (int)gridDim.x, nparts, A.Minv, A.b, A.x, A.p, A.r, A.z, alpha, go, recompute, A.part_Q, A.part_rho);
+      else
+        for (int vb = blockIdx.x; vb < nparts; vb += gridDim.x)
+          pcg_update_block(L.n_cams, vb, A.Minv, A.b, A.x, A.p, A.r, A.z, alpha, go, recompute, A.part_Q, A.part_rho);
       if (recompute) finish = false;                 // r = b - S x from one more product: the next trip
     } else {
       for (int vb = blockIdx.x; vb < nparts; vb += gridDim.x)

@@ -17,12 +17,14 @@ ids = [api.Communicator.unique_id() if rank == 0 else None]
 dist.broadcast_object_list(ids, src=0)
 comm = api.Communicator(ids[0], rank, world)
 shape = sys.argv[1] if len(sys.argv) > 1 else "ladybug-49"
-d = synth.make_bal(shape, seed=1)
+# "wide": more virtual blocks of 8 cameras than persistent CTAs -- the packed (three blocks per round) vector phases of the fused solve
+d = synth.make_bal(n_cam=2500, n_pt=40000, n_obs=400000, seed=7) if shape == "wide" else synth.make_bal(shape, seed=1)
 
 def solve(use_comm, local=False, data=None):
     bal = api.BalProblem.fromArrays(d if data is None else data)
     prob = bal.buildLocalProblem(rank, world) if local else bal.buildProblem()
     o = api.Solver.Options(); o.setLinearSolverType(_abi.ITERATIVE_SCHUR); o.setPreconditionerType(_abi.SCHUR_JACOBI)
+    if len(sys.argv) > 2: o.setMaxNumIterations(int(sys.argv[2]))     # ill-conditioned shapes: compare the first rows only
     if use_comm: o.comm = comm
     o.residual_blocks_are_local = 1 if local else 0
     s = api.Solver.Summary()
@@ -59,16 +61,24 @@ for local_mode in (False, True):
     xb, sb, dtb = solve(True, local=local_mode, data=dbad)
     assert sb.termination_type == _abi.FAILURE and len(sb.iterations) == 0, (rank, sb.termination_type, sb.message)
 print(f"rank {rank}: NaN on the last rank -> every rank terminates with FAILURE ({sb.message})", flush=True)
+failed = None
 if rank == 0:
-    for g in gathered[1:]:
-        assert g[0] == gathered[0][0], "ranks disagree on the solution"
-        assert g[1] == gathered[0][1], "ranks disagree on the trajectory"
-    x1, s1, dt1 = solve(False)
-    rel = np.max(np.abs(x - x1) / np.maximum(np.abs(x1), 1e-2))
-    print(f"single GPU: final {s1.final_cost:.9e} its {len(s1.iterations)} pcg {[r.linear_solver_iterations for r in s1.iterations]} {dt1:.3f}s")
-    print(f"multi vs single: cost rel diff {abs(s.final_cost - s1.final_cost) / s1.final_cost:.2e}, max rel param diff {rel:.2e}")
-    assert abs(s.final_cost - s1.final_cost) <= 1e-6 * s1.final_cost
-    assert len(s.iterations) == len(s1.iterations)
-    print("MULTI-GPU CHECK OK")
+  try:
+      for g in gathered[1:]:
+          assert g[0] == gathered[0][0], "ranks disagree on the solution"
+          assert g[1] == gathered[0][1], "ranks disagree on the trajectory"
+      x1, s1, dt1 = solve(False)
+      rel = np.max(np.abs(x - x1) / np.maximum(np.abs(x1), 1e-2))
+      print(f"single GPU: final {s1.final_cost:.9e} its {len(s1.iterations)} pcg {[r.linear_solver_iterations for r in s1.iterations]} {dt1:.3f}s")
+      print(f"multi vs single: cost rel diff {abs(s.final_cost - s1.final_cost) / s1.final_cost:.2e}, max rel param diff {rel:.2e}")
+      assert abs(s.final_cost - s1.final_cost) <= 1e-6 * s1.final_cost
+      assert len(s.iterations) == len(s1.iterations)
+      print("MULTI-GPU CHECK OK")
+  except AssertionError as e:                  # rank 0 must still reach the barrier: the other ranks wait there
+    import traceback
+    traceback.print_exc()
+    failed = e
 dist.barrier()
 dist.destroy_process_group()
+if failed is not None:
+    sys.exit(1)
