@@ -113,6 +113,12 @@ BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHo
     SK_CUDA(cudaStreamSynchronize(s));
     const char* e = getenv("SKERES_PEER_GATHER");                  // development: SKERES_PEER_GATHER=all reads every rank's window
     peer_.win.cam_mask = (e != nullptr && e[0] == 'a') ? nullptr : peer_.cam_mask.p;
+    // virtual blocks of 8 cameras this rank contributes to: the fused solve skips the others when it reduces its own partials
+    std::vector<unsigned char> own((size_t)cdiv(H.n_cams, 8), 0);
+    for (int c = 0; c < H.n_cams; ++c) if ((mask[c] >> comm_->rank) & 1u) own[(size_t)c / 8] = 1;
+    peer_.vb_own.upload(own, s);
+    SK_CUDA(cudaStreamSynchronize(s));
+    peer_.win.vb_own = peer_.win.cam_mask != nullptr ? peer_.vb_own.p : nullptr;   // without masks every rank's window is read everywhere
   }
   SK_REQUIRE(cdiv(H.n_cams, 8) <= kMaxPartials, SK_ERR_UNSUPPORTED, "more than %d cameras", kMaxPartials * 256 / 9);
   const int lst = opt.linear_solver_type;

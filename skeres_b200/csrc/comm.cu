@@ -122,7 +122,7 @@ void peer_allreduce_create(sk_comm* c, size_t count, cudaStream_t stream, PeerAl
     c->peer_cache.erase(c->peer_cache.begin() + (long)i);
     *pa = std::move(*cached);
     delete cached;
-    pa->win.cam_mask = nullptr;
+    pa->win.cam_mask = nullptr; pa->win.vb_own = nullptr;
     return;
   }
   const int world = c->world, rank = c->rank;

@@ -42,6 +42,8 @@ struct PeerWindow {
   unsigned long long timeout_ns;            // bound of one wait for the peers (SKERES_PEER_TIMEOUT_S, default 60 s)
   const unsigned char* cam_mask;            // [n_cams] bit r: rank r holds observations of the camera, i.e. contributes to its sums;
                                             // the gather reads a camera only from those ranks (nullptr: from all)
+  const unsigned char* vb_own;              // [ceil(n_cams / 8)] != 0: this rank holds observations of a camera of that virtual block of 8
+                                            // cameras (pcg_device.cuh), i.e. has something to contribute for it (nullptr: assume all)
   int rank, world;                          // world == 0: no peer window (single GPU or NCCL path)
 };
 struct PeerAllreduce {
@@ -49,6 +51,7 @@ struct PeerAllreduce {
   void* opened[kMaxPeers] = {};
   DBuf<double> mem;
   DBuf<unsigned char> cam_mask;             // see PeerWindow::cam_mask
+  DBuf<unsigned char> vb_own;               // see PeerWindow::vb_own
   unsigned long long seq = 0;               // sequence number of the last exchange
   bool ok = false;
   sk_comm* owner = nullptr;                 // the communicator whose cache takes the window back

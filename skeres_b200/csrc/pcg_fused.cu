@@ -117,7 +117,15 @@ __global__ void __launch_bounds__(T, 2) k_pcg_solve(const __grid_constant__ CUte
       const unsigned long long seq = ctl.seq;
       parity = (int)(seq & 1ull);
       double* y = A.win.data[A.win.rank] + (size_t)parity * A.win.stride;
-      for (int vb = blockIdx.x; vb < nparts; vb += gridDim.x) cam_reduce9_block<1>(L, vb, A.seg_y, y);
+      // only the virtual blocks this rank holds observations for (the peers read a camera's slot from the ranks in its mask only);
+      // the flags of all rounds are fetched together
+      unsigned own = 0xffffffffu;
+      if (A.win.vb_own != nullptr && nparts <= 32 * (int)gridDim.x) {
+        own = 0u;
+        for (int vb = blockIdx.x, k = 0; vb < nparts; vb += gridDim.x, ++k) own |= (A.win.vb_own[vb] != 0 ? 1u : 0u) << k;
+      }
+      for (int vb = blockIdx.x, k = 0; vb < nparts; vb += gridDim.x, ++k)
+        if ((own >> (k & 31)) & 1u) cam_reduce9_block<1>(L, vb, A.seg_y, y);
       grid_sync(A.grid_bar, &ctl.bar_target);        // this rank's contribution is complete
       if (blockIdx.x == 0) peer_store_flags(A.win, parity, seq);
       peer_wait(A.win, parity, seq);                 // a time-out raises win.error; checked by all CTAs after the next barrier
