@@ -444,10 +444,11 @@ def main():
             runs.append((time.time() - t0, summ.preprocessor_time_in_seconds, max(summ.num_iterations - 1, 0), final_cost, out.nbytes))
             del problem2, bal2
         t1, pre_s, its, final_cost, out_bytes = min(runs)
-        # observations (16 B) + tile-local ids (6 B) + per-tile metadata records of the prefetching product (~11 B) per observation,
-        # point / camera tables, parameters
-        h2d = host_params.nbytes + o1 * (16 + 6 + 11) + 4 * p1 + 72 * n_cam
-        d2h = out_bytes + 4096
+        # what actually crosses: the parameters, the residual-block table as it is (16 B of block offsets + 16 B of observation per
+        # residual block: the layout is built from it on the device) and the tile table packed on the host (12 B per tile);
+        # back: the point CSR the tile packing reads (4 B per point), the camera table, the solution, the summary
+        h2d = host_params.nbytes + o1 * (16 + 16) + 12 * (o1 // 200)
+        d2h = out_bytes + 4 * p1 + 12 * n_cam + 4096
         e2e = {"value": n_obs * its / t1, "unit": UNIT, "h2d_bytes_per_step": int(h2d / max(its, 1)), "d2h_bytes_per_step": int(d2h / max(its, 1)),
                "lm_iterations": its, "wall_s": t1, "wall_s_runs": [r[0] for r in runs], "preprocessor_s": pre_s, "final_cost": final_cost,
                "what": "DoubleArray upload + addResidualBlocks + ceres.solve (preprocess, layout upload, K LM iterations) + parameter download; "
