@@ -150,7 +150,11 @@ int sk_functor_info(int functor_id, int* num_residuals, int* num_parameter_block
  * log, sin, cos are overloaded (jet.cuh, the operator set spire gives a Jet); `consts` are the per-residual-block constants given to
  * sk_cost_function_create (the constructor arguments of the Scala functor).
  * Returns a functor id (>= 1000) usable wherever a built-in id is: sk_functor_info, sk_cost_function_create / _evaluate,
- * sk_problem_add_residual_block(s) with the dense back end (DENSE_QR and the normal-Cholesky types).  Compiling needs no device;
+ * sk_problem_add_residual_block(s) with the dense back end (DENSE_QR and the normal-Cholesky types).  A functor of the
+ * bundle-adjustment shape -- 2 residuals, parameter blocks of 9 and 3, 2 constants (the observation), i.e. another camera model in
+ * place of SnavelyReprojectionError (SimpleBundleAdjuster.scala:79-119) -- is ALSO compiled into the tile evaluation kernel of the
+ * Schur solvers and is accepted by DENSE_SCHUR / SPARSE_SCHUR / ITERATIVE_SCHUR (one functor per problem); sk::angle_axis_rotate_point
+ * (Rotation.angleAxisRotatePoint, Rotation.scala:449-522) is available to the source.  Compiling needs no device;
  * the module is loaded on first use.  SK_ERR_INVALID_ARGUMENT with the compiler log in sk_last_error() when the source does not
  * compile; SK_ERR_UNSUPPORTED when libnvrtc is not available.  Limits: <= 16 residuals, <= 10 blocks, <= 32 parameters in total. */
 int sk_functor_register_source(const char* name, const char* cuda_source, int num_residuals, int num_parameter_blocks,

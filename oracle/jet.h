@@ -146,6 +146,29 @@ inline bool snavelyReprojectionError(const double* consts, T const* const* param
   return true;
 }
 
+// NOT in the reference: a camera model of the bundle-adjustment shape (2; 9, 3) the GPU library has no built-in for -- the
+// division model of radial distortion; fails for a point behind the camera.  The GPU tests hand the library the same body as
+// CUDA source (tests/user_functor_sources.py: DIVISION_MODEL, sk_functor_register_source) and check its tile kernels
+// against this one.
+template <class T>
+inline bool divisionModelReprojectionError(const double* consts, T const* const* params, T* residuals) {
+  const T* camera = params[0];
+  const T* point = params[1];
+  T p[3];
+  angleAxisRotatePoint(camera, point, p);
+  p[0] = p[0] + camera[3];
+  p[1] = p[1] + camera[4];
+  p[2] = p[2] + camera[5];
+  if (!((-p[2]) > 0.0)) return false;
+  const T xp = (-p[0]) / p[2];
+  const T yp = (-p[1]) / p[2];
+  const T r2 = xp * xp + yp * yp;
+  const T distortion = 1.0 / (1.0 + r2 * (camera[7] + camera[8] * r2));
+  residuals[0] = camera[6] * distortion * xp - consts[0];
+  residuals[1] = camera[6] * distortion * yp - consts[1];
+  return true;
+}
+
 // CurveFitting.scala:92-98. consts = (x, y); params = m (1), c (1).
 template <class T>
 inline bool exponentialResidual(const double* consts, T const* const* params, T* residuals) {

@@ -48,6 +48,7 @@ constexpr int kMaxConsts = SK_MAX_CONSTS;
 // Functor registry + AutoDiffCostFunction.evaluate (AutodiffCostFunction.scala:74-134)
 // ------------------------------------------------------------------------------------------------
 struct FunctorInfo { int id, nres, nblk, sizes[kMaxBlocks], nconsts; };
+constexpr int kOracleFunctorDivisionModel = 900;   // checker-only (jet.h: divisionModelReprojectionError); not an id of include/skeres.h
 static const FunctorInfo kFunctors[] = {
     {SK_FUNCTOR_SNAVELY_REPROJECTION_ERROR, 2, 2, {9, 3}, 2},
     {SK_FUNCTOR_EXPONENTIAL_RESIDUAL, 1, 2, {1, 1}, 2},
@@ -60,6 +61,7 @@ static const FunctorInfo kFunctors[] = {
     {SK_FUNCTOR_TEST_BILINEAR_SCALAR, 1, 2, {2, 2}, 1},
     {SK_FUNCTOR_TEST_BILINEAR_VECTOR3, 3, 2, {2, 2}, 1},
     {SK_FUNCTOR_TEST_SUM10, 1, 10, {1, 1, 1, 1, 1, 1, 1, 1, 1, 1}, 0},
+    {kOracleFunctorDivisionModel, 2, 2, {9, 3}, 2},
 };
 static const FunctorInfo* find_functor(int id) {
   for (const auto& f : kFunctors) if (f.id == id) return &f;
@@ -135,6 +137,9 @@ static bool evaluate_functor(const FunctorInfo& fi, const double* consts, double
     case SK_FUNCTOR_TEST_SUM10:
       return autodiff_evaluate<1, 10, 10>([](const double* c, auto const* const* p, auto* r) {
         return testSum10(c, p, r); }, fi.sizes, consts, params, residuals, jacobians);
+    case kOracleFunctorDivisionModel:
+      return autodiff_evaluate<2, 2, 12>([](const double* c, auto const* const* p, auto* r) {
+        return divisionModelReprojectionError(c, p, r); }, fi.sizes, consts, params, residuals, jacobians);
   }
   return false;
 }

@@ -585,12 +585,12 @@ class BalProblem:
                                        _vp(off)))
         return off
 
-    def buildProblem(self, loss=None):
-        """The residual-block loop of SimpleBundleAdjuster.scala:134-145, in bulk."""
+    def buildProblem(self, loss=None, functor_id=_abi.FUNCTOR_SNAVELY_REPROJECTION_ERROR):
+        """The residual-block loop of SimpleBundleAdjuster.scala:134-145, in bulk.  functor_id: SnavelyReprojectionError, or a
+        functor of the same shape (2; 9, 3; constants = the observation) defined from source (SourceCostFunctor.define)."""
         problem = Problem()
         loss = loss if loss is not None else PredefinedLossFunctions.trivialLoss()
-        problem.addResidualBlocks(_abi.FUNCTOR_SNAVELY_REPROJECTION_ERROR, self.observations.reshape(-1, 2), loss,
-                                  self.parameters, self.blockOffsets())
+        problem.addResidualBlocks(functor_id, self.observations.reshape(-1, 2), loss, self.parameters, self.blockOffsets())
         return problem
 
     def localRange(self, rank, world_size):

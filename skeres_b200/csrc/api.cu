@@ -466,16 +466,22 @@ int sk_solver_summary_is_solution_usable(const sk_solver_summary* s) {
 static bool is_schur(int t) { return t == SK_DENSE_SCHUR || t == SK_SPARSE_SCHUR || t == SK_ITERATIVE_SCHUR; }
 
 static std::unique_ptr<LmSolver> prepare_ba(const sk_solver_options& opt, sk_problem* p, cudaStream_t stream) {
-  // All residual blocks must be SnavelyReprojectionError(2; 9, 3) over one DoubleArray with one loss —
+  // All residual blocks must be SnavelyReprojectionError(2; 9, 3) -- or ONE functor of that shape registered from source
+  // (sk_functor_register_source: it is compiled into the same tile kernel) -- over one DoubleArray with one loss:
   // the SchurEliminator<2, 3, 9> shape (cameras = f-blocks, points = e-blocks).
   sk_double_array* array = nullptr;
   LossSpec loss{SK_LOSS_TRIVIAL, 0.0};
   int64_t n = 0;
   bool first = true;
+  int functor = SK_FUNCTOR_SNAVELY_REPROJECTION_ERROR;
   for (auto& g : p->groups) {
     if (g.n == 0) continue;
-    SK_REQUIRE(g.functor_id == SK_FUNCTOR_SNAVELY_REPROJECTION_ERROR, SK_ERR_UNSUPPORTED,
-               "Schur-type linear solvers are implemented for bundle adjustment (SnavelyReprojectionError residual blocks) only; functor %d found", g.functor_id);
+    SK_REQUIRE(g.functor_id == SK_FUNCTOR_SNAVELY_REPROJECTION_ERROR || (g.functor_id >= kUserFunctorBase && user_functor_runs_on_tiles(g.functor_id)),
+               SK_ERR_UNSUPPORTED,
+               "Schur-type linear solvers are implemented for bundle adjustment only: SnavelyReprojectionError residual blocks, or a functor "
+               "of the same shape (2 residuals; blocks of 9 and 3; 2 constants) registered from source; functor %d found", g.functor_id);
+    if (first) functor = g.functor_id;
+    SK_REQUIRE(g.functor_id == functor, SK_ERR_UNSUPPORTED, "one cost functor per bundle adjustment problem (functors %d and %d found)", functor, g.functor_id);
     for (size_t a = 0; a < g.arrays.size(); ++a) {
       if (array == nullptr) array = g.arrays[a];
       SK_REQUIRE(g.arrays[a] == array, SK_ERR_UNSUPPORTED, "bundle adjustment parameter blocks must live in one DoubleArray");
@@ -528,7 +534,7 @@ static std::unique_ptr<LmSolver> prepare_ba(const sk_solver_options& opt, sk_pro
     total_points = (int64_t)all_pt.size();
   }
   const int64_t n_cams = H.n_cams;
-  std::unique_ptr<BaSolver> solver(new BaSolver(opt, stream, std::move(H), array->d.p, array->n, loss, &dev));
+  std::unique_ptr<BaSolver> solver(new BaSolver(opt, stream, std::move(H), array->d.p, array->n, loss, &dev, functor));
   solver->fill_totals(n, n_cams + total_points, 9 * n_cams + 3 * total_points, std::move(all_pt));
   if (local && opt.comm != nullptr && opt.comm->world > 1) solver->exchange_local_totals();
   if (trace) fprintf(stderr, "[skeres] preprocess: flatten %.3f s, layout %.3f s, device set-up %.3f s\n", tp1 - tp0, tp2 - tp1, wall() - tp2);

@@ -2,36 +2,13 @@
 #pragma once
 #include <cuda.h>   // CUtensorMap (type only; the encoder is fetched with cudaGetDriverEntryPoint, no libcuda link)
 
+#include "ba_dev.cuh"
 #include "ba_layout.h"
 #include "ba_tile_rec.h"
 #include "common.cuh"
 #include "jet.cuh"
 
 namespace sk {
-
-// Device view of BaLayoutHost (plain pointers, passed to kernels by value).
-struct BaDev {
-  int n_obs, n_pts, n_cams, n_tiles, n_segs, max_seg_tile, max_pt_tile;
-  int n_giant, n_chunks;               // tracks longer than one tile and the chunk tiles they are cut into (ba_layout.h)
-  const int* tile_obs; const int* tile_pt; const int* tile_seg; const int* pt_ptr;
-  const int* tile_np;                  // [T] > 0: points of a regular tile;  < 0: chunk tile, ordinal = -tile_np - 1
-  const int* gp_tile_begin; const int* gp_tile_count; const int* gp_point;   // [n_giant]
-  // per-tile metadata records for the prefetching matvec (ba_kernels.cu: RecView); nullptr when not built
-  const unsigned char* tile_rec; int rec_stride, rec_sp, rec_pp, rec_sc;
-  int matvec_classic;                  // 0: k_ba_matvec_tma / the fused PCG solve; 1: k_ba_matvec (SKERES_MATVEC=classic); read per solver
-  int matvec_serial_sums;              // 1 (default): per-point / per-segment sums as one serial chain each; 0: the chunked
-                                       // two-level sums (SKERES_MATVEC_SUMS=chunked)
-  const unsigned short* obs_slot; const unsigned short* obs_ptl; const unsigned short* seg_perm;
-  const int* seg_ptr; const int* seg_cam; const int* cam_seg_ptr; const int* cam_seg;
-  const int* seg_pos;                  // [S] inverse of cam_seg: the implicit-Schur product stores a segment's partial at its camera-major position
-  const double2* obs;   // [n_obs] observed (x, y)
-};
-
-// Stored Jacobian: 12 planes of double2, plane k at J2 + k * n_obs.
-//   planes 0..8 : (F[0][k], F[1][k])  d res / d camera parameter k
-//   planes 9..11: (E[0][k], E[1][k])  d res / d point coordinate k
-// i.e. 192 bytes per observation, every access a coalesced 16-byte vector.
-constexpr int kJPlanes = 12;
 
 struct Flags {           // device-resident control block shared by the LM / PCG kernels
   int skip;              // != 0: guarded kernels return immediately
@@ -47,10 +24,11 @@ struct Flags {           // device-resident control block shared by the LM / PCG
 //   tile_cost    [n_tiles] partial costs
 //   chunk_pt     [n_chunks][6] scratch: point-part partials of the chunk tiles of long tracks (with_jacobian)
 //   guard        kernel returns immediately when *guard == 0 (nullptr = always run)
+//   functor_id   the built-in SnavelyReprojectionError, or a functor of the same shape registered from source (user_functor.cuh)
 void launch_ba_evaluate(const BaDev& L, const double* x, const double* scale, LossSpec loss, bool with_jacobian,
                         bool write_jacobian, double2* J2, double2* r2, double* grad, double* cnorm2,
                         double* seg_g, double* seg_n, double* tile_cost, double* chunk_pt, int* fail_flag, const int* guard,
-                        cudaStream_t s);
+                        cudaStream_t s, int functor_id = SK_FUNCTOR_SNAVELY_REPROJECTION_ERROR);
 
 // out[c*K + k] = sum over the camera's segments of seg[s*K + k]   (deterministic, tile order)
 void launch_cam_reduce(const BaDev& L, int K, const double* seg, double* out, const int* guard, cudaStream_t s);

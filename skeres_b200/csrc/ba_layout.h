@@ -15,9 +15,9 @@
 #include <string>
 #include <vector>
 
-namespace sk {
+#include "ba_tile_obs.h"   // kTileObs
 
-constexpr int kTileObs = 256;   // observations per tile == threads per CTA
+namespace sk {
 
 struct BaLayoutHost {
   int32_t n_obs = 0, n_pts = 0, n_cams = 0, n_tiles = 0, n_segs = 0;

@@ -4,24 +4,10 @@
 // and therefore produce the same bits.
 #pragma once
 #include "ba_kernels.cuh"
+#include "ba_tile.cuh"
 
 namespace sk {
 namespace {
-
-constexpr int T = kTileObs;
-constexpr int VLD = T + 1;   // padded leading dimension of the per-observation staging planes
-
-struct Tile { int ob, no, pb, np, sb, ns, chunk; };   // chunk >= 0: chunk tile of a long track (np == 1), else -1
-
-__device__ __forceinline__ Tile load_tile(const BaDev& L, int t) {
-  Tile q;
-  q.ob = L.tile_obs[t]; q.no = L.tile_obs[t + 1] - q.ob;
-  q.pb = L.tile_pt[t];
-  const int np = L.tile_np[t];
-  q.np = np < 0 ? 1 : np; q.chunk = np < 0 ? -np - 1 : -1;
-  q.sb = L.tile_seg[t]; q.ns = L.tile_seg[t + 1] - q.sb;
-  return q;
-}
 
 // ---- two-level sums of the implicit-Schur product --------------------------------------------------------------------
 // Round 1 formed every per-point sum and every per-(segment, component) sum as ONE serial chain of dependent shared-memory

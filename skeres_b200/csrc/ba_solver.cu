@@ -37,8 +37,8 @@ __global__ void k_scatter_blocks(int nblocks, int bsize, const long long* __rest
 }  // namespace
 
 BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHost&& layout, double* user_params,
-                   int64_t user_n, LossSpec loss, BaLayoutDevice* dev)
-    : LmSolver(opt, stream), H_(std::move(layout)), user_(user_params), user_n_(user_n), loss_(loss) {
+                   int64_t user_n, LossSpec loss, BaLayoutDevice* dev, int functor_id)
+    : LmSolver(opt, stream), H_(std::move(layout)), user_(user_params), user_n_(user_n), loss_(loss), functor_(functor_id) {
   const auto& H = H_;
   cudaStream_t s = stream_;
   if (dev != nullptr && dev->valid) {
@@ -250,7 +250,7 @@ void BaSolver::eval_jacobian(bool scale_valid, bool store, const int* guard) {
     KScope k(prof_, SK_KF_EVALUATE_JACOBIAN, 3 + (L_.n_giant ? 1 : 0));
     launch_ba_evaluate(L_, x_.p, scale_valid ? scale_.p : nullptr, loss_, true, store, reinterpret_cast<double2*>(J2_.p),
                        reinterpret_cast<double2*>(r2_.p), grad_.p, cnorm2_.p, seg_a_.p, seg_b_.p, tile_cost_.p,
-                       chunk_pt_.p, &st_.p->eval_failed, guard, stream_);
+                       chunk_pt_.p, &st_.p->eval_failed, guard, stream_, functor_);
     launch_cam_reduce(L_, 9, seg_a_.p, grad_.p, guard, stream_);
     launch_cam_reduce(L_, 9, seg_b_.p, cnorm2_.p, guard, stream_);
   }
@@ -266,7 +266,7 @@ void BaSolver::eval_jacobian(bool scale_valid, bool store, const int* guard) {
 void BaSolver::eval_cost(const double* xv, const int* guard) {
   KScope k(prof_, SK_KF_EVALUATE_COST);
   launch_ba_evaluate(L_, xv, nullptr, loss_, false, false, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, tile_cost_.p,
-                     nullptr, &st_.p->eval_failed, guard, stream_);
+                     nullptr, &st_.p->eval_failed, guard, stream_, functor_);
 }
 
 // seg_a_ = segment partials of S_local * v, where v = `in` or (pcg_dir) the PCG direction z + beta p.

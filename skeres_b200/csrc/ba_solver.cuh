@@ -11,8 +11,10 @@ class BaSolver : public LmSolver {
   // user_params: device pointer of the user's parameter DoubleArray (all blocks live in it).
   // dev != nullptr && dev->valid: the layout arrays are already on the device (ba_layout_device.cu) and are adopted; `layout`
   // then carries counts, per-tile maxima and the camera table only.
+  // functor_id: the cost functor of every residual block -- the built-in SnavelyReprojectionError or a functor of the same
+  // shape (2; 9, 3; 2 constants) registered from source, which runs in the same tile kernel (user_functor.cuh).
   BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHost&& layout, double* user_params,
-           int64_t user_n, LossSpec loss, BaLayoutDevice* dev = nullptr);
+           int64_t user_n, LossSpec loss, BaLayoutDevice* dev = nullptr, int functor_id = SK_FUNCTOR_SNAVELY_REPROJECTION_ERROR);
   ~BaSolver() override;
   void fill_totals(int64_t total_obs, int64_t total_blocks, int64_t total_params, std::vector<int64_t>&& all_pt_off);
   // Rank-local ingestion (sk_solver_options.residual_blocks_are_local): sums the per-rank observation / point counts for
@@ -45,6 +47,7 @@ class BaSolver : public LmSolver {
   BaDev L_{};
   double* user_; int64_t user_n_;
   LossSpec loss_;
+  int functor_;                        // cost functor of the residual blocks (tile evaluation kernel)
   bool explicit_schur_ = false;
   PeerAllreduce peer_;                 // multi-GPU: NVLink peer window for the per-PCG-iteration exchange (comm.cuh)
   bool local_blocks_ = false;          // this rank was given only its own residual blocks (no publication of foreign points)

@@ -4,8 +4,15 @@
 //
 // Each thread runs exactly the iteration the single-problem path runs (TrustRegionMinimizer A.3,
 // LevenbergMarquardtStrategy A.4, Householder QR of the 2-column [J; D] A.8), with the problem's LM
-// state kept in SoA device arrays between launches.  The 67 exponentials of a pass are stashed in
-// shared memory so the second Householder pass re-uses them.
+// state kept in SoA device arrays between launches.
+//
+// Two passes over a problem's observations per LM iteration.  The sums a Jacobian evaluation at the current point feeds into
+// the iteration (cost, gradient, column norms, the first Householder reflector's dot products: `Sums`) are part of the saved
+// state: they are produced by the pass that evaluates the CANDIDATE point (which an accepted step turns into the current point;
+// TrustRegionMinimizer evaluates cost and Jacobian there anyway) and stay valid after a rejected step.  An iteration therefore
+// reads the observations once for the second Householder reflector and once for the candidate -- 134 exponentials -- where the
+// first version of this file read them four times (201 exponentials, 69 KB of shared memory per CTA for the stashed
+// exponentials: 12 resident warps per SM).  Same arithmetic in the same order for every quantity that is used.
 #include "batch.cuh"
 
 #include <cfloat>
@@ -22,21 +29,50 @@ constexpr int BT = 128;            // threads (= problems) per CTA
 
 struct BatchState {                // SoA, index = problem
   double *radius, *decrease, *x_cost, *x_norm, *scale1, *scale2, *diag1, *diag2, *initial_cost, *final_cost, *grad_max;
+  double* sums;                    // [kSums][np]: the Sums of the Jacobian evaluation at the current point
   int *iteration, *reuse, *nci, *done, *term, *nsucc, *nunsucc;
 };
 
 struct Sums { double cost, g1, g2, n1, n2, a0, b0, r0, S11, S12, S1r, S22, S2r; };
+constexpr int kSums = sizeof(Sums) / sizeof(double);
+static_assert(kSums == 13, "Sums is saved field by field");
+__device__ __forceinline__ void save_sums(double* base, int64_t np, int64_t p, const Sums& s) {
+  const double v[kSums] = {s.cost, s.g1, s.g2, s.n1, s.n2, s.a0, s.b0, s.r0, s.S11, s.S12, s.S1r, s.S22, s.S2r};
+#pragma unroll
+  for (int k = 0; k < kSums; ++k) base[(int64_t)k * np + p] = v[k];
+}
+__device__ __forceinline__ Sums load_sums(const double* base, int64_t np, int64_t p) {
+  double v[kSums];
+#pragma unroll
+  for (int k = 0; k < kSums; ++k) v[k] = base[(int64_t)k * np + p];
+  return Sums{v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11], v[12]};
+}
 
 // Pass over the observations at (m, c): stashes e_i = exp(m x_i + c) and accumulates everything the
 // iteration needs from the (optionally column-scaled) Jacobian  J_i = (-x_i e_i, -e_i)  — the
 // infinitesimal parts spire's Jet yields for ExponentialResidual (CurveFitting.scala:96).
+// exp(m x + c) with the multiply-add spelled out: the passes must agree on every e_i bit for bit.
+__device__ __forceinline__ double model(double m, double x, double c) { return exp(__fma_rn(m, x, c)); }
+
+// Measured on a B200 (1M problems, profiles/r02_v12_batch_curve_fits.md): four rows per load batch and five CTAs per SM (96
+// registers, 120 bytes of spills) 8.6 ms for the whole batch; no cap (140 registers, three CTAs) 9.5 ms; one / two rows per
+// batch 11.1 / 10.3 ms; the four-pass version with the shared-memory stash 24.1 ms.
+#ifndef SK_BATCH_RB                // development only (tools/gpu/build_variants.sh): A/B of the load batching and of the register cap
+#define SK_BATCH_RB 4
+#endif
+#ifndef SK_BATCH_MINB
+#define SK_BATCH_MINB 5
+#endif
+constexpr int RB = SK_BATCH_RB;    // observation rows whose loads are issued together (the adds keep the row order)
+
+// Pass over the observations at (m, c): accumulates everything an iteration needs from the (optionally column-scaled)
+// Jacobian  J_i = (-x_i e_i, -e_i), e_i = exp(m x_i + c)  -- the infinitesimal parts spire's Jet yields for
+// ExponentialResidual (CurveFitting.scala:96).
 __device__ __forceinline__ void pass_jacobian(const double* __restrict__ x, const double* __restrict__ y, int64_t np, int64_t p,
-                                              int nobs, double m, double c, double s1, double s2, double* e_s, Sums* o) {
+                                              int nobs, double m, double c, double s1, double s2, Sums* o) {
   Sums s{};
-  for (int i = 0; i < nobs; ++i) {
-    const double xi = x[(int64_t)i * np + p], yi = y[(int64_t)i * np + p];
-    const double e = exp(m * xi + c);
-    e_s[i * BT] = e;
+  auto row = [&](int i, double xi, double yi) {
+    const double e = model(m, xi, c);
     const double r = yi - e;
     const double j1 = -(e * xi), j2 = -e;
     s.cost += r * r;
@@ -46,19 +82,18 @@ __device__ __forceinline__ void pass_jacobian(const double* __restrict__ x, cons
     if (i == 0) { s.a0 = a; s.b0 = b; s.r0 = r; }
     else { s.S11 += a * a; s.S12 += a * b; s.S1r += a * r; }
     s.S22 += a * b; s.S2r += b * r;                 // full sums (including row 0) for the model cost
+  };
+  int i = 0;
+  for (; i + RB <= nobs; i += RB) {
+    double xi[RB], yi[RB];
+#pragma unroll
+    for (int u = 0; u < RB; ++u) { xi[u] = __ldcs(x + (int64_t)(i + u) * np + p); yi[u] = __ldcs(y + (int64_t)(i + u) * np + p); }
+#pragma unroll
+    for (int u = 0; u < RB; ++u) row(i + u, xi[u], yi[u]);
   }
+  for (; i < nobs; ++i) row(i, __ldcs(x + (int64_t)i * np + p), __ldcs(y + (int64_t)i * np + p));
   s.cost *= 0.5;
   *o = s;
-}
-
-__device__ __forceinline__ double residual_cost(const double* __restrict__ x, const double* __restrict__ y, int64_t np, int64_t p,
-                                                int nobs, double m, double c) {
-  double s = 0.0;
-  for (int i = 0; i < nobs; ++i) {
-    const double r = y[(int64_t)i * np + p] - exp(m * x[(int64_t)i * np + p] + c);
-    s += r * r;
-  }
-  return 0.5 * s;
 }
 
 __device__ __forceinline__ bool finalize(BatchState st, int64_t p, bool successful, double grad_max, double row_cost,
@@ -83,7 +118,6 @@ __device__ __forceinline__ void publish_active(bool active, int* active_count) {
 __global__ void __launch_bounds__(BT) k_batch_init(int64_t np, int nobs, const double* __restrict__ x, const double* __restrict__ y,
                                                    const double* __restrict__ mc, BatchState st, LmParams prm, double radius0,
                                                    int jacobi_scaling, int* active_count) {
-  extern __shared__ double e_s[];
   const int64_t p = blockIdx.x * (int64_t)BT + threadIdx.x;
   // No thread may leave before publish_active: it contains a CTA-wide barrier, and a warp whose lanes reach
   // a barrier at two different program points (n_problems not a multiple of 32) is undefined behaviour.
@@ -91,9 +125,11 @@ __global__ void __launch_bounds__(BT) k_batch_init(int64_t np, int nobs, const d
   if (p < np) {
     const double m = mc[p], c = mc[np + p];
     Sums s;
-    pass_jacobian(x, y, np, p, nobs, m, c, 1.0, 1.0, e_s + threadIdx.x, &s);
+    pass_jacobian(x, y, np, p, nobs, m, c, 1.0, 1.0, &s);
     const double s1 = jacobi_scaling ? 1.0 / (1.0 + sqrt(s.n1)) : 1.0, s2 = jacobi_scaling ? 1.0 / (1.0 + sqrt(s.n2)) : 1.0;
     st.scale1[p] = s1; st.scale2[p] = s2;
+    if (jacobi_scaling) pass_jacobian(x, y, np, p, nobs, m, c, s1, s2, &s);   // the sums of the column-scaled Jacobian (cost and gradient: the same bits)
+    save_sums(st.sums, np, p, s);
     st.radius[p] = radius0; st.decrease[p] = 2.0; st.reuse[p] = 0; st.nci[p] = 0;
     st.x_cost[p] = s.cost; st.x_norm[p] = sqrt(m * m + c * c);
     st.initial_cost[p] = s.cost; st.final_cost[p] = s.cost;
@@ -107,13 +143,12 @@ __global__ void __launch_bounds__(BT) k_batch_init(int64_t np, int nobs, const d
 
 // One LM iteration of problem p; returns whether the problem is still active afterwards.
 __device__ bool iterate_one(int64_t np, int nobs, const double* __restrict__ x, const double* __restrict__ y,
-                            double* __restrict__ mc, BatchState st, LmParams prm, int64_t p, double* e_s) {
+                            double* __restrict__ mc, BatchState st, LmParams prm, int64_t p) {
   const double m = mc[p], c = mc[np + p];
   const double s1 = st.scale1[p], s2 = st.scale2[p];
   double radius = st.radius[p];
   st.iteration[p] += 1;
-  Sums s;
-  pass_jacobian(x, y, np, p, nobs, m, c, s1, s2, e_s, &s);
+  const Sums s = load_sums(st.sums, np, p);          // Jacobian evaluation at (m, c): done by the iteration that moved here
   const double x_cost = st.x_cost[p];
   // LevenbergMarquardtStrategy::ComputeStep
   double d1, d2;
@@ -139,15 +174,25 @@ __device__ bool iterate_one(int64_t np, int nobs, const double* __restrict__ x, 
   const double bD1 = -tau1 * sc2 * essD1, rD1 = -tau1 * scr * essD1, bD2 = D2;
   // second pass: column 2 and rhs after the first reflector, rows 1..m-1
   double b1p = 0.0, r1p = 0.0, T22 = 0.0, T2r = 0.0;
-  for (int i = 1; i < nobs; ++i) {
-    const double xi = x[(int64_t)i * np + p], yi = y[(int64_t)i * np + p];
-    const double e = e_s[i * BT];
-    const double r = yi - e;
-    const double a = -(e * xi) * s1, b = -e * s2;
-    const double ess = a * inv1;
-    const double bp = b - tau1 * sc2 * ess, rp = r - tau1 * scr * ess;
-    if (i == 1) { b1p = bp; r1p = rp; }
-    else { T22 += bp * bp; T2r += bp * rp; }
+  {
+    auto row = [&](int i, double xi, double yi) {
+      const double e = model(m, xi, c);
+      const double r = yi - e;
+      const double a = -(e * xi) * s1, b = -e * s2;
+      const double ess = a * inv1;
+      const double bp = b - tau1 * sc2 * ess, rp = r - tau1 * scr * ess;
+      if (i == 1) { b1p = bp; r1p = rp; }
+      else { T22 += bp * bp; T2r += bp * rp; }
+    };
+    int i = 1;
+    for (; i + RB <= nobs; i += RB) {                 // plain loads: the candidate pass below reads the same lines again
+      double xi[RB], yi[RB];
+#pragma unroll
+      for (int u = 0; u < RB; ++u) { xi[u] = __ldg(x + (int64_t)(i + u) * np + p); yi[u] = __ldg(y + (int64_t)(i + u) * np + p); }
+#pragma unroll
+      for (int u = 0; u < RB; ++u) row(i + u, xi[u], yi[u]);
+    }
+    for (; i < nobs; ++i) row(i, __ldg(x + (int64_t)i * np + p), __ldg(y + (int64_t)i * np + p));
   }
   double tau2, beta2, dv2;
   {
@@ -176,7 +221,9 @@ __device__ bool iterate_one(int64_t np, int nobs, const double* __restrict__ x, 
   st.nci[p] = 0;
   const double dm = st1 * s1, dc = st2 * s2;
   const double mcand = m + dm, ccand = c + dc;
-  const double cand_cost = residual_cost(x, y, np, p, nobs, mcand, ccand);
+  Sums t;                                            // cost AND Jacobian sums at the candidate: an accepted step needs both
+  pass_jacobian(x, y, np, p, nobs, mcand, ccand, s1, s2, &t);
+  const double cand_cost = t.cost;
   const double cc = (cand_cost == cand_cost) ? cand_cost : DBL_MAX;
   const double dxm = m - mcand, dxc = c - ccand;
   const double step_norm = sqrt(dxm * dxm + dxc * dxc);
@@ -186,8 +233,7 @@ __device__ bool iterate_one(int64_t np, int nobs, const double* __restrict__ x, 
   const double rho = cost_change / mcc;
   if (rho > prm.min_relative_decrease) {              // HandleSuccessfulStep
     mc[p] = mcand; mc[np + p] = ccand;
-    Sums t;
-    pass_jacobian(x, y, np, p, nobs, mcand, ccand, s1, s2, e_s, &t);
+    save_sums(st.sums, np, p, t);
     st.x_cost[p] = t.cost; st.x_norm[p] = sqrt(mcand * mcand + ccand * ccand);
     const double gm = fmax(fabs(mcand - (mcand + (-t.g1))), fabs(ccand - (ccand + (-t.g2))));
     st.grad_max[p] = gm;
@@ -201,12 +247,11 @@ __device__ bool iterate_one(int64_t np, int nobs, const double* __restrict__ x, 
   return finalize(st, p, false, st.grad_max[p], cc, prm);
 }
 
-__global__ void __launch_bounds__(BT) k_batch_iterate(int64_t np, int nobs, const double* __restrict__ x, const double* __restrict__ y,
+__global__ void __launch_bounds__(BT, SK_BATCH_MINB) k_batch_iterate(int64_t np, int nobs, const double* __restrict__ x, const double* __restrict__ y,
                                                       double* __restrict__ mc, BatchState st, LmParams prm, int* active_count) {
-  extern __shared__ double e_sh[];
   const int64_t p = blockIdx.x * (int64_t)BT + threadIdx.x;
   bool active = false;
-  if (p < np && !st.done[p]) active = iterate_one(np, nobs, x, y, mc, st, prm, p, e_sh + threadIdx.x);
+  if (p < np && !st.done[p]) active = iterate_one(np, nobs, x, y, mc, st, prm, p);
   publish_active(active, active_count);
 }
 
@@ -220,7 +265,7 @@ void curve_fit_batch_solve(const sk_solver_options& opt, int64_t np, int nobs, c
   cudaStream_t stream;
   SK_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } sg{stream};
-  DBuf<double> dbl((size_t)11 * np);
+  DBuf<double> dbl((size_t)(11 + kSums) * np);
   DBuf<int> ints((size_t)7 * np);
   DBuf<int> active(1);
   HBuf<int> active_h(1);
@@ -228,7 +273,7 @@ void curve_fit_batch_solve(const sk_solver_options& opt, int64_t np, int nobs, c
   double* dp = dbl.p;
   st.radius = dp; st.decrease = dp + np; st.x_cost = dp + 2 * np; st.x_norm = dp + 3 * np; st.scale1 = dp + 4 * np;
   st.scale2 = dp + 5 * np; st.diag1 = dp + 6 * np; st.diag2 = dp + 7 * np; st.initial_cost = dp + 8 * np;
-  st.final_cost = dp + 9 * np; st.grad_max = dp + 10 * np;
+  st.final_cost = dp + 9 * np; st.grad_max = dp + 10 * np; st.sums = dp + 11 * np;
   int* ip = ints.p;
   st.iteration = ip; st.reuse = ip + np; st.nci = ip + 2 * np; st.done = ip + 3 * np; st.term = ip + 4 * np;
   st.nsucc = ip + 5 * np; st.nunsucc = ip + 6 * np;
@@ -239,17 +284,11 @@ void curve_fit_batch_solve(const sk_solver_options& opt, int64_t np, int nobs, c
   prm.function_tolerance = opt.function_tolerance; prm.gradient_tolerance = opt.gradient_tolerance;
   prm.parameter_tolerance = opt.parameter_tolerance; prm.eta = opt.eta;
   const int blocks = cdiv(np, BT);
-  const size_t smem = sizeof(double) * (size_t)nobs * BT;
-  SK_REQUIRE(smem <= 200 * 1024, SK_ERR_UNSUPPORTED, "batched curve fits support at most %d observations per problem", 200 * 1024 / 8 / BT);
-  if (smem > 48 * 1024) {
-    SK_CUDA(cudaFuncSetAttribute(k_batch_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SK_CUDA(cudaFuncSetAttribute(k_batch_iterate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
   Profiler prof; prof.enabled = opt.profile_kernels != 0; prof.stream = stream;
   int launches = 0;
   active.zero(stream);
   { KScope k(prof, SK_KF_EVALUATE_JACOBIAN);
-    k_batch_init<<<blocks, BT, smem, stream>>>(np, nobs, x, y, mc, st, prm, opt.initial_trust_region_radius, opt.jacobi_scaling, active.p); }
+    k_batch_init<<<blocks, BT, 0, stream>>>(np, nobs, x, y, mc, st, prm, opt.initial_trust_region_radius, opt.jacobi_scaling, active.p); }
   check_launch("k_batch_init"); ++launches;
   SK_CUDA(cudaMemcpyAsync(active_h.p, active.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
   SK_CUDA(cudaStreamSynchronize(stream));
@@ -260,7 +299,7 @@ void curve_fit_batch_solve(const sk_solver_options& opt, int64_t np, int nobs, c
                "batched solve: %d problems still active after %d launches (max_num_iterations %d)", *active_h.p, lm_iters, opt.max_num_iterations);
     active.zero(stream);
     { KScope k(prof, SK_KF_DENSE);
-      k_batch_iterate<<<blocks, BT, smem, stream>>>(np, nobs, x, y, mc, st, prm, active.p); }
+      k_batch_iterate<<<blocks, BT, 0, stream>>>(np, nobs, x, y, mc, st, prm, active.p); }
     check_launch("k_batch_iterate"); ++launches; ++lm_iters;
     SK_CUDA(cudaMemcpyAsync(active_h.p, active.p, sizeof(int), cudaMemcpyDeviceToHost, stream));   // the one scalar readback
     SK_CUDA(cudaStreamSynchronize(stream));

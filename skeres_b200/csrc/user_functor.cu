@@ -7,6 +7,9 @@
 // blocks (eval_abi.cuh) and two kernels with the sizes baked in:
 //     sk_user_evaluate_single   AutoDiffCostFunction.evaluate for one residual block (AutodiffCostFunction.scala:74-134)
 //     sk_user_dense_evaluate    the residual blocks of this functor inside a DENSE_QR problem (dense_kernels.cu: k_dense_evaluate)
+// and -- for a functor of the bundle-adjustment shape (2 residuals; blocks of 9 and 3; 2 constants), e.g. another camera model --
+//     sk_user_ba_evaluate_jac / _cost   the TILE evaluation kernel of the Schur solvers (ba_evaluate.cuh: the body k_ba_evaluate
+//                               runs for the built-in SnavelyReprojectionError), so that such a functor runs on the hot path
 // compiles it with NVRTC for sm_100a (libnvrtc is loaded lazily with dlopen: no link-time dependency, and nothing is loaded
 // unless a functor is registered) and loads the cubin with cudaLibraryLoadData.  Seeding order, Jacobian layout and the
 // success convention are those of the built-in functors, so the reference's own AutodiffCostFuntionSpec vectors are reproduced
@@ -21,13 +24,14 @@
 #include <string>
 #include <vector>
 
+#include "ba_dev.cuh"
 #include "common.cuh"
 
 namespace sk {
 
 namespace {
 
-#include "build/embedded_sources.inc"   // kSrcSkeresH, kSrcJetCuh, kSrcEvalAbi
+#include "build/embedded_sources.inc"   // kSrcSkeresH, kSrcJetCuh, kSrcEvalAbi, kSrcBaTileObs, kSrcBaDev, kSrcBaTile, kSrcBaEvaluate
 
 // ---- NVRTC through dlopen -----------------------------------------------------------------------------------------------
 typedef struct _nvrtcProgram* nvrtcProgram;
@@ -67,7 +71,7 @@ NvrtcApi& nvrtc() {
   return a;
 }
 
-struct Loaded { cudaLibrary_t lib = nullptr; cudaKernel_t single = nullptr, dense = nullptr; };
+struct Loaded { cudaLibrary_t lib = nullptr; cudaKernel_t single = nullptr, dense = nullptr, ba_jac = nullptr, ba_cost = nullptr; size_t ba_smem[2] = {0, 0}; };
 struct UserFunctor {
   FunctorInfo info{};
   std::string name;
@@ -84,10 +88,14 @@ bool valid_identifier(const char* s) {
   return true;
 }
 
+// The bundle-adjustment shape: SchurEliminator<2, 3, 9> with the observation as the two constants.
+bool ba_shaped(const FunctorInfo& fi) { return fi.nres == 2 && fi.nblk == 2 && fi.sizes[0] == 9 && fi.sizes[1] == 3 && fi.nconsts == 2; }
+
 // The translation unit handed to NVRTC.
 std::string generate(const char* name, const char* source, const FunctorInfo& fi) {
   std::string s;
   s += "#include \"../../include/skeres.h\"\n#include \"eval_abi.cuh\"\n#include \"jet.cuh\"\n";
+  if (ba_shaped(fi)) s += "#include \"ba_evaluate.cuh\"\n";
   s += "using sk::Jet;\n";
   s += "#line 1 \"user_functor_source\"\n";
   s += source;
@@ -179,6 +187,47 @@ extern "C" __global__ void sk_user_dense_evaluate(int functor_id, int with_jac, 
   }
 }
 )SKGEN";
+  if (ba_shaped(fi)) s += R"SKGEN(
+// The functor as the tile kernels of the Schur solvers see it (ba_evaluate.cuh): constants = the observed (x, y), blocks = (camera 9, point 3).
+namespace sk_user {
+struct BaFunctor {
+  static __device__ __forceinline__ bool residual(const double* cam, const double* pt, double ox, double oy, double* res) {
+    const double c[2] = {ox, oy};
+    double xx[12];
+    for (int k = 0; k < 9; ++k) xx[k] = cam[k];
+    for (int k = 0; k < 3; ++k) xx[9 + k] = pt[k];
+    return evaluate(c, xx, res, nullptr);
+  }
+  static __device__ __forceinline__ bool residual_jacobian(const double* cam, const double* pt, double ox, double oy, double* res,
+                                                           double* F, double* E) {
+    const double c[2] = {ox, oy};
+    double xx[12], jac[24];
+    for (int k = 0; k < 9; ++k) xx[k] = cam[k];
+    for (int k = 0; k < 3; ++k) xx[9 + k] = pt[k];
+    if (!evaluate(c, xx, res, jac)) return false;
+    for (int q = 0; q < 2; ++q) {
+      for (int k = 0; k < 9; ++k) F[q * 9 + k] = jac[q * 12 + k];
+      for (int k = 0; k < 3; ++k) E[q * 3 + k] = jac[q * 12 + 9 + k];
+    }
+    return true;
+  }
+};
+}  // namespace sk_user
+extern "C" __global__ void __launch_bounds__(sk::kTileObs, 2)
+sk_user_ba_evaluate_jac(sk::BaDev L, const double* __restrict__ x, const double* __restrict__ scale, sk::LossSpec loss, int write_j,
+                        double2* __restrict__ J2, double2* __restrict__ r2, double* __restrict__ grad, double* __restrict__ cnorm2,
+                        double* __restrict__ seg_g, double* __restrict__ seg_n, double* __restrict__ tile_cost,
+                        double* __restrict__ chunk_pt, int* fail_flag, const int* guard) {
+  sk::ba_evaluate_tile<true, sk_user::BaFunctor>(L, x, scale, loss, write_j, J2, r2, grad, cnorm2, seg_g, seg_n, tile_cost, chunk_pt, fail_flag, guard);
+}
+extern "C" __global__ void __launch_bounds__(sk::kTileObs)
+sk_user_ba_evaluate_cost(sk::BaDev L, const double* __restrict__ x, const double* __restrict__ scale, sk::LossSpec loss, int write_j,
+                         double2* __restrict__ J2, double2* __restrict__ r2, double* __restrict__ grad, double* __restrict__ cnorm2,
+                         double* __restrict__ seg_g, double* __restrict__ seg_n, double* __restrict__ tile_cost,
+                         double* __restrict__ chunk_pt, int* fail_flag, const int* guard) {
+  sk::ba_evaluate_tile<false, sk_user::BaFunctor>(L, x, scale, loss, write_j, J2, r2, grad, cnorm2, seg_g, seg_n, tile_cost, chunk_pt, fail_flag, guard);
+}
+)SKGEN";
   return s;
 }
 
@@ -191,6 +240,10 @@ Loaded& loaded_on_current_device(UserFunctor& f) {
   SK_CUDA(cudaLibraryLoadData(&l.lib, f.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
   SK_CUDA(cudaLibraryGetKernel(&l.single, l.lib, "sk_user_evaluate_single"));
   SK_CUDA(cudaLibraryGetKernel(&l.dense, l.lib, "sk_user_dense_evaluate"));
+  if (ba_shaped(f.info)) {
+    SK_CUDA(cudaLibraryGetKernel(&l.ba_jac, l.lib, "sk_user_ba_evaluate_jac"));
+    SK_CUDA(cudaLibraryGetKernel(&l.ba_cost, l.lib, "sk_user_ba_evaluate_cost"));
+  }
   return f.per_device.emplace(dev, l).first->second;
 }
 
@@ -219,13 +272,14 @@ int register_user_functor(const char* name, const char* source, int nres, int nb
   SK_REQUIRE(fi.ntot <= 32, SK_ERR_INVALID_ARGUMENT, "sk_functor_register_source: at most 32 scalar parameters per residual block (Jet<32>)");
   const std::string tu = generate(name, source, fi);
   NvrtcApi& rt = nvrtc();
-  const char* header_names[] = {"../../include/skeres.h", "eval_abi.cuh", "jet.cuh", "stdint.h", "stddef.h", "math.h"};
+  const char* header_names[] = {"../../include/skeres.h", "eval_abi.cuh", "jet.cuh", "stdint.h", "stddef.h", "math.h",
+                                "ba_tile_obs.h", "ba_dev.cuh", "ba_tile.cuh", "ba_evaluate.cuh"};
   const char* header_srcs[] = {kSrcSkeresH, kSrcEvalAbi, kSrcJetCuh,
                                "typedef signed char int8_t; typedef short int16_t; typedef int int32_t; typedef long long int64_t;\n"
                                "typedef unsigned char uint8_t; typedef unsigned short uint16_t; typedef unsigned int uint32_t; typedef unsigned long long uint64_t;\n",
-                               "", ""};
+                               "", "", kSrcBaTileObs, kSrcBaDev, kSrcBaTile, kSrcBaEvaluate};
   nvrtcProgram prog = nullptr;
-  int r = rt.CreateProgram(&prog, tu.c_str(), "skeres_user_functor.cu", 6, header_srcs, header_names);
+  int r = rt.CreateProgram(&prog, tu.c_str(), "skeres_user_functor.cu", 10, header_srcs, header_names);
   SK_REQUIRE(r == 0, SK_ERR_INTERNAL, "nvrtcCreateProgram failed: %s", rt.GetErrorString ? rt.GetErrorString(r) : "?");
   const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-default-device", "--fmad=true"};
   r = rt.CompileProgram(prog, 4, opts);
@@ -241,6 +295,9 @@ int register_user_functor(const char* name, const char* source, int nres, int nb
   if (r == 0 && n > 0) { f->cubin.resize(n); r = rt.GetCUBIN(prog, f->cubin.data()); }
   rt.DestroyProgram(&prog);
   SK_REQUIRE(r == 0 && !f->cubin.empty(), SK_ERR_INTERNAL, "nvrtcGetCUBIN failed for functor '%s'", name);
+  if (const char* dir = getenv("SKERES_DUMP_USER_CUBIN")) {   // development: <dir>/<name>.cubin for cuobjdump -res-usage / -sass
+    if (FILE* fp = fopen(fmt("%s/%s.cubin", dir, name).c_str(), "wb")) { fwrite(f->cubin.data(), 1, f->cubin.size(), fp); fclose(fp); }
+  }
   std::lock_guard<std::mutex> g(g_mu);
   const int id = g_next_id++;
   fi.id = id;
@@ -262,6 +319,30 @@ void launch_user_evaluate_single(int id, const EvalArgs& a, int* ok_out, cudaStr
   EvalArgs args = a;
   void* params[] = {&args, &ok_out};
   SK_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(l.single), dim3(1), dim3(1), params, 0, s));
+}
+
+bool user_functor_runs_on_tiles(int id) {
+  std::lock_guard<std::mutex> g(g_mu);
+  auto it = g_functors.find(id);
+  return it != g_functors.end() && ba_shaped(it->second->info);
+}
+
+void launch_user_ba_evaluate(int id, bool with_jacobian, size_t smem, const BaDev& L, const double* x, const double* scale, LossSpec loss,
+                             int write_j, double2* J2, double2* r2, double* grad, double* cnorm2, double* seg_g, double* seg_n,
+                             double* tile_cost, double* chunk_pt, int* fail_flag, const int* guard, cudaStream_t s) {
+  std::lock_guard<std::mutex> g(g_mu);
+  UserFunctor& f = find(id);
+  SK_REQUIRE(ba_shaped(f.info), SK_ERR_UNSUPPORTED, "functor %d does not have the bundle-adjustment shape (2; 9, 3; 2 constants)", id);
+  Loaded& l = loaded_on_current_device(f);
+  cudaKernel_t k = with_jacobian ? l.ba_jac : l.ba_cost;
+  size_t& cfg = l.ba_smem[with_jacobian ? 1 : 0];
+  if (smem > 48 * 1024 && smem > cfg) {
+    SK_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(k), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cfg = smem;
+  }
+  BaDev Lc = L;
+  void* params[] = {&Lc, &x, &scale, &loss, &write_j, &J2, &r2, &grad, &cnorm2, &seg_g, &seg_n, &tile_cost, &chunk_pt, &fail_flag, &guard};
+  SK_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3(L.n_tiles), dim3(kTileObs), params, smem, s));
 }
 
 void launch_user_dense_evaluate(int id, bool with_jacobian, int nrb, const DenseRb* rbs, const double* x, double* J, int m, double* b,

@@ -2,6 +2,7 @@
 // the device counterpart of a Scala `class F extends CostFunctor(kNumResiduals, N0, N1, ...) { def apply[T](x: Array[T]*) }`
 // (core/.../CostFunctor.scala:31-51), which the reference evaluates on the JVM through ~45 JNI crossings per residual block.
 #pragma once
+#include "ba_dev.cuh"
 #include "eval_abi.cuh"
 #include "jet.cuh"
 
@@ -20,5 +21,12 @@ void launch_user_evaluate_single(int id, const EvalArgs& a, int* ok_out, cudaStr
 // evaluation writes them; the CTA's cost is ADDED to block_cost[blockIdx.x] (the built-in kernel has written the slot before).
 void launch_user_dense_evaluate(int id, bool with_jacobian, int nrb, const DenseRb* rbs, const double* x, double* J, int m, double* b,
                                 double* block_cost, int* fail_flag, const int* guard, cudaStream_t s);
+// A functor of the bundle-adjustment shape (2 residuals; parameter blocks of 9 and 3; 2 constants = the observation) is also
+// compiled into the TILE evaluation kernel of the Schur solvers (ba_evaluate.cuh) and can stand in for the built-in
+// SnavelyReprojectionError there: same arguments as k_ba_evaluate<with_jacobian> (ba_kernels.cu), smem = its dynamic shared memory.
+bool user_functor_runs_on_tiles(int id);
+void launch_user_ba_evaluate(int id, bool with_jacobian, size_t smem, const BaDev& L, const double* x, const double* scale, LossSpec loss,
+                             int write_j, double2* J2, double2* r2, double* grad, double* cnorm2, double* seg_g, double* seg_n,
+                             double* tile_cost, double* chunk_pt, int* fail_flag, const int* guard, cudaStream_t s);
 
 }  // namespace sk

@@ -50,12 +50,12 @@ def oracle_ba(oracle, d, lst, prec=_abi.SCHUR_JACOBI, loss=(_abi.LOSS_TRIVIAL, 0
     return p, p.solve(o)
 
 
-def gpu_ba(sk, d, lst, prec=_abi.SCHUR_JACOBI, loss=None, order=None, **opts):
+def gpu_ba(sk, d, lst, prec=_abi.SCHUR_JACOBI, loss=None, order=None, functor_id=_abi.FUNCTOR_SNAVELY_REPROJECTION_ERROR, **opts):
     bal = sk.BalProblem.fromArrays(d)
     if order is not None:
         bal.cameraIndex, bal.pointIndex = bal.cameraIndex[order], bal.pointIndex[order]
         bal.observations = bal.observations.reshape(-1, 2)[order].ravel()
-    problem = bal.buildProblem(loss)
+    problem = bal.buildProblem(loss, functor_id)
     o = sk.Solver.Options()
     o.setLinearSolverType(lst)
     o.setPreconditionerType(prec)
@@ -144,7 +144,81 @@ def test_user_functor_solves_curve_fitting_like_the_builtin(sk):
     assert [float(f"{v:.6f}") for v in x1] == [0.291861, 0.131439]
 
 
+@pytest.mark.parametrize("shape,seed,lst,prec,loss", [("small", 2, _abi.ITERATIVE_SCHUR, _abi.SCHUR_JACOBI, None),
+                                                      ("small", 5, _abi.ITERATIVE_SCHUR, _abi.JACOBI, ("huber", 1.0)),
+                                                      ("tiny", 1, _abi.DENSE_SCHUR, _abi.JACOBI, None),
+                                                      ("ladybug-49", 1, _abi.SPARSE_SCHUR, _abi.JACOBI, None)])
+def test_user_ba_functor_runs_in_the_tile_kernels(sk, oracle, shape, seed, lst, prec, loss):
+    """SURVEY 8(f) rank 4 on the hot path: SnavelyReprojectionError ported from SimpleBundleAdjuster.scala:79-119 AS A SOURCE
+    STRING (sk_functor_register_source) is compiled by NVRTC into the tile evaluation kernel of the Schur solvers
+    (ba_evaluate.cuh: the body the built-in functor runs in) and solves bundle adjustment like the built-in registration --
+    same LM rows and PCG iteration counts, costs to 1e-9 (a full-width Jet<12> against the built-in's two 6-wide stages: the
+    same derivatives, different roundings) -- and like the oracle."""
+    import user_functor_sources as U
+    F = sk.SourceCostFunctor.define(*U.BA_SHAPED[0])
+    d = synth.make_bal(shape, seed=seed)
+    mk = (lambda: getattr(sk.PredefinedLossFunctions, loss[0] + "Loss")(loss[1])) if loss else (lambda: None)
+    bal0, s0 = gpu_ba(sk, d, lst, prec, loss=mk())
+    bal1, s1 = gpu_ba(sk, d, lst, prec, loss=mk(), functor_id=F.functor_id)
+    assert_same_trajectory(s1, s0, row_rtol=1e-9)
+    assert rel_param_diff(bal1.parameters.toArray(), bal0.parameters.toArray(), 1e-2) <= 1e-6
+    assert s1.num_kernel_launches == s0.num_kernel_launches
+    if loss is None:
+        p, so = oracle_ba(oracle, d, lst, prec)
+        assert_same_trajectory(s1, so, row_rtol=1e-6)
+
+
+def test_unseen_camera_model_on_the_tile_path(sk, oracle):
+    """A camera model the library has never seen (division model of radial distortion, same (2; 9, 3) shape, reports failure
+    for a point behind the camera), given as source: the Schur solvers run it in the tile kernels, DENSE_QR runs it on the
+    dense back end (per-block addResidualBlock, AutoDiffCostFunctor.toAutoDiffCostFunction).  Checked against the oracle,
+    which holds the same functor as a checker-only registration (oracle/jet.h: divisionModelReprojectionError, id 900): exact
+    solvers row for row at 1e-9, ITERATIVE_SCHUR like the built-in functor's runs (same rows, same PCG counts); the two
+    exact device paths agree with each other.  A functor failure at the initial point is a FAILURE of the solve."""
+    import user_functor_sources as U
+    F = sk.SourceCostFunctor.define(*U.BA_SHAPED[1])
+    d = synth.make_bal("tiny", seed=4)
+
+    def oracle_solve(lst, prec=_abi.JACOBI):
+        p = oracle.OracleProblem(d.parameters)
+        p.add_residual_blocks(900, d.observations.reshape(-1, 2), d.block_offsets())
+        o = _abi.default_options()
+        o.linear_solver_type, o.preconditioner_type, o.max_num_iterations = lst, prec, 8
+        return p, p.solve(o)
+    bal1, s1 = gpu_ba(sk, d, _abi.DENSE_SCHUR, functor_id=F.functor_id, max_num_iterations=8)
+    bal2, s2 = gpu_ba(sk, d, _abi.ITERATIVE_SCHUR, _abi.SCHUR_JACOBI, functor_id=F.functor_id, max_num_iterations=8)
+    bal3 = sk.BalProblem.fromArrays(d)
+    problem = sk.Problem()
+    o = d.observations
+    for i in range(d.num_observations):
+        problem.addResidualBlock(F(o[2 * i], o[2 * i + 1]).toAutoDiffCostFunction(), None, bal3.mutableCameraForObservation(i), bal3.mutablePointForObservation(i))
+    opt = sk.Solver.Options()
+    opt.setLinearSolverType(_abi.DENSE_QR); opt.setMaxNumIterations(8)
+    s3 = sk.Solver.Summary()
+    sk.ceres.solve(opt, problem, s3)
+    assert len(s1.iterations) >= 3 and s1.final_cost < 0.1 * s1.initial_cost
+    p1, so1 = oracle_solve(_abi.DENSE_SCHUR)
+    p2, so2 = oracle_solve(_abi.ITERATIVE_SCHUR, _abi.SCHUR_JACOBI)
+    p3, so3 = oracle_solve(_abi.DENSE_QR)
+    assert_same_trajectory(s1, so1, row_rtol=1e-9)
+    assert_same_trajectory(s2, so2, row_rtol=1e-6)
+    assert_same_trajectory(s3, so3, row_rtol=1e-9)
+    assert rel_param_diff(bal1.parameters.toArray(), p1.params, 1e-2) <= PARAM_RTOL
+    assert rel_param_diff(bal3.parameters.toArray(), p3.params, 1e-2) <= PARAM_RTOL
+    for a, b in zip(s1.iterations, s3.iterations):                       # tile path == dense path (two exact linear solvers)
+        assert np.isclose(a.cost, b.cost, rtol=1e-9)
+    # the built-in model on the same data is a different problem: the functor in the tile kernel really is the user's
+    bal0, s0 = gpu_ba(sk, d, _abi.DENSE_SCHUR, max_num_iterations=8)
+    assert abs(s0.iterations[0].cost - s1.iterations[0].cost) > 1e-6 * s1.iterations[0].cost
+    # functor failure: camera 0 turned around (t -> -t puts everything it sees behind it)
+    bad = synth.make_bal("tiny", seed=4)
+    bad.parameters[3:6] *= -1.0
+    balf, sf = gpu_ba(sk, bad, _abi.DENSE_SCHUR, functor_id=F.functor_id, max_num_iterations=3)
+    assert sf.termination_type == _abi.FAILURE
+
+
 def test_user_functor_is_rejected_by_the_schur_solvers(sk):
+    """... unless it has the bundle-adjustment shape (the tests above)."""
     import user_functor_sources as U
     F = sk.SourceCostFunctor.define("UserExponentialResidual", U.EXPONENTIAL, 1, [1, 1], 2)
     m, c = sk.DoubleArray(1), sk.DoubleArray(1)

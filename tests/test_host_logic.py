@@ -580,7 +580,9 @@ def test_user_functor_sources_compile_without_a_gpu():
     from skeres_b200 import _abi
     from skeres_b200._lib import lib
     ids = []
-    for name, src, nres, sizes, nconsts in U.SPEC + [("UserExponentialResidual", U.EXPONENTIAL, 1, [1, 1], 2)]:
+    # the last two have the bundle-adjustment shape (2; 9, 3; 2 constants): their translation unit also holds the TILE evaluation
+    # kernels of the Schur solvers (ba_evaluate.cuh, handed to NVRTC with the library's own ba_dev.cuh / ba_tile.cuh)
+    for name, src, nres, sizes, nconsts in U.SPEC + [("UserExponentialResidual", U.EXPONENTIAL, 1, [1, 1], 2)] + U.BA_SHAPED:
         fid = C.c_int(0)
         st = lib.sk_functor_register_source(name.encode(), src.encode(), nres, len(sizes), (C.c_int * len(sizes))(*sizes), nconsts, C.byref(fid))
         assert st == _abi.OK, lib.sk_last_error().decode()

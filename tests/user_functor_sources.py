@@ -46,3 +46,50 @@ template <class T> __device__ bool UserExponentialResidual(const double* consts,
 # name, source, kNumResiduals, N, num_consts -- in the order of tests/golden/autodiff_spec_vectors.json
 SPEC = [("BinaryScalarCost", BILINEAR_SCALAR, 1, [2, 2], 1), ("BinaryVectorCost", BILINEAR_VECTOR3, 3, [2, 2], 1),
         ("TenParamsCost", SUM10, 1, [1] * 10, 0)]
+
+SNAVELY = """
+// SimpleBundleAdjuster.scala:79-119   class SnavelyReprojectionError(observedX, observedY) extends AutoDiffCostFunctor(2, 9, 3)
+// Rotation.angleAxisRotatePoint (core/.../Rotation.scala:449-522) is part of the library on both sides: sk::angle_axis_rotate_point.
+template <class T> __device__ bool UserSnavelyReprojectionError(const double* consts, T const* const* params, T* residuals) {
+  const double observedX = consts[0], observedY = consts[1];
+  const T* camera = params[0];
+  const T* point = params[1];
+  T p[3];
+  sk::angle_axis_rotate_point(camera, point, p);   // camera(0, 1, 2) are the angle-axis rotation
+  p[0] = p[0] + camera[3];                          // camera(3, 4, 5) are the translation
+  p[1] = p[1] + camera[4];
+  p[2] = p[2] + camera[5];
+  const T xp = (-p[0]) / p[2];                      // Bundler's camera looks down the negative z axis
+  const T yp = (-p[1]) / p[2];
+  const T l1 = camera[7], l2 = camera[8];
+  const T r2 = xp * xp + yp * yp;
+  const T distortion = 1.0 + r2 * (l1 + l2 * r2);
+  const T focal = camera[6];
+  residuals[0] = focal * distortion * xp - observedX;
+  residuals[1] = focal * distortion * yp - observedY;
+  return true;
+}
+"""
+
+DIVISION_MODEL = """
+// A camera model the library has never seen: the same (2; 9, 3) shape with the DIVISION model of radial distortion,
+// distortion = 1 / (1 + l1 r^2 + l2 r^4), and a functor that reports failure for a point behind the camera.
+template <class T> __device__ bool DivisionModelReprojectionError(const double* consts, T const* const* params, T* residuals) {
+  const T* camera = params[0];
+  const T* point = params[1];
+  T p[3];
+  sk::angle_axis_rotate_point(camera, point, p);
+  p[0] = p[0] + camera[3]; p[1] = p[1] + camera[4]; p[2] = p[2] + camera[5];
+  if (!((-p[2]) > 0.0)) return false;
+  const T xp = (-p[0]) / p[2];
+  const T yp = (-p[1]) / p[2];
+  const T r2 = xp * xp + yp * yp;
+  const T distortion = 1.0 / (1.0 + r2 * (camera[7] + camera[8] * r2));
+  residuals[0] = camera[6] * distortion * xp - consts[0];
+  residuals[1] = camera[6] * distortion * yp - consts[1];
+  return true;
+}
+"""
+
+# bundle-adjustment shaped functors: compiled into the tile evaluation kernel of the Schur solvers as well
+BA_SHAPED = [("UserSnavelyReprojectionError", SNAVELY, 2, [9, 3], 2), ("DivisionModelReprojectionError", DIVISION_MODEL, 2, [9, 3], 2)]
