@@ -296,6 +296,51 @@ def test_iterative_schur_converges_to_the_exact_schur_optimum(oracle):
         assert abs(v - ref) <= 1e-8 * ref
 
 
+
+def _snavely_residuals_scipy(x, d):
+    """Independent of the oracle and of the device code: SciPy's rotation-vector class for R(angle-axis), numpy for the rest
+    (SimpleBundleAdjuster.scala:79-119 as a formula: p = R X + t, projection through -z, two radial terms)."""
+    from scipy.spatial.transform import Rotation
+    nc = d.num_cameras
+    cams = x[:9 * nc].reshape(nc, 9)[d.camera_index]
+    pts = x[9 * nc:].reshape(-1, 3)[d.point_index]
+    p = Rotation.from_rotvec(cams[:, :3]).apply(pts) + cams[:, 3:6]
+    xp, yp = -p[:, 0] / p[:, 2], -p[:, 1] / p[:, 2]
+    r2 = xp * xp + yp * yp
+    f = cams[:, 6] * (1.0 + r2 * (cams[:, 7] + cams[:, 8] * r2))
+    return (np.stack([f * xp, f * yp], 1) - d.observations.reshape(-1, 2)).ravel()
+
+
+@pytest.mark.parametrize("seed", [1, 4])
+def test_ba_residuals_and_optimum_against_scipy(oracle, seed):
+    """an independent cross-check of bundle-adjustment OPTIMA (not trajectories).  The residual vector of the
+    oracle equals SciPy's own rotation-vector arithmetic to 1e-11 px, and the cost the oracle's trust-region / Schur solve
+    converges to equals -- to 1e-7, from below -- the cost scipy.optimize.least_squares (trust-region reflective, finite-
+    difference Jacobian: none of the restated Ceres algebra) reaches from the same start."""
+    from scipy.optimize import least_squares
+    from scipy.sparse import lil_matrix
+    d, p = ba_problem(oracle, "tiny", seed)
+    cost, r, g, Jv = p.evaluate()
+    r0 = _snavely_residuals_scipy(d.parameters, d)
+    assert np.abs(r0 - r).max() < 1e-11 and abs(0.5 * r0 @ r0 - cost) <= 1e-13 * cost
+    o = _abi.default_options()
+    o.linear_solver_type, o.max_num_iterations = _abi.DENSE_SCHUR, 200
+    o.function_tolerance = o.gradient_tolerance = o.parameter_tolerance = 1e-14
+    s = p.solve(o)
+    assert s.termination_type == _abi.CONVERGENCE
+    n_obs = d.num_observations
+    A = lil_matrix((2 * n_obs, d.parameters.size), dtype=int)
+    i = np.arange(n_obs)
+    for k in range(9):
+        A[2 * i, 9 * d.camera_index + k] = 1; A[2 * i + 1, 9 * d.camera_index + k] = 1
+    for k in range(3):
+        A[2 * i, 9 * d.num_cameras + 3 * d.point_index + k] = 1; A[2 * i + 1, 9 * d.num_cameras + 3 * d.point_index + k] = 1
+    sol = least_squares(_snavely_residuals_scipy, d.parameters, args=(d,), jac_sparsity=A, method="trf", x_scale="jac",
+                        xtol=1e-15, ftol=1e-15, gtol=1e-15, max_nfev=200)
+    assert abs(sol.cost - s.final_cost) <= 1e-7 * s.final_cost
+    assert s.final_cost <= sol.cost * (1 + 1e-12)          # scipy, limited by its finite differences, stops just above
+
+
 def test_tight_pcg_matches_exact_schur_step(oracle):
     """With eta -> 0 the implicit-Schur PCG solves the same reduced system the eliminator factorises (A.6/A.7)."""
     d, p1 = ba_problem(oracle)
