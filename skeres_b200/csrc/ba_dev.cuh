@@ -18,6 +18,9 @@ struct BaDev {
   int matvec_classic;                  // 0: k_ba_matvec_tma / the fused PCG solve; 1: k_ba_matvec (SKERES_MATVEC=classic); read per solver
   int matvec_serial_sums;              // 1 (default): per-point / per-segment sums as one serial chain each; 0: the chunked
                                        // two-level sums (SKERES_MATVEC_SUMS=chunked)
+  int l2_keep_tiles;                   // implicit-Schur product: tiles [0, l2_keep_tiles) are copied with the L2 evict_last policy, the
+                                       // rest evict_first (the stored Jacobian does not change during a linear solve: this part of it
+                                       // stays in the 126 MB L2 from one product to the next); < 0: no cache hints
   const unsigned short* obs_slot; const unsigned short* obs_ptl; const unsigned short* seg_perm;
   const int* seg_ptr; const int* seg_cam; const int* cam_seg_ptr; const int* cam_seg;
   const int* seg_pos;                  // [S] inverse of cam_seg: the implicit-Schur product stores a segment's partial at its camera-major position

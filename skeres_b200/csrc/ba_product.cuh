@@ -85,6 +85,22 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::
                "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
 }
+// The same copies with an L2 cache policy (createpolicy): evict_last keeps the lines resident across the products of a linear
+// solve, evict_first marks a pure stream.
+__device__ __forceinline__ unsigned long long l2_policy(bool keep) {
+  unsigned long long pol;
+  if (keep) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_box_2d_hint(void* dst, const CUtensorMap* map, int c0, int c1, unsigned long long* b, unsigned long long pol) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;\n" ::
+               "r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(smem_u32(b)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, unsigned bytes, unsigned long long* b, unsigned long long pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n" ::
+               "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)), "l"(pol) : "memory");
+}
 
 // ---- the persistent, fully prefetching product ------------------------------------------------------------------------
 // Each CTA walks a strided list of tiles (tile blockIdx.x + it * gridDim.x) and, while it computes tile i from registers, the TMA
@@ -161,6 +177,23 @@ struct ProductPass {
     unsigned long long* bar_full = m.bar_full; unsigned long long* bar_rec = m.bar_rec;
     const size_t O = (size_t)L.n_obs;
     mbar_expect_tx(bar_rec + buf, (unsigned)L.rec_stride);
+    if (L.l2_keep_tiles >= 0) {            // the same copies with an L2 policy: the first l2_keep_tiles tiles stay resident between products
+      const unsigned long long pol = l2_policy(t < L.l2_keep_tiles);
+      bulk_g2s_hint(recbuf + (size_t)buf * L.rec_stride, L.tile_rec + (size_t)t * L.rec_stride, (unsigned)L.rec_stride, bar_rec + buf, pol);
+      if (TMAP) {
+        const int boxes = (q.no + T / 2 - 1) / (T / 2);
+        mbar_expect_tx(bar_full + buf, (unsigned)(boxes * kJPlanes * (T / 2) * 16 + q.np * 48));
+        for (int h = 0; h < boxes; ++h) tma_box_2d_hint(Jbuf + h * kJPlanes * (T / 2), tmapJ, 2 * (q.ob + h * (T / 2)), 0, bar_full + buf, pol);
+      } else {
+        mbar_expect_tx(bar_full + buf, (unsigned)(q.no * kJPlanes * 16 + q.np * 48));
+        if (q.no > 0) {
+#pragma unroll
+          for (int k = 0; k < kJPlanes; ++k) bulk_g2s_hint(Jbuf + k * T, J2 + k * O + q.ob, (unsigned)q.no * 16u, bar_full + buf, pol);
+        }
+      }
+      if (q.np > 0) bulk_g2s_hint(eibuf + (size_t)buf * L.max_pt_tile * 6, einv + (size_t)q.pb * 6, (unsigned)q.np * 48u, bar_full + buf, pol);
+      return;
+    }
     bulk_g2s(recbuf + (size_t)buf * L.rec_stride, L.tile_rec + (size_t)t * L.rec_stride, (unsigned)L.rec_stride, bar_rec + buf);
     if (TMAP) {
       static_assert(T == 256, "the tensor-map box is 128 observations: two boxes per tile");

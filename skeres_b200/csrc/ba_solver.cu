@@ -36,6 +36,12 @@ __global__ void k_scatter_blocks(int nblocks, int bsize, const long long* __rest
 }
 }  // namespace
 
+// Default of SKERES_L2_KEEP_MB (see the constructor).  Measured on the Venice shape (profiles/r02_v13_l2_policy.md): with the
+// product's copies marked evict_first the camera-sized vectors, the preconditioner blocks and the segment partials of the vector
+// phases survive the 1 GB Jacobian stream in L2 -- 18.1 -> 13.3 us of vector phases per PCG iteration; keeping part of the
+// Jacobian itself resident (evict_last) does not speed the product up (24 / 48 MB: neutral; 80 / 110 MB: slower).
+constexpr double kL2KeepMB = 24.0;
+
 BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHost&& layout, double* user_params,
                    int64_t user_n, LossSpec loss, BaLayoutDevice* dev, int functor_id)
     : LmSolver(opt, stream), H_(std::move(layout)), user_(user_params), user_n_(user_n), loss_(loss), functor_(functor_id) {
@@ -83,6 +89,7 @@ BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHo
   // per-point / per-segment sums of the product: serial chains (default: measured 1.5 % faster back to back, r02) or the chunked
   // two-level sums (SKERES_MATVEC_SUMS=chunked)
   { const char* e = getenv("SKERES_MATVEC_SUMS"); L_.matvec_serial_sums = (e != nullptr && e[0] == 'c') ? 0 : 1; }
+  L_.l2_keep_tiles = -1;               // set with the tile records (build_tile_records)
   const int64_t nc = (int64_t)9 * H.n_cams, n = nc + (int64_t)3 * H.n_pts;
   allocate(n, nc);
   J2_.alloc((size_t)2 * kJPlanes * std::max(H.n_obs, 1)); r2_.alloc((size_t)2 * std::max(H.n_obs, 1));
@@ -126,6 +133,16 @@ BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHo
   if (!explicit_schur_) {
     const auto t0 = std::chrono::steady_clock::now();
     build_tile_records();
+    {
+      // L2 residency of the product's operands: SKERES_L2_KEEP_MB megabytes of tiles (Jacobian planes + record + (E^T E)^-1
+      // blocks) are copied evict_last, the rest evict_first; negative: plain copies
+      const char* e = getenv("SKERES_L2_KEEP_MB");
+      const double mb = e != nullptr ? atof(e) : kL2KeepMB;
+      if (mb >= 0.0 && H.n_tiles > 0) {
+        const double per_tile = (double)kJPlanes * kTileObs * 16 + L_.rec_stride + 48.0 * H.n_pts / H.n_tiles;
+        L_.l2_keep_tiles = (int)std::min<double>(H.n_tiles, mb * 1e6 / per_tile);
+      }
+    }
     { const char* e = getenv("SKERES_MATVEC_TMAP");   // development: SKERES_MATVEC_TMAP=0 keeps one bulk copy per plane
       if (!(e && e[0] == '0')) have_tmapJ_ = make_jacobian_tensor_map(reinterpret_cast<const double2*>(J2_.p), H_.n_obs, &tmapJ_); }
     if (getenv("SKERES_TRACE_HOST")) fprintf(stderr, "[skeres] tile records: %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());

@@ -54,16 +54,56 @@ __device__ __forceinline__ Sums load_sums(const double* base, int64_t np, int64_
 // exp(m x + c) with the multiply-add spelled out: the passes must agree on every e_i bit for bit.
 __device__ __forceinline__ double model(double m, double x, double c) { return exp(__fma_rn(m, x, c)); }
 
-// Measured on a B200 (1M problems, profiles/r02_v12_batch_curve_fits.md): four rows per load batch and five CTAs per SM (96
-// registers, 120 bytes of spills) 8.6 ms for the whole batch; no cap (140 registers, three CTAs) 9.5 ms; one / two rows per
-// batch 11.1 / 10.3 ms; the four-pass version with the shared-memory stash 24.1 ms.
+// Measured on a B200 (1M problems, profiles/r02_v12_batch_curve_fits.md): four rows per load batch, the next batch loaded ahead,
+// four CTAs per SM (128 registers) 7.9 ms for the whole batch; without the load-ahead and five CTAs per SM (96 registers, 120
+// bytes of spills) 8.6 ms; no cap (140 registers, three CTAs) 9.5 ms; one / two rows per batch 11.1 / 10.3 ms; the four-pass
+// version with the shared-memory stash 24.1 ms.
 #ifndef SK_BATCH_RB                // development only (tools/gpu/build_variants.sh): A/B of the load batching and of the register cap
 #define SK_BATCH_RB 4
 #endif
 #ifndef SK_BATCH_MINB
-#define SK_BATCH_MINB 5
+#define SK_BATCH_MINB 4
 #endif
 constexpr int RB = SK_BATCH_RB;    // observation rows whose loads are issued together (the adds keep the row order)
+
+#ifndef SK_BATCH_PIPE              // 1 = the loads of the next batch of rows are issued before the current batch is used (0: development A/B)
+#define SK_BATCH_PIPE 1
+#endif
+// row(i, x_i, y_i) for i = first .. nobs - 1, in that order; the loads are issued RB rows at a time.  STREAM: last use of the
+// lines (evict-first), else plain read-only loads (the same lines are read again by a later pass of this launch).
+template <bool STREAM, class F>
+__device__ __forceinline__ void for_rows(const double* __restrict__ x, const double* __restrict__ y, int64_t np, int64_t p, int first,
+                                         int nobs, F&& row) {
+  auto ld = [&](const double* a, int i) { return STREAM ? __ldcs(a + (int64_t)i * np + p) : __ldg(a + (int64_t)i * np + p); };
+  int i = first;
+#if SK_BATCH_PIPE
+  double xn[RB], yn[RB];
+  if (i + RB <= nobs) {
+#pragma unroll
+    for (int u = 0; u < RB; ++u) { xn[u] = ld(x, i + u); yn[u] = ld(y, i + u); }
+  }
+  for (; i + RB <= nobs; i += RB) {
+    double xi[RB], yi[RB];
+#pragma unroll
+    for (int u = 0; u < RB; ++u) { xi[u] = xn[u]; yi[u] = yn[u]; }
+    if (i + 2 * RB <= nobs) {
+#pragma unroll
+      for (int u = 0; u < RB; ++u) { xn[u] = ld(x, i + RB + u); yn[u] = ld(y, i + RB + u); }
+    }
+#pragma unroll
+    for (int u = 0; u < RB; ++u) row(i + u, xi[u], yi[u]);
+  }
+#else
+  for (; i + RB <= nobs; i += RB) {
+    double xi[RB], yi[RB];
+#pragma unroll
+    for (int u = 0; u < RB; ++u) { xi[u] = ld(x, i + u); yi[u] = ld(y, i + u); }
+#pragma unroll
+    for (int u = 0; u < RB; ++u) row(i + u, xi[u], yi[u]);
+  }
+#endif
+  for (; i < nobs; ++i) row(i, ld(x, i), ld(y, i));
+}
 
 // Pass over the observations at (m, c): accumulates everything an iteration needs from the (optionally column-scaled)
 // Jacobian  J_i = (-x_i e_i, -e_i), e_i = exp(m x_i + c)  -- the infinitesimal parts spire's Jet yields for
@@ -83,15 +123,7 @@ __device__ __forceinline__ void pass_jacobian(const double* __restrict__ x, cons
     else { s.S11 += a * a; s.S12 += a * b; s.S1r += a * r; }
     s.S22 += a * b; s.S2r += b * r;                 // full sums (including row 0) for the model cost
   };
-  int i = 0;
-  for (; i + RB <= nobs; i += RB) {
-    double xi[RB], yi[RB];
-#pragma unroll
-    for (int u = 0; u < RB; ++u) { xi[u] = __ldcs(x + (int64_t)(i + u) * np + p); yi[u] = __ldcs(y + (int64_t)(i + u) * np + p); }
-#pragma unroll
-    for (int u = 0; u < RB; ++u) row(i + u, xi[u], yi[u]);
-  }
-  for (; i < nobs; ++i) row(i, __ldcs(x + (int64_t)i * np + p), __ldcs(y + (int64_t)i * np + p));
+  for_rows<true>(x, y, np, p, 0, nobs, row);
   s.cost *= 0.5;
   *o = s;
 }
@@ -184,15 +216,7 @@ __device__ bool iterate_one(int64_t np, int nobs, const double* __restrict__ x, 
       if (i == 1) { b1p = bp; r1p = rp; }
       else { T22 += bp * bp; T2r += bp * rp; }
     };
-    int i = 1;
-    for (; i + RB <= nobs; i += RB) {                 // plain loads: the candidate pass below reads the same lines again
-      double xi[RB], yi[RB];
-#pragma unroll
-      for (int u = 0; u < RB; ++u) { xi[u] = __ldg(x + (int64_t)(i + u) * np + p); yi[u] = __ldg(y + (int64_t)(i + u) * np + p); }
-#pragma unroll
-      for (int u = 0; u < RB; ++u) row(i + u, xi[u], yi[u]);
-    }
-    for (; i < nobs; ++i) row(i, __ldg(x + (int64_t)i * np + p), __ldg(y + (int64_t)i * np + p));
+    for_rows<false>(x, y, np, p, 1, nobs, row);      // plain loads: the candidate pass below reads the same lines again
   }
   double tau2, beta2, dv2;
   {
