@@ -36,11 +36,14 @@ __global__ void k_scatter_blocks(int nblocks, int bsize, const long long* __rest
 }
 }  // namespace
 
-// Default of SKERES_L2_KEEP_MB (see the constructor).  Measured on the Venice shape (profiles/r02_v13_l2_policy.md): with the
-// product's copies marked evict_first the camera-sized vectors, the preconditioner blocks and the segment partials of the vector
-// phases survive the 1 GB Jacobian stream in L2 -- 18.1 -> 13.3 us of vector phases per PCG iteration; keeping part of the
-// Jacobian itself resident (evict_last) does not speed the product up (24 / 48 MB: neutral; 80 / 110 MB: slower).
+// L2 cache policies on the copies of the implicit-Schur product (ba_product.cuh: ProductPass::issue).  Measured
+// (profiles/r02_v13_l2_policy.md): with the copies marked evict_first the operands of the vector phases -- the (tile, camera)
+// partials, the preconditioner blocks, the camera-sized vectors -- survive the Jacobian stream in the 126 MB L2 as long as they
+// fit: 2-4 % per PCG iteration at working sets of 26-61 MB (Venice shape: 18.1 -> 13.3 us of vector phases), 1.2-1.4 % LOSS at
+// 104-190 MB (Final-13682 shape on one or two GPUs).  Keeping part of the Jacobian itself resident (evict_last) does not speed the
+// product up (24 / 48 MB neutral, 80 / 110 MB slower).  SKERES_L2_KEEP_MB overrides: megabytes of tiles kept, negative = plain copies.
 constexpr double kL2KeepMB = 24.0;
+constexpr double kL2PolicyMaxWorkingSetMB = 80.0;
 
 BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHost&& layout, double* user_params,
                    int64_t user_n, LossSpec loss, BaLayoutDevice* dev, int functor_id)
@@ -137,7 +140,8 @@ BaSolver::BaSolver(const sk_solver_options& opt, cudaStream_t stream, BaLayoutHo
       // L2 residency of the product's operands: SKERES_L2_KEEP_MB megabytes of tiles (Jacobian planes + record + (E^T E)^-1
       // blocks) are copied evict_last, the rest evict_first; negative: plain copies
       const char* e = getenv("SKERES_L2_KEEP_MB");
-      const double mb = e != nullptr ? atof(e) : kL2KeepMB;
+      const double working_set_mb = (72.0 * H.n_segs + (648.0 + 720.0) * H.n_cams) / 1e6;   // partials + M^-1 blocks + ten camera-sized vectors
+      const double mb = e != nullptr ? atof(e) : (working_set_mb <= kL2PolicyMaxWorkingSetMB ? kL2KeepMB : -1.0);
       if (mb >= 0.0 && H.n_tiles > 0) {
         const double per_tile = (double)kJPlanes * kTileObs * 16 + L_.rec_stride + 48.0 * H.n_pts / H.n_tiles;
         L_.l2_keep_tiles = (int)std::min<double>(H.n_tiles, mb * 1e6 / per_tile);

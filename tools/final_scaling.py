@@ -37,7 +37,11 @@ def main():
         dist.broadcast_object_list(ids, src=0)
         comm = api.Communicator(ids[0], rank, world)
     t0 = time.time()
-    d = synth.make_bal(args.shape, seed=1)
+    if "," in args.shape:                                     # development: "cameras,points,observations" (e.g. one rank's share on one GPU)
+        c_, p_, o_ = (int(v) for v in args.shape.split(","))
+        d = synth.make_bal(n_cam=c_, n_pt=p_, n_obs=o_, seed=1)
+    else:
+        d = synth.make_bal(args.shape, seed=1)
     t_gen = time.time() - t0
     K, W = args.steps, args.warmup
 
