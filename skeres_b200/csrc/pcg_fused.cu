@@ -51,7 +51,7 @@ __device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int* targe
     const unsigned int t = *target + gridDim.x;
     *target = t;
     __threadfence();
-    atomicAdd(bar, 1u);
+    atomicAdd(bar, 1u);                                // (arriving with red.release.gpu instead of fence + atomic: measured, no difference)
     while (ld_acquire_gpu(bar) < t) { }
   }
   __syncthreads();

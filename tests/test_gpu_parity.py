@@ -739,6 +739,28 @@ def test_fused_pcg_matches_kernel_sequence_bitwise(sk, monkeypatch, case, prec, 
     assert runs[0][3] == runs[1][3]                                         # products executed: counted by the host / derived from the readback
 
 
+@pytest.mark.parametrize("pcg", ["fused", "sequence"])
+def test_l2_copy_policies_do_not_change_results(sk, monkeypatch, pcg):
+    """The copies of the implicit-Schur product carry L2 cache policies (ba_product.cuh: evict_first for the Jacobian stream,
+    evict_last for the first SKERES_L2_KEEP_MB megabytes of tiles; chosen by the working set of the vector phases, ba_solver.cu).
+    A cache policy moves no bit: plain copies (-1), an all-stream policy (0), the default and an everything-resident policy
+    give identical LM rows, PCG counts and parameters -- in the fused solve and in the kernel sequence, whose stand-alone
+    product kernel issues the same copies."""
+    d = synth.make_bal(n_cam=300, n_pt=60000, n_obs=400000, seed=3)
+    monkeypatch.setenv("SKERES_PCG", pcg)
+    runs = []
+    for mb in ("-1", "0", None, "1000"):
+        if mb is None:
+            monkeypatch.delenv("SKERES_L2_KEEP_MB", raising=False)
+        else:
+            monkeypatch.setenv("SKERES_L2_KEEP_MB", mb)
+        bal, s = gpu_ba(sk, d, _abi.ITERATIVE_SCHUR, _abi.SCHUR_JACOBI, max_num_iterations=6)
+        runs.append(([r.cost for r in s.iterations], [r.linear_solver_iterations for r in s.iterations], bal.parameters.toArray()))
+    assert len(runs[0][0]) == 7 and sum(runs[0][1]) > 20
+    for r in runs[1:]:
+        assert r[0] == runs[0][0] and r[1] == runs[0][1] and np.array_equal(r[2], runs[0][2])
+
+
 @pytest.mark.parametrize("sums", ["serial", "chunked"])
 @pytest.mark.parametrize("case", [dict(shape="ladybug-49", seed=1), MEDIUM_TRACK_CASE, LONG_TRACK_SMALL])
 def test_device_built_tile_records_equal_the_host_builder(sk, monkeypatch, case, sums):
