@@ -571,14 +571,16 @@ def test_local_range_equals_partition_points(world):
         assert bal.localRange(0, world)[0] == 0 and bal.localRange(world - 1, world)[1] == d.num_observations
 
 
-def test_user_functor_sources_compile_without_a_gpu():
+def test_user_functor_sources_compile_without_a_gpu(tmp_path, monkeypatch):
     """sk_functor_register_source: NVRTC turns the functor source plus the library's own jet.cuh into
     sm_100a kernels; compiling needs no device (the module is loaded at first use), so the generated translation unit is
     checked here.  A source that does not compile comes back as INVALID_ARGUMENT with the compiler's log."""
     import ctypes as C
+    import shutil
     import user_functor_sources as U
     from skeres_b200 import _abi
     from skeres_b200._lib import lib
+    monkeypatch.setenv("SKERES_DUMP_USER_CUBIN", str(tmp_path))        # development aid of user_functor.cu: <dir>/<name>.cubin
     ids = []
     # the last two have the bundle-adjustment shape (2; 9, 3; 2 constants): their translation unit also holds the TILE evaluation
     # kernels of the Schur solvers (ba_evaluate.cuh, handed to NVRTC with the library's own ba_dev.cuh / ba_tile.cuh)
@@ -592,6 +594,14 @@ def test_user_functor_sources_compile_without_a_gpu():
         bs = (C.c_int * 10)()
         assert lib.sk_functor_info(fid.value, C.byref(nr), C.byref(nb), bs, C.byref(nc)) == _abi.OK
         assert (nr.value, nb.value, nc.value, list(bs)[:len(sizes)]) == (nres, len(sizes), nconsts, sizes)
+    # which kernels a translation unit holds: the two generic ones always, the tile kernels of the Schur solvers for the BA shape only
+    if shutil.which("cuobjdump"):
+        def kernels(name):
+            out = subprocess.run(["cuobjdump", "--dump-resource-usage", str(tmp_path / f"{name}.cubin")], capture_output=True, text=True).stdout
+            return {k for k in ("sk_user_evaluate_single", "sk_user_dense_evaluate", "sk_user_ba_evaluate_jac", "sk_user_ba_evaluate_cost") if k in out}
+        assert kernels("BinaryScalarCost") == {"sk_user_evaluate_single", "sk_user_dense_evaluate"}
+        for name, *_ in U.BA_SHAPED:
+            assert kernels(name) == {"sk_user_evaluate_single", "sk_user_dense_evaluate", "sk_user_ba_evaluate_jac", "sk_user_ba_evaluate_cost"}
     fid = C.c_int(0)
     bad = "template <class T> __device__ bool Broken(const double* c, T const* const* x, T* r) { r[0] = undefined_symbol; return true; }"
     st = lib.sk_functor_register_source(b"Broken", bad.encode(), 1, 1, (C.c_int * 1)(1), 0, C.byref(fid))
