@@ -72,16 +72,9 @@ __device__ __forceinline__ double2 ldcs2(const double2* p) { return __ldcs(p); }
 // ------------------------------------------------------------------------------------------------
 // Residuals (+ Jacobian) of one tile: ba_evaluate.cuh (the body is shared with the kernels NVRTC compiles for functors given
 // as source); here with the built-in SnavelyReprojectionError (jet.cuh: two 6-wide dual stages).
-#ifdef SK_EVAL_MINB                // development only: resident CTAs per SM the register allocation of the set-up kernels aims at
-#define SK_EVAL_BOUNDS __launch_bounds__(T, JAC ? SK_EVAL_MINB : 1)
-#else
-#define SK_EVAL_BOUNDS __launch_bounds__(T)
-#endif
-#ifndef SK_SETUP_MINB
-#define SK_SETUP_MINB 2
-#endif
+// (Register caps for 3 CTAs per SM -- here and in k_ba_schur_setup -- were measured and buy nothing: profiles/r02_v11_setup_kernels.md.)
 template <bool JAC>
-__global__ void SK_EVAL_BOUNDS k_ba_evaluate(BaDev L, const double* __restrict__ x, const double* __restrict__ scale,
+__global__ void __launch_bounds__(T) k_ba_evaluate(BaDev L, const double* __restrict__ x, const double* __restrict__ scale,
                                                    LossSpec loss, int write_j, double2* __restrict__ J2,
                                                    double2* __restrict__ r2, double* __restrict__ grad,
                                                    double* __restrict__ cnorm2, double* __restrict__ seg_g,
@@ -153,7 +146,7 @@ __device__ __forceinline__ void stage_block_entries(double* vt, const double2 (&
 }
 
 constexpr int kSetupPlanes = 18;     // staged planes per round of k_ba_schur_setup: 9 rhs + 45 block entries = 3 rounds of 18
-__global__ void __launch_bounds__(T, SK_SETUP_MINB) k_ba_schur_setup(BaDev L, const double2* __restrict__ J2, const double2* __restrict__ r2,
+__global__ void __launch_bounds__(T, 2) k_ba_schur_setup(BaDev L, const double2* __restrict__ J2, const double2* __restrict__ r2,
                                                       const double* __restrict__ D, double* __restrict__ einv,
                                                       double* __restrict__ seg_rhs, double* __restrict__ seg_M,
                                                       int* error_flag, int ftf_only) {
